@@ -1,0 +1,253 @@
+// extern "C" surface of libromhc.so (declared in include/romhc.h).
+#include "../../include/romhc.h"
+#include "romhc_internal.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <atomic>
+#include <new>
+
+namespace romhc {
+
+static thread_local char g_err[1024] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+void Context::release() {
+    if (scratch) cudaFree(scratch);
+    if (ws_base) cudaFree(ws_base);
+    if (ws_flags) cudaFree(ws_flags);
+    if (h_flags) cudaFreeHost(h_flags);
+    scratch = nullptr; ws_base = nullptr; ws_flags = nullptr; h_flags = nullptr;
+    scratch_bytes = 0; ws_K = 0;
+}
+
+}  // namespace romhc
+
+using namespace romhc;
+
+struct romhc_context { Context c; };
+
+#define H(h) (&(h)->c)
+#define ST(s) ((cudaStream_t)(s))
+#define CHECK_H(h) do { if (!(h)) { set_error("null context"); return ROMHC_ERR_ARG; } \
+                        cudaError_t e__ = cudaSetDevice((h)->c.device); \
+                        if (e__ != cudaSuccess) { set_error("cudaSetDevice: %s", cudaGetErrorString(e__)); return ROMHC_ERR_CUDA; } } while (0)
+
+extern "C" {
+
+int romhc_version(void) { return 100; }
+const char* romhc_last_error(void) { return last_error(); }
+int64_t romhc_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int romhc_create(int nrb, int ncb, int N, int device, romhc_handle* out) {
+    if (!out) { set_error("out is null"); return ROMHC_ERR_ARG; }
+    *out = nullptr;
+    if (nrb < 1 || ncb < 1 || N < 1 || nrb * ncb > ROMHC_MAX_BLOCKS) {
+        set_error("bad geometry (%d, %d), N=%d (need 1 <= nrb*ncb <= %d)", nrb, ncb, N, ROMHC_MAX_BLOCKS);
+        return ROMHC_ERR_ARG;
+    }
+    if (nrb * N < 2 || ncb * N < 2) { set_error("mesh has no interior vertex"); return ROMHC_ERR_ARG; }
+    if ((long long)(nrb * (long long)N + 1) * (ncb * (long long)N + 8) > (1LL << 30)) {
+        set_error("mesh too large"); return ROMHC_ERR_ARG;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device available (%s): the ROMHighContrast B200 path has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return ROMHC_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (0..%d)", device, ndev - 1); return ROMHC_ERR_ARG; }
+    CK(cudaSetDevice(device));
+    romhc_context* h = new (std::nothrow) romhc_context();
+    if (!h) { set_error("out of host memory"); return ROMHC_ERR_ARG; }
+    h->c.nrb = nrb; h->c.ncb = ncb; h->c.N = N; h->c.device = device;
+    h->c.build_levels();
+    *out = h;
+    return ROMHC_OK;
+}
+
+int romhc_destroy(romhc_handle h) {
+    if (!h) return ROMHC_OK;
+    cudaSetDevice(h->c.device);
+    h->c.release();
+    delete h;
+    return ROMHC_OK;
+}
+
+int romhc_set_option(romhc_handle h, const char* name, double value) {
+    if (!h || !name) { set_error("null argument"); return ROMHC_ERR_ARG; }
+    Context* c = H(h);
+    if (!strcmp(name, "rtol")) c->rtol = value;
+    else if (!strcmp(name, "maxit")) c->maxit = (int)value;
+    else if (!strcmp(name, "coarse_sweeps")) { c->coarse_sweeps = std::max(1, (int)value); c->build_levels(); }
+    else if (!strcmp(name, "workspace_gb")) c->ws_budget_bytes = (size_t)(value * double(1 << 30));
+    else if (!strcmp(name, "check_every")) c->check_every = std::max(1, (int)value);
+    else if (!strcmp(name, "min_check_iter")) c->min_check_iter = std::max(1, (int)value);
+    else { set_error("unknown option '%s'", name); return ROMHC_ERR_ARG; }
+    return ROMHC_OK;
+}
+
+int romhc_get_info(romhc_handle h, int64_t* info) {
+    if (!h || !info) { set_error("null argument"); return ROMHC_ERR_ARG; }
+    const Context* c = H(h);
+    const LevelGeo& g = c->levels[0];
+    memset(info, 0, 16 * sizeof(int64_t));
+    info[0] = int64_t(g.R - 1) * (g.C - 1); info[1] = g.Dp; info[2] = g.P; info[3] = g.R; info[4] = g.C;
+    info[5] = (int64_t)c->levels.size(); info[6] = c->tail_level; info[7] = c->coarse_D; info[8] = c->coarse_direct;
+    info[9] = c->nrb; info[10] = c->ncb; info[11] = c->N; info[12] = (int64_t)c->solve_bytes_per_system();
+    info[13] = (int64_t)c->tail_smem;
+    return ROMHC_OK;
+}
+
+int romhc_malloc(void** p, size_t bytes) { CK(cudaMalloc(p, bytes ? bytes : 8)); return ROMHC_OK; }
+int romhc_free(void* p) { if (p) CK(cudaFree(p)); return ROMHC_OK; }
+int romhc_malloc_host(void** p, size_t bytes) { CK(cudaMallocHost(p, bytes ? bytes : 8)); return ROMHC_OK; }
+int romhc_free_host(void* p) { if (p) CK(cudaFreeHost(p)); return ROMHC_OK; }
+int romhc_memcpy_h2d(void* d, const void* s, size_t n, void* st) {
+    CK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, ST(st))); return ROMHC_OK;
+}
+int romhc_memcpy_d2h(void* d, const void* s, size_t n, void* st) {
+    CK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, ST(st))); return ROMHC_OK;
+}
+int romhc_memset(void* d, int v, size_t n, void* st) { CK(cudaMemsetAsync(d, v, n, ST(st))); return ROMHC_OK; }
+int romhc_stream_sync(void* st) { CK(cudaStreamSynchronize(ST(st))); return ROMHC_OK; }
+
+int romhc_pack(romhc_handle h, const double* c, double* p, int64_t K, void* st) { CHECK_H(h); return H(h)->pack(c, p, K, ST(st)); }
+int romhc_unpack(romhc_handle h, const double* p, double* c, int64_t K, void* st) { CHECK_H(h); return H(h)->unpack(p, c, K, ST(st)); }
+
+int romhc_apply(romhc_handle h, const double* y, const double* u, double* out, int64_t K, void* st) {
+    CHECK_H(h); return H(h)->apply(y, u, out, K, ST(st));
+}
+int romhc_energy_norm(romhc_handle h, const double* y, const double* u, int64_t K, double* out, void* st) {
+    CHECK_H(h); return H(h)->energy(y, u, nullptr, nullptr, 0, out, K, 0, 1, ST(st));
+}
+int romhc_l2_norm(romhc_handle h, const double* u, int64_t K, double* out, void* st) {
+    CHECK_H(h); return H(h)->energy(nullptr, u, nullptr, nullptr, 0, out, K, 1, 1, ST(st));
+}
+int romhc_error_norm(romhc_handle h, const double* U, const double* coef, const double* basis, int n, int64_t K,
+                     double* out, void* st) {
+    CHECK_H(h);
+    if (n < 0 || n > 256) { set_error("error_norm: bad n"); return ROMHC_ERR_ARG; }
+    return H(h)->energy(nullptr, U, n > 0 ? coef : nullptr, basis, n, out, K, 0, 1, ST(st));
+}
+
+int romhc_solve(romhc_handle h, const double* y, int64_t K, double* x, int* iters, double* relres, void* st,
+                int64_t* stats4) {
+    CHECK_H(h);
+    SolveStats s{0, 0, 0};
+    const int rc = H(h)->solve(y, K, x, iters, relres, ST(st), &s);
+    if (stats4) { stats4[0] = s.launched_iterations; stats4[1] = s.chunks; stats4[2] = s.status; stats4[3] = (int64_t)H(h)->ws_bytes; }
+    return rc;
+}
+int romhc_precond(romhc_handle h, const double* y, const double* r, double* z, int64_t K, void* st) {
+    CHECK_H(h); return H(h)->precond(y, r, z, K, ST(st));
+}
+
+int romhc_project_operators(romhc_handle h, const double* basis, int n, double* Ahat, double* bhat, void* st) {
+    CHECK_H(h); return H(h)->project_operators(basis, n, Ahat, bhat, ST(st));
+}
+int romhc_reduced_solve(const double* y, int nb, const double* Ahat, const double* rhs, int rps, int n, int64_t K,
+                        double* C, int* info, void* st) {
+    return reduced_solve(y, nb, Ahat, rhs, rps, n, K, C, info, ST(st));
+}
+
+int romhc_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M,
+                  int64_t N, int64_t Kd, int sym, void* st) { return gemm_nt(A, lda, B, ldb, C, ldc, M, N, Kd, sym, ST(st)); }
+int romhc_gemm_nn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M,
+                  int64_t N, int64_t Kd, void* st) { return gemm_nn(A, lda, B, ldb, C, ldc, M, N, Kd, ST(st)); }
+int romhc_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M,
+                  int64_t N, int64_t Kd, void* st) { return gemm_tn(A, lda, B, ldb, C, ldc, M, N, Kd, ST(st)); }
+int romhc_column_mean(const double* X, int64_t ld, int64_t K, int64_t D, double* mean, void* st) {
+    return column_mean(X, ld, K, D, mean, ST(st));
+}
+int romhc_center_rows(double* X, int64_t ld, int64_t K, int64_t D, const double* mean, void* st) {
+    return center_rows(X, ld, K, D, mean, ST(st));
+}
+
+int romhc_evaluate(romhc_handle h, const double* pts, int m, const double* u, int64_t K, double* out, void* st) {
+    CHECK_H(h); return H(h)->evaluate(pts, m, u, K, out, ST(st));
+}
+int romhc_estimator(const double* c, int64_t K, int n, const double* ab, int nb, int invert, double* out, void* st) {
+    return estimator_contract(c, K, n, ab, nb, invert, out, ST(st));
+}
+int romhc_argmax(const double* v, int64_t K, int64_t* idx, double* val, void* st) { return argmax_first(v, K, idx, val, ST(st)); }
+
+// ---- host-buffer entry points --------------------------------------------------------------------------------------------
+int romhc_generate_solutions_host(romhc_handle h, const double* y_host, int64_t K, double* U_host, int* iters_host,
+                                  double* relres_host) {
+    CHECK_H(h);
+    if (K <= 0) return ROMHC_OK;
+    Context* c = H(h);
+    const LevelGeo& g = c->levels[0];
+    const int nb = c->nrb * c->ncb;
+    const int64_t D = int64_t(g.R - 1) * (g.C - 1);
+    // chunk so that padded + compact staging of the outputs stay within a quarter of the workspace budget
+    const size_t per = size_t(g.Dp + D) * 8 + c->solve_bytes_per_system();
+    int64_t chunk = std::max<int64_t>(1, std::min<int64_t>({(int64_t)(c->ws_budget_bytes / per), (int64_t)32768, K}));
+    double *y_d = nullptr, *x_d = nullptr, *u_d = nullptr, *rel_d = nullptr;
+    int* it_d = nullptr;
+    int rc = ROMHC_OK;
+    cudaStream_t st = 0;
+    auto cleanup = [&]() { cudaFree(y_d); cudaFree(x_d); cudaFree(u_d); cudaFree(rel_d); cudaFree(it_d); };
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_error("%s: %s", #call, cudaGetErrorString(e_)); cleanup(); return ROMHC_ERR_CUDA; } } while (0)
+    CKC(cudaMalloc(&y_d, size_t(chunk) * nb * 8));
+    CKC(cudaMalloc(&x_d, size_t(chunk) * g.Dp * 8));
+    CKC(cudaMalloc(&u_d, size_t(chunk) * D * 8));
+    CKC(cudaMalloc(&rel_d, size_t(chunk) * 8));
+    CKC(cudaMalloc(&it_d, size_t(chunk) * 4));
+    for (int64_t k0 = 0; k0 < K && rc == ROMHC_OK; k0 += chunk) {
+        const int64_t kc = std::min<int64_t>(chunk, K - k0);
+        CKC(cudaMemcpyAsync(y_d, y_host + k0 * nb, size_t(kc) * nb * 8, cudaMemcpyHostToDevice, st));
+        rc = c->solve(y_d, kc, x_d, it_d, rel_d, st, nullptr);
+        if (rc) break;
+        rc = c->unpack(x_d, u_d, kc, st);
+        if (rc) break;
+        CKC(cudaMemcpyAsync(U_host + k0 * D, u_d, size_t(kc) * D * 8, cudaMemcpyDeviceToHost, st));
+        if (iters_host) CKC(cudaMemcpyAsync(iters_host + k0, it_d, size_t(kc) * 4, cudaMemcpyDeviceToHost, st));
+        if (relres_host) CKC(cudaMemcpyAsync(relres_host + k0, rel_d, size_t(kc) * 8, cudaMemcpyDeviceToHost, st));
+        CKC(cudaStreamSynchronize(st));
+    }
+    cleanup();
+    return rc;
+}
+
+int romhc_reduced_galerkin_host(romhc_handle h, const double* y_host, const double* Ahat_host, const double* bhat_host,
+                                int n, int64_t K, double* C_host, int* info_host) {
+    CHECK_H(h);
+    if (K <= 0) return ROMHC_OK;
+    Context* c = H(h);
+    const int nb = c->nrb * c->ncb;
+    double *y_d = nullptr, *A_d = nullptr, *b_d = nullptr, *C_d = nullptr;
+    int* info_d = nullptr;
+    cudaStream_t st = 0;
+    auto cleanup = [&]() { cudaFree(y_d); cudaFree(A_d); cudaFree(b_d); cudaFree(C_d); cudaFree(info_d); };
+    CKC(cudaMalloc(&y_d, size_t(K) * nb * 8));
+    CKC(cudaMalloc(&A_d, size_t(nb) * n * n * 8));
+    CKC(cudaMalloc(&b_d, size_t(n) * 8));
+    CKC(cudaMalloc(&C_d, size_t(K) * n * 8));
+    CKC(cudaMalloc(&info_d, size_t(K) * 4));
+    CKC(cudaMemcpyAsync(y_d, y_host, size_t(K) * nb * 8, cudaMemcpyHostToDevice, st));
+    CKC(cudaMemcpyAsync(A_d, Ahat_host, size_t(nb) * n * n * 8, cudaMemcpyHostToDevice, st));
+    CKC(cudaMemcpyAsync(b_d, bhat_host, size_t(n) * 8, cudaMemcpyHostToDevice, st));
+    int rc = reduced_solve(y_d, nb, A_d, b_d, 0, n, K, C_d, info_d, st);
+    if (rc == ROMHC_OK) {
+        CKC(cudaMemcpyAsync(C_host, C_d, size_t(K) * n * 8, cudaMemcpyDeviceToHost, st));
+        if (info_host) CKC(cudaMemcpyAsync(info_host, info_d, size_t(K) * 4, cudaMemcpyDeviceToHost, st));
+        CKC(cudaStreamSynchronize(st));
+    }
+    cleanup();
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+// Internal C++ declarations shared by the .cu translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <vector>
+
+#include "common.cuh"
+
+#define ROMHC_OK 0
+#define ROMHC_ERR_ARG 1
+#define ROMHC_ERR_CUDA 2
+#define ROMHC_ERR_NUMERIC 3   // singular / non-SPD system (reference: numpy.linalg.LinAlgError)
+#define ROMHC_ERR_NOTCONVERGED 4
+
+namespace romhc {
+
+extern std::atomic<long long> g_launches;   // every kernel launch of the library
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+#define CK(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) {                                                                           \
+            ::romhc::set_error("%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));      \
+            return ROMHC_ERR_CUDA;                                                                         \
+        }                                                                                                  \
+    } while (0)
+
+struct SolveStats {
+    int launched_iterations;
+    int chunks;
+    int status;
+};
+
+struct SolveWorkspace {
+    std::vector<double*> r, za, zb;   // per level
+    double* p[2];
+    double* cfac;
+    double *part_pAp, *part_rz;
+    int np;
+    double *alpha, *beta, *rz, *rz0, *relres;
+    int *active, *iters;
+};
+
+// multigrid tail (levels handled by one CTA per system in shared memory); POD, passed by value
+struct TailParams {
+    int nlev;                         // number of levels handled by the tail kernel
+    LevelGeo geo[ROMHC_MAX_LEVELS];   // geo[0] = first tail level
+    int off_r[ROMHC_MAX_LEVELS];      // smem offsets (doubles) of r_l and z_l
+    int off_z[ROMHC_MAX_LEVELS];
+    int off_fac;                      // smem offset of the Cholesky factor (direct solve)
+    int direct;                       // 1: dense Cholesky on the last level, 0: coarse_sweeps of symmetric GS
+    int DL, LD;                       // coarsest DOFs, factor pitch
+    int coarse_sweeps;
+};
+
+struct Context {
+    int nrb = 0, ncb = 0, N = 0, device = 0;
+    // multigrid hierarchy
+    std::vector<LevelGeo> levels;
+    int tail_level = 0;        // first level handled by the tail kernel (levels.size() if none)
+    int coarse_D = 0, coarse_LD = 1;
+    bool coarse_direct = false;
+    int coarse_sweeps = 8;
+    TailParams tail;
+    size_t tail_smem = 0;
+    // PCG controls
+    double rtol = 1e-12;
+    int maxit = 1000;
+    int min_check_iter = 8, check_every = 2;
+    size_t ws_budget_bytes = size_t(48) << 30;
+    // state
+    bool kernels_configured = false;
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void* ws_base = nullptr;
+    int64_t ws_K = 0;
+    size_t ws_bytes = 0;
+    SolveWorkspace ws;
+    int* ws_flags = nullptr;
+    int* h_flags = nullptr;
+    int64_t launches = 0;      // kernels launched through this context (bench "gpu_launches")
+
+    int build_levels();
+    int configure_kernels();
+    int ensure_scratch(size_t bytes);
+    int ensure_solve_ws(int64_t Kc);
+    size_t solve_bytes_per_system() const;
+    void release();
+
+    // solver.cu
+    int apply(const double* y, const double* u, double* out, int64_t K, cudaStream_t st);
+    int energy(const double* y, const double* u, const double* coef, const double* basis, int nbasis, double* out,
+               int64_t K, int mode, int take_sqrt, cudaStream_t st);
+    int pack(const double* compact, double* padded, int64_t K, cudaStream_t st);
+    int unpack(const double* padded, double* compact, int64_t K, cudaStream_t st);
+    int vcycle(const double* y, int Kc, cudaStream_t st, const double** z_result, int* np_rz);
+    int solve_chunk(const double* y, int Kc, double* x, int* iters_out, double* relres_out, cudaStream_t st,
+                    SolveStats* stats);
+    int solve(const double* y, int64_t K, double* x, int* iters_out, double* relres_out, cudaStream_t st,
+              SolveStats* stats);
+    int precond(const double* y, const double* r, double* z, int64_t K, cudaStream_t st);
+
+    // reduced.cu
+    int project_operators(const double* basis, int n, double* Ahat, double* bhat, cudaStream_t st);
+    int evaluate(const double* points, int m, const double* u, int64_t K, double* out, cudaStream_t st);
+};
+
+// reduced.cu (geometry independent)
+int reduced_solve(const double* y, int nb, const double* Ahat, const double* rhs, int rhs_per_system, int n,
+                  int64_t K, double* C, int* info, cudaStream_t st);
+int argmax_first(const double* v, int64_t K, int64_t* idx_out, double* val_out, cudaStream_t st);
+int estimator_contract(const double* c, int64_t K, int n, const double* abasis, int nb, int invert, double* out,
+                       cudaStream_t st);
+
+// gram.cu
+int gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M, int64_t Nn,
+            int64_t Kd, int symmetric, cudaStream_t st);   // C[M,N] = A[M,Kd] * B[N,Kd]^T  (DMMA)
+int gemm_nn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M, int64_t Nn,
+            int64_t Kd, cudaStream_t st);                  // C[M,N] = A[M,Kd] * B[Kd,N]
+int gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M, int64_t Nn,
+            int64_t Kd, cudaStream_t st);                  // C[M,N] = A[Kd,M]^T * B[Kd,N]
+int column_mean(const double* X, int64_t ld, int64_t K, int64_t D, double* mean, cudaStream_t st);
+int center_rows(double* X, int64_t ld, int64_t K, int64_t D, const double* mean, cudaStream_t st);
+
+}  // namespace romhc

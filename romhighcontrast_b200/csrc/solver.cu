@@ -1,0 +1,1013 @@
+// K1/K2: matrix-free P1 stiffness kernels and the batched fp64 GMG-preconditioned CG snapshot solver.
+//
+// Replaces, for the whole batch at once, the reference's per-sample dense assembly + direct solve
+//   galerkin()              /root/reference/src/lib/SolutionsManagers.py:17-40
+//   generate_solutions()    :64-68
+//   H10norm() / l2norm()    :56-62
+// Algorithm (validated against the reference in tests/): CG on A(y) u = b preconditioned by one
+// V(1,1) geometric multigrid cycle -- red/black Gauss-Seidel (RB before, BR after => symmetric), P1
+// (anti-diagonal) prolongation, its transpose as restriction, rediscretised coarse operators (exactly the
+// Galerkin operators because subdomain interfaces stay mesh aligned), dense Cholesky on the coarsest grid.
+// Every kernel works on row strips of the padded grid staged in shared memory by 1-D TMA bulk copies.
+#include "common.cuh"
+#include "romhc_internal.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+
+namespace romhc {
+
+// ------------------------------------------------------------------------------------------------------
+// thread <-> point mapping shared by all strip kernels: blockDim = (TXW, TYW); a thread owns columns
+// tx, tx+TXW, ... and a contiguous chunk of the phase's rows, walking down the rows so that the stencil
+// weights (ColW) are updated incrementally.  color: -1 all points, 0 red ((r+c) even), 1 black.
+// ------------------------------------------------------------------------------------------------------
+template <bool NEED_W, typename F>
+__device__ __forceinline__ void for_points(const LevelGeo& g, const double* sa, int tx, int ty, int TXW, int TYW,
+                                           int rlo, int rhi, int color, F f) {
+    rlo = max(rlo, 1);
+    rhi = min(rhi, g.R - 1);
+    const int nrows = rhi - rlo + 1;
+    if (nrows <= 0) return;
+    const int ch = (nrows + TYW - 1) / TYW;
+    const int my_lo = rlo + ty * ch, my_hi = min(my_lo + ch - 1, rhi);
+    for (int c = tx; c < g.C; c += TXW) {
+        if (c < 1) continue;
+        int r = my_lo, step = 1;
+        if (color >= 0) { r += (my_lo + c + color) & 1; step = 2; }
+        if (r > my_hi) continue;
+        ColW w;
+        if (NEED_W) w.init(sa, g, c, r);
+        for (;;) {
+            f(r, c, w);
+            r += step;
+            if (r > my_hi) break;
+            if (NEED_W) w.advance(step);
+        }
+    }
+}
+
+__device__ __forceinline__ double apply_diff(const double* s, int i, int P, const ColW& w) {
+    const double u = s[i];
+    return w.wW * (u - s[i - 1]) + w.wE * (u - s[i + 1]) + w.wN * (u - s[i - P]) + w.wS * (u - s[i + P]);
+}
+__device__ __forceinline__ double offdiag_sum(const double* s, int i, int P, const ColW& w) {
+    return w.wW * s[i - 1] + w.wE * s[i + 1] + w.wN * s[i - P] + w.wS * s[i + P];
+}
+
+// dynamic smem carve-up helper (all kernels): [coef table | reduction scratch | mbarrier | data...]
+struct SmemHdr {
+    double* sa;
+    double* red;
+    uint64_t* bar;
+    double* data;
+};
+__device__ __forceinline__ SmemHdr smem_carve(unsigned char* base, int nb) {
+    SmemHdr h;
+    h.sa = reinterpret_cast<double*>(base);
+    const int nbp = (nb + 7) & ~7;
+    h.red = h.sa + nbp;
+    h.bar = reinterpret_cast<uint64_t*>(h.red + 32);
+    h.data = h.red + 40;   // 64-byte aligned: (nbp + 40) * 8
+    return h;
+}
+static inline size_t smem_hdr_bytes(int nb) { return size_t(((nb + 7) & ~7) + 40) * 8; }
+
+// ======================================================================================================
+// simple element-wise kernels
+// ======================================================================================================
+__global__ void k_fill_interior(LevelGeo g, double* v, double value, int64_t K) {
+    const int64_t row = blockIdx.x;   // k*(R-1) + (r-1)
+    const int64_t k = row / (g.R - 1);
+    const int r = int(row - k * (g.R - 1)) + 1;
+    if (k >= K) return;
+    double* p = v + k * g.Dp + size_t(r) * g.P;
+    for (int c = 1 + threadIdx.x; c < g.C; c += blockDim.x) p[c] = value;
+}
+
+// compact (K, D) <-> padded (K, Dp)
+__global__ void k_pack(LevelGeo g, const double* __restrict__ compact, double* __restrict__ padded, int64_t K) {
+    const int64_t row = blockIdx.x;
+    const int64_t k = row / (g.R - 1);
+    const int r = int(row - k * (g.R - 1)) + 1;
+    const double* src = compact + (k * (g.R - 1) + (r - 1)) * int64_t(g.C - 1);
+    double* dst = padded + k * g.Dp + size_t(r) * g.P;
+    for (int c = 1 + threadIdx.x; c < g.C; c += blockDim.x) dst[c] = src[c - 1];
+}
+__global__ void k_unpack(LevelGeo g, const double* __restrict__ padded, double* __restrict__ compact, int64_t K) {
+    const int64_t row = blockIdx.x;
+    const int64_t k = row / (g.R - 1);
+    const int r = int(row - k * (g.R - 1)) + 1;
+    double* dst = compact + (k * (g.R - 1) + (r - 1)) * int64_t(g.C - 1);
+    const double* src = padded + k * g.Dp + size_t(r) * g.P;
+    for (int c = 1 + threadIdx.x; c < g.C; c += blockDim.x) dst[c - 1] = src[c];
+}
+
+// ======================================================================================================
+// strip kernels on one level.  grid = (nstrips, K), block = (TXW, TYW), strip s owns rows [s*TY, s*TY+TY)
+// ======================================================================================================
+
+// out = A(y) u  (y == nullptr: A_1).  K1a of SURVEY 8b.
+__global__ void __launch_bounds__(256)
+k_apply(LevelGeo g, const double* __restrict__ y, const double* __restrict__ u, double* __restrict__ out, int TY) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int nb = g.nrb * g.ncb;
+    SmemHdr h = smem_carve(smem_raw, nb);
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+    const int64_t k = blockIdx.y;
+    const int y0 = blockIdx.x * TY;
+    if (tid == 0) { mbar_init(h.bar, 1); mbar_fence_init(); }
+    load_coef(h.sa, y, k, nb, tid, nt);
+    __syncthreads();
+    const int row0 = y0 - 1, nrow = TY + 2;
+    strip_load_issue(h.data, u + k * g.Dp, g, row0, row0 + nrow, h.bar, tid, nt);
+    mbar_wait(h.bar, 0);
+    __syncthreads();
+    double* o = out + k * g.Dp;
+    for_points<true>(g, h.sa, threadIdx.x, threadIdx.y, blockDim.x, blockDim.y, y0, y0 + TY - 1, -1,
+                     [&](int r, int c, const ColW& w) {
+                         o[size_t(r) * g.P + c] = apply_diff(h.data, (r - row0) * g.P + c, g.P, w);
+                     });
+}
+
+// energy[k] = u_k^T A(y_k) u_k as a sum over mesh edges of w_e (u_i - u_j)^2 (never negative);
+// partial sums per strip, reduced deterministically by k_reduce_partials.  K2 of SURVEY 8b.
+// Optional fused difference: e = sum_j coef[k][j] * basis[j] - u  (greedy error sweep, ReducedBasis.py:129).
+__global__ void __launch_bounds__(256)
+k_energy(LevelGeo g, const double* __restrict__ y, const double* __restrict__ u, const double* __restrict__ coef,
+         const double* __restrict__ basis, int nbasis, double* __restrict__ part, int TY, int nstrips, int mode) {
+    // mode 0: energy (edge form); mode 1: euclidean sum of squares
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int nb = g.nrb * g.ncb;
+    SmemHdr h = smem_carve(smem_raw, nb);
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+    const int64_t k = blockIdx.y;
+    const int y0 = blockIdx.x * TY;
+    const int row0 = y0, nrow = TY + 1;   // one halo row below (edges to the south)
+    load_coef(h.sa, y, k, nb, tid, nt);
+    double* ck = h.data;                   // nbasis coefficients, then the strip
+    double* s = h.data + ((nbasis + 7) & ~7);
+    for (int j = tid; j < nbasis; j += nt) ck[j] = coef[k * nbasis + j];
+    __syncthreads();
+    const double* us = u + k * g.Dp;
+    const int n = nrow * g.P;
+    for (int i = tid; i < n; i += nt) {
+        const int gi = row0 * g.P + i;
+        double v = 0.0;
+        if (gi < g.Dp) {
+            v = us[gi];
+            if (nbasis > 0) {
+                double acc = 0.0;
+                for (int j = 0; j < nbasis; ++j) acc = fma(ck[j], basis[size_t(j) * g.Dp + gi], acc);
+                v = acc - v;
+            }
+        }
+        s[i] = v;
+    }
+    __syncthreads();
+    double acc = 0.0;
+    if (mode == 0) {
+        for_points<true>(g, h.sa, threadIdx.x, threadIdx.y, blockDim.x, blockDim.y, y0, y0 + TY - 1, -1,
+                         [&](int r, int c, const ColW& w) {
+                             const int i = (r - row0) * g.P + c;
+                             const double v = s[i];
+                             const double dE = v - s[i + 1], dS = v - s[i + g.P];
+                             double e = w.wE * dE * dE + w.wS * dS * dS;
+                             if (c == 1) e += w.wW * v * v;
+                             if (r == 1) e += w.wN * v * v;
+                             acc += e;
+                         });
+    } else {
+        for_points<false>(g, h.sa, threadIdx.x, threadIdx.y, blockDim.x, blockDim.y, y0, y0 + TY - 1, -1,
+                          [&](int r, int c, const ColW&) {
+                              const double v = s[(r - row0) * g.P + c];
+                              acc += v * v;
+                          });
+    }
+    const double tot = block_sum(acc, h.red, tid, nt);
+    if (tid == 0) part[k * nstrips + blockIdx.x] = tot;
+}
+
+__global__ void k_reduce_partials(const double* __restrict__ part, int np, double* __restrict__ out, int64_t K,
+                                  int take_sqrt) {
+    const int64_t k = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (k >= K) return;
+    double s = 0.0;
+    for (int i = 0; i < np; ++i) s += part[k * np + i];
+    out[k] = take_sqrt ? sqrt(s) : s;
+}
+
+// ---- PCG: p = z + beta p (double buffered), pAp partials ---------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_pcg_p_apply(LevelGeo g, const double* __restrict__ y, const double* __restrict__ z, const double* __restrict__ p_in,
+              double* __restrict__ p_out, const double* __restrict__ beta, const int* __restrict__ active,
+              double* __restrict__ part_pAp, int TY, int nstrips) {
+    const int64_t k = blockIdx.y;
+    if (!active[k]) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int nb = g.nrb * g.ncb;
+    SmemHdr h = smem_carve(smem_raw, nb);
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+    const int y0 = blockIdx.x * TY;
+    load_coef(h.sa, y, k, nb, tid, nt);
+    const double b = beta[k];
+    const int row0 = y0 - 1, nrow = TY + 2;
+    const double* zs = z + k * g.Dp;
+    const double* ps = p_in + k * g.Dp;
+    double* po = p_out + k * g.Dp;
+    double* s = h.data;
+    const int n = nrow * g.P;
+    const int own_lo = y0 * g.P, own_hi = min((y0 + TY) * g.P, g.Dp);
+    for (int i = tid; i < n; i += nt) {
+        const int gi = row0 * g.P + i;
+        double v = 0.0;
+        if (gi >= 0 && gi < g.Dp) {
+            v = fma(b, ps[gi], zs[gi]);
+            if (gi >= own_lo && gi < own_hi) po[gi] = v;
+        }
+        s[i] = v;
+    }
+    __syncthreads();
+    double acc = 0.0;
+    for_points<true>(g, h.sa, threadIdx.x, threadIdx.y, blockDim.x, blockDim.y, y0, y0 + TY - 1, -1,
+                     [&](int r, int c, const ColW& w) {
+                         const int i = (r - row0) * g.P + c;
+                         acc = fma(s[i], apply_diff(s, i, g.P, w), acc);
+                     });
+    const double tot = block_sum(acc, h.red, tid, nt);
+    if (tid == 0) part_pAp[k * nstrips + blockIdx.x] = tot;
+}
+
+// ---- PCG: x += alpha p ; r -= alpha A p --------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_pcg_update(LevelGeo g, const double* __restrict__ y, const double* __restrict__ p, double* __restrict__ x,
+             double* __restrict__ r, const double* __restrict__ alpha, const int* __restrict__ active, int TY) {
+    const int64_t k = blockIdx.y;
+    if (!active[k]) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int nb = g.nrb * g.ncb;
+    SmemHdr h = smem_carve(smem_raw, nb);
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+    const int y0 = blockIdx.x * TY;
+    if (tid == 0) { mbar_init(h.bar, 1); mbar_fence_init(); }
+    load_coef(h.sa, y, k, nb, tid, nt);
+    __syncthreads();
+    const int row0 = y0 - 1, nrow = TY + 2;
+    strip_load_issue(h.data, p + k * g.Dp, g, row0, row0 + nrow, h.bar, tid, nt);
+    const double al = alpha[k];
+    double* xs = x + k * g.Dp;
+    double* rs = r + k * g.Dp;
+    mbar_wait(h.bar, 0);
+    __syncthreads();
+    for_points<true>(g, h.sa, threadIdx.x, threadIdx.y, blockDim.x, blockDim.y, y0, y0 + TY - 1, -1,
+                     [&](int rr, int c, const ColW& w) {
+                         const int i = (rr - row0) * g.P + c;
+                         const size_t gi = size_t(rr) * g.P + c;
+                         const double Ap = apply_diff(h.data, i, g.P, w);
+                         xs[gi] = fma(al, h.data[i], xs[gi]);
+                         rs[gi] = fma(-al, Ap, rs[gi]);
+                     });
+}
+
+// ---- multigrid, going down: z = RB-GS(0, r); r_coarse = P^T (r - A z) -----------------------------------------
+__global__ void __launch_bounds__(256)
+k_mg_down(LevelGeo g, LevelGeo gc, const double* __restrict__ y, const double* __restrict__ r_in,
+          double* __restrict__ z_out, double* __restrict__ rc_out, const int* __restrict__ active, int TY,
+          int has_coarse) {
+    const int64_t k = blockIdx.y;
+    if (!active[k]) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int nb = g.nrb * g.ncb;
+    SmemHdr h = smem_carve(smem_raw, nb);
+    const int tx = threadIdx.x, ty = threadIdx.y, TXW = blockDim.x, TYW = blockDim.y;
+    const int tid = ty * TXW + tx, nt = TXW * TYW;
+    const int y0 = blockIdx.x * TY;
+    if (tid == 0) { mbar_init(h.bar, 1); mbar_fence_init(); }
+    load_coef(h.sa, y, k, nb, tid, nt);
+    __syncthreads();
+    const int halo_top = has_coarse ? 3 : 1, halo_bot = has_coarse ? 2 : 1;
+    const int row0 = y0 - halo_top, nrow = TY + halo_top + halo_bot;
+    double* s = h.data;
+    const int P = g.P;
+    strip_load_issue(s, r_in + k * g.Dp, g, row0, row0 + nrow, h.bar, tid, nt);
+    mbar_wait(h.bar, 0);
+    __syncthreads();
+    // red half sweep from a zero guess: z = r / diag
+    for_points<true>(g, h.sa, tx, ty, TXW, TYW, row0, row0 + nrow - 1, 0, [&](int r, int c, const ColW& w) {
+        const int i = (r - row0) * P + c;
+        s[i] *= w.idg;
+    });
+    __syncthreads();
+    // black half sweep
+    for_points<true>(g, h.sa, tx, ty, TXW, TYW, row0 + 1, row0 + nrow - 2, 1, [&](int r, int c, const ColW& w) {
+        const int i = (r - row0) * P + c;
+        s[i] = (s[i] + offdiag_sum(s, i, P, w)) * w.idg;
+    });
+    __syncthreads();
+    double* zo = z_out + k * g.Dp;
+    for_points<false>(g, h.sa, tx, ty, TXW, TYW, y0, y0 + TY - 1, -1, [&](int r, int c, const ColW&) {
+        zo[size_t(r) * P + c] = s[(r - row0) * P + c];
+    });
+    if (!has_coarse) return;
+    __syncthreads();
+    // residual: zero on black points (just relaxed); on red points d = sum_nb w_nb z_nb
+    for_points<true>(g, h.sa, tx, ty, TXW, TYW, y0 - 1, y0 + TY - 1, 0, [&](int r, int c, const ColW& w) {
+        const int i = (r - row0) * P + c;
+        s[i] = offdiag_sum(s, i, P, w);
+    });
+    __syncthreads();
+    // restriction r_c(I,J) = d(2I,2J) + (d(2I-1,2J+1) + d(2I+1,2J-1)) / 2   (the E/W/N/S neighbours are black: d = 0)
+    const int I_lo = max(y0 / 2, 1), I_hi = min((y0 + TY) / 2 - 1, gc.R - 1);
+    const int nJ = gc.C - 1, nI = I_hi - I_lo + 1;
+    double* rc = rc_out + k * gc.Dp;
+    for (int idx = tid; idx < nI * nJ; idx += nt) {
+        const int I = I_lo + idx / nJ, J = 1 + idx % nJ;
+        const int i = (2 * I - row0) * P + 2 * J;
+        rc[size_t(I) * gc.P + J] = s[i] + 0.5 * (s[i - P + 1] + s[i + P - 1]);
+    }
+}
+
+// ---- multigrid, going up: z += P e (red points suffice), BR-GS; optional r.z partials ------------------------------
+__global__ void __launch_bounds__(256)
+k_mg_up(LevelGeo g, LevelGeo gc, const double* __restrict__ y, const double* __restrict__ e_c,
+        const double* __restrict__ z_in, const double* __restrict__ r, double* __restrict__ z_out,
+        const int* __restrict__ active, double* __restrict__ part_rz, int TY, int nstrips, int has_coarse) {
+    const int64_t k = blockIdx.y;
+    if (!active[k]) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int nb = g.nrb * g.ncb;
+    SmemHdr h = smem_carve(smem_raw, nb);
+    const int tx = threadIdx.x, ty = threadIdx.y, TXW = blockDim.x, TYW = blockDim.y;
+    const int tid = ty * TXW + tx, nt = TXW * TYW;
+    const int y0 = blockIdx.x * TY;
+    if (tid == 0) { mbar_init(h.bar, 1); mbar_fence_init(); }
+    load_coef(h.sa, y, k, nb, tid, nt);
+    __syncthreads();
+    const int P = g.P, Pc = gc.P;
+    const int row0 = y0 - 2, nrow = TY + 4;
+    const int I0 = y0 / 2 - 1, nI = TY / 2 + 3;
+    double* s = h.data;
+    double* e = s + size_t(nrow) * P;
+    // two bulk copies on one mbarrier
+    {
+        const int lo = max(row0, 0), hi = min(row0 + nrow, g.R + 1);
+        const int clo = max(I0, 0), chi = has_coarse ? min(I0 + nI, gc.R + 1) : clo;
+        const uint32_t b1 = hi > lo ? uint32_t(hi - lo) * P * 8u : 0u;
+        const uint32_t b2 = chi > clo ? uint32_t(chi - clo) * Pc * 8u : 0u;
+        if (tid == 0) {
+            mbar_expect_tx(h.bar, b1 + b2);
+            if (b1) bulk_g2s(s + size_t(lo - row0) * P, z_in + k * g.Dp + size_t(lo) * P, b1, h.bar);
+            if (b2) bulk_g2s(e + size_t(clo - I0) * Pc, e_c + k * gc.Dp + size_t(clo) * Pc, b2, h.bar);
+        }
+        for (int i = tid; i < (lo - row0) * P; i += nt) s[i] = 0.0;
+        for (int i = (max(hi, row0) - row0) * P + tid; i < nrow * P; i += nt) s[i] = 0.0;
+        if (has_coarse) {
+            for (int i = tid; i < (clo - I0) * Pc; i += nt) e[i] = 0.0;
+            for (int i = (max(chi, I0) - I0) * Pc + tid; i < nI * Pc; i += nt) e[i] = 0.0;
+        }
+    }
+    mbar_wait(h.bar, 0);
+    __syncthreads();
+    if (has_coarse) {
+        // prolongation on red points: (even, even) copies the coarse vertex, (odd, odd) is the midpoint of
+        // the coarse cell's anti-diagonal (I, J+1)-(I+1, J).  Black values are overwritten by the sweep below.
+        for_points<false>(g, h.sa, tx, ty, TXW, TYW, row0, row0 + nrow - 1, 0, [&](int r, int c, const ColW&) {
+            const int i = (r - row0) * P + c;
+            const int I = (r >> 1) - I0, J = c >> 1;
+            if (r & 1) s[i] += 0.5 * (e[I * Pc + J + 1] + e[(I + 1) * Pc + J]);
+            else       s[i] += e[I * Pc + J];
+        });
+        __syncthreads();
+    }
+    const double* rs = r + k * g.Dp;
+    double* zo = z_out + k * g.Dp;
+    double acc = 0.0;
+    for_points<true>(g, h.sa, tx, ty, TXW, TYW, y0 - 1, y0 + TY, 1, [&](int rr, int c, const ColW& w) {
+        const int i = (rr - row0) * P + c;
+        const size_t gi = size_t(rr) * P + c;
+        const double rv = rs[gi];
+        const double v = (rv + offdiag_sum(s, i, P, w)) * w.idg;
+        s[i] = v;
+        if (rr >= y0 && rr < y0 + TY) { zo[gi] = v; acc = fma(rv, v, acc); }
+    });
+    __syncthreads();
+    for_points<true>(g, h.sa, tx, ty, TXW, TYW, y0, y0 + TY - 1, 0, [&](int rr, int c, const ColW& w) {
+        const int i = (rr - row0) * P + c;
+        const size_t gi = size_t(rr) * P + c;
+        const double rv = rs[gi];
+        const double v = (rv + offdiag_sum(s, i, P, w)) * w.idg;
+        zo[gi] = v;
+        acc = fma(rv, v, acc);
+    });
+    if (part_rz) {
+        const double tot = block_sum(acc, h.red, tid, nt);
+        if (tid == 0) part_rz[k * nstrips + blockIdx.x] = tot;
+    }
+}
+
+// ---- multigrid tail: levels T..L of one system entirely in shared memory (one CTA per system) --------------------
+
+__device__ __forceinline__ void tail_map(const LevelGeo& g, int tid, int nt, int& tx, int& ty, int& TXW, int& TYW) {
+    TXW = 1;
+    while (TXW < g.C && TXW < nt) TXW <<= 1;
+    TYW = nt / TXW;
+    tx = tid & (TXW - 1);
+    ty = tid / TXW;
+}
+
+__device__ __forceinline__ void tail_gs_half(const LevelGeo& g, const double* sa, double* z, const double* r,
+                                             int color, bool zero_guess, int tid, int nt) {
+    int tx, ty, TXW, TYW;
+    tail_map(g, tid, nt, tx, ty, TXW, TYW);
+    const int P = g.P;
+    for_points<true>(g, sa, tx, ty, TXW, TYW, 1, g.R - 1, color, [&](int rr, int c, const ColW& w) {
+        const int i = rr * P + c;
+        z[i] = zero_guess ? r[i] * w.idg : (r[i] + offdiag_sum(z, i, P, w)) * w.idg;
+    });
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+k_mg_tail(TailParams tp, const double* __restrict__ y, const double* __restrict__ r_in, double* __restrict__ z_out,
+          const double* __restrict__ cfac, const int* __restrict__ active, double* __restrict__ part_rz) {
+    const int64_t k = blockIdx.x;
+    if (!active[k]) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const LevelGeo& g0 = tp.geo[0];
+    const int nb = g0.nrb * g0.ncb;
+    SmemHdr h = smem_carve(smem_raw, nb);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) { mbar_init(h.bar, 1); mbar_fence_init(); }
+    load_coef(h.sa, y, k, nb, tid, nt);
+    __syncthreads();
+    double* S = h.data;
+    // r_T by one bulk copy; everything else starts at zero
+    if (tid == 0) {
+        mbar_expect_tx(h.bar, uint32_t(g0.Dp) * 8u);
+        bulk_g2s(S + tp.off_r[0], r_in + k * g0.Dp, uint32_t(g0.Dp) * 8u, h.bar);
+    }
+    for (int l = 0; l < tp.nlev; ++l) {
+        const int n = tp.geo[l].Dp;
+        double* z = S + tp.off_z[l];
+        for (int i = tid; i < n; i += nt) z[i] = 0.0;
+        if (l > 0) {
+            double* r = S + tp.off_r[l];
+            for (int i = tid; i < n; i += nt) r[i] = 0.0;
+        }
+    }
+    if (tp.direct) {
+        const double* src = cfac + k * size_t(tp.DL) * tp.LD;
+        double* F = S + tp.off_fac;
+        for (int i = tid; i < tp.DL * tp.LD; i += nt) F[i] = src[i];
+    }
+    mbar_wait(h.bar, 0);
+    __syncthreads();
+    const int last = tp.nlev - 1;
+    // ---- down ----
+    for (int l = 0; l < last; ++l) {
+        const LevelGeo& g = tp.geo[l];
+        const LevelGeo& gc = tp.geo[l + 1];
+        double* r = S + tp.off_r[l];
+        double* z = S + tp.off_z[l];
+        double* rc = S + tp.off_r[l + 1];
+        tail_gs_half(g, h.sa, z, r, 0, true, tid, nt);
+        tail_gs_half(g, h.sa, z, r, 1, false, tid, nt);
+        // restriction of the (red-only) residual, computed on the fly from z
+        const int nJ = gc.C - 1, nI = gc.R - 1, P = g.P;
+        for (int idx = tid; idx < nI * nJ; idx += nt) {
+            const int I = 1 + idx / nJ, J = 1 + idx % nJ;
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int rr = 2 * I + (q == 1 ? -1 : (q == 2 ? 1 : 0));
+                const int cc = 2 * J + (q == 1 ? 1 : (q == 2 ? -1 : 0));
+                if (rr >= 1 && rr <= g.R - 1 && cc >= 1 && cc <= g.C - 1) {
+                    double wW, wE, wN, wS;
+                    vertex_weights(h.sa, g, rr, cc, wW, wE, wN, wS);
+                    const int i = rr * P + cc;
+                    const double d = wW * z[i - 1] + wE * z[i + 1] + wN * z[i - P] + wS * z[i + P];
+                    acc += (q == 0) ? d : 0.5 * d;
+                }
+            }
+            rc[I * gc.P + J] = acc;
+        }
+        __syncthreads();
+    }
+    // ---- coarsest ----
+    {
+        const LevelGeo& g = tp.geo[last];
+        double* r = S + tp.off_r[last];
+        double* z = S + tp.off_z[last];
+        if (tp.direct) {
+            // L L^T z = r with the packed factor (diagonal stores 1 / L_ii); warp 0, lanes own rows lane, lane+32
+            if (tid < 32) {
+                const int D = tp.DL, LD = tp.LD, W = g.C - 1;
+                const double* F = S + tp.off_fac;
+                const int j0 = tid, j1 = tid + 32;
+                double b0 = 0.0, b1 = 0.0;
+                if (j0 < D) b0 = r[(1 + j0 / W) * g.P + 1 + j0 % W];
+                if (j1 < D) b1 = r[(1 + j1 / W) * g.P + 1 + j1 % W];
+                for (int i = 0; i < D; ++i) {
+                    const double bi = __shfl_sync(0xffffffffu, i < 32 ? b0 : b1, i & 31);
+                    const double yi = bi * F[i * LD + i];
+                    if (j0 == i) b0 = yi;
+                    if (j1 == i) b1 = yi;
+                    if (j0 > i && j0 < D) b0 = fma(-F[j0 * LD + i], yi, b0);
+                    if (j1 > i && j1 < D) b1 = fma(-F[j1 * LD + i], yi, b1);
+                }
+                for (int i = D - 1; i >= 0; --i) {
+                    const double bi = __shfl_sync(0xffffffffu, i < 32 ? b0 : b1, i & 31);
+                    const double xi = bi * F[i * LD + i];
+                    if (j0 == i) b0 = xi;
+                    if (j1 == i) b1 = xi;
+                    if (j0 < i) b0 = fma(-F[i * LD + j0], xi, b0);
+                    if (j1 < i) b1 = fma(-F[i * LD + j1], xi, b1);
+                }
+                if (j0 < D) z[(1 + j0 / W) * g.P + 1 + j0 % W] = b0;
+                if (j1 < D) z[(1 + j1 / W) * g.P + 1 + j1 % W] = b1;
+            }
+            __syncthreads();
+        } else {
+            for (int sw = 0; sw < tp.coarse_sweeps; ++sw) {
+                tail_gs_half(g, h.sa, z, r, 0, sw == 0, tid, nt);
+                tail_gs_half(g, h.sa, z, r, 1, false, tid, nt);
+            }
+            for (int sw = 0; sw < tp.coarse_sweeps; ++sw) {
+                tail_gs_half(g, h.sa, z, r, 1, false, tid, nt);
+                tail_gs_half(g, h.sa, z, r, 0, false, tid, nt);
+            }
+        }
+    }
+    // ---- up ----
+    for (int l = last - 1; l >= 0; --l) {
+        const LevelGeo& g = tp.geo[l];
+        const LevelGeo& gc = tp.geo[l + 1];
+        double* r = S + tp.off_r[l];
+        double* z = S + tp.off_z[l];
+        const double* e = S + tp.off_z[l + 1];
+        int tx, ty, TXW, TYW;
+        tail_map(g, tid, nt, tx, ty, TXW, TYW);
+        const int P = g.P, Pc = gc.P;
+        for_points<false>(g, h.sa, tx, ty, TXW, TYW, 1, g.R - 1, 0, [&](int rr, int c, const ColW&) {
+            const int i = rr * P + c;
+            const int I = rr >> 1, J = c >> 1;
+            if (rr & 1) z[i] += 0.5 * (e[I * Pc + J + 1] + e[(I + 1) * Pc + J]);
+            else        z[i] += e[I * Pc + J];
+        });
+        __syncthreads();
+        tail_gs_half(g, h.sa, z, r, 1, false, tid, nt);
+        tail_gs_half(g, h.sa, z, r, 0, false, tid, nt);
+    }
+    // ---- output ----
+    {
+        const double* z = S + tp.off_z[0];
+        const double* r = S + tp.off_r[0];
+        double* zo = z_out + k * g0.Dp;
+        double acc = 0.0;
+        for (int i = tid; i < g0.Dp; i += nt) {
+            const double v = z[i];
+            zo[i] = v;
+            acc = fma(r[i], v, acc);
+        }
+        if (part_rz) {
+            const double tot = block_sum(acc, h.red, tid, nt);
+            if (tid == 0) part_rz[k] = tot;
+        }
+    }
+}
+
+// ---- setup: dense Cholesky factor of the coarsest operator, one CTA per system -----------------------------------
+__global__ void __launch_bounds__(64)
+k_coarse_factor(LevelGeo g, const double* __restrict__ y, double* __restrict__ cfac, int D, int LD,
+                int* __restrict__ status) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int nb = g.nrb * g.ncb;
+    SmemHdr h = smem_carve(smem_raw, nb);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int64_t k = blockIdx.x;
+    load_coef(h.sa, y, k, nb, tid, nt);
+    double* A = h.data;
+    for (int i = tid; i < D * LD; i += nt) A[i] = 0.0;
+    __syncthreads();
+    const int W = g.C - 1;
+    if (tid < D) {
+        const int r = 1 + tid / W, c = 1 + tid % W;
+        double wW, wE, wN, wS;
+        vertex_weights(h.sa, g, r, c, wW, wE, wN, wS);
+        A[tid * LD + tid] = (wW + wE) + (wN + wS);
+        if (c > 1) A[tid * LD + tid - 1] = -wW;
+        if (r > 1) A[tid * LD + tid - W] = -wN;
+    }
+    __syncthreads();
+    for (int kc = 0; kc < D; ++kc) {
+        if (tid == 0) {
+            const double d = A[kc * LD + kc];
+            if (!(d > 0.0)) atomicOr(status, 1);
+            A[kc * LD + kc] = sqrt(fabs(d) > 0.0 ? fabs(d) : 1.0);
+        }
+        __syncthreads();
+        if (tid > kc && tid < D) A[tid * LD + kc] /= A[kc * LD + kc];
+        __syncthreads();
+        if (tid > kc && tid < D) {
+            const double lik = A[tid * LD + kc];
+            for (int j = kc + 1; j <= tid; ++j) A[tid * LD + j] = fma(-lik, A[j * LD + kc], A[tid * LD + j]);
+        }
+        __syncthreads();
+    }
+    if (tid < D) A[tid * LD + tid] = 1.0 / A[tid * LD + tid];
+    __syncthreads();
+    double* dst = cfac + k * size_t(D) * LD;
+    for (int i = tid; i < D * LD; i += nt) dst[i] = A[i];
+}
+
+// ---- per-system scalars ---------------------------------------------------------------------------------------------
+__global__ void k_scalar_alpha(int64_t K, int np, const double* __restrict__ part_pAp, const double* __restrict__ rz,
+                               double* __restrict__ alpha, int* __restrict__ active, int* __restrict__ status) {
+    const int64_t k = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (k >= K || !active[k]) return;
+    double s = 0.0;
+    for (int i = 0; i < np; ++i) s += part_pAp[k * np + i];
+    if (!(s > 0.0)) { active[k] = 0; atomicOr(status, 2); alpha[k] = 0.0; return; }   // breakdown (not SPD / NaN)
+    alpha[k] = rz[k] / s;
+}
+
+// it == 0: initialisation (rz0); afterwards convergence test on the preconditioned residual sqrt(r.z / r0.z0)
+__global__ void k_scalar_beta(int64_t K, int np, const double* __restrict__ part_rz, double* __restrict__ rz,
+                              double* __restrict__ rz0, double* __restrict__ beta, int* __restrict__ active,
+                              int* __restrict__ iters, double* __restrict__ relres, int it, double tol2,
+                              int* __restrict__ n_active, int* __restrict__ status) {
+    const int64_t k = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (k >= K || !active[k]) return;
+    double s = 0.0;
+    for (int i = 0; i < np; ++i) s += part_rz[k * np + i];
+    if (it == 0) {
+        rz0[k] = s; rz[k] = s; beta[k] = 0.0; relres[k] = 1.0;
+        if (!(s > 0.0)) { active[k] = 0; iters[k] = 0; relres[k] = 0.0; if (s != 0.0) atomicOr(status, 4); return; }
+    } else {
+        const double rel2 = s / rz0[k];
+        relres[k] = sqrt(fabs(rel2));
+        iters[k] = it;
+        if (!(s > tol2 * rz0[k])) {   // converged (or NaN)
+            active[k] = 0;
+            if (s != s) atomicOr(status, 4);
+            return;
+        }
+        beta[k] = s / rz[k];
+        rz[k] = s;
+    }
+    atomicAdd(n_active, 1);
+}
+
+// ======================================================================================================
+// host side
+// ======================================================================================================
+static void strip_block(const LevelGeo& g, dim3& block) {
+    int txw = 32;
+    while (txw < g.P && txw < 256) txw <<= 1;
+    block = dim3(txw, 256 / txw, 1);
+}
+
+// pick the strip height so that rows*P*8 + header stays under `budget` bytes (even, >= 2)
+static int pick_ty(const LevelGeo& g, int extra_rows, size_t extra_bytes, size_t budget, int ty_max) {
+    const size_t hdr = smem_hdr_bytes(g.nrb * g.ncb) + extra_bytes;
+    long rows = long((budget > hdr ? budget - hdr : 0) / (size_t(g.P) * 8)) - extra_rows;
+    long ty = std::min<long>(rows, ty_max);
+    ty = std::min<long>(ty, ((g.R + 1) / 2) * 2);
+    ty &= ~1L;
+    return int(std::max<long>(ty, 2));
+}
+
+int Context::build_levels() {
+    levels.clear();
+    int n = N;
+    for (;;) {
+        levels.push_back(make_level(nrb, ncb, n));
+        if (n % 2 != 0) break;
+        const int nn = n / 2;
+        if (nrb * nn < 2 || ncb * nn < 2) break;
+        if ((int)levels.size() >= ROMHC_MAX_LEVELS) break;
+        n = nn;
+    }
+    const int L = int(levels.size()) - 1;
+    tail_level = L + 1;
+    for (int l = 0; l <= L; ++l)
+        if (levels[l].Dp <= ROMHC_TAIL_MAX_DP) { tail_level = l; break; }
+    const LevelGeo& gl = levels[L];
+    coarse_D = (gl.R - 1) * (gl.C - 1);
+    coarse_direct = (tail_level <= L) && coarse_D <= ROMHC_DIRECT_MAX;
+    coarse_LD = coarse_D | 1;
+    // tail smem layout
+    memset(&tail, 0, sizeof(tail));
+    tail_smem = 0;
+    if (tail_level <= L) {
+        tail.nlev = L - tail_level + 1;
+        int off = 0;
+        for (int l = 0; l < tail.nlev; ++l) {
+            tail.geo[l] = levels[tail_level + l];
+            tail.off_r[l] = off; off += tail.geo[l].Dp;
+            tail.off_z[l] = off; off += tail.geo[l].Dp;
+        }
+        tail.direct = coarse_direct ? 1 : 0;
+        tail.DL = coarse_D; tail.LD = coarse_LD;
+        tail.off_fac = off;
+        if (coarse_direct) off += coarse_D * coarse_LD;
+        tail.coarse_sweeps = coarse_sweeps;
+        tail_smem = smem_hdr_bytes(nrb * ncb) + size_t(off) * 8;
+    }
+    return 0;
+}
+
+
+static const size_t SMEM_2PER_SM = 100 * 1024;   // target: >= 2 CTAs per SM so loads overlap compute
+static const size_t SMEM_3PER_SM = 72 * 1024;
+
+int Context::configure_kernels() {
+    if (kernels_configured) return ROMHC_OK;
+    const int maxs = 227 * 1024;
+    CK(cudaFuncSetAttribute(k_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    CK(cudaFuncSetAttribute(k_energy, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    CK(cudaFuncSetAttribute(k_pcg_p_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    CK(cudaFuncSetAttribute(k_pcg_update, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    CK(cudaFuncSetAttribute(k_mg_down, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    CK(cudaFuncSetAttribute(k_mg_up, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    CK(cudaFuncSetAttribute(k_mg_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    CK(cudaFuncSetAttribute(k_coarse_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    kernels_configured = true;
+    return ROMHC_OK;
+}
+
+// ---- public single-kernel entry points (device pointers) -----------------------------------------------------------------
+int Context::apply(const double* y, const double* u, double* out, int64_t K, cudaStream_t st) {
+    int rc = configure_kernels(); if (rc) return rc;
+    const LevelGeo& g = levels[0];
+    dim3 block; strip_block(g, block);
+    const int TY = pick_ty(g, 2, 0, SMEM_3PER_SM, 64);
+    const int ns = (g.R + TY - 1) / TY;
+    const size_t sm = smem_hdr_bytes(nrb * ncb) + size_t(TY + 2) * g.P * 8;
+    for (int64_t k0 = 0; k0 < K; k0 += 32768) {
+        const int kc = int(std::min<int64_t>(32768, K - k0));
+        ++g_launches; k_apply<<<dim3(ns, kc), block, sm, st>>>(g, y ? y + k0 * nrb * ncb : nullptr, u + k0 * g.Dp, out + k0 * g.Dp, TY);
+    }
+    CK(cudaGetLastError());
+    return ROMHC_OK;
+}
+
+int Context::energy(const double* y, const double* u, const double* coef, const double* basis, int nbasis,
+                    double* out, int64_t K, int mode, int take_sqrt, cudaStream_t st) {
+    int rc = configure_kernels(); if (rc) return rc;
+    const LevelGeo& g = levels[0];
+    dim3 block; strip_block(g, block);
+    const size_t extra = size_t((nbasis + 7) & ~7) * 8;
+    const int TY = pick_ty(g, 1, extra, 40 * 1024, 32);
+    const int ns = (g.R + TY - 1) / TY;
+    const size_t sm = smem_hdr_bytes(nrb * ncb) + extra + size_t(TY + 1) * g.P * 8;
+    for (int64_t k0 = 0; k0 < K; k0 += 32768) {
+        const int kc = int(std::min<int64_t>(32768, K - k0));
+        rc = ensure_scratch(size_t(kc) * ns * 8); if (rc) return rc;
+        ++g_launches; k_energy<<<dim3(ns, kc), block, sm, st>>>(g, y ? y + k0 * nrb * ncb : nullptr, u + k0 * g.Dp,
+                                                  coef ? coef + k0 * nbasis : nullptr, basis, nbasis,
+                                                  (double*)scratch, TY, ns, mode);
+        ++g_launches; k_reduce_partials<<<(kc + 127) / 128, 128, 0, st>>>((double*)scratch, ns, out + k0, kc, take_sqrt);
+    }
+    CK(cudaGetLastError());
+    return ROMHC_OK;
+}
+
+int Context::pack(const double* compact, double* padded, int64_t K, cudaStream_t st) {
+    const LevelGeo& g = levels[0];
+    CK(cudaMemsetAsync(padded, 0, size_t(K) * g.Dp * 8, st));
+    ++g_launches; k_pack<<<(unsigned)(K * (g.R - 1)), 128, 0, st>>>(g, compact, padded, K);
+    CK(cudaGetLastError());
+    return ROMHC_OK;
+}
+int Context::unpack(const double* padded, double* compact, int64_t K, cudaStream_t st) {
+    const LevelGeo& g = levels[0];
+    ++g_launches; k_unpack<<<(unsigned)(K * (g.R - 1)), 128, 0, st>>>(g, padded, compact, K);
+    CK(cudaGetLastError());
+    return ROMHC_OK;
+}
+
+// ---- solver workspace ------------------------------------------------------------------------------------------------------
+size_t Context::solve_bytes_per_system() const {
+    size_t d = 0;
+    const int L = int(levels.size()) - 1;
+    d += size_t(levels[0].Dp) * 5;                           // r, p0, p1, zA, zB  (x is the caller's output)
+    for (int l = 1; l <= L && l <= tail_level; ++l) d += size_t(levels[l].Dp) * 3;   // r_l, zA_l, zB_l
+    if (coarse_direct) d += size_t(coarse_D) * coarse_LD;
+    d += 64 + 4 * size_t((levels[0].R + 1) / 2);              // scalars + partials (upper bound)
+    return d * 8;
+}
+
+int Context::ensure_scratch(size_t bytes) {
+    if (bytes <= scratch_bytes) return ROMHC_OK;
+    if (scratch) cudaFree(scratch);
+    scratch = nullptr; scratch_bytes = 0;
+    CK(cudaMalloc(&scratch, bytes));
+    scratch_bytes = bytes;
+    return ROMHC_OK;
+}
+
+int Context::ensure_solve_ws(int64_t Kc) {
+    if (Kc <= ws_K) return ROMHC_OK;
+    if (ws_base) cudaFree(ws_base);
+    ws_base = nullptr; ws_K = 0;
+    const int L = int(levels.size()) - 1;
+    const int nlev_strip = std::min(tail_level, L + 1);       // levels 0..nlev_strip-1 use strip kernels
+    auto al = [](size_t n) { return (n + 31) & ~size_t(31); };   // 256-byte granularity in doubles
+    size_t off = 0;
+    auto take = [&](size_t n) { size_t o = off; off += al(n); return o; };
+    std::vector<size_t> o_r(L + 2, 0), o_za(L + 2, 0), o_zb(L + 2, 0);
+    const int top = std::min(tail_level, L);                   // deepest level with global-memory vectors
+    for (int l = 0; l <= top; ++l) {
+        o_r[l] = take(size_t(Kc) * levels[l].Dp);
+        o_za[l] = take(size_t(Kc) * levels[l].Dp);
+        o_zb[l] = (l < nlev_strip) ? take(size_t(Kc) * levels[l].Dp) : o_za[l];
+    }
+    const size_t o_p0 = take(size_t(Kc) * levels[0].Dp), o_p1 = take(size_t(Kc) * levels[0].Dp);
+    const size_t o_fac = coarse_direct ? take(size_t(Kc) * coarse_D * coarse_LD) : 0;
+    const int np = std::max(1, (levels[0].R + 1) / 2 + 1);
+    const size_t o_pp = take(size_t(Kc) * np), o_pr = take(size_t(Kc) * np);
+    const size_t o_sc = take(size_t(Kc) * 6);
+    const size_t o_int = take(size_t(Kc) + 64);                 // active + iters as int32 pairs
+    CK(cudaMalloc(&ws_base, off * 8));
+    CK(cudaMemset(ws_base, 0, off * 8));
+    double* b = (double*)ws_base;
+    ws.r.assign(L + 2, nullptr); ws.za.assign(L + 2, nullptr); ws.zb.assign(L + 2, nullptr);
+    for (int l = 0; l <= top; ++l) { ws.r[l] = b + o_r[l]; ws.za[l] = b + o_za[l]; ws.zb[l] = b + o_zb[l]; }
+    ws.p[0] = b + o_p0; ws.p[1] = b + o_p1;
+    ws.cfac = coarse_direct ? b + o_fac : nullptr;
+    ws.part_pAp = b + o_pp; ws.part_rz = b + o_pr; ws.np = np;
+    ws.alpha = b + o_sc; ws.beta = ws.alpha + Kc; ws.rz = ws.beta + Kc; ws.rz0 = ws.rz + Kc; ws.relres = ws.rz0 + Kc;
+    ws.active = (int*)(b + o_int); ws.iters = ws.active + Kc;
+    if (!ws_flags) {
+        CK(cudaMalloc(&ws_flags, 64 * sizeof(int)));
+        CK(cudaMallocHost(&h_flags, 64 * sizeof(int)));
+    }
+    ws_K = Kc;
+    ws_bytes = off * 8;
+    return ROMHC_OK;
+}
+
+// one V-cycle: z_0 (ws.zb[0] or ws.za[0] when the tail starts at level 0) = M r_0; writes r.z partials
+int Context::vcycle(const double* y, int Kc, cudaStream_t st, const double** z_result, int* np_rz) {
+    const int L = int(levels.size()) - 1;
+    const int nb = nrb * ncb;
+    const int nstrip_levels = std::min(tail_level, L + 1);
+    std::vector<int> TYd(nstrip_levels), TYu(nstrip_levels);
+    for (int l = 0; l < nstrip_levels; ++l) {
+        const LevelGeo& g = levels[l];
+        const bool has_c = l < L;
+        dim3 block; strip_block(g, block);
+        const int extra_rows = has_c ? 5 : 2;
+        const int TY = pick_ty(g, extra_rows, 0, SMEM_3PER_SM, 64);
+        TYd[l] = TY;
+        const int ns = (g.R + TY - 1) / TY;
+        const size_t sm = smem_hdr_bytes(nb) + size_t(TY + extra_rows) * g.P * 8;
+        ++g_launches; k_mg_down<<<dim3(ns, Kc), block, sm, st>>>(g, has_c ? levels[l + 1] : g, y, ws.r[l], ws.za[l],
+                                                   has_c ? ws.r[l + 1] : nullptr, ws.active, TY, has_c ? 1 : 0);
+    }
+    if (tail_level <= L) {
+        ++g_launches; k_mg_tail<<<Kc, 256, tail_smem, st>>>(tail, y, ws.r[tail_level], ws.za[tail_level], ws.cfac, ws.active,
+                                              tail_level == 0 ? ws.part_rz : nullptr);
+    }
+    for (int l = nstrip_levels - 1; l >= 0; --l) {
+        const LevelGeo& g = levels[l];
+        const bool has_c = l < L;
+        const LevelGeo& gc = has_c ? levels[l + 1] : g;
+        dim3 block; strip_block(g, block);
+        // smem = (TY+4) rows of level l + (TY/2+3) rows of level l+1
+        const size_t hdr = smem_hdr_bytes(nb);
+        int TY = 64;
+        for (; TY > 2; TY -= 2) {
+            const size_t need = hdr + size_t(TY + 4) * g.P * 8 + (has_c ? size_t(TY / 2 + 3) * gc.P * 8 : 0);
+            if (need <= SMEM_2PER_SM && TY <= ((g.R + 1) / 2) * 2) break;
+        }
+        TYu[l] = TY;
+        const int ns = (g.R + TY - 1) / TY;
+        const size_t sm = hdr + size_t(TY + 4) * g.P * 8 + (has_c ? size_t(TY / 2 + 3) * gc.P * 8 : 0);
+        // coarse correction comes from the level below: its post-smoothed zb, or za if that level is the tail's top
+        const double* e = has_c ? ((l + 1 < nstrip_levels) ? ws.zb[l + 1] : ws.za[l + 1]) : nullptr;
+        ++g_launches; k_mg_up<<<dim3(ns, Kc), block, sm, st>>>(g, gc, y, e, ws.za[l], ws.r[l], ws.zb[l], ws.active,
+                                                 l == 0 ? ws.part_rz : nullptr, TY, ns, has_c ? 1 : 0);
+        if (l == 0) *np_rz = ns;
+    }
+    if (nstrip_levels == 0) { *z_result = ws.za[0]; *np_rz = 1; }
+    else *z_result = ws.zb[0];
+    CK(cudaGetLastError());
+    return ROMHC_OK;
+}
+
+// Solve A(y_k) u_k = b for Kc systems; x (padded, Kc*Dp) is written.  y: device (Kc, nb).
+int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, double* relres_out, cudaStream_t st,
+                         SolveStats* stats) {
+    const LevelGeo& g = levels[0];
+    const int nb = nrb * ncb;
+    int rc = ensure_solve_ws(Kc); if (rc) return rc;
+    dim3 block; strip_block(g, block);
+    // x = 0, r = b, active = 1
+    CK(cudaMemsetAsync(x, 0, size_t(Kc) * g.Dp * 8, st));
+    CK(cudaMemsetAsync(ws.r[0], 0, size_t(Kc) * g.Dp * 8, st));
+    CK(cudaMemsetAsync(ws.p[0], 0, size_t(Kc) * g.Dp * 8, st));
+    CK(cudaMemsetAsync(ws.p[1], 0, size_t(Kc) * g.Dp * 8, st));
+    ++g_launches; k_fill_interior<<<(unsigned)(int64_t(Kc) * (g.R - 1)), 128, 0, st>>>(g, ws.r[0], 1.0 / (double(N) * double(N)), Kc);
+    {
+        std::vector<int> ones(Kc, 1);
+        CK(cudaMemcpyAsync(ws.active, ones.data(), size_t(Kc) * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    CK(cudaMemsetAsync(ws.iters, 0, size_t(Kc) * 4, st));
+    CK(cudaMemsetAsync(ws_flags, 0, 64 * sizeof(int), st));
+    if (coarse_direct) {
+        const LevelGeo& gl = levels.back();
+        const size_t sm = smem_hdr_bytes(nb) + size_t(coarse_D) * coarse_LD * 8;
+        ++g_launches; k_coarse_factor<<<Kc, 64, sm, st>>>(gl, y, ws.cfac, coarse_D, coarse_LD, ws_flags + 0);
+    }
+    const int TYp = pick_ty(g, 2, 0, SMEM_3PER_SM, 64);
+    const int nsp = (g.R + TYp - 1) / TYp;
+    const size_t smp = smem_hdr_bytes(nb) + size_t(TYp + 2) * g.P * 8;
+    const int gs = (Kc + 127) / 128;
+    const double* z = nullptr;
+    int np_rz = 1;
+    rc = vcycle(y, Kc, st, &z, &np_rz); if (rc) return rc;
+    const double tol2 = rtol * rtol;
+    int* n_active = ws_flags + 8;   // one counter per iteration slot (mod 32)
+    ++g_launches; k_scalar_beta<<<gs, 128, 0, st>>>(Kc, np_rz, ws.part_rz, ws.rz, ws.rz0, ws.beta, ws.active, ws.iters, ws.relres, 0,
+                                      tol2, n_active, ws_flags + 0);
+    int it = 0, cur = 0;
+    int total_launch_iters = 0;
+    for (it = 1; it <= maxit; ++it) {
+        ++g_launches; k_pcg_p_apply<<<dim3(nsp, Kc), block, smp, st>>>(g, y, z, ws.p[cur], ws.p[cur ^ 1], ws.beta, ws.active,
+                                                        ws.part_pAp, TYp, nsp);
+        cur ^= 1;
+        ++g_launches; k_scalar_alpha<<<gs, 128, 0, st>>>(Kc, nsp, ws.part_pAp, ws.rz, ws.alpha, ws.active, ws_flags + 0);
+        ++g_launches; k_pcg_update<<<dim3(nsp, Kc), block, smp, st>>>(g, y, ws.p[cur], x, ws.r[0], ws.alpha, ws.active, TYp);
+        rc = vcycle(y, Kc, st, &z, &np_rz); if (rc) return rc;
+        int* ctr = n_active + 1 + (it % 32);
+        CK(cudaMemsetAsync(ctr, 0, sizeof(int), st));
+        ++g_launches; k_scalar_beta<<<gs, 128, 0, st>>>(Kc, np_rz, ws.part_rz, ws.rz, ws.rz0, ws.beta, ws.active, ws.iters, ws.relres,
+                                          it, tol2, ctr, ws_flags + 0);
+        ++total_launch_iters;
+        if (it >= min_check_iter && ((it - min_check_iter) % check_every == 0 || it == maxit)) {
+            CK(cudaMemcpyAsync(h_flags, ctr, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (h_flags[0] == 0) break;
+        }
+    }
+    CK(cudaMemcpyAsync(h_flags, ws_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (iters_out) CK(cudaMemcpyAsync(iters_out, ws.iters, size_t(Kc) * 4, cudaMemcpyDeviceToDevice, st));
+    if (relres_out) CK(cudaMemcpyAsync(relres_out, ws.relres, size_t(Kc) * 8, cudaMemcpyDeviceToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    if (stats) {
+        stats->launched_iterations += total_launch_iters;
+        stats->chunks += 1;
+        stats->status |= h_flags[0];
+    }
+    if (h_flags[0] & 1) { set_error("coarse Cholesky hit a non-positive pivot (coefficients must be > 0)"); return ROMHC_ERR_NUMERIC; }
+    return ROMHC_OK;
+}
+
+int Context::solve(const double* y, int64_t K, double* x, int* iters_out, double* relres_out, cudaStream_t st,
+                   SolveStats* stats) {
+    int rc = configure_kernels(); if (rc) return rc;
+    if (tail_smem > 227 * 1024) { set_error("tail kernel needs %zu B of shared memory", tail_smem); return ROMHC_ERR_ARG; }
+    const size_t per = solve_bytes_per_system();
+    int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(int64_t(ws_budget_bytes / per), 32768));
+    chunk = std::min<int64_t>(chunk, K);
+    if (stats) { stats->launched_iterations = 0; stats->chunks = 0; stats->status = 0; }
+    for (int64_t k0 = 0; k0 < K; k0 += chunk) {
+        const int kc = int(std::min<int64_t>(chunk, K - k0));
+        rc = solve_chunk(y + k0 * nrb * ncb, kc, x + k0 * levels[0].Dp, iters_out ? iters_out + k0 : nullptr,
+                         relres_out ? relres_out + k0 : nullptr, st, stats);
+        if (rc) return rc;
+    }
+    return ROMHC_OK;
+}
+
+// apply the preconditioner once (test hook): z = M r
+int Context::precond(const double* y, const double* r, double* z, int64_t K, cudaStream_t st) {
+    int rc = configure_kernels(); if (rc) return rc;
+    if (K > 32768) { set_error("precond: K too large"); return ROMHC_ERR_ARG; }
+    const int Kc = int(K);
+    const LevelGeo& g = levels[0];
+    rc = ensure_solve_ws(Kc); if (rc) return rc;
+    std::vector<int> ones(Kc, 1);
+    CK(cudaMemcpyAsync(ws.active, ones.data(), size_t(Kc) * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaMemcpyAsync(ws.r[0], r, size_t(Kc) * g.Dp * 8, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemsetAsync(ws_flags, 0, 64 * sizeof(int), st));
+    if (coarse_direct) {
+        const LevelGeo& gl = levels.back();
+        const size_t sm = smem_hdr_bytes(nrb * ncb) + size_t(coarse_D) * coarse_LD * 8;
+        ++g_launches; k_coarse_factor<<<Kc, 64, sm, st>>>(gl, y, ws.cfac, coarse_D, coarse_LD, ws_flags + 0);
+    }
+    const double* zr = nullptr; int np = 1;
+    rc = vcycle(y, Kc, st, &zr, &np); if (rc) return rc;
+    CK(cudaMemcpyAsync(z, zr, size_t(Kc) * g.Dp * 8, cudaMemcpyDeviceToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    return ROMHC_OK;
+}
+
+}  // namespace romhc

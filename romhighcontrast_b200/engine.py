@@ -1,0 +1,236 @@
+"""Device engine: one `Engine` per (blocks_geometry, N, device).
+
+PyTorch is used only as plumbing (device memory, streams, torch.distributed); every numerical
+operation on the hot path is a hand-written sm_100a kernel reached through the C ABI in
+include/romhc.h.  No CPU fallback: constructing an Engine without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+F64 = torch.float64
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "device tensors passed to libromhc must be contiguous CUDA tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    def __init__(self, blocks_geometry, N, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.RomhcError("no CUDA device: the ROMHighContrast B200 path has no CPU fallback")
+        self.lib = _lib.load()
+        nrb, ncb = int(blocks_geometry[0]), int(blocks_geometry[1])
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        self.handle = C.c_void_p()
+        _lib.check(self.lib.romhc_create(nrb, ncb, int(N), self.device.index, C.byref(self.handle)))
+        info = (C.c_int64 * 16)()
+        _lib.check(self.lib.romhc_get_info(self.handle, info))
+        (self.D, self.Dp, self.P, self.R, self.C, self.nlevels, self.tail_level, self.coarse_D, self.coarse_direct,
+         self.nrb, self.ncb, self.N, self.solve_bytes_per_system, self.tail_smem) = [int(v) for v in info[:14]]
+        self.nb = nrb * ncb
+        self.last_solve_stats = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.romhc_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ---- plumbing ---------------------------------------------------------------------------------
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_option(self, name, value):
+        _lib.check(self.lib.romhc_set_option(self.handle, name.encode(), float(value)))
+
+    def dev(self, a, dtype=F64):
+        """ndarray / list / tensor -> contiguous device tensor."""
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=dtype).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.float64)), dtype=dtype).to(self.device)
+
+    def empty(self, *shape, dtype=F64):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def params(self, a):
+        """(K, nrb, ncb) array-like -> (K, nb) device tensor."""
+        y = self.dev(a)
+        return y.reshape(-1, self.nb).contiguous()
+
+    # ---- layout -----------------------------------------------------------------------------------
+    def pad(self, compact):
+        """(K, D) compact (reference layout) -> (K, Dp) padded-grid device tensor."""
+        c = self.dev(compact).reshape(-1, self.D)
+        out = self.empty(c.shape[0], self.Dp)
+        _lib.check(self.lib.romhc_pack(self.handle, _ptr(c), _ptr(out), c.shape[0], self.stream()))
+        return out
+
+    def unpad(self, padded):
+        K = padded.shape[0]
+        out = self.empty(K, self.D)
+        _lib.check(self.lib.romhc_unpack(self.handle, _ptr(padded), _ptr(out), K, self.stream()))
+        return out
+
+    # ---- K1a / K2 -----------------------------------------------------------------------------------
+    def apply(self, y, u_pad):
+        out = torch.zeros_like(u_pad)
+        _lib.check(self.lib.romhc_apply(self.handle, _ptr(y), _ptr(u_pad), _ptr(out), u_pad.shape[0], self.stream()))
+        return out
+
+    def energy_norm(self, y, u_pad):
+        out = self.empty(u_pad.shape[0])
+        _lib.check(self.lib.romhc_energy_norm(self.handle, _ptr(y), _ptr(u_pad), u_pad.shape[0], _ptr(out),
+                                              self.stream()))
+        return out
+
+    def h10_norm(self, u_pad):
+        return self.energy_norm(None, u_pad)
+
+    def l2_norm(self, u_pad):
+        out = self.empty(u_pad.shape[0])
+        _lib.check(self.lib.romhc_l2_norm(self.handle, _ptr(u_pad), u_pad.shape[0], _ptr(out), self.stream()))
+        return out
+
+    def error_norm(self, U_pad, coef, basis_pad):
+        """|| coef @ basis - U ||_{H10} per row (coef None / empty basis: ||U||)."""
+        K = U_pad.shape[0]
+        n = 0 if basis_pad is None else basis_pad.shape[0]
+        out = self.empty(K)
+        _lib.check(self.lib.romhc_error_norm(self.handle, _ptr(U_pad), _ptr(coef) if n else None,
+                                             _ptr(basis_pad) if n else None, n, K, _ptr(out), self.stream()))
+        return out
+
+    # ---- K1 --------------------------------------------------------------------------------------------
+    def solve(self, y, out=None):
+        """Batched snapshot solves; y (K, nb) device -> (x_pad (K, Dp), iters (K,), relres (K,))."""
+        K = y.shape[0]
+        x = self.empty(K, self.Dp) if out is None else out
+        iters = self.empty(K, dtype=torch.int32)
+        relres = self.empty(K)
+        stats = (C.c_int64 * 4)()
+        _lib.check(self.lib.romhc_solve(self.handle, _ptr(y), K, _ptr(x), _ptr(iters), _ptr(relres), self.stream(),
+                                        stats))
+        self.last_solve_stats = {"launched_iterations": int(stats[0]), "chunks": int(stats[1]),
+                                 "status": int(stats[2]), "workspace_bytes": int(stats[3])}
+        return x, iters, relres
+
+    def precond(self, y, r_pad):
+        z = torch.zeros_like(r_pad)
+        _lib.check(self.lib.romhc_precond(self.handle, _ptr(y), _ptr(r_pad), _ptr(z), r_pad.shape[0], self.stream()))
+        return z
+
+    # ---- K4 / K5 ----------------------------------------------------------------------------------------
+    def project_operators(self, basis_pad):
+        n = basis_pad.shape[0]
+        Ahat = self.empty(self.nb, n, n)
+        bhat = self.empty(n)
+        _lib.check(self.lib.romhc_project_operators(self.handle, _ptr(basis_pad), n, _ptr(Ahat), _ptr(bhat),
+                                                    self.stream()))
+        return Ahat, bhat
+
+    def reduced_solve(self, y, Ahat, rhs, check=True):
+        """(sum_q y[k,q] Ahat[q]) c_k = rhs ; rhs (n,) shared or (K, n)."""
+        K, n = y.shape[0], Ahat.shape[-1]
+        per = 1 if rhs.dim() == 2 else 0
+        Cc = self.empty(K, n)
+        info = self.empty(K, dtype=torch.int32)
+        _lib.check(self.lib.romhc_reduced_solve(_ptr(y), self.nb, _ptr(Ahat), _ptr(rhs), per, n, K, _ptr(Cc),
+                                                _ptr(info), self.stream()))
+        if check and bool(info.any().item()):
+            raise np.linalg.LinAlgError("reduced Galerkin matrix is not positive definite")
+        return Cc
+
+    # ---- dense helpers -------------------------------------------------------------------------------------
+    def gemm_nt(self, A, B, symmetric=False):
+        M, Kd = A.shape
+        Nn = B.shape[0]
+        out = self.empty(M, Nn)
+        _lib.check(self.lib.romhc_gemm_nt(_ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(out), Nn, M, Nn, Kd,
+                                          1 if symmetric else 0, self.stream()))
+        return out
+
+    def gemm_nn(self, A, B):
+        M, Kd = A.shape
+        Nn = B.shape[1]
+        out = self.empty(M, Nn)
+        _lib.check(self.lib.romhc_gemm_nn(_ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(out), Nn, M, Nn, Kd,
+                                          self.stream()))
+        return out
+
+    def gemm_tn(self, A, B):
+        Kd, M = A.shape
+        Nn = B.shape[1]
+        out = self.empty(M, Nn)
+        _lib.check(self.lib.romhc_gemm_tn(_ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(out), Nn, M, Nn, Kd,
+                                          self.stream()))
+        return out
+
+    def column_mean(self, X):
+        K, D = X.shape
+        mean = self.empty(D)
+        _lib.check(self.lib.romhc_column_mean(_ptr(X), X.stride(0), K, D, _ptr(mean), self.stream()))
+        return mean
+
+    def center_rows_(self, X, mean):
+        K, D = X.shape
+        _lib.check(self.lib.romhc_center_rows(_ptr(X), X.stride(0), K, D, _ptr(mean), self.stream()))
+        return X
+
+    # ---- K6 -----------------------------------------------------------------------------------------------------
+    def evaluate(self, points, u_pad):
+        pts = self.dev(points).reshape(-1, 2).contiguous()
+        K, m = u_pad.shape[0], pts.shape[0]
+        out = self.empty(K, m)
+        _lib.check(self.lib.romhc_evaluate(self.handle, _ptr(pts), m, _ptr(u_pad), K, _ptr(out), self.stream()))
+        return out
+
+    def estimator(self, c, a_basis, invert):
+        """c (n, K), a_basis (n, nb) -> (K, nb)."""
+        n, K = c.shape
+        out = self.empty(K, a_basis.shape[1])
+        _lib.check(self.lib.romhc_estimator(_ptr(c), K, n, _ptr(a_basis), a_basis.shape[1], 1 if invert else 0,
+                                            _ptr(out), self.stream()))
+        return out
+
+    def argmax(self, v):
+        idx = self.empty(1, dtype=torch.int64)
+        val = self.empty(1)
+        _lib.check(self.lib.romhc_argmax(_ptr(v), v.shape[0], _ptr(idx), _ptr(val), self.stream()))
+        return int(idx.item()), float(val.item())
+
+    # ---- host-buffer entry points -----------------------------------------------------------------------------------
+    def generate_solutions_host(self, y_host, out=None, return_stats=False):
+        y = np.ascontiguousarray(np.asarray(y_host, dtype=np.float64).reshape(-1, self.nb))
+        K = y.shape[0]
+        U = np.empty((K, self.D)) if out is None else out
+        iters = np.empty(K, dtype=np.int32)
+        relres = np.empty(K)
+        _lib.check(self.lib.romhc_generate_solutions_host(
+            self.handle, y.ctypes.data_as(C.c_void_p), K, C.c_void_p(U.ctypes.data) if isinstance(U, np.ndarray)
+            else C.c_void_p(U.data_ptr()), iters.ctypes.data_as(C.c_void_p), relres.ctypes.data_as(C.c_void_p)))
+        return (U, iters, relres) if return_stats else U
+
+    def reduced_galerkin_host(self, y_host, Ahat_host, bhat_host):
+        y = np.ascontiguousarray(np.asarray(y_host, dtype=np.float64).reshape(-1, self.nb))
+        A = np.ascontiguousarray(np.asarray(Ahat_host, dtype=np.float64))
+        b = np.ascontiguousarray(np.asarray(bhat_host, dtype=np.float64))
+        K, n = y.shape[0], b.shape[0]
+        Cc = np.empty((K, n))
+        info = np.empty(K, dtype=np.int32)
+        _lib.check(self.lib.romhc_reduced_galerkin_host(
+            self.handle, y.ctypes.data_as(C.c_void_p), A.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), n, K,
+            Cc.ctypes.data_as(C.c_void_p), info.ctypes.data_as(C.c_void_p)))
+        if info.any():
+            raise np.linalg.LinAlgError("reduced Galerkin matrix is not positive definite")
+        return Cc

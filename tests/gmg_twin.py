@@ -1,0 +1,152 @@
+"""numpy twin of the CUDA GMG-PCG algorithm (romhighcontrast_b200/csrc/solver.cu) on the full vertex grid.
+
+Test infrastructure: used to check single kernels (stencil apply, one V-cycle, iteration counts)
+at sizes where running it takes milliseconds.  Same algorithm, different code: red/black GS V(1,1),
+P1 anti-diagonal transfers, rediscretised coarse operators, dense coarsest solve, difference-form apply.
+"""
+import numpy as np
+
+
+def cell_coef(a, N):
+    return np.kron(np.asarray(a, float), np.ones((N, N)))
+
+
+class Level:
+    def __init__(self, a, N):
+        k = cell_coef(a, N)
+        self.N = N
+        self.R, self.C = k.shape
+        R, C = self.R, self.C
+        kp = np.zeros((R + 2, C + 2))
+        kp[1:-1, 1:-1] = k
+        ul, ur = kp[0:R + 1, 0:C + 1], kp[0:R + 1, 1:C + 2]
+        dl, dr = kp[1:R + 2, 0:C + 1], kp[1:R + 2, 1:C + 2]
+        self.diag = (ul + ur) + (dl + dr)
+        self.wE = 0.5 * (ur + dr)
+        self.wS = 0.5 * (dl + dr)
+        self.mask = np.zeros((R + 1, C + 1), bool)
+        self.mask[1:R, 1:C] = True
+        rr, cc = np.meshgrid(np.arange(R + 1), np.arange(C + 1), indexing="ij")
+        self.red = self.mask & ((rr + cc) % 2 == 0)
+        self.black = self.mask & ((rr + cc) % 2 == 1)
+
+    def offdiag(self, u):
+        s = np.zeros_like(u)
+        s[:, :-1] += self.wE[:, :-1] * u[:, 1:]
+        s[:, 1:] += self.wE[:, :-1] * u[:, :-1]
+        s[:-1, :] += self.wS[:-1, :] * u[1:, :]
+        s[1:, :] += self.wS[:-1, :] * u[:-1, :]
+        return s
+
+    def apply(self, u):
+        out = np.zeros_like(u)
+        dE = u[:, :-1] - u[:, 1:]
+        out[:, :-1] += self.wE[:, :-1] * dE
+        out[:, 1:] -= self.wE[:, :-1] * dE
+        dS = u[:-1, :] - u[1:, :]
+        out[:-1, :] += self.wS[:-1, :] * dS
+        out[1:, :] -= self.wS[:-1, :] * dS
+        out[~self.mask] = 0
+        return out
+
+    def energy(self, u):
+        dE = u[:, :-1] - u[:, 1:]
+        dS = u[:-1, :] - u[1:, :]
+        return float((self.wE[:, :-1] * dE * dE).sum() + (self.wS[:-1, :] * dS * dS).sum())
+
+    def gs_half(self, z, r, color):
+        s = self.offdiag(z)
+        z[color] = (r[color] + s[color]) / self.diag[color]
+
+
+def restrict(d):
+    R, C = d.shape[0] - 1, d.shape[1] - 1
+    dp = np.zeros((R + 3, C + 3))
+    dp[1:-1, 1:-1] = d
+    c = lambda dr, dc: dp[1 + dr:R + 2 + dr:2, 1 + dc:C + 2 + dc:2]
+    out = c(0, 0) + 0.5 * (c(0, 1) + c(0, -1) + c(1, 0) + c(-1, 0) + c(-1, 1) + c(1, -1))
+    out[0, :] = 0; out[-1, :] = 0; out[:, 0] = 0; out[:, -1] = 0
+    return out
+
+
+def prolong(e, shape):
+    z = np.zeros(shape)
+    z[::2, ::2] = e
+    z[::2, 1::2] = 0.5 * (e[:, :-1] + e[:, 1:])
+    z[1::2, ::2] = 0.5 * (e[:-1, :] + e[1:, :])
+    z[1::2, 1::2] = 0.5 * (e[:-1, 1:] + e[1:, :-1])
+    return z
+
+
+class GMG:
+    DIRECT_MAX = 64
+    TAIL_MAX_DP = 4352
+
+    def __init__(self, a, N, coarse_sweeps=8):
+        a = np.asarray(a, float)
+        nrb, ncb = a.shape
+        self.levels = []
+        n = N
+        while True:
+            self.levels.append(Level(a, n))
+            if n % 2:
+                break
+            nn = n // 2
+            if nrb * nn < 2 or ncb * nn < 2:
+                break
+            n = nn
+        self.coarse_sweeps = coarse_sweeps
+        L = self.levels[-1]
+        D = (L.R - 1) * (L.C - 1)
+        P = (L.C + 7) // 8 * 8
+        in_tail = (L.R + 1) * P <= self.TAIL_MAX_DP
+        self.direct = in_tail and D <= self.DIRECT_MAX
+        self.smooth_only = not in_tail          # coarsest level handled by the strip kernels: one symmetric sweep
+        if self.direct:
+            M = np.zeros((D, D))
+            for j in range(D):
+                u = np.zeros((L.R + 1, L.C + 1)); u[1:-1, 1:-1].flat[j] = 1
+                M[:, j] = L.apply(u)[1:-1, 1:-1].ravel()
+            self.coarse_matrix = M
+
+    def coarse_solve(self, r):
+        L = self.levels[-1]
+        z = np.zeros_like(r)
+        if self.direct:
+            z[1:-1, 1:-1] = np.linalg.solve(self.coarse_matrix, r[1:-1, 1:-1].ravel()).reshape(L.R - 1, L.C - 1)
+            return z
+        sweeps = 1 if self.smooth_only else self.coarse_sweeps
+        for _ in range(sweeps):
+            L.gs_half(z, r, L.red); L.gs_half(z, r, L.black)
+        for _ in range(sweeps):
+            L.gs_half(z, r, L.black); L.gs_half(z, r, L.red)
+        return z
+
+    def vcycle(self, r, l=0):
+        if l == len(self.levels) - 1:
+            return self.coarse_solve(r)
+        L = self.levels[l]
+        z = np.zeros_like(r)
+        L.gs_half(z, r, L.red); L.gs_half(z, r, L.black)
+        d = r - L.apply(z); d[~L.mask] = 0
+        z = z + prolong(self.vcycle(restrict(d), l + 1), r.shape)
+        z[~L.mask] = 0
+        L.gs_half(z, r, L.black); L.gs_half(z, r, L.red)
+        return z
+
+
+def pcg(a, N, tol=1e-12, maxit=1000, coarse_sweeps=8):
+    g = GMG(a, N, coarse_sweeps)
+    L = g.levels[0]
+    b = np.zeros((L.R + 1, L.C + 1)); b[1:-1, 1:-1] = 1.0 / N ** 2
+    x = np.zeros_like(b); r = b.copy()
+    z = g.vcycle(r); p = z.copy(); rz = (r * z).sum(); rz0 = rz
+    it = 0
+    for it in range(1, maxit + 1):
+        Ap = L.apply(p); al = rz / (p * Ap).sum()
+        x += al * p; r -= al * Ap
+        z = g.vcycle(r); rzn = (r * z).sum()
+        if not rzn > tol ** 2 * rz0:
+            break
+        p = z + (rzn / rz) * p; rz = rzn
+    return x[1:-1, 1:-1].ravel(), it

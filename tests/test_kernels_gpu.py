@@ -1,0 +1,265 @@
+"""GPU parity tests, one CUDA kernel family at a time, through the C ABI (libromhc.so).
+
+Checker: the CPU oracle (oracle/) and the numpy twin of the multigrid algorithm (tests/gmg_twin.py).
+Tolerances: 1e-9 relative (north_star) for solves / reduced solutions, 1e-12 for pure stencil / gather
+arithmetic; integer results (argmax, greedy indices) exact.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+GEOS = [((2, 2), 8), ((3, 2), 4), ((4, 4), 16), ((2, 3), 6), ((3, 3), 5), ((1, 3), 8), ((2, 2), 32), ((3, 3), 43),
+        ((4, 4), 20)]
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def make_engine(geo, N):
+    from romhighcontrast_b200.engine import Engine
+    return Engine(geo, N)
+
+
+def rand_y(geo, K, cmax=1e6, seed=0):
+    return 10 ** np.random.default_rng(seed).uniform(0, np.log10(cmax), (K,) + tuple(geo))
+
+
+def grid_of(eng, u_compact):
+    """compact (D,) -> full vertex grid (R+1, C+1)"""
+    g = np.zeros((eng.R + 1, eng.C + 1))
+    g[1:-1, 1:-1] = u_compact.reshape(eng.R - 1, eng.C - 1)
+    return g
+
+
+@pytest.mark.parametrize("geo,N", GEOS)
+def test_pack_unpack_apply_norms(torch_mod, geo, N):
+    from oracle import FEMOracle
+    eng = make_engine(geo, N)
+    o = FEMOracle(geo, N)
+    assert eng.D == o.vspace_dim
+    K = 5
+    rng = np.random.default_rng(1)
+    U = rng.standard_normal((K, eng.D))
+    y = rand_y(geo, K)
+    Up = eng.pad(U)
+    assert Up.shape == (K, eng.Dp)
+    np.testing.assert_array_equal(eng.unpad(Up).cpu().numpy(), U)
+    # padding slots are zero
+    assert abs(float(Up.sum()) - U.sum()) < 1e-9 * np.abs(U).sum()
+    yd = eng.params(y)
+    AU = eng.unpad(eng.apply(yd, Up)).cpu().numpy()
+    for k in range(K):
+        ref = o.matrix(y[k]) @ U[k]
+        assert relerr(AU[k], ref) < 1e-13, (geo, N, k)
+    A1U = eng.unpad(eng.apply(None, Up)).cpu().numpy()
+    assert relerr(A1U, (o.A1 @ U.T).T) < 1e-13
+    np.testing.assert_allclose(eng.h10_norm(Up).cpu().numpy(), o.H10norm(U), rtol=1e-12)
+    np.testing.assert_allclose(eng.l2_norm(Up).cpu().numpy(), o.l2norm(U), rtol=1e-13)
+    en = eng.energy_norm(yd, Up).cpu().numpy()
+    ref = np.sqrt([U[k] @ (o.matrix(y[k]) @ U[k]) for k in range(K)])
+    np.testing.assert_allclose(en, ref, rtol=1e-12)
+
+
+@pytest.mark.parametrize("geo,N", GEOS)
+def test_precond_matches_twin(torch_mod, geo, N):
+    from gmg_twin import GMG
+    eng = make_engine(geo, N)
+    K = 3
+    y = rand_y(geo, K, seed=2)
+    rng = np.random.default_rng(3)
+    Rr = rng.standard_normal((K, eng.D))
+    z = eng.unpad(eng.precond(eng.params(y), eng.pad(Rr))).cpu().numpy()
+    for k in range(K):
+        tw = GMG(y[k], N)
+        zt = tw.vcycle(grid_of(eng, Rr[k]))[1:-1, 1:-1].ravel()
+        assert relerr(z[k], zt) < 1e-9, (geo, N, k, relerr(z[k], zt))
+
+
+@pytest.mark.parametrize("geo,N", GEOS)
+def test_solve_matches_oracle(torch_mod, geo, N):
+    from oracle import FEMOracle
+    from gmg_twin import pcg
+    eng = make_engine(geo, N)
+    o = FEMOracle(geo, N)
+    K = 7
+    y = rand_y(geo, K, seed=4)
+    y[0] = 1.0
+    x, iters, relres = eng.solve(eng.params(y))
+    U = eng.unpad(x).cpu().numpy()
+    Uo = o.generate_solutions(y)
+    h = o.H10norm(U - Uo) / o.H10norm(Uo)
+    l2 = o.l2norm(U - Uo) / o.l2norm(Uo)
+    assert h.max() < 1e-9 and l2.max() < 1e-9, (geo, N, h, l2)
+    it = iters.cpu().numpy()
+    assert (relres.cpu().numpy() <= 1e-12 * 1.0000001).all()
+    _, it_twin = pcg(y[1], N)
+    assert abs(int(it[1]) - it_twin) <= 2, (it, it_twin)
+    assert eng.last_solve_stats["status"] == 0
+
+
+def test_solve_golden_and_host_entry(torch_mod):
+    g = golden("g2_solve_2x2_N10.npz")
+    eng = make_engine((2, 2), 10)
+    U, iters, relres = eng.generate_solutions_host(g["y"], return_stats=True)
+    assert relerr(U, g["U_lsq"]) < 1e-9 and relerr(U, g["U_lsqsparse"]) < 1e-9
+    assert abs(np.linalg.norm(U[0]) - 0.3253564554055284) < 1e-11
+    g = golden("g2_solve_3x2_N4.npz")
+    eng = make_engine((3, 2), 4)
+    U = eng.generate_solutions_host(g["y"])
+    assert relerr(U, g["U_lsq"]) < 1e-9
+
+
+def test_solve_floating_inclusion_beats_reference(torch_mod):
+    g = golden("g8_floating_4x4_N8.npz")
+    eng = make_engine((4, 4), 8)
+    U = eng.generate_solutions_host(g["a"])
+    ours = relerr(U[0], g["U_truth"])
+    ref = min(relerr(g["U_lsq"], g["U_truth"]), relerr(g["U_lsqsparse"], g["U_truth"]))
+    assert ours < 1e-9 and ours < ref, (ours, ref)
+
+
+def test_solve_contrast_sweep_iterations(torch_mod):
+    """iteration counts against contrast (north_star (1)); also exercises INFINIT_A = 1e10 inputs"""
+    geo, N = (4, 4), 16
+    from oracle import FEMOracle
+    eng = make_engine(geo, N)
+    o = FEMOracle(geo, N)
+    for cmax in (1.0, 1e2, 1e6, 1e10):
+        y = rand_y(geo, 8, cmax if cmax > 1 else 1.0000001, seed=11)
+        x, iters, _ = eng.solve(eng.params(y))
+        U = eng.unpad(x).cpu().numpy()
+        Uo = o.generate_solutions(y)
+        err = (o.l2norm(U - Uo) / o.l2norm(Uo)).max()
+        print(f"contrast {cmax:g}: iterations {iters.cpu().numpy().tolist()} max rel l2 err {err:.2e}")
+        assert iters.max().item() <= 60
+        if cmax <= 1e6:
+            assert err < 1e-9
+
+
+@pytest.mark.parametrize("geo,N,n", [((3, 2), 4, 5), ((4, 4), 16, 20), ((2, 2), 32, 10), ((3, 3), 5, 7)])
+def test_projection_and_reduced_solve(torch_mod, geo, N, n):
+    from oracle import FEMOracle
+    eng = make_engine(geo, N)
+    o = FEMOracle(geo, N)
+    rng = np.random.default_rng(6)
+    K = 33
+    y = rand_y(geo, K, seed=7)
+    U = o.generate_solutions(y[:n])
+    Phi = np.linalg.qr(U.T)[0].T
+    Phip = eng.pad(Phi)
+    Ahat, bhat = eng.project_operators(Phip)
+    Ao, bo = o.reduced_operators(Phi)
+    assert relerr(Ahat.cpu().numpy().reshape(Ao.shape), Ao) < 1e-11
+    assert relerr(bhat.cpu().numpy(), bo) < 1e-12
+    Cg = eng.reduced_solve(eng.params(y), Ahat, bhat).cpu().numpy()
+    Co = o.reduced_coefficients(y, Phi)
+    assert relerr(Cg @ Phi, Co @ Phi) < 1e-9
+    # host entry point
+    Ch = eng.reduced_galerkin_host(y, Ao.reshape(-1, n, n), bo)
+    assert relerr(Ch @ Phi, Co @ Phi) < 1e-9
+    # per-system right-hand sides: H10 projection coefficients
+    Uall = o.generate_solutions(y)
+    Up = eng.pad(Uall)
+    W = eng.apply(None, Phip)
+    B = eng.gemm_nt(Up, W)                        # (K, n) = U A_1 Phi^T
+    ones = torch_mod.ones(K, eng.nb, dtype=torch_mod.float64, device=eng.device)
+    Cp = eng.reduced_solve(ones, Ahat, B).cpu().numpy()
+    assert relerr(Cp, o.projection_coefficients(Uall, Phi)) < 1e-9
+    # fused greedy error norm ||C Phi - U||_H10 vs oracle
+    err = eng.error_norm(Up, eng.dev(Cg), Phip).cpu().numpy()
+    np.testing.assert_allclose(err, o.H10norm(Co @ Phi - Uall), rtol=1e-6, atol=1e-13)
+    np.testing.assert_allclose(eng.error_norm(Up, None, None).cpu().numpy(), o.H10norm(Uall), rtol=1e-12)
+    # reconstruction GEMM
+    rec = eng.unpad(eng.gemm_nn(eng.dev(Cg), Phip)).cpu().numpy()
+    assert relerr(rec, Cg @ Phi) < 1e-13
+
+
+def test_reduced_solve_flags_indefinite(torch_mod):
+    eng = make_engine((2, 2), 4)
+    torch = torch_mod
+    n = 3
+    Ahat = torch.zeros(4, n, n, dtype=torch.float64, device=eng.device)
+    Ahat[0] = torch.eye(n, dtype=torch.float64) * -1.0
+    y = torch.ones(2, 4, dtype=torch.float64, device=eng.device)
+    rhs = torch.ones(n, dtype=torch.float64, device=eng.device)
+    with pytest.raises(np.linalg.LinAlgError):
+        eng.reduced_solve(y, Ahat, rhs)
+
+
+@pytest.mark.parametrize("M,N,Kd,sym", [(200, 200, 1000, True), (130, 20, 777, False), (257, 300, 64, False),
+                                        (64, 5, 4161, False), (1000, 1000, 300, True)])
+def test_gemm_nt(torch_mod, M, N, Kd, sym):
+    torch = torch_mod
+    eng = make_engine((2, 2), 4)
+    gen = torch.Generator(device="cpu").manual_seed(0)
+    A = torch.randn(M, Kd, dtype=torch.float64, generator=gen).cuda()
+    B = A if sym else torch.randn(N, Kd, dtype=torch.float64, generator=gen).cuda()
+    Cg = eng.gemm_nt(A, B, symmetric=sym)
+    ref = A @ B.T
+    assert float((Cg - ref).abs().max() / ref.abs().max()) < 1e-13
+    if sym:
+        assert torch.equal(Cg, Cg.T)
+
+
+def test_gemm_tn_mean_center(torch_mod):
+    torch = torch_mod
+    eng = make_engine((2, 2), 4)
+    gen = torch.Generator(device="cpu").manual_seed(1)
+    X = torch.randn(700, 1031, dtype=torch.float64, generator=gen).cuda()
+    V = torch.randn(700, 12, dtype=torch.float64, generator=gen).cuda()
+    out = eng.gemm_tn(V, X)
+    ref = V.T @ X
+    assert float((out - ref).abs().max() / ref.abs().max()) < 1e-13
+    mean = eng.column_mean(X)
+    assert float((mean - X.mean(dim=0)).abs().max()) < 1e-14
+    Xc = eng.center_rows_(X.clone(), mean)
+    assert float((Xc - (X - X.mean(dim=0))).abs().max()) < 1e-13
+
+
+def test_evaluate_estimators_argmax(torch_mod):
+    from oracle import FEMOracle, estimator_inv, estimator_linear
+    torch = torch_mod
+    g = golden("g3_reduced_3x2_N4.npz")
+    eng = make_engine((3, 2), 4)
+    Up = eng.pad(g["U"])
+    ev = eng.evaluate(g["pts"], Up).cpu().numpy()
+    np.testing.assert_allclose(ev, g["ev"], rtol=1e-12, atol=1e-18)
+    evn = eng.evaluate(g["nodes"], Up[:2]).cpu().numpy()
+    np.testing.assert_allclose(evn, g["U"][:2], rtol=1e-12, atol=1e-18)
+    # points on grid lines / domain boundary
+    o = FEMOracle((3, 2), 4)
+    edge = np.array([[o.points_c[0], 0.1], [o.points_c[-1], -0.2], [0.0, o.points_r[0]], [0.3, o.points_r[-1]],
+                     [o.points_c[3], o.points_r[5]], [0.25, 0.5]])
+    np.testing.assert_allclose(eng.evaluate(edge, Up).cpu().numpy(), o.evaluate_solutions(edge, g["U"]),
+                               rtol=1e-12, atol=1e-16)
+    g5 = golden("g5_builders_2x2_N10.npz")
+    c = eng.dev(g5["se_c"])
+    ab = eng.dev(g5["greedy6_a"]).reshape(6, 4)
+    np.testing.assert_allclose(eng.estimator(c, ab, True).cpu().numpy().reshape(-1, 2, 2), g5["inv"], rtol=1e-12)
+    np.testing.assert_allclose(eng.estimator(c, ab, False).cpu().numpy().reshape(-1, 2, 2), g5["lin"], rtol=1e-12)
+    v = np.array([0.5, 3.0, 1.0, 3.0, 2.0])
+    assert eng.argmax(eng.dev(v))[0] == 1
+    v = np.ones(100000); assert eng.argmax(eng.dev(v))[0] == 0
+    v = np.random.default_rng(0).standard_normal(300000); v[77777] = v.max(); v[123456] = v.max()
+    assert eng.argmax(eng.dev(v))[0] == int(np.argmax(v))
+    v[200000] = np.nan
+    assert eng.argmax(eng.dev(v))[0] == int(np.argmax(v)) == 200000
+
+
+def test_c_abi_rejects_bad_arguments(torch_mod):
+    from romhighcontrast_b200 import _lib
+    from romhighcontrast_b200.engine import Engine
+    with pytest.raises(_lib.RomhcError):
+        Engine((0, 2), 4)
+    with pytest.raises(_lib.RomhcError):
+        Engine((1, 1), 1)
+    eng = Engine((2, 2), 4)
+    with pytest.raises(_lib.RomhcError):
+        eng.set_option("nonsense", 1.0)
