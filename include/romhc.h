@@ -121,6 +121,10 @@ int romhc_center_rows(double* X_dev, int64_t ld, int64_t K, int64_t D, const dou
  * romhc_argmax: first maximum, NaN counts as maximal (np.argmax)                              ReducedBasis.py:129 */
 int romhc_evaluate(romhc_handle h, const double* points_dev, int m, const double* u_pad_dev, int64_t K,
                    double* out_dev, void* stream);
+/* (padded index or -1, weight) x 3 per point: the sparse rows of generate_riesz(x, norm="l2")  SolutionsManagers.py:70-77 */
+int romhc_interp_weights(romhc_handle h, const double* points_dev, int m, int* idx3_dev, double* w3_dev, void* stream);
+/* out[k] = ||X[k, :D]||_2 for a generic row-major matrix (SolutionsManager.l2norm is a staticmethod)  :60-62 */
+int romhc_row_norms(const double* X_dev, int64_t ld, int64_t K, int64_t D, double* out_dev, void* stream);
 int romhc_estimator(const double* c_dev, int64_t K, int n, const double* abasis_dev, int nb, int invert,
                     double* out_dev, void* stream);
 int romhc_argmax(const double* v_dev, int64_t K, int64_t* idx_dev, double* val_dev, void* stream);

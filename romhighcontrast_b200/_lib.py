@@ -58,6 +58,8 @@ SIGNATURES = {
     "romhc_column_mean": (_i, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "romhc_center_rows": (_i, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "romhc_evaluate": (_i, [_vp, _vp, _i, _vp, _i64, _vp, _vp]),
+    "romhc_interp_weights": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "romhc_row_norms": (_i, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "romhc_estimator": (_i, [_vp, _i64, _i, _vp, _i, _i, _vp, _vp]),
     "romhc_argmax": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "romhc_generate_solutions_host": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),

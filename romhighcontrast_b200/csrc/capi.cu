@@ -178,6 +178,12 @@ int romhc_center_rows(double* X, int64_t ld, int64_t K, int64_t D, const double*
 int romhc_evaluate(romhc_handle h, const double* pts, int m, const double* u, int64_t K, double* out, void* st) {
     CHECK_H(h); return H(h)->evaluate(pts, m, u, K, out, ST(st));
 }
+int romhc_interp_weights(romhc_handle h, const double* pts, int m, int* idx3, double* w3, void* st) {
+    CHECK_H(h); return H(h)->interp_weights(pts, m, idx3, w3, ST(st));
+}
+int romhc_row_norms(const double* X, int64_t ld, int64_t K, int64_t D, double* out, void* st) {
+    return row_norms(X, ld, K, D, out, ST(st));
+}
 int romhc_estimator(const double* c, int64_t K, int n, const double* ab, int nb, int invert, double* out, void* st) {
     return estimator_contract(c, K, n, ab, nb, invert, out, ST(st));
 }

@@ -300,6 +300,32 @@ int Context::evaluate(const double* points, int m, const double* u, int64_t K, d
     return ROMHC_OK;
 }
 
+// (padded index, weight) triples of every point -- the rows of the l2 "Riesz" matrix, generate_riesz(norm="l2")
+// (SolutionsManagers.py:70-77) without evaluating the D unit vectors.
+int Context::interp_weights(const double* points, int m, int* idx3, double* w3, cudaStream_t st) {
+    if (m <= 0) return ROMHC_OK;
+    ++g_launches; k_eval_setup<<<(m + 127) / 128, 128, 0, st>>>(levels[0], points, m, idx3, w3);
+    CK(cudaGetLastError());
+    return ROMHC_OK;
+}
+
+// euclidean row norms of a generic row-major matrix (SolutionsManager.l2norm is a staticmethod: no geometry)
+__global__ void __launch_bounds__(256) k_row_norms(const double* __restrict__ X, int64_t ld, int64_t D,
+                                                   double* __restrict__ out) {
+    __shared__ double red[32];
+    const double* x = X + int64_t(blockIdx.x) * ld;
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < D; i += blockDim.x) acc = fma(x[i], x[i], acc);
+    const double tot = block_sum(acc, red, threadIdx.x, blockDim.x);
+    if (threadIdx.x == 0) out[blockIdx.x] = sqrt(tot);
+}
+int row_norms(const double* X, int64_t ld, int64_t K, int64_t D, double* out, cudaStream_t st) {
+    if (K <= 0) return ROMHC_OK;
+    ++g_launches; k_row_norms<<<(unsigned)K, 256, 0, st>>>(X, ld, D, out);
+    CK(cudaGetLastError());
+    return ROMHC_OK;
+}
+
 // ======================================================================================================
 // argmax with numpy semantics: first maximum wins, NaN beats everything (np.argmax returns the first NaN)
 // ======================================================================================================

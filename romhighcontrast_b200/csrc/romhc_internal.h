@@ -106,11 +106,13 @@ struct Context {
     // reduced.cu
     int project_operators(const double* basis, int n, double* Ahat, double* bhat, cudaStream_t st);
     int evaluate(const double* points, int m, const double* u, int64_t K, double* out, cudaStream_t st);
+    int interp_weights(const double* points, int m, int* idx3, double* w3, cudaStream_t st);
 };
 
 // reduced.cu (geometry independent)
 int reduced_solve(const double* y, int nb, const double* Ahat, const double* rhs, int rhs_per_system, int n,
                   int64_t K, double* C, int* info, cudaStream_t st);
+int row_norms(const double* X, int64_t ld, int64_t K, int64_t D, double* out, cudaStream_t st);
 int argmax_first(const double* v, int64_t K, int64_t* idx_out, double* val_out, cudaStream_t st);
 int estimator_contract(const double* c, int64_t K, int n, const double* abasis, int nb, int invert, double* out,
                        cudaStream_t st);

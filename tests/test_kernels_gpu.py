@@ -174,7 +174,7 @@ def test_projection_and_reduced_solve(torch_mod, geo, N, n):
     assert relerr(Cp, o.projection_coefficients(Uall, Phi)) < 1e-9
     # fused greedy error norm ||C Phi - U||_H10 vs oracle
     err = eng.error_norm(Up, eng.dev(Cg), Phip).cpu().numpy()
-    np.testing.assert_allclose(err, o.H10norm(Co @ Phi - Uall), rtol=1e-6, atol=1e-13)
+    np.testing.assert_allclose(err, o.H10norm(Co @ Phi - Uall), rtol=1e-6, atol=1e-10 * o.H10norm(Uall).max())
     np.testing.assert_allclose(eng.error_norm(Up, None, None).cpu().numpy(), o.H10norm(Uall), rtol=1e-12)
     # reconstruction GEMM
     rec = eng.unpad(eng.gemm_nn(eng.dev(Cg), Phip)).cpu().numpy()
