@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the ROMHighContrast hot path on B200.
+
+One "step" = one pass of the batched FEM snapshot solver (GMG-preconditioned fp64 CG, libromhc.so) over the
+K parameter vectors of this rank (BASELINE.json configs[2]: (4,4) subdomains, N=64 -> 256^2 cells, D=65025,
+K=10000 random-contrast samples up to 1e6).  `value` = snapshot solves/s with y resident in HBM; `e2e` = the same
+through the host-buffer C-ABI entry point romhc_generate_solutions_host (y from pinned host memory, U copied
+back to pinned host memory every step).  The same JSON line carries the secondary metrics of the path (POD Gram
+GEMM on the fp64 tensor cores, 1M online reduced Galerkin solves), the live roofline of the dominant solver
+kernel and the CPU baseline (the oracle's SuperLU path on the host cores).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--k-snap 10000] [--quick]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GEO, NPB = (4, 4), 64            # configs[2] of BASELINE.json
+CMAX = 1e6
+KIND_NAMES = ["k_pcg_p_apply", "k_pcg_update", "k_mg_down(l0)", "k_mg_down(l>=1)", "k_mg_tail", "k_mg_up(l0)",
+              "k_mg_up(l>=1)"]
+# algorithmic fp64 streams per fine-level DOF per launch (SURVEY 8d stream counting; DESIGN.md "kernels")
+KIND_STREAMS = [3.0, 5.0, 2.25, 2.25 / 4, 2.0 / 16, 3.25, 3.25 / 4]
+
+
+def sample_params(K, seed):
+    return 10 ** np.random.default_rng(seed).uniform(0, np.log10(CMAX), size=(K,) + GEO)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's sparse direct path (scipy SuperLU), one worker per host core
+# ----------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    geo, N, ys = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from oracle import FEMOracle
+    o = FEMOracle(geo, N)
+    t0 = time.perf_counter()
+    U = o.generate_solutions(ys)
+    return time.perf_counter() - t0, float(np.abs(U).sum())
+
+
+def cpu_snapshot_rate(per_core, cores=None, geo=GEO, N=NPB, seed=123):
+    import multiprocessing as mp
+    cores = cores or max(1, (os.cpu_count() or 1))
+    ys = sample_params(per_core * cores, seed)
+    chunks = [(geo, N, ys[i::cores]) for i in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context("spawn").Pool(cores) as pool:
+        pool.map(_cpu_worker, chunks)
+    wall = time.perf_counter() - t0
+    return len(ys) / wall, cores, len(ys), wall
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's CPU path (oracle port: sparse assembly + SuperLU) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = max(1, os.cpu_count() or 1)
+    per_core = 2
+    for _ in range(args.warmup if args.warmup is not None else 1):
+        cpu_snapshot_rate(1, cores)
+    rates, t_all = [], 0.0
+    steps = args.steps or 2
+    for s in range(steps):
+        r, c, n, wall = cpu_snapshot_rate(per_core, cores, seed=1000 + s)
+        rates.append(r); t_all += wall
+    val = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": "fem_snapshot_solves_per_s", "value": val, "unit": "solves/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup if args.warmup is not None else 1,
+        "ms_per_step": 1e3 * t_all / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[2]: (4,4) subdomains, N=64 (256x256 cells, D=65025), contrast 10^U(0,6)",
+                   "note": "each step is a bounded sample of the 10k-snapshot workload"},
+        "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port",
+                         "sample": f"{per_core * cores} snapshot solves per step (oracle: scipy CSR + SuperLU, "
+                                   f"{cores} worker processes)"},
+        "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--k-snap", type=int, default=10000, help="snapshot solves per GPU per step")
+    ap.add_argument("--k-online", type=int, default=1000000)
+    ap.add_argument("--n-rb", type=int, default=20)
+    ap.add_argument("--quick", action="store_true", help="small sizes (debug)")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    steps = args.steps or 3
+    warmup = args.warmup if args.warmup is not None else 3
+    if args.quick:
+        args.k_snap, args.k_online = 512, 100000
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from romhighcontrast_b200 import _lib
+    from romhighcontrast_b200.engine import Engine
+
+    eng = Engine(GEO, NPB)
+    K = args.k_snap
+    y_host = sample_params(K, seed=42 + rank)                   # this rank's shard of the training set
+    y = eng.params(y_host)
+    x = eng.empty(K, eng.Dp)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident: warm-up, then `steps` timed passes -----------------------------------------------------
+    for _ in range(warmup):
+        eng.solve(y, out=x)
+    eng.set_option("profile", 1)
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _lib.launch_count()
+    barrier()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(steps):
+        _, iters, relres = eng.solve(y, out=x)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    eng.set_option("profile", 0) if False else None
+    import ctypes as C
+    pms, pn = (C.c_double * 8)(), (C.c_int64 * 8)()
+    _lib.check(eng.lib.romhc_get_profile(eng.handle, pms, pn))
+    eng.set_option("profile", 0)
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = float(tmax.item()) / steps
+    value = world * K / (ms_step * 1e-3)
+    it_np = iters.cpu().numpy()
+    stats = dict(eng.last_solve_stats)
+
+    # ---- end to end through the host-buffer C ABI (pinned host memory both ways) --------------------------------
+    U_pin = torch.empty((K, eng.D), dtype=torch.float64, pin_memory=True)
+    y_pin = torch.from_numpy(np.ascontiguousarray(y_host.reshape(K, -1))).pin_memory()
+    U_np, y_np = U_pin.numpy(), y_pin.numpy()
+    eng.generate_solutions_host(y_np, out=U_np)                 # warm-up (allocations)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(steps, 2))
+    for _ in range(e2e_steps):
+        eng.generate_solutions_host(y_np, out=U_np)
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_val = world * K / float(t_e2e.item())
+    clocks = sampler.stop()
+
+    # ---- parity spot check of what was just timed (sub-sample against the CPU oracle) ------------------------------
+    parity = None
+    if rank == 0:
+        from oracle import FEMOracle
+        o = FEMOracle(GEO, NPB)
+        sel = [0, K // 2, K - 1]
+        Uo = o.generate_solutions(y_host[sel])
+        parity = float(np.max(np.linalg.norm(U_np[sel] - Uo, axis=1) / np.linalg.norm(Uo, axis=1)))
+
+    # ---- roofline of the dominant solver kernel (live CUDA-event times of the first iterations, all systems active)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json)") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+    per_kind = []
+    for i, nm in enumerate(KIND_NAMES):
+        if pn[i] > 0:
+            avg_ms = pms[i] / pn[i]
+            gb = KIND_STREAMS[i] * 8.0 * eng.D * K / 1e9
+            per_kind.append({"kernel": nm, "launches": int(pn[i]), "avg_ms": avg_ms, "share": 0.0,
+                             "algorithmic_GB": gb, "GBps": gb / (avg_ms * 1e-3)})
+    tot_ms = sum(k["avg_ms"] for k in per_kind) or 1.0
+    for k in per_kind:
+        k["share"] = k["avg_ms"] / tot_ms
+    dom = max(per_kind, key=lambda k: k["avg_ms"]) if per_kind else None
+    roofline = None
+    if dom:
+        roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["GBps"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": dom["GBps"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "whole_iteration_GBps": sum(k["algorithmic_GB"] for k in per_kind) / (tot_ms * 1e-3)}
+
+    secondary = {}
+    if not args.no_secondary:
+        secondary = run_secondary(eng, x, y, K, args, world, rank, barrier, ev)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        r, cores, n, wall = cpu_snapshot_rate(2, None)
+        cpu = {"value": r, "unit": "solves/s", "cores": cores, "kind": "port",
+               "sample": f"{n} snapshot solves of the same workload (oracle: scipy CSR + SuperLU, {cores} processes, {wall:.1f} s)"}
+
+    if rank == 0:
+        line = {
+            "metric": "fem_snapshot_solves_per_s", "value": value, "unit": "solves/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[2]: (4,4) subdomains, N=64 (256x256 cells, D=65025), "
+                                   f"{K} snapshots per GPU, contrast 10^U(0,6); batched GMG-PCG to rtol 1e-12",
+                       "l2": "inputs larger than L2 (%.1f GB working set per step)" % (stats["workspace_bytes"] / 1e9),
+                       "pcg_iterations": {"min": int(it_np.min()), "mean": float(it_np.mean()), "max": int(it_np.max())},
+                       "parity_rel_l2_vs_oracle": parity},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": int(y_np.nbytes),
+                    "d2h_bytes_per_step": int(U_np.nbytes + K * 12)},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "kernels": per_kind, "cpu_baseline": cpu, "secondary": secondary,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_secondary(eng, x, y, K, args, world, rank, barrier, ev):
+    """POD (centred Gram on the fp64 tensor cores) and 1M online reduced Galerkin solves on the snapshots in `x`."""
+    import torch
+    out = {}
+    n = args.n_rb
+    # measured fp64 GEMM peak of this GPU (cuBLAS DGEMM 8192^3) as the tensor-pipe denominator
+    a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+    b = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+    torch.matmul(a, b)
+    best = 1e9
+    for _ in range(3):
+        e0, e1 = ev(), ev()
+        e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    dgemm_peak = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+    del a, b
+    # POD: mean, centre in place, Gram (lower tiles), top-n eigenpairs, back-projection
+    Kg = min(K, 10000)
+    X = x[:Kg]
+    mean = eng.column_mean(X)
+    eng.center_rows_(X, mean)
+    G = eng.gemm_nt(X, X, symmetric=True)        # warm-up
+    barrier()
+    e0, e1 = ev(), ev()
+    e0.record()
+    G = eng.gemm_nt(X, X, symmetric=True)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    flop = float(Kg) * (Kg + 1) * eng.D            # triangle only, algorithmic D
+    out["gram"] = {"K": Kg, "ms": ms, "TFLOPs": flop / (ms * 1e-3) / 1e12, "peak_TFLOPs_cublas_dgemm_8192": dgemm_peak,
+                   "frac": flop / (ms * 1e-3) / 1e12 / dgemm_peak, "flop_counted": "K(K+1)D (lower triangle)"}
+    if world > 1:
+        import torch.distributed as dist
+        e0, e1 = ev(), ev()
+        barrier(); e0.record(); dist.all_reduce(G); e1.record(); torch.cuda.synchronize()
+        out["gram_allreduce_ms"] = e0.elapsed_time(e1)
+    from romhighcontrast_b200.pod import top_eigenpairs
+    t0 = time.perf_counter()
+    lam, V = top_eigenpairs(eng, G, n)
+    comps = eng.gemm_tn(V, X) / torch.sqrt(lam)[:, None]
+    torch.cuda.synchronize()
+    out["pod_eig_backproject_ms"] = 1e3 * (time.perf_counter() - t0)
+    out["pod_singular_values_head"] = [float(v) for v in torch.sqrt(lam)[:5].cpu()]
+    # online stage: reduced operators once, then k_online reduced Galerkin solves
+    Ahat, bhat = eng.project_operators(comps.contiguous())
+    Ko = args.k_online
+    yo = eng.params(sample_params(Ko, seed=43 + rank))
+    Cc = eng.reduced_solve(yo, Ahat, bhat, check=False)
+    barrier()
+    e0, e1 = ev(), ev()
+    e0.record()
+    reps = 5
+    for _ in range(reps):
+        Cc = eng.reduced_solve(yo, Ahat, bhat, check=False)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    nb = eng.nb
+    flop_per = 2 * nb * n * (n + 1) / 2 + n ** 3 / 3 + 2 * n * n
+    out["reduced_galerkin"] = {"K": Ko, "n": n, "ms": ms, "solves_per_s": world * Ko / (ms * 1e-3),
+                               "GFLOPs": Ko * flop_per / (ms * 1e-3) / 1e9}
+    yh = yo.cpu().numpy(); Ah = Ahat.cpu().numpy(); bh = bhat.cpu().numpy()
+    eng.reduced_galerkin_host(yh[:1000], Ah, bh)
+    t0 = time.perf_counter()
+    try:
+        eng.reduced_galerkin_host(yh, Ah, bh)
+        out["reduced_galerkin"]["e2e_solves_per_s"] = world * Ko / (time.perf_counter() - t0)
+    except np.linalg.LinAlgError:
+        out["reduced_galerkin"]["e2e_solves_per_s"] = None
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -46,6 +46,10 @@ int romhc_destroy(romhc_handle h);
 int romhc_set_option(romhc_handle h, const char* name, double value);
 /* info[0..15] = D, Dp, P, R, C, nlevels, tail_level, coarse_D, coarse_direct, nrb, ncb, N, 0... */
 int romhc_get_info(romhc_handle h, int64_t* info16);
+/* with option "profile" = 1: accumulated CUDA-event time (ms) and launch count per solver kernel over the first
+ * min_check_iter PCG iterations of every solve (all systems active there).  Index: 0 k_pcg_p_apply, 1 k_pcg_update,
+ * 2 k_mg_down level 0, 3 k_mg_down levels >= 1, 4 k_mg_tail, 5 k_mg_up level 0, 6 k_mg_up levels >= 1. */
+int romhc_get_profile(romhc_handle h, double* ms8, int64_t* n8);
 /* number of CUDA kernels launched by this library in this process (bench.py "gpu_launches") */
 int64_t romhc_launch_count(void);
 

@@ -92,6 +92,7 @@ int romhc_set_option(romhc_handle h, const char* name, double value) {
     else if (!strcmp(name, "maxit")) c->maxit = (int)value;
     else if (!strcmp(name, "coarse_sweeps")) { c->coarse_sweeps = std::max(1, (int)value); c->build_levels(); }
     else if (!strcmp(name, "workspace_gb")) c->ws_budget_bytes = (size_t)(value * double(1 << 30));
+    else if (!strcmp(name, "profile")) { c->prof_on = value != 0.0; for (int i = 0; i < PROF_NKIND; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; } }
     else if (!strcmp(name, "check_every")) c->check_every = std::max(1, (int)value);
     else if (!strcmp(name, "min_check_iter")) c->min_check_iter = std::max(1, (int)value);
     else { set_error("unknown option '%s'", name); return ROMHC_ERR_ARG; }
@@ -107,6 +108,12 @@ int romhc_get_info(romhc_handle h, int64_t* info) {
     info[5] = (int64_t)c->levels.size(); info[6] = c->tail_level; info[7] = c->coarse_D; info[8] = c->coarse_direct;
     info[9] = c->nrb; info[10] = c->ncb; info[11] = c->N; info[12] = (int64_t)c->solve_bytes_per_system();
     info[13] = (int64_t)c->tail_smem;
+    return ROMHC_OK;
+}
+
+int romhc_get_profile(romhc_handle h, double* ms8, int64_t* n8) {
+    if (!h || !ms8 || !n8) { set_error("null argument"); return ROMHC_ERR_ARG; }
+    for (int i = 0; i < 8; ++i) { ms8[i] = i < PROF_NKIND ? H(h)->prof_ms[i] : 0.0; n8[i] = i < PROF_NKIND ? H(h)->prof_n[i] : 0; }
     return ROMHC_OK;
 }
 

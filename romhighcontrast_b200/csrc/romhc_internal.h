@@ -56,6 +56,9 @@ struct TailParams {
     int coarse_sweeps;
 };
 
+enum ProfKind { PROF_PAPPLY = 0, PROF_UPDATE, PROF_DOWN0, PROF_DOWN1, PROF_TAIL, PROF_UP0, PROF_UP1, PROF_NKIND };
+struct ProfEvent { int kind; cudaEvent_t a, b; };
+
 struct Context {
     int nrb = 0, ncb = 0, N = 0, device = 0;
     // multigrid hierarchy
@@ -81,7 +84,14 @@ struct Context {
     SolveWorkspace ws;
     int* ws_flags = nullptr;
     int* h_flags = nullptr;
-    int64_t launches = 0;      // kernels launched through this context (bench "gpu_launches")
+    // per-kernel timing (option "profile")
+    bool prof_on = false, prof_window = false;
+    std::vector<ProfEvent> prof_events;
+    double prof_ms[PROF_NKIND] = {0, 0, 0, 0, 0, 0, 0};
+    long long prof_n[PROF_NKIND] = {0, 0, 0, 0, 0, 0, 0};
+    void prof_begin(int kind, cudaStream_t st);
+    void prof_end(cudaStream_t st);
+    void prof_collect();
 
     int build_levels();
     int configure_kernels();

@@ -664,6 +664,27 @@ __global__ void k_scalar_beta(int64_t K, int np, const double* __restrict__ part
 // ======================================================================================================
 // host side
 // ======================================================================================================
+// Optional per-kernel timing (option "profile" = 1): CUDA events around every launch of the first
+// `min_check_iter` PCG iterations (all systems still active there), read back after the solve.
+void Context::prof_begin(int kind, cudaStream_t st) {
+    if (!prof_on || !prof_window) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, st);
+    prof_events.push_back({kind, a, b});
+}
+void Context::prof_end(cudaStream_t st) {
+    if (!prof_on || !prof_window || prof_events.empty()) return;
+    cudaEventRecord(prof_events.back().b, st);
+}
+void Context::prof_collect() {
+    for (auto& e : prof_events) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) { prof_ms[e.kind] += ms; prof_n[e.kind] += 1; }
+        cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    }
+    prof_events.clear();
+}
 static void strip_block(const LevelGeo& g, dim3& block) {
     int txw = 32;
     while (txw < g.P && txw < 256) txw <<= 1;
@@ -866,12 +887,16 @@ int Context::vcycle(const double* y, int Kc, cudaStream_t st, const double** z_r
         TYd[l] = TY;
         const int ns = (g.R + TY - 1) / TY;
         const size_t sm = smem_hdr_bytes(nb) + size_t(TY + extra_rows) * g.P * 8;
+        prof_begin(PROF_DOWN0 + std::min(l, 1), st);
         ++g_launches; k_mg_down<<<dim3(ns, Kc), block, sm, st>>>(g, has_c ? levels[l + 1] : g, y, ws.r[l], ws.za[l],
                                                    has_c ? ws.r[l + 1] : nullptr, ws.active, TY, has_c ? 1 : 0);
+        prof_end(st);
     }
     if (tail_level <= L) {
+        prof_begin(PROF_TAIL, st);
         ++g_launches; k_mg_tail<<<Kc, 256, tail_smem, st>>>(tail, y, ws.r[tail_level], ws.za[tail_level], ws.cfac, ws.active,
                                               tail_level == 0 ? ws.part_rz : nullptr);
+        prof_end(st);
     }
     for (int l = nstrip_levels - 1; l >= 0; --l) {
         const LevelGeo& g = levels[l];
@@ -890,8 +915,10 @@ int Context::vcycle(const double* y, int Kc, cudaStream_t st, const double** z_r
         const size_t sm = hdr + size_t(TY + 4) * g.P * 8 + (has_c ? size_t(TY / 2 + 3) * gc.P * 8 : 0);
         // coarse correction comes from the level below: its post-smoothed zb, or za if that level is the tail's top
         const double* e = has_c ? ((l + 1 < nstrip_levels) ? ws.zb[l + 1] : ws.za[l + 1]) : nullptr;
+        prof_begin(PROF_UP0 + std::min(l, 1), st);
         ++g_launches; k_mg_up<<<dim3(ns, Kc), block, sm, st>>>(g, gc, y, e, ws.za[l], ws.r[l], ws.zb[l], ws.active,
                                                  l == 0 ? ws.part_rz : nullptr, TY, ns, has_c ? 1 : 0);
+        prof_end(st);
         if (l == 0) *np_rz = ns;
     }
     if (nstrip_levels == 0) { *z_result = ws.za[0]; *np_rz = 1; }
@@ -931,6 +958,7 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
     const int gs = (Kc + 127) / 128;
     const double* z = nullptr;
     int np_rz = 1;
+    prof_window = false;
     rc = vcycle(y, Kc, st, &z, &np_rz); if (rc) return rc;
     const double tol2 = rtol * rtol;
     int* n_active = ws_flags + 8;   // one counter per iteration slot (mod 32)
@@ -939,11 +967,16 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
     int it = 0, cur = 0;
     int total_launch_iters = 0;
     for (it = 1; it <= maxit; ++it) {
+        prof_window = (it <= min_check_iter);
+        prof_begin(PROF_PAPPLY, st);
         ++g_launches; k_pcg_p_apply<<<dim3(nsp, Kc), block, smp, st>>>(g, y, z, ws.p[cur], ws.p[cur ^ 1], ws.beta, ws.active,
                                                         ws.part_pAp, TYp, nsp);
+        prof_end(st);
         cur ^= 1;
         ++g_launches; k_scalar_alpha<<<gs, 128, 0, st>>>(Kc, nsp, ws.part_pAp, ws.rz, ws.alpha, ws.active, ws_flags + 0);
+        prof_begin(PROF_UPDATE, st);
         ++g_launches; k_pcg_update<<<dim3(nsp, Kc), block, smp, st>>>(g, y, ws.p[cur], x, ws.r[0], ws.alpha, ws.active, TYp);
+        prof_end(st);
         rc = vcycle(y, Kc, st, &z, &np_rz); if (rc) return rc;
         int* ctr = n_active + 1 + (it % 32);
         CK(cudaMemsetAsync(ctr, 0, sizeof(int), st));
@@ -960,6 +993,8 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
     if (iters_out) CK(cudaMemcpyAsync(iters_out, ws.iters, size_t(Kc) * 4, cudaMemcpyDeviceToDevice, st));
     if (relres_out) CK(cudaMemcpyAsync(relres_out, ws.relres, size_t(Kc) * 8, cudaMemcpyDeviceToDevice, st));
     CK(cudaStreamSynchronize(st));
+    prof_window = false;
+    prof_collect();
     if (stats) {
         stats->launched_iterations += total_launch_iters;
         stats->chunks += 1;

@@ -1,0 +1,239 @@
+"""Drop-in for the reference's `src/lib/ReducedBasis.py` backed by the B200 kernels.
+
+Same names, signatures and quirks as /root/reference/src/lib/ReducedBasis.py (line numbers cited).  Host-side
+bookkeeping (selection order, the double permutation of `sort_orthogonalize_base`, numpy's legacy RNG, the
+inf-split) is kept literally because the stored results depend on it; everything that touches (K, D) data runs
+on the device and stays there between greedy steps.
+"""
+from logging import warning
+from typing import List
+
+import numpy as np
+
+from .Estimators import EstimatorInv, EstimatorLinear
+from .SolutionsManagers import SolutionsManager
+
+try:                                    # tqdm is optional here; the reference uses it for a progress bar (:120)
+    from tqdm import tqdm
+except Exception:                       # pragma: no cover
+    def tqdm(it, **kwargs):
+        return it
+
+INFINIT_A = 1e10  # reference :11
+
+
+def get_high_contrast_coefficient(a):
+    return np.array([np.max(coefs, axis=(-1, -2)) for coefs in a])           # reference :14-15
+
+
+def orthonormalize_base(rb):
+    q, r = np.linalg.qr(np.array(rb).T)                                     # reference :18-21 (host LAPACK, (D, n))
+    rb = q.T
+    return rb
+
+
+def sort_orthogonalize_base(a_selected, rb):
+    order = np.argsort(1 / a_selected)                                       # reference :24-29, `order` applied twice
+    a_selected = a_selected[order]
+    rb = rb[order, :]
+    rb = orthonormalize_base(rb[order, :])
+    return a_selected, rb
+
+
+class BaseReducedBasis:
+    def __init__(self):
+        self.basis = None
+        self.a = None
+        self.inverse_parameter_estimator = None
+        self.linear_parameter_estimator = None
+
+    def build(self, **kwargs):
+        raise Exception("Not implemented.")
+
+    def set(self, basis, a):
+        self.basis = basis
+        self.a = a
+        self.inverse_parameter_estimator = EstimatorInv(a)
+        self.linear_parameter_estimator = EstimatorLinear(a)
+
+    @property
+    def dim(self):
+        return np.shape(self.basis)[0]
+
+    @property
+    def ambient_space_dim(self):
+        return np.shape(self.basis)[1]
+
+    def __str__(self):
+        return self.__class__.__name__
+
+    def forward_modeling(self, sm: SolutionsManager, a: np.ndarray, **kwargs):
+        return sm.generate_fm_solutions(a=a, coefficients_rom=self.basis, **kwargs)      # reference :59-60
+
+    def projection(self, sm: SolutionsManager, true_solutions: np.ndarray, **kwargs):
+        return sm.project_solutions(true_solutions, self.basis, **kwargs)                # reference :62-63
+
+    def state_estimation(self, sm: SolutionsManager, measurement_points: np.ndarray, measurements: np.ndarray,
+                         return_coefs=False):
+        """Least-squares fit of the basis to point measurements (reference :65-70).
+
+        The (m, n) collocation matrix is factorised once on the host (np.linalg.lstsq against the identity gives its
+        pseudo-inverse with the same gelsd/rcond=-1 semantics); applying it to the K measurement vectors and
+        reconstructing c^T basis are device GEMMs."""
+        eng = sm._engine_()
+        rb_evaluations_in_points = sm.evaluate_solutions(measurement_points, self.basis)           # (n, m)
+        Z = np.asarray(measurements, dtype=np.float64)
+        m = rb_evaluations_in_points.shape[1]
+        pinv = np.linalg.lstsq(rb_evaluations_in_points.T, np.eye(m), rcond=-1)[0]                # (n, m)
+        Zd = eng.dev(Z.reshape(-1, m))
+        c_dev = eng.gemm_nt(eng.dev(pinv), Zd)                                                    # (n, K)
+        basis_pad = sm._pad_rows(self.basis)
+        est = eng.unpad(eng.gemm_nn(c_dev.T.contiguous(), basis_pad))                              # c^T basis
+        solution_estimations = est.cpu().numpy()
+        c = c_dev.cpu().numpy()
+        return (c, solution_estimations) if return_coefs else solution_estimations
+
+    def parameter_estimation_inverse(self, c):
+        return self.inverse_parameter_estimator.estimate_parameter(c_values=c)                     # reference :72-78
+
+    def parameter_estimation_linear(self, c):
+        return self.linear_parameter_estimator.estimate_parameter(c_values=c)                      # reference :80-86
+
+    def __getitem__(self, item):
+        rb = BaseReducedBasis()                                                                    # reference :88-92
+        rb.set(basis=self.basis[item], a=self.a[item])
+        return rb
+
+    def orthonormalize(self):
+        _, self.basis = sort_orthogonalize_base(                                                   # reference :94-98
+            get_high_contrast_coefficient(self.a),
+            np.reshape(self.basis, (-1, self.ambient_space_dim))
+        )
+
+
+GREEDY_FOR_H10 = r"$H^1_0$"
+GREEDY_FOR_GALERKIN = "galerkin"
+
+
+class ReducedBasisGreedy(BaseReducedBasis):
+    def __init__(self, greedy_for=GREEDY_FOR_GALERKIN):
+        self.greedy_for = greedy_for
+        self.name = "Greedy " + self.greedy_for
+        self.linestyle = "solid" if greedy_for == GREEDY_FOR_H10 else "dashed"
+        super().__init__()
+
+    def build(self, n: int, sm: SolutionsManager, solutions2train, a2train: List[np.ndarray] = (()),
+              solutions2train_h1norm=1, **kwargs):
+        """Weak greedy with the true H10 error (reference :112-139).
+
+        Per step, on the device: reduced operators of the current orthonormal basis, K reduced solves (Galerkin) or K
+        projections (H10), the fused error sweep || c Phi - u ||_{A_1} over the resident snapshots and an argmax with
+        np.argmax semantics.  Host: the O(n) bookkeeping and the (D, n) QR, exactly as the reference does them."""
+        if self.greedy_for not in (GREEDY_FOR_H10, GREEDY_FOR_GALERKIN):
+            raise Exception(f"Not implemented greedy for {self.greedy_for}, "
+                            f"should be one of [{GREEDY_FOR_H10}, {GREEDY_FOR_GALERKIN}]")
+        import torch
+        eng = sm._engine_()
+        high_contrast_a = get_high_contrast_coefficient(a2train)
+        solutions2train = np.asarray(solutions2train, dtype=np.float64)
+        U = eng.pad(solutions2train)                                     # resident for the whole build
+        y = eng.params(np.asarray(a2train, dtype=np.float64))
+        inv_norm = 1.0 / eng.dev(np.broadcast_to(np.asarray(solutions2train_h1norm, dtype=np.float64),
+                                                 (len(solutions2train),)).copy())
+        ones = torch.ones(len(solutions2train), eng.nb, dtype=torch.float64, device=eng.device)
+
+        basis = np.empty((0, 0))
+        basis_orth = basis.copy()
+        a_selected = []
+        a = []
+        self.selected_indices = []
+        self.max_errors = []
+        for _ in tqdm(range(n), desc="Obtaining greedy basis."):
+            if len(basis_orth) == 0:
+                err = eng.error_norm(U, None, None)                      # approximation == 0  (:89-91, :109-111)
+            else:
+                Phi = eng.pad(basis_orth)
+                if self.greedy_for == GREEDY_FOR_H10:
+                    Cc = sm._projection_coefficients_dev(eng, U, Phi)    # :122
+                else:
+                    Ahat, bhat = eng.project_operators(Phi)              # :124
+                    Cc = eng.reduced_solve(y, Ahat, bhat)
+                err = eng.error_norm(U, Cc, Phi)
+            max_error_index, max_err = eng.argmax(err * inv_norm)        # :129
+            self.selected_indices.append(max_error_index)
+            self.max_errors.append(max_err)
+            max_element = np.reshape(solutions2train[max_error_index], (1, -1))
+            basis = max_element if len(basis) == 0 else np.concatenate((basis, max_element), axis=0)
+            a.append(a2train[max_error_index])
+
+            # orthonormalize for stability and choose the ordering by the contrast of the higher coefficient (:134-136)
+            a_selected = np.append(a_selected, np.ravel(high_contrast_a[max_error_index]))
+            a_selected, basis_orth = sort_orthogonalize_base(a_selected, np.reshape(basis, (len(basis), -1)))
+
+        super().set(basis=basis, a=a)
+        return self
+
+
+def get_inf_solutions_starting_basis(solutions2train, a2train, only_one_block=True):
+    """Split off the snapshots with INFINIT_A blocks (reference :142-150)."""
+    num_hc_blocks = np.sum(np.array(a2train) == INFINIT_A, axis=(-1, -2))
+    chosen_ix = np.ravel(np.where(num_hc_blocks == 1 if only_one_block else num_hc_blocks != 0))
+    free_ix = np.ravel(np.where(num_hc_blocks != 1 if only_one_block else num_hc_blocks == 0))
+    return solutions2train[chosen_ix], a2train[chosen_ix], solutions2train[free_ix], a2train[free_ix]
+
+
+def get_starting_basis(solutions2train, a2train, add_inf_solutions=True):
+    basis, a, solutions2train, a2train = get_inf_solutions_starting_basis(solutions2train, a2train,   # :153-164
+                                                                          only_one_block=False)
+    if not add_inf_solutions:
+        basis = np.empty((0, np.shape(solutions2train)[1]))
+        a = np.empty((0,) + np.shape(a2train)[1:])
+    return basis, a, solutions2train, a2train
+
+
+class ReducedBasisRandom(BaseReducedBasis):
+    def __init__(self, add_inf_solutions=True):
+        self.add_inf_solutions = add_inf_solutions
+        self.name = "Random" + (r" $\infty$" if add_inf_solutions else "")
+        super().__init__()
+
+    def build(self, n: int, sm: SolutionsManager, solutions2train, a2train: List[np.ndarray] = (()),
+              solutions2train_h1norm=1, seed=42, **kwargs):
+        """Host only: numpy's legacy global RNG must pick the same rows as the reference (:173-180)."""
+        solutions2train, a2train = np.asarray(solutions2train), np.asarray(a2train)
+        basis, a, solutions2train, a2train = get_starting_basis(solutions2train, a2train, self.add_inf_solutions)
+        np.random.seed(seed)
+        chosen_ix = np.random.choice(len(solutions2train), size=n, replace=False)
+        super().set(basis=np.vstack((basis, solutions2train[chosen_ix]))[:n],
+                    a=np.vstack((a, a2train[chosen_ix]))[:n])
+        return self
+
+
+class ReducedBasisPCA(BaseReducedBasis):
+    def __init__(self, add_inf_solutions=True):
+        self.add_inf_solutions = add_inf_solutions
+        self.name = "PCA" + (r" $\infty$" if add_inf_solutions else "")
+        super().__init__()
+
+    def build(self, n: int, sm: SolutionsManager, solutions2train, a2train: List[np.ndarray] = (()),
+              solutions2train_h1norm=1, add_inf_solutions=True, seed=42, **kwargs):
+        """POD of the (inf-stripped) snapshots (reference :189-200).
+
+        sklearn's PCA(n_components=n) is replaced by the method of snapshots on the device (column mean, centred
+        Gram matrix on the fp64 tensor cores, top-n eigenpairs, back-projection) with sklearn's sign convention; it
+        is deterministic, whereas the reference's randomized solver (random_state=None) moves by ~1e-8 run to run."""
+        from ..pod import pca_components
+        solutions2train, a2train = np.asarray(solutions2train, dtype=np.float64), np.asarray(a2train)
+        basis, a, solutions2train, a2train = get_starting_basis(solutions2train, a2train, self.add_inf_solutions)
+        K, D = solutions2train.shape
+        if not 0 <= n <= min(K, D):
+            raise ValueError(f"n_components={n!r} must be between 0 and min(n_samples, n_features)={min(K, D)!r} "
+                             "with svd_solver='full'")
+        eng = sm._engine_()
+        comps_pad, sing, mean = pca_components(eng, eng.pad(solutions2train), n, center_in_place=True)
+        self.singular_values_ = sing.cpu().numpy()
+        components = eng.unpad(comps_pad.contiguous()).cpu().numpy()
+        super().set(basis=np.vstack((basis, components))[:n],
+                    a=np.vstack((a, a2train))[:n])
+        warning("PCA method has not been adapted for inverse parameter estimation, the a coefficients are not correct.")
+        return self
