@@ -148,6 +148,10 @@ def main():
     ap.add_argument("--quick", action="store_true", help="small sizes (debug)")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--strip-kb", type=float, default=None, help="shared memory per strip CTA (tuning)")
+    ap.add_argument("--nu", type=int, default=None, help="Gauss-Seidel sweeps of the V(nu,nu) cycle (tuning)")
+    ap.add_argument("--nu-tail", type=int, default=None)
+    ap.add_argument("--threads", type=int, default=None)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -169,6 +173,14 @@ def main():
     from romhighcontrast_b200.engine import Engine
 
     eng = Engine(GEO, NPB)
+    if args.strip_kb:
+        eng.set_option("strip_kb", args.strip_kb)
+    if args.nu:
+        eng.set_option("nu", args.nu)
+    if args.nu_tail:
+        eng.set_option("nu_tail", args.nu_tail)
+    if args.threads:
+        eng.set_option("threads", args.threads)
     K = args.k_snap
     y_host = sample_params(K, seed=42 + rank)                   # this rank's shard of the training set
     y = eng.params(y_host)
@@ -277,6 +289,7 @@ def main():
             "config": {"workload": "configs[2]: (4,4) subdomains, N=64 (256x256 cells, D=65025), "
                                    f"{K} snapshots per GPU, contrast 10^U(0,6); batched GMG-PCG to rtol 1e-12",
                        "l2": "inputs larger than L2 (%.1f GB working set per step)" % (stats["workspace_bytes"] / 1e9),
+                       "tuning": {"strip_kb": args.strip_kb, "nu": args.nu, "nu_tail": args.nu_tail, "threads": args.threads},
                        "pcg_iterations": {"min": int(it_np.min()), "mean": float(it_np.mean()), "max": int(it_np.max())},
                        "parity_rel_l2_vs_oracle": parity},
             "clocks": clocks,

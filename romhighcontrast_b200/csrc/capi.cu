@@ -29,6 +29,42 @@ void Context::release() {
     if (h_flags) cudaFreeHost(h_flags);
     scratch = nullptr; ws_base = nullptr; ws_flags = nullptr; h_flags = nullptr;
     scratch_bytes = 0; ws_K = 0;
+    free_host_stage();
+}
+
+void Context::free_host_stage() {
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(hstage.y[i]); cudaFree(hstage.x[i]); cudaFree(hstage.u[i]); cudaFree(hstage.it[i]); cudaFree(hstage.rel[i]);
+        hstage.y[i] = hstage.x[i] = hstage.u[i] = hstage.rel[i] = nullptr; hstage.it[i] = nullptr;
+        if (hstage.done[i]) cudaEventDestroy(hstage.done[i]);
+        if (hstage.copied[i]) cudaEventDestroy(hstage.copied[i]);
+        hstage.done[i] = hstage.copied[i] = nullptr;
+    }
+    if (hstage.compute) cudaStreamDestroy(hstage.compute);
+    if (hstage.copy) cudaStreamDestroy(hstage.copy);
+    hstage.compute = hstage.copy = nullptr;
+    hstage.cap = 0;
+}
+
+int Context::ensure_host_stage(int64_t chunk) {
+    if (chunk <= hstage.cap) return ROMHC_OK;
+    free_host_stage();
+    const LevelGeo& g = levels[0];
+    const int nb = nrb * ncb;
+    const int64_t D = int64_t(g.R - 1) * (g.C - 1);
+    CK(cudaStreamCreateWithFlags(&hstage.compute, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&hstage.copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaMalloc(&hstage.y[i], size_t(chunk) * nb * 8));
+        CK(cudaMalloc(&hstage.x[i], size_t(chunk) * g.Dp * 8));
+        CK(cudaMalloc(&hstage.u[i], size_t(chunk) * D * 8));
+        CK(cudaMalloc(&hstage.rel[i], size_t(chunk) * 8));
+        CK(cudaMalloc(&hstage.it[i], size_t(chunk) * 4));
+        CK(cudaEventCreateWithFlags(&hstage.done[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&hstage.copied[i], cudaEventDisableTiming));
+    }
+    hstage.cap = chunk;
+    return ROMHC_OK;
 }
 
 }  // namespace romhc
@@ -91,6 +127,10 @@ int romhc_set_option(romhc_handle h, const char* name, double value) {
     if (!strcmp(name, "rtol")) c->rtol = value;
     else if (!strcmp(name, "maxit")) c->maxit = (int)value;
     else if (!strcmp(name, "coarse_sweeps")) { c->coarse_sweeps = std::max(1, (int)value); c->build_levels(); }
+    else if (!strcmp(name, "nu")) { c->nu = std::max(1, std::min(4, (int)value)); }
+    else if (!strcmp(name, "nu_tail")) { c->nu_tail = std::max(1, std::min(8, (int)value)); c->build_levels(); }
+    else if (!strcmp(name, "threads")) c->strip_threads = ((int)value >= 512) ? 512 : 256;
+    else if (!strcmp(name, "strip_kb")) c->strip_budget = (size_t)std::max(16.0, std::min(227.0, value)) * 1024;
     else if (!strcmp(name, "workspace_gb")) c->ws_budget_bytes = (size_t)(value * double(1 << 30));
     else if (!strcmp(name, "profile")) { c->prof_on = value != 0.0; for (int i = 0; i < PROF_NKIND; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; } }
     else if (!strcmp(name, "check_every")) c->check_every = std::max(1, (int)value);
@@ -205,36 +245,37 @@ int romhc_generate_solutions_host(romhc_handle h, const double* y_host, int64_t 
     const LevelGeo& g = c->levels[0];
     const int nb = c->nrb * c->ncb;
     const int64_t D = int64_t(g.R - 1) * (g.C - 1);
-    // chunk so that padded + compact staging of the outputs stay within a quarter of the workspace budget
-    const size_t per = size_t(g.Dp + D) * 8 + c->solve_bytes_per_system();
+    // Chunked, double-buffered pipeline: the D2H copy of chunk i (copy stream) overlaps the solve of chunk i+1
+    // (compute stream).  Staging buffers persist in the context.
+    const size_t per = 2 * size_t(g.Dp + D) * 8 + c->solve_bytes_per_system();
     int64_t chunk = std::max<int64_t>(1, std::min<int64_t>({(int64_t)(c->ws_budget_bytes / per), (int64_t)32768, K}));
-    double *y_d = nullptr, *x_d = nullptr, *u_d = nullptr, *rel_d = nullptr;
-    int* it_d = nullptr;
-    int rc = ROMHC_OK;
-    cudaStream_t st = 0;
-    auto cleanup = [&]() { cudaFree(y_d); cudaFree(x_d); cudaFree(u_d); cudaFree(rel_d); cudaFree(it_d); };
-#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_error("%s: %s", #call, cudaGetErrorString(e_)); cleanup(); return ROMHC_ERR_CUDA; } } while (0)
-    CKC(cudaMalloc(&y_d, size_t(chunk) * nb * 8));
-    CKC(cudaMalloc(&x_d, size_t(chunk) * g.Dp * 8));
-    CKC(cudaMalloc(&u_d, size_t(chunk) * D * 8));
-    CKC(cudaMalloc(&rel_d, size_t(chunk) * 8));
-    CKC(cudaMalloc(&it_d, size_t(chunk) * 4));
-    for (int64_t k0 = 0; k0 < K && rc == ROMHC_OK; k0 += chunk) {
+    if (K >= 4096) chunk = std::min<int64_t>(chunk, (K + 3) / 4);
+    int rc = c->ensure_host_stage(chunk);
+    if (rc) return rc;
+    HostStage& s = c->hstage;
+    int64_t nchunk = 0;
+    for (int64_t k0 = 0; k0 < K; k0 += chunk, ++nchunk) {
         const int64_t kc = std::min<int64_t>(chunk, K - k0);
-        CKC(cudaMemcpyAsync(y_d, y_host + k0 * nb, size_t(kc) * nb * 8, cudaMemcpyHostToDevice, st));
-        rc = c->solve(y_d, kc, x_d, it_d, rel_d, st, nullptr);
+        const int slot = int(nchunk & 1);
+        if (nchunk >= 2) CK(cudaStreamWaitEvent(s.compute, s.copied[slot], 0));
+        CK(cudaMemcpyAsync(s.y[slot], y_host + k0 * nb, size_t(kc) * nb * 8, cudaMemcpyHostToDevice, s.compute));
+        rc = c->solve(s.y[slot], kc, s.x[slot], s.it[slot], s.rel[slot], s.compute, nullptr);
         if (rc) break;
-        rc = c->unpack(x_d, u_d, kc, st);
+        rc = c->unpack(s.x[slot], s.u[slot], kc, s.compute);
         if (rc) break;
-        CKC(cudaMemcpyAsync(U_host + k0 * D, u_d, size_t(kc) * D * 8, cudaMemcpyDeviceToHost, st));
-        if (iters_host) CKC(cudaMemcpyAsync(iters_host + k0, it_d, size_t(kc) * 4, cudaMemcpyDeviceToHost, st));
-        if (relres_host) CKC(cudaMemcpyAsync(relres_host + k0, rel_d, size_t(kc) * 8, cudaMemcpyDeviceToHost, st));
-        CKC(cudaStreamSynchronize(st));
+        CK(cudaEventRecord(s.done[slot], s.compute));
+        CK(cudaStreamWaitEvent(s.copy, s.done[slot], 0));
+        CK(cudaMemcpyAsync(U_host + k0 * D, s.u[slot], size_t(kc) * D * 8, cudaMemcpyDeviceToHost, s.copy));
+        if (iters_host) CK(cudaMemcpyAsync(iters_host + k0, s.it[slot], size_t(kc) * 4, cudaMemcpyDeviceToHost, s.copy));
+        if (relres_host) CK(cudaMemcpyAsync(relres_host + k0, s.rel[slot], size_t(kc) * 8, cudaMemcpyDeviceToHost, s.copy));
+        CK(cudaEventRecord(s.copied[slot], s.copy));
     }
-    cleanup();
+    CK(cudaStreamSynchronize(s.copy));
+    CK(cudaStreamSynchronize(s.compute));
     return rc;
 }
 
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_error("%s: %s", #call, cudaGetErrorString(e_)); cleanup(); return ROMHC_ERR_CUDA; } } while (0)
 int romhc_reduced_galerkin_host(romhc_handle h, const double* y_host, const double* Ahat_host, const double* bhat_host,
                                 int n, int64_t K, double* C_host, int* info_host) {
     CHECK_H(h);

@@ -70,6 +70,43 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// smem -> global bulk store (async proxy), bulk-group completion
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// make generic-proxy smem writes visible to the async proxy (before a bulk store reads them)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- operand strips: rows [row0, row0 + nrow) of one system's padded grid, staged in smem with row pitch P ----------
+__device__ __forceinline__ uint32_t strip_tx_bytes(const LevelGeo& g, int row0, int nrow) {
+    const int lo = max(row0, 0), hi = min(row0 + nrow, g.R + 1);
+    return hi > lo ? uint32_t(hi - lo) * uint32_t(g.P) * 8u : 0u;
+}
+// one thread: issue the bulk load of the in-range rows (the caller has armed `bar` with the byte count)
+__device__ __forceinline__ void strip_issue(double* sm, const double* gsys, const LevelGeo& g, int row0, int nrow,
+                                            uint64_t* bar) {
+    const int lo = max(row0, 0), hi = min(row0 + nrow, g.R + 1);
+    if (hi > lo) bulk_g2s(sm + size_t(lo - row0) * g.P, gsys + size_t(lo) * g.P, uint32_t(hi - lo) * uint32_t(g.P) * 8u, bar);
+}
+// all threads: rows outside [0, R] behave as zeros
+__device__ __forceinline__ void strip_zero_oob(double* sm, const LevelGeo& g, int row0, int nrow, int tid, int nt) {
+    const int lo = min(max(row0, 0), row0 + nrow), hi = max(min(row0 + nrow, g.R + 1), lo);
+    const int ntop = (lo - row0) * g.P;
+    for (int i = tid; i < ntop; i += nt) sm[i] = 0.0;
+    for (int i = (hi - row0) * g.P + tid; i < nrow * g.P; i += nt) sm[i] = 0.0;
+}
+// one thread: bulk store of rows [r_lo, r_hi) (clamped to the grid) from a strip whose first row is row0
+__device__ __forceinline__ void strip_store(double* gsys, const double* sm, const LevelGeo& g, int row0, int r_lo,
+                                            int r_hi) {
+    const int lo = max(r_lo, 0), hi = min(r_hi, g.R + 1);
+    if (hi > lo) bulk_s2g(gsys + size_t(lo) * g.P, sm + size_t(lo - row0) * g.P, uint32_t(hi - lo) * uint32_t(g.P) * 8u);
+}
+
 // Load rows [row_lo, row_hi) of one system's padded grid into smem (row pitch P) with ONE bulk copy
 // for the in-range part [max(row_lo,0), min(row_hi,R+1)) and zero fill for rows outside the grid.
 // Must be called by all threads; `bar` must have been initialised (count 1) and made visible by a

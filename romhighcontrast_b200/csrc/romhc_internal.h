@@ -54,10 +54,20 @@ struct TailParams {
     int direct;                       // 1: dense Cholesky on the last level, 0: coarse_sweeps of symmetric GS
     int DL, LD;                       // coarsest DOFs, factor pitch
     int coarse_sweeps;
+    int nu;                           // smoothing sweeps per level inside the tail
 };
 
 enum ProfKind { PROF_PAPPLY = 0, PROF_UPDATE, PROF_DOWN0, PROF_DOWN1, PROF_TAIL, PROF_UP0, PROF_UP1, PROF_NKIND };
 struct ProfEvent { int kind; cudaEvent_t a, b; };
+
+// persistent staging of the host-buffer entry point (double buffered: compute stream + copy stream)
+struct HostStage {
+    double *y[2] = {nullptr, nullptr}, *x[2] = {nullptr, nullptr}, *u[2] = {nullptr, nullptr}, *rel[2] = {nullptr, nullptr};
+    int* it[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    cudaStream_t compute = nullptr, copy = nullptr;
+    int64_t cap = 0;
+};
 
 struct Context {
     int nrb = 0, ncb = 0, N = 0, device = 0;
@@ -67,6 +77,9 @@ struct Context {
     int coarse_D = 0, coarse_LD = 1;
     bool coarse_direct = false;
     int coarse_sweeps = 8;
+    int nu = 1, nu_tail = 2;   // red/black Gauss-Seidel sweeps before and after the coarse correction: V(nu, nu)
+    int strip_threads = 256;            // threads per strip CTA (256 or 512)
+    size_t strip_budget = 100 * 1024;   // shared memory per strip CTA (>= 2 CTAs per SM so TMA loads overlap compute)
     TailParams tail;
     size_t tail_smem = 0;
     // PCG controls
@@ -99,6 +112,9 @@ struct Context {
     int ensure_solve_ws(int64_t Kc);
     size_t solve_bytes_per_system() const;
     void release();
+    HostStage hstage;
+    int ensure_host_stage(int64_t chunk);
+    void free_host_stage();
 
     // solver.cu
     int apply(const double* y, const double* u, double* out, int64_t K, cudaStream_t st);

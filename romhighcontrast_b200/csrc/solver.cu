@@ -40,12 +40,21 @@ __device__ __forceinline__ void for_points(const LevelGeo& g, const double* sa, 
         if (color >= 0) { r += (my_lo + c + color) & 1; step = 2; }
         if (r > my_hi) continue;
         ColW w;
-        if (NEED_W) w.init(sa, g, c, r);
+        if (!NEED_W) {
+            for (; r <= my_hi; r += step) f(r, c, w);
+            continue;
+        }
+        // rows between two horizontal subdomain interfaces share their weights: one weight evaluation per
+        // segment, then a branch-free inner loop
+        w.init(sa, g, c, r);
         for (;;) {
-            f(r, c, w);
-            r += step;
+            const int seg_end = min(my_hi, (w.rm == 0) ? r : r + (g.N - 1 - w.rm));
+            const int r0 = r;
+            for (; r <= seg_end; r += step) f(r, c, w);
             if (r > my_hi) break;
-            if (NEED_W) w.advance(step);
+            w.rm += r - r0;
+            while (w.rm >= g.N) { w.rm -= g.N; ++w.rb; }
+            w.compute();
         }
     }
 }
@@ -200,8 +209,13 @@ __global__ void k_reduce_partials(const double* __restrict__ part, int np, doubl
     out[k] = take_sqrt ? sqrt(s) : s;
 }
 
-// ---- PCG: p = z + beta p (double buffered), pAp partials ---------------------------------------------------
-__global__ void __launch_bounds__(256)
+// =====================================================================================================
+// v2 strip kernels: every global operand arrives by a 1-D TMA bulk load (cp.async.bulk + mbarrier) and every
+// result leaves by a bulk store from shared memory; compute phases touch shared memory only.
+// =====================================================================================================
+
+// ---- PCG: p = z + beta p (double buffered in global memory), pAp partials ------------------------------------
+__global__ void __launch_bounds__(512)
 k_pcg_p_apply(LevelGeo g, const double* __restrict__ y, const double* __restrict__ z, const double* __restrict__ p_in,
               double* __restrict__ p_out, const double* __restrict__ beta, const int* __restrict__ active,
               double* __restrict__ part_pAp, int TY, int nstrips) {
@@ -212,37 +226,49 @@ k_pcg_p_apply(LevelGeo g, const double* __restrict__ y, const double* __restrict
     SmemHdr h = smem_carve(smem_raw, nb);
     const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
     const int y0 = blockIdx.x * TY;
+    if (tid == 0) { mbar_init(h.bar, 1); mbar_fence_init(); }
     load_coef(h.sa, y, k, nb, tid, nt);
-    const double b = beta[k];
-    const int row0 = y0 - 1, nrow = TY + 2;
-    const double* zs = z + k * g.Dp;
-    const double* ps = p_in + k * g.Dp;
-    double* po = p_out + k * g.Dp;
-    double* s = h.data;
-    const int n = nrow * g.P;
-    const int own_lo = y0 * g.P, own_hi = min((y0 + TY) * g.P, g.Dp);
-    for (int i = tid; i < n; i += nt) {
-        const int gi = row0 * g.P + i;
-        double v = 0.0;
-        if (gi >= 0 && gi < g.Dp) {
-            v = fma(b, ps[gi], zs[gi]);
-            if (gi >= own_lo && gi < own_hi) po[gi] = v;
-        }
-        s[i] = v;
-    }
     __syncthreads();
+    const int row0 = y0 - 1, nrow = TY + 2, P = g.P;
+    double* Zs = h.data;
+    double* Ps = Zs + size_t(nrow) * P;
+    if (tid == 0) {
+        mbar_expect_tx(h.bar, 2u * strip_tx_bytes(g, row0, nrow));
+        strip_issue(Zs, z + k * g.Dp, g, row0, nrow, h.bar);
+        strip_issue(Ps, p_in + k * g.Dp, g, row0, nrow, h.bar);
+    }
+    strip_zero_oob(Zs, g, row0, nrow, tid, nt);
+    strip_zero_oob(Ps, g, row0, nrow, tid, nt);
+    const double b = beta[k];
+    mbar_wait(h.bar, 0);
+    __syncthreads();
+    {
+        double2* P2 = reinterpret_cast<double2*>(Ps);
+        const double2* Z2 = reinterpret_cast<const double2*>(Zs);
+        const int n2 = nrow * P / 2;
+        for (int i = tid; i < n2; i += nt) {
+            double2 pv = P2[i];
+            const double2 zv = Z2[i];
+            pv.x = fma(b, pv.x, zv.x);
+            pv.y = fma(b, pv.y, zv.y);
+            P2[i] = pv;
+        }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) { strip_store(p_out + k * g.Dp, Ps, g, row0, y0, y0 + TY); bulk_commit(); }
     double acc = 0.0;
     for_points<true>(g, h.sa, threadIdx.x, threadIdx.y, blockDim.x, blockDim.y, y0, y0 + TY - 1, -1,
                      [&](int r, int c, const ColW& w) {
-                         const int i = (r - row0) * g.P + c;
-                         acc = fma(s[i], apply_diff(s, i, g.P, w), acc);
+                         const int i = (r - row0) * P + c;
+                         acc = fma(Ps[i], apply_diff(Ps, i, P, w), acc);
                      });
     const double tot = block_sum(acc, h.red, tid, nt);
-    if (tid == 0) part_pAp[k * nstrips + blockIdx.x] = tot;
+    if (tid == 0) { part_pAp[k * nstrips + blockIdx.x] = tot; bulk_wait_all(); }
 }
 
-// ---- PCG: x += alpha p ; r -= alpha A p --------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+// ---- PCG: x += alpha p ; r -= alpha A p --------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
 k_pcg_update(LevelGeo g, const double* __restrict__ y, const double* __restrict__ p, double* __restrict__ x,
              double* __restrict__ r, const double* __restrict__ alpha, const int* __restrict__ active, int TY) {
     const int64_t k = blockIdx.y;
@@ -255,28 +281,42 @@ k_pcg_update(LevelGeo g, const double* __restrict__ y, const double* __restrict_
     if (tid == 0) { mbar_init(h.bar, 1); mbar_fence_init(); }
     load_coef(h.sa, y, k, nb, tid, nt);
     __syncthreads();
-    const int row0 = y0 - 1, nrow = TY + 2;
-    strip_load_issue(h.data, p + k * g.Dp, g, row0, row0 + nrow, h.bar, tid, nt);
+    const int row0 = y0 - 1, nrow = TY + 2, P = g.P;
+    double* Ps = h.data;
+    double* Xs = Ps + size_t(nrow) * P;
+    double* Rs = Xs + size_t(TY) * P;
+    if (tid == 0) {
+        mbar_expect_tx(h.bar, strip_tx_bytes(g, row0, nrow) + 2u * strip_tx_bytes(g, y0, TY));
+        strip_issue(Ps, p + k * g.Dp, g, row0, nrow, h.bar);
+        strip_issue(Xs, x + k * g.Dp, g, y0, TY, h.bar);
+        strip_issue(Rs, r + k * g.Dp, g, y0, TY, h.bar);
+    }
+    strip_zero_oob(Ps, g, row0, nrow, tid, nt);
     const double al = alpha[k];
-    double* xs = x + k * g.Dp;
-    double* rs = r + k * g.Dp;
     mbar_wait(h.bar, 0);
     __syncthreads();
     for_points<true>(g, h.sa, threadIdx.x, threadIdx.y, blockDim.x, blockDim.y, y0, y0 + TY - 1, -1,
                      [&](int rr, int c, const ColW& w) {
-                         const int i = (rr - row0) * g.P + c;
-                         const size_t gi = size_t(rr) * g.P + c;
-                         const double Ap = apply_diff(h.data, i, g.P, w);
-                         xs[gi] = fma(al, h.data[i], xs[gi]);
-                         rs[gi] = fma(-al, Ap, rs[gi]);
+                         const int i = (rr - row0) * P + c, j = (rr - y0) * P + c;
+                         const double Ap = apply_diff(Ps, i, P, w);
+                         Xs[j] = fma(al, Ps[i], Xs[j]);
+                         Rs[j] = fma(-al, Ap, Rs[j]);
                      });
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+        strip_store(x + k * g.Dp, Xs, g, y0, y0, y0 + TY);
+        strip_store(r + k * g.Dp, Rs, g, y0, y0, y0 + TY);
+        bulk_commit();
+        bulk_wait_all();
+    }
 }
 
-// ---- multigrid, going down: z = RB-GS(0, r); r_coarse = P^T (r - A z) -----------------------------------------
-__global__ void __launch_bounds__(256)
+// ---- multigrid, going down: z = nu RB-GS sweeps from 0; r_coarse = P^T (r - A z) ------------------------------------
+__global__ void __launch_bounds__(512)
 k_mg_down(LevelGeo g, LevelGeo gc, const double* __restrict__ y, const double* __restrict__ r_in,
           double* __restrict__ z_out, double* __restrict__ rc_out, const int* __restrict__ active, int TY,
-          int has_coarse) {
+          int has_coarse, int nu) {
     const int64_t k = blockIdx.y;
     if (!active[k]) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -288,53 +328,72 @@ k_mg_down(LevelGeo g, LevelGeo gc, const double* __restrict__ y, const double* _
     if (tid == 0) { mbar_init(h.bar, 1); mbar_fence_init(); }
     load_coef(h.sa, y, k, nb, tid, nt);
     __syncthreads();
-    const int halo_top = has_coarse ? 3 : 1, halo_bot = has_coarse ? 2 : 1;
-    const int row0 = y0 - halo_top, nrow = TY + halo_top + halo_bot;
-    double* s = h.data;
-    const int P = g.P;
-    strip_load_issue(s, r_in + k * g.Dp, g, row0, row0 + nrow, h.bar, tid, nt);
+    // validity cone: every half sweep consumes one row on each side
+    const int halo_top = has_coarse ? 2 * nu + 1 : 2 * nu - 1, halo_bot = has_coarse ? 2 * nu : 2 * nu - 1;
+    const int row0 = y0 - halo_top, nrow = TY + halo_top + halo_bot, last = row0 + nrow - 1;
+    const int P = g.P, Pc = gc.P;
+    double* Rs = h.data;
+    double* Zs = Rs + size_t(nrow) * P;
+    double* Cs = Zs + size_t(nrow) * P;      // coarse staging, TY/2 rows of pitch Pc
+    if (tid == 0) {
+        mbar_expect_tx(h.bar, strip_tx_bytes(g, row0, nrow));
+        strip_issue(Rs, r_in + k * g.Dp, g, row0, nrow, h.bar);
+    }
+    strip_zero_oob(Rs, g, row0, nrow, tid, nt);
+    for (int i = tid; i < nrow * P; i += nt) Zs[i] = 0.0;
+    if (has_coarse) for (int i = tid; i < (TY / 2) * Pc; i += nt) Cs[i] = 0.0;
     mbar_wait(h.bar, 0);
     __syncthreads();
-    // red half sweep from a zero guess: z = r / diag
-    for_points<true>(g, h.sa, tx, ty, TXW, TYW, row0, row0 + nrow - 1, 0, [&](int r, int c, const ColW& w) {
-        const int i = (r - row0) * P + c;
-        s[i] *= w.idg;
-    });
-    __syncthreads();
-    // black half sweep
-    for_points<true>(g, h.sa, tx, ty, TXW, TYW, row0 + 1, row0 + nrow - 2, 1, [&](int r, int c, const ColW& w) {
-        const int i = (r - row0) * P + c;
-        s[i] = (s[i] + offdiag_sum(s, i, P, w)) * w.idg;
-    });
-    __syncthreads();
-    double* zo = z_out + k * g.Dp;
-    for_points<false>(g, h.sa, tx, ty, TXW, TYW, y0, y0 + TY - 1, -1, [&](int r, int c, const ColW&) {
-        zo[size_t(r) * P + c] = s[(r - row0) * P + c];
-    });
-    if (!has_coarse) return;
-    __syncthreads();
-    // residual: zero on black points (just relaxed); on red points d = sum_nb w_nb z_nb
-    for_points<true>(g, h.sa, tx, ty, TXW, TYW, y0 - 1, y0 + TY - 1, 0, [&](int r, int c, const ColW& w) {
-        const int i = (r - row0) * P + c;
-        s[i] = offdiag_sum(s, i, P, w);
-    });
-    __syncthreads();
-    // restriction r_c(I,J) = d(2I,2J) + (d(2I-1,2J+1) + d(2I+1,2J-1)) / 2   (the E/W/N/S neighbours are black: d = 0)
-    const int I_lo = max(y0 / 2, 1), I_hi = min((y0 + TY) / 2 - 1, gc.R - 1);
-    const int nJ = gc.C - 1, nI = I_hi - I_lo + 1;
-    double* rc = rc_out + k * gc.Dp;
-    for (int idx = tid; idx < nI * nJ; idx += nt) {
-        const int I = I_lo + idx / nJ, J = 1 + idx % nJ;
-        const int i = (2 * I - row0) * P + 2 * J;
-        rc[size_t(I) * gc.P + J] = s[i] + 0.5 * (s[i - P + 1] + s[i + P - 1]);
+    for (int s = 0; s < nu; ++s) {
+        if (s == 0) {
+            for_points<true>(g, h.sa, tx, ty, TXW, TYW, row0, last, 0, [&](int r, int c, const ColW& w) {
+                const int i = (r - row0) * P + c;
+                Zs[i] = Rs[i] * w.idg;
+            });
+        } else {
+            for_points<true>(g, h.sa, tx, ty, TXW, TYW, row0 + 2 * s, last - 2 * s, 0, [&](int r, int c, const ColW& w) {
+                const int i = (r - row0) * P + c;
+                Zs[i] = (Rs[i] + offdiag_sum(Zs, i, P, w)) * w.idg;
+            });
+        }
+        __syncthreads();
+        for_points<true>(g, h.sa, tx, ty, TXW, TYW, row0 + 2 * s + 1, last - 2 * s - 1, 1, [&](int r, int c, const ColW& w) {
+            const int i = (r - row0) * P + c;
+            Zs[i] = (Rs[i] + offdiag_sum(Zs, i, P, w)) * w.idg;
+        });
+        if (s == nu - 1) fence_proxy_async();
+        __syncthreads();
     }
+    if (tid == 0) { strip_store(z_out + k * g.Dp, Zs, g, row0, y0, y0 + TY); bulk_commit(); }
+    if (has_coarse) {
+        // residual after the last full sweep: zero on black points (just relaxed); on red points
+        // d = r - diag z + sum_nb w_nb z_nb (kept in the r strip)
+        for_points<true>(g, h.sa, tx, ty, TXW, TYW, y0 - 1, y0 + TY - 1, 0, [&](int r, int c, const ColW& w) {
+            const int i = (r - row0) * P + c;
+            Rs[i] = (Rs[i] - w.dg * Zs[i]) + offdiag_sum(Zs, i, P, w);
+        });
+        __syncthreads();
+        // r_c(I,J) = d(2I,2J) + (d(2I-1,2J+1) + d(2I+1,2J-1)) / 2   (E/W/N/S neighbours are black: d = 0)
+        const int Ib = y0 / 2;
+        const int I_lo = max(Ib, 1), I_hi = min(Ib + TY / 2 - 1, gc.R - 1);
+        const int nJ = gc.C - 1, nI = I_hi - I_lo + 1;
+        for (int idx = tid; idx < nI * nJ; idx += nt) {
+            const int I = I_lo + idx / nJ, J = 1 + idx % nJ;
+            const int i = (2 * I - row0) * P + 2 * J;
+            Cs[(I - Ib) * Pc + J] = Rs[i] + 0.5 * (Rs[i - P + 1] + Rs[i + P - 1]);
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) { strip_store(rc_out + k * gc.Dp, Cs, gc, Ib, Ib, Ib + TY / 2); bulk_commit(); }
+    }
+    if (tid == 0) bulk_wait_all();
 }
 
-// ---- multigrid, going up: z += P e (red points suffice), BR-GS; optional r.z partials ------------------------------
-__global__ void __launch_bounds__(256)
+// ---- multigrid, going up: z += P e (red points suffice), nu BR-GS sweeps; optional r.z partials ------------------------
+__global__ void __launch_bounds__(512)
 k_mg_up(LevelGeo g, LevelGeo gc, const double* __restrict__ y, const double* __restrict__ e_c,
         const double* __restrict__ z_in, const double* __restrict__ r, double* __restrict__ z_out,
-        const int* __restrict__ active, double* __restrict__ part_rz, int TY, int nstrips, int has_coarse) {
+        const int* __restrict__ active, double* __restrict__ part_rz, int TY, int nstrips, int has_coarse, int nu) {
     const int64_t k = blockIdx.y;
     if (!active[k]) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -347,65 +406,59 @@ k_mg_up(LevelGeo g, LevelGeo gc, const double* __restrict__ y, const double* __r
     load_coef(h.sa, y, k, nb, tid, nt);
     __syncthreads();
     const int P = g.P, Pc = gc.P;
-    const int row0 = y0 - 2, nrow = TY + 4;
-    const int I0 = y0 / 2 - 1, nI = TY / 2 + 3;
-    double* s = h.data;
-    double* e = s + size_t(nrow) * P;
-    // two bulk copies on one mbarrier
-    {
-        const int lo = max(row0, 0), hi = min(row0 + nrow, g.R + 1);
-        const int clo = max(I0, 0), chi = has_coarse ? min(I0 + nI, gc.R + 1) : clo;
-        const uint32_t b1 = hi > lo ? uint32_t(hi - lo) * P * 8u : 0u;
-        const uint32_t b2 = chi > clo ? uint32_t(chi - clo) * Pc * 8u : 0u;
-        if (tid == 0) {
-            mbar_expect_tx(h.bar, b1 + b2);
-            if (b1) bulk_g2s(s + size_t(lo - row0) * P, z_in + k * g.Dp + size_t(lo) * P, b1, h.bar);
-            if (b2) bulk_g2s(e + size_t(clo - I0) * Pc, e_c + k * gc.Dp + size_t(clo) * Pc, b2, h.bar);
-        }
-        for (int i = tid; i < (lo - row0) * P; i += nt) s[i] = 0.0;
-        for (int i = (max(hi, row0) - row0) * P + tid; i < nrow * P; i += nt) s[i] = 0.0;
-        if (has_coarse) {
-            for (int i = tid; i < (clo - I0) * Pc; i += nt) e[i] = 0.0;
-            for (int i = (max(chi, I0) - I0) * Pc + tid; i < nI * Pc; i += nt) e[i] = 0.0;
-        }
+    const int row0 = y0 - 2 * nu, nrow = TY + 4 * nu, last = row0 + nrow - 1;
+    const int rrow0 = row0 + 1, nrrow = nrow - 2;
+    const int I0 = y0 / 2 - nu, nI = TY / 2 + 2 * nu + 1;
+    double* Zs = h.data;
+    double* Rs = Zs + size_t(nrow) * P;
+    double* Es = Rs + size_t(nrrow) * P;
+    if (tid == 0) {
+        mbar_expect_tx(h.bar, strip_tx_bytes(g, row0, nrow) + strip_tx_bytes(g, rrow0, nrrow) +
+                                  (has_coarse ? strip_tx_bytes(gc, I0, nI) : 0u));
+        strip_issue(Zs, z_in + k * g.Dp, g, row0, nrow, h.bar);
+        strip_issue(Rs, r + k * g.Dp, g, rrow0, nrrow, h.bar);
+        if (has_coarse) strip_issue(Es, e_c + k * gc.Dp, gc, I0, nI, h.bar);
     }
+    strip_zero_oob(Zs, g, row0, nrow, tid, nt);
+    strip_zero_oob(Rs, g, rrow0, nrrow, tid, nt);
+    if (has_coarse) strip_zero_oob(Es, gc, I0, nI, tid, nt);
     mbar_wait(h.bar, 0);
     __syncthreads();
     if (has_coarse) {
-        // prolongation on red points: (even, even) copies the coarse vertex, (odd, odd) is the midpoint of
-        // the coarse cell's anti-diagonal (I, J+1)-(I+1, J).  Black values are overwritten by the sweep below.
-        for_points<false>(g, h.sa, tx, ty, TXW, TYW, row0, row0 + nrow - 1, 0, [&](int r, int c, const ColW&) {
-            const int i = (r - row0) * P + c;
-            const int I = (r >> 1) - I0, J = c >> 1;
-            if (r & 1) s[i] += 0.5 * (e[I * Pc + J + 1] + e[(I + 1) * Pc + J]);
-            else       s[i] += e[I * Pc + J];
+        // prolongation on red points: (even, even) copies the coarse vertex, (odd, odd) is the midpoint of the
+        // coarse cell's anti-diagonal (I, J+1)-(I+1, J).  Black values are overwritten by the first half sweep.
+        for_points<false>(g, h.sa, tx, ty, TXW, TYW, row0, last, 0, [&](int rr, int c, const ColW&) {
+            const int i = (rr - row0) * P + c;
+            const int I = (rr >> 1) - I0, J = c >> 1;
+            if (rr & 1) Zs[i] += 0.5 * (Es[I * Pc + J + 1] + Es[(I + 1) * Pc + J]);
+            else        Zs[i] += Es[I * Pc + J];
         });
         __syncthreads();
     }
-    const double* rs = r + k * g.Dp;
-    double* zo = z_out + k * g.Dp;
-    double acc = 0.0;
-    for_points<true>(g, h.sa, tx, ty, TXW, TYW, y0 - 1, y0 + TY, 1, [&](int rr, int c, const ColW& w) {
-        const int i = (rr - row0) * P + c;
-        const size_t gi = size_t(rr) * P + c;
-        const double rv = rs[gi];
-        const double v = (rv + offdiag_sum(s, i, P, w)) * w.idg;
-        s[i] = v;
-        if (rr >= y0 && rr < y0 + TY) { zo[gi] = v; acc = fma(rv, v, acc); }
-    });
-    __syncthreads();
-    for_points<true>(g, h.sa, tx, ty, TXW, TYW, y0, y0 + TY - 1, 0, [&](int rr, int c, const ColW& w) {
-        const int i = (rr - row0) * P + c;
-        const size_t gi = size_t(rr) * P + c;
-        const double rv = rs[gi];
-        const double v = (rv + offdiag_sum(s, i, P, w)) * w.idg;
-        zo[gi] = v;
-        acc = fma(rv, v, acc);
-    });
+    for (int s = 0; s < nu; ++s) {
+        for_points<true>(g, h.sa, tx, ty, TXW, TYW, row0 + 2 * s + 1, last - 2 * s - 1, 1, [&](int rr, int c, const ColW& w) {
+            const int i = (rr - row0) * P + c;
+            Zs[i] = (Rs[i - P] + offdiag_sum(Zs, i, P, w)) * w.idg;     // Rs starts one row below Zs
+        });
+        __syncthreads();
+        for_points<true>(g, h.sa, tx, ty, TXW, TYW, row0 + 2 * s + 2, last - 2 * s - 2, 0, [&](int rr, int c, const ColW& w) {
+            const int i = (rr - row0) * P + c;
+            Zs[i] = (Rs[i - P] + offdiag_sum(Zs, i, P, w)) * w.idg;
+        });
+        if (s == nu - 1) fence_proxy_async();
+        __syncthreads();
+    }
+    if (tid == 0) { strip_store(z_out + k * g.Dp, Zs, g, row0, y0, y0 + TY); bulk_commit(); }
     if (part_rz) {
+        double acc = 0.0;
+        for_points<false>(g, h.sa, tx, ty, TXW, TYW, y0, y0 + TY - 1, -1, [&](int rr, int c, const ColW&) {
+            const int i = (rr - row0) * P + c;
+            acc = fma(Rs[i - P], Zs[i], acc);
+        });
         const double tot = block_sum(acc, h.red, tid, nt);
         if (tid == 0) part_rz[k * nstrips + blockIdx.x] = tot;
     }
+    if (tid == 0) bulk_wait_all();
 }
 
 // ---- multigrid tail: levels T..L of one system entirely in shared memory (one CTA per system) --------------------
@@ -473,9 +526,11 @@ k_mg_tail(TailParams tp, const double* __restrict__ y, const double* __restrict_
         double* r = S + tp.off_r[l];
         double* z = S + tp.off_z[l];
         double* rc = S + tp.off_r[l + 1];
-        tail_gs_half(g, h.sa, z, r, 0, true, tid, nt);
-        tail_gs_half(g, h.sa, z, r, 1, false, tid, nt);
-        // restriction of the (red-only) residual, computed on the fly from z
+        for (int sw = 0; sw < tp.nu; ++sw) {
+            tail_gs_half(g, h.sa, z, r, 0, sw == 0, tid, nt);
+            tail_gs_half(g, h.sa, z, r, 1, false, tid, nt);
+        }
+        // restriction of the residual (zero on the just-relaxed black points), computed on the fly at the red points
         const int nJ = gc.C - 1, nI = gc.R - 1, P = g.P;
         for (int idx = tid; idx < nI * nJ; idx += nt) {
             const int I = 1 + idx / nJ, J = 1 + idx % nJ;
@@ -488,7 +543,8 @@ k_mg_tail(TailParams tp, const double* __restrict__ y, const double* __restrict_
                     double wW, wE, wN, wS;
                     vertex_weights(h.sa, g, rr, cc, wW, wE, wN, wS);
                     const int i = rr * P + cc;
-                    const double d = wW * z[i - 1] + wE * z[i + 1] + wN * z[i - P] + wS * z[i + P];
+                    const double d = (r[i] - ((wW + wE) + (wN + wS)) * z[i]) +
+                                     (wW * z[i - 1] + wE * z[i + 1] + wN * z[i - P] + wS * z[i + P]);
                     acc += (q == 0) ? d : 0.5 * d;
                 }
             }
@@ -558,8 +614,10 @@ k_mg_tail(TailParams tp, const double* __restrict__ y, const double* __restrict_
             else        z[i] += e[I * Pc + J];
         });
         __syncthreads();
-        tail_gs_half(g, h.sa, z, r, 1, false, tid, nt);
-        tail_gs_half(g, h.sa, z, r, 0, false, tid, nt);
+        for (int sw = 0; sw < tp.nu; ++sw) {
+            tail_gs_half(g, h.sa, z, r, 1, false, tid, nt);
+            tail_gs_half(g, h.sa, z, r, 0, false, tid, nt);
+        }
     }
     // ---- output ----
     {
@@ -685,10 +743,10 @@ void Context::prof_collect() {
     }
     prof_events.clear();
 }
-static void strip_block(const LevelGeo& g, dim3& block) {
+static void strip_block(const LevelGeo& g, dim3& block, int nthreads = 256) {
     int txw = 32;
     while (txw < g.P && txw < 256) txw <<= 1;
-    block = dim3(txw, 256 / txw, 1);
+    block = dim3(txw, nthreads / txw, 1);
 }
 
 // pick the strip height so that rows*P*8 + header stays under `budget` bytes (even, >= 2)
@@ -736,14 +794,31 @@ int Context::build_levels() {
         tail.off_fac = off;
         if (coarse_direct) off += coarse_D * coarse_LD;
         tail.coarse_sweeps = coarse_sweeps;
+        tail.nu = nu_tail;
         tail_smem = smem_hdr_bytes(nrb * ncb) + size_t(off) * 8;
     }
     return 0;
 }
 
 
-static const size_t SMEM_2PER_SM = 100 * 1024;   // target: >= 2 CTAs per SM so loads overlap compute
 static const size_t SMEM_3PER_SM = 72 * 1024;
+static const size_t SMEM_MAX = 227 * 1024;
+
+// largest even strip height (<= 64, <= grid height) whose shared-memory footprint fits the budget; when the
+// budget would force strips thinner than 8 rows (wide meshes) fall back to one CTA per SM.
+template <typename F>
+static int pick_ty_fn(const LevelGeo& g, size_t budget, F bytes_of_ty) {
+    const int cap = std::max(2, std::min(64, ((g.R + 1) / 2) * 2));
+    auto pick = [&](size_t b) {
+        int TY = cap;
+        for (; TY > 2; TY -= 2)
+            if (bytes_of_ty(TY) <= b) break;
+        return TY;
+    };
+    int TY = pick(budget);
+    if (TY < 8 && TY < cap) TY = pick(SMEM_MAX);
+    return TY;
+}
 
 int Context::configure_kernels() {
     if (kernels_configured) return ROMHC_OK;
@@ -877,19 +952,20 @@ int Context::vcycle(const double* y, int Kc, cudaStream_t st, const double** z_r
     const int L = int(levels.size()) - 1;
     const int nb = nrb * ncb;
     const int nstrip_levels = std::min(tail_level, L + 1);
-    std::vector<int> TYd(nstrip_levels), TYu(nstrip_levels);
+    const size_t hdr = smem_hdr_bytes(nb);
     for (int l = 0; l < nstrip_levels; ++l) {
         const LevelGeo& g = levels[l];
         const bool has_c = l < L;
-        dim3 block; strip_block(g, block);
-        const int extra_rows = has_c ? 5 : 2;
-        const int TY = pick_ty(g, extra_rows, 0, SMEM_3PER_SM, 64);
-        TYd[l] = TY;
+        const LevelGeo& gc = has_c ? levels[l + 1] : g;
+        dim3 block; strip_block(g, block, strip_threads);
+        const int halo = has_c ? 4 * nu + 1 : 4 * nu - 2;
+        auto bytes = [&](int TY) { return hdr + size_t(2) * (TY + halo) * g.P * 8 + (has_c ? size_t(TY / 2) * gc.P * 8 : 0); };
+        const int TY = pick_ty_fn(g, strip_budget, bytes);
+        if (bytes(TY) > SMEM_MAX) { set_error("mesh too wide for the multigrid strip kernels (C = %d)", g.C); return ROMHC_ERR_ARG; }
         const int ns = (g.R + TY - 1) / TY;
-        const size_t sm = smem_hdr_bytes(nb) + size_t(TY + extra_rows) * g.P * 8;
         prof_begin(PROF_DOWN0 + std::min(l, 1), st);
-        ++g_launches; k_mg_down<<<dim3(ns, Kc), block, sm, st>>>(g, has_c ? levels[l + 1] : g, y, ws.r[l], ws.za[l],
-                                                   has_c ? ws.r[l + 1] : nullptr, ws.active, TY, has_c ? 1 : 0);
+        ++g_launches; k_mg_down<<<dim3(ns, Kc), block, bytes(TY), st>>>(g, gc, y, ws.r[l], ws.za[l], has_c ? ws.r[l + 1] : nullptr,
+                                                          ws.active, TY, has_c ? 1 : 0, nu);
         prof_end(st);
     }
     if (tail_level <= L) {
@@ -902,22 +978,18 @@ int Context::vcycle(const double* y, int Kc, cudaStream_t st, const double** z_r
         const LevelGeo& g = levels[l];
         const bool has_c = l < L;
         const LevelGeo& gc = has_c ? levels[l + 1] : g;
-        dim3 block; strip_block(g, block);
-        // smem = (TY+4) rows of level l + (TY/2+3) rows of level l+1
-        const size_t hdr = smem_hdr_bytes(nb);
-        int TY = 64;
-        for (; TY > 2; TY -= 2) {
-            const size_t need = hdr + size_t(TY + 4) * g.P * 8 + (has_c ? size_t(TY / 2 + 3) * gc.P * 8 : 0);
-            if (need <= SMEM_2PER_SM && TY <= ((g.R + 1) / 2) * 2) break;
-        }
-        TYu[l] = TY;
+        dim3 block; strip_block(g, block, strip_threads);
+        auto bytes = [&](int TY) {
+            return hdr + size_t(2 * TY + 8 * nu - 2) * g.P * 8 + (has_c ? size_t(TY / 2 + 2 * nu + 1) * gc.P * 8 : 0);
+        };
+        const int TY = pick_ty_fn(g, strip_budget, bytes);
+        if (bytes(TY) > SMEM_MAX) { set_error("mesh too wide for the multigrid strip kernels (C = %d)", g.C); return ROMHC_ERR_ARG; }
         const int ns = (g.R + TY - 1) / TY;
-        const size_t sm = hdr + size_t(TY + 4) * g.P * 8 + (has_c ? size_t(TY / 2 + 3) * gc.P * 8 : 0);
         // coarse correction comes from the level below: its post-smoothed zb, or za if that level is the tail's top
         const double* e = has_c ? ((l + 1 < nstrip_levels) ? ws.zb[l + 1] : ws.za[l + 1]) : nullptr;
         prof_begin(PROF_UP0 + std::min(l, 1), st);
-        ++g_launches; k_mg_up<<<dim3(ns, Kc), block, sm, st>>>(g, gc, y, e, ws.za[l], ws.r[l], ws.zb[l], ws.active,
-                                                 l == 0 ? ws.part_rz : nullptr, TY, ns, has_c ? 1 : 0);
+        ++g_launches; k_mg_up<<<dim3(ns, Kc), block, bytes(TY), st>>>(g, gc, y, e, ws.za[l], ws.r[l], ws.zb[l], ws.active,
+                                                        l == 0 ? ws.part_rz : nullptr, TY, ns, has_c ? 1 : 0, nu);
         prof_end(st);
         if (l == 0) *np_rz = ns;
     }
@@ -933,7 +1005,7 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
     const LevelGeo& g = levels[0];
     const int nb = nrb * ncb;
     int rc = ensure_solve_ws(Kc); if (rc) return rc;
-    dim3 block; strip_block(g, block);
+    dim3 block; strip_block(g, block, strip_threads);
     // x = 0, r = b, active = 1
     CK(cudaMemsetAsync(x, 0, size_t(Kc) * g.Dp * 8, st));
     CK(cudaMemsetAsync(ws.r[0], 0, size_t(Kc) * g.Dp * 8, st));
@@ -952,9 +1024,12 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
         const size_t sm = smem_hdr_bytes(nb) + size_t(coarse_D) * coarse_LD * 8;
         ++g_launches; k_coarse_factor<<<Kc, 64, sm, st>>>(gl, y, ws.cfac, coarse_D, coarse_LD, ws_flags + 0);
     }
-    const int TYp = pick_ty(g, 2, 0, SMEM_3PER_SM, 64);
-    const int nsp = (g.R + TYp - 1) / TYp;
-    const size_t smp = smem_hdr_bytes(nb) + size_t(TYp + 2) * g.P * 8;
+    const size_t hdr = smem_hdr_bytes(nb);
+    auto bytes_p = [&](int TY) { return hdr + size_t(2) * (TY + 2) * g.P * 8; };
+    auto bytes_u = [&](int TY) { return hdr + size_t(3 * TY + 2) * g.P * 8; };
+    const int TYp = pick_ty_fn(g, strip_budget, bytes_p), TYu = pick_ty_fn(g, strip_budget, bytes_u);
+    if (bytes_p(TYp) > SMEM_MAX || bytes_u(TYu) > SMEM_MAX) { set_error("mesh too wide for the PCG strip kernels (C = %d)", g.C); return ROMHC_ERR_ARG; }
+    const int nsp = (g.R + TYp - 1) / TYp, nsu = (g.R + TYu - 1) / TYu;
     const int gs = (Kc + 127) / 128;
     const double* z = nullptr;
     int np_rz = 1;
@@ -969,13 +1044,13 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
     for (it = 1; it <= maxit; ++it) {
         prof_window = (it <= min_check_iter);
         prof_begin(PROF_PAPPLY, st);
-        ++g_launches; k_pcg_p_apply<<<dim3(nsp, Kc), block, smp, st>>>(g, y, z, ws.p[cur], ws.p[cur ^ 1], ws.beta, ws.active,
+        ++g_launches; k_pcg_p_apply<<<dim3(nsp, Kc), block, bytes_p(TYp), st>>>(g, y, z, ws.p[cur], ws.p[cur ^ 1], ws.beta, ws.active,
                                                         ws.part_pAp, TYp, nsp);
         prof_end(st);
         cur ^= 1;
         ++g_launches; k_scalar_alpha<<<gs, 128, 0, st>>>(Kc, nsp, ws.part_pAp, ws.rz, ws.alpha, ws.active, ws_flags + 0);
         prof_begin(PROF_UPDATE, st);
-        ++g_launches; k_pcg_update<<<dim3(nsp, Kc), block, smp, st>>>(g, y, ws.p[cur], x, ws.r[0], ws.alpha, ws.active, TYp);
+        ++g_launches; k_pcg_update<<<dim3(nsu, Kc), block, bytes_u(TYu), st>>>(g, y, ws.p[cur], x, ws.r[0], ws.alpha, ws.active, TYu);
         prof_end(st);
         rc = vcycle(y, Kc, st, &z, &np_rz); if (rc) return rc;
         int* ctr = n_active + 1 + (it % 32);

@@ -1,0 +1,240 @@
+"""Multi-GPU layer: one process per GPU, torch.distributed (NCCL over NVLink / NVSwitch) for the plumbing.
+
+The parameter training set shards naturally: snapshot solves, reduced solves, point evaluation and
+state / parameter estimation are independent per parameter vector, so every rank works on a contiguous slice and
+no data-path collective is needed.  Only two stages exchange data:
+
+  * greedy:  all_gather of one (error, global index) pair per rank and step, merged with np.argmax semantics
+             (first maximum wins, NaN is maximal), then a broadcast of the selected snapshot (8 D bytes) and its
+             parameter from the owning rank;
+  * POD:     one all_to_all that turns the K-sharded snapshot matrix into a D-sharded one (full columns local, so
+             the column mean needs no further exchange), a local centred SYRK (fp64 DMMA) over the D slice, one
+             all_reduce of the K x K partial Gram matrices, a replicated small eigensolve and an all_gather of the
+             (n, D / G) back-projected component slices.
+
+All collective helpers work on CPU tensors with the gloo backend as well; tests/test_dist_cpu.py runs them with
+world_size 2 on the host.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank():
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def shard_bounds(K: int, nshards: int):
+    """Contiguous, balanced slices: shard r owns [b[r], b[r+1])."""
+    return [(K * r) // nshards for r in range(nshards + 1)]
+
+
+def local_slice(K: int, r=None, w=None):
+    r = rank() if r is None else r
+    w = world() if w is None else w
+    b = shard_bounds(K, w)
+    return slice(b[r], b[r + 1])
+
+
+def column_bounds(Dp: int, nshards: int, align: int = 8):
+    """Column slices of the padded layout, aligned to `align` doubles (64 bytes) so TMA / cp.async stay aligned."""
+    units = Dp // align
+    b = [((units * r) // nshards) * align for r in range(nshards + 1)]
+    b[-1] = Dp
+    return b
+
+
+def merge_argmax(vals, idxs):
+    """np.argmax over the concatenation, given each shard's (local max value, its GLOBAL index); idx < 0 = empty shard."""
+    best_v, best_i, best_r = None, -1, -1
+    for r, (v, i) in enumerate(zip(vals, idxs)):
+        if i < 0:
+            continue
+        v = float(v)
+        if best_i < 0:
+            better = True
+        else:
+            vn, bn = math.isnan(v), math.isnan(best_v)
+            if vn != bn:
+                better = vn
+            elif vn and bn:
+                better = i < best_i
+            else:
+                better = v > best_v or (v == best_v and i < best_i)
+        if better:
+            best_v, best_i, best_r = v, int(i), r
+    return best_v, best_i, best_r
+
+
+def global_argmax(local_val: float, local_global_idx: int, device=None):
+    """all_gather one (value, global index) pair per rank -> (value, global index, owner rank), identical on all ranks."""
+    if world() == 1:
+        return float(local_val), int(local_global_idx), 0
+    dev = device if device is not None else torch.device("cpu")
+    v = torch.tensor([float(local_val)], dtype=torch.float64, device=dev)
+    i = torch.tensor([int(local_global_idx)], dtype=torch.int64, device=dev)
+    vs = [torch.empty_like(v) for _ in range(world())]
+    is_ = [torch.empty_like(i) for _ in range(world())]
+    dist.all_gather(vs, v)
+    dist.all_gather(is_, i)
+    return merge_argmax([float(t.item()) for t in vs], [int(t.item()) for t in is_])
+
+
+def broadcast_from(t: torch.Tensor, owner: int):
+    if world() > 1:
+        dist.broadcast(t, src=owner)
+    return t
+
+
+def k_to_d_shards(X_local: torch.Tensor, counts=None):
+    """(K_r, Dp) K-sharded -> (K, Dp_r) D-sharded with one all_to_all; rows keep their global order.
+
+    counts[r] = number of rows held by rank r (default: all equal to X_local.shape[0])."""
+    w, me = world(), rank()
+    if w == 1:
+        return X_local
+    Kl, Dp = X_local.shape
+    counts = [Kl] * w if counts is None else list(counts)
+    cb = column_bounds(Dp, w)
+    send = [X_local[:, cb[j]:cb[j + 1]].contiguous() for j in range(w)]
+    recv = [torch.empty(counts[j], cb[me + 1] - cb[me], dtype=X_local.dtype, device=X_local.device) for j in range(w)]
+    dist.all_to_all(recv, send) if X_local.is_cuda else _all_to_all_fallback(recv, send)
+    return torch.cat(recv, dim=0)
+
+
+def _all_to_all_fallback(recv, send):
+    """gloo has no all_to_all: w broadcasts-worth of point-to-point traffic via all_gather of padded blocks (tests only)."""
+    w, me = world(), rank()
+    for src in range(w):
+        for dst in range(w):
+            if src == dst:
+                if me == src:
+                    recv[src].copy_(send[dst])
+                continue
+            if me == src:
+                dist.send(send[dst], dst=dst)
+            elif me == dst:
+                dist.recv(recv[src], src=src)
+
+
+def all_gather_cols(t_local: torch.Tensor, Dp: int):
+    """(n, Dp_r) column slices -> (n, Dp) on every rank."""
+    w = world()
+    if w == 1:
+        return t_local
+    cb = column_bounds(Dp, w)
+    parts = [torch.empty(t_local.shape[0], cb[j + 1] - cb[j], dtype=t_local.dtype, device=t_local.device)
+             for j in range(w)]
+    dist.all_gather(parts, t_local.contiguous()) if len({p.shape for p in parts}) == 1 else _all_gather_uneven(parts, t_local)
+    return torch.cat(parts, dim=1)
+
+
+def _all_gather_uneven(parts, t_local):
+    for src in range(world()):
+        buf = t_local.contiguous() if src == rank() else parts[src]
+        dist.broadcast(buf, src=src)
+        if src == rank():
+            parts[src].copy_(buf)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# sharded POD and greedy on top of the device engine
+# --------------------------------------------------------------------------------------------------------------
+def distributed_pca(eng, X_local_pad: torch.Tensor, n: int, counts=None, timings=None):
+    """PCA(n) of the K-sharded padded snapshots; returns (components (n, Dp), singular values (n,)) on every rank."""
+    from .pod import top_eigenpairs
+    Dp = X_local_pad.shape[1]
+    ev = (lambda: torch.cuda.Event(enable_timing=True)) if X_local_pad.is_cuda else None
+    marks = []
+
+    def mark(name):
+        if timings is not None and ev is not None:
+            e = ev(); e.record(); marks.append((name, e))
+
+    mark("start")
+    Xs = k_to_d_shards(X_local_pad, counts).contiguous()            # (K, Dp_r)
+    mark("all_to_all")
+    mean = eng.column_mean(Xs)
+    eng.center_rows_(Xs, mean)
+    G = eng.gemm_nt(Xs, Xs, symmetric=True)                         # partial Gram over this rank's columns
+    mark("gram_partial")
+    if world() > 1:
+        dist.all_reduce(G)
+    mark("gram_allreduce")
+    lam, V = top_eigenpairs(eng, G, n)
+    lam = torch.clamp(lam, min=0.0)
+    sig = torch.sqrt(lam)
+    comps_local = eng.gemm_tn(V.contiguous(), Xs) / torch.where(sig > 0, sig, torch.ones_like(sig))[:, None]
+    comps = all_gather_cols(comps_local, Dp)
+    mark("eig_backproject")
+    idx = comps.abs().argmax(dim=1)
+    sign = torch.sign(comps[torch.arange(comps.shape[0], device=comps.device), idx])
+    sign = torch.where(sign == 0, torch.ones_like(sign), sign)
+    if timings is not None and marks:
+        torch.cuda.synchronize()
+        for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+            timings[n1] = e0.elapsed_time(e1)
+    return comps * sign[:, None], sig
+
+
+def greedy_build_sharded(sm, n, U_local, a_local, h1_local, K_total, greedy_for="galerkin"):
+    """Weak greedy (reference ReducedBasis.py:112-139) on a K-sharded training set.
+
+    Every rank passes its contiguous slice (local_slice(K_total)); all ranks return the same
+    (basis (n, D), a list, global indices).  Errors never leave the device; per step one 16-byte pair per rank is
+    exchanged and the winning snapshot is broadcast by its owner."""
+    from .lib.ReducedBasis import (GREEDY_FOR_GALERKIN, GREEDY_FOR_H10, get_high_contrast_coefficient,
+                                   sort_orthogonalize_base)
+    eng = sm._engine_()
+    off = shard_bounds(K_total, world())[rank()]
+    U_local = np.asarray(U_local, dtype=np.float64)
+    a_local = np.asarray(a_local, dtype=np.float64)
+    U = eng.pad(U_local) if len(U_local) else None
+    y = eng.params(a_local) if len(a_local) else None
+    norm = eng.dev(np.broadcast_to(np.asarray(h1_local, dtype=np.float64), (len(U_local),)).copy()) if len(U_local) else None
+    basis = np.empty((0, 0))
+    basis_orth = basis.copy()
+    a_selected, a, picked = [], [], []
+    D, geo = sm.vspace_dim, tuple(sm.blocks_geometry)
+    for _ in range(n):
+        if U is None:
+            lv, li = 0.0, -1
+        else:
+            if len(basis_orth) == 0:
+                err = eng.error_norm(U, None, None)
+            else:
+                Phi = eng.pad(basis_orth)
+                if greedy_for == GREEDY_FOR_H10:
+                    Cc = sm._projection_coefficients_dev(eng, U, Phi)
+                elif greedy_for == GREEDY_FOR_GALERKIN:
+                    Ahat, bhat = eng.project_operators(Phi)
+                    Cc = eng.reduced_solve(y, Ahat, bhat)
+                else:
+                    raise Exception(f"Not implemented greedy for {greedy_for}")
+                err = eng.error_norm(U, Cc, Phi)
+            li, lv = eng.argmax(err / norm)
+            li += off
+        _, gi, owner = global_argmax(lv, li, device=eng.device)
+        row = torch.empty(D, dtype=torch.float64, device=eng.device)
+        par = torch.empty(geo, dtype=torch.float64, device=eng.device)
+        if rank() == owner:
+            row.copy_(torch.as_tensor(U_local[gi - off]))
+            par.copy_(torch.as_tensor(a_local[gi - off]))
+        broadcast_from(row, owner)
+        broadcast_from(par, owner)
+        picked.append(gi)
+        max_element = row.cpu().numpy().reshape(1, -1)
+        a_new = par.cpu().numpy()
+        basis = max_element if len(basis) == 0 else np.concatenate((basis, max_element), axis=0)
+        a.append(a_new)
+        a_selected = np.append(a_selected, np.ravel(get_high_contrast_coefficient([a_new])[0]))
+        a_selected, basis_orth = sort_orthogonalize_base(a_selected, np.reshape(basis, (len(basis), -1)))
+    return basis, a, picked

@@ -138,8 +138,8 @@ class ReducedBasisGreedy(BaseReducedBasis):
         solutions2train = np.asarray(solutions2train, dtype=np.float64)
         U = eng.pad(solutions2train)                                     # resident for the whole build
         y = eng.params(np.asarray(a2train, dtype=np.float64))
-        inv_norm = 1.0 / eng.dev(np.broadcast_to(np.asarray(solutions2train_h1norm, dtype=np.float64),
-                                                 (len(solutions2train),)).copy())
+        norm = eng.dev(np.broadcast_to(np.asarray(solutions2train_h1norm, dtype=np.float64),
+                                       (len(solutions2train),)).copy())
         ones = torch.ones(len(solutions2train), eng.nb, dtype=torch.float64, device=eng.device)
 
         basis = np.empty((0, 0))
@@ -159,7 +159,7 @@ class ReducedBasisGreedy(BaseReducedBasis):
                     Ahat, bhat = eng.project_operators(Phi)              # :124
                     Cc = eng.reduced_solve(y, Ahat, bhat)
                 err = eng.error_norm(U, Cc, Phi)
-            max_error_index, max_err = eng.argmax(err * inv_norm)        # :129
+            max_error_index, max_err = eng.argmax(err / norm)            # :129 (true division: the round-1 tie is exactly 1.0)
             self.selected_indices.append(max_error_index)
             self.max_errors.append(max_err)
             max_element = np.reshape(solutions2train[max_error_index], (1, -1))

@@ -82,8 +82,9 @@ class GMG:
     DIRECT_MAX = 64
     TAIL_MAX_DP = 4352
 
-    def __init__(self, a, N, coarse_sweeps=8):
+    def __init__(self, a, N, coarse_sweeps=8, nu=1, nu_tail=2):
         a = np.asarray(a, float)
+        self.nu, self.nu_tail = nu, nu_tail
         nrb, ncb = a.shape
         self.levels = []
         n = N
@@ -115,7 +116,7 @@ class GMG:
         if self.direct:
             z[1:-1, 1:-1] = np.linalg.solve(self.coarse_matrix, r[1:-1, 1:-1].ravel()).reshape(L.R - 1, L.C - 1)
             return z
-        sweeps = 1 if self.smooth_only else self.coarse_sweeps
+        sweeps = self.nu if self.smooth_only else self.coarse_sweeps
         for _ in range(sweeps):
             L.gs_half(z, r, L.red); L.gs_half(z, r, L.black)
         for _ in range(sweeps):
@@ -126,17 +127,21 @@ class GMG:
         if l == len(self.levels) - 1:
             return self.coarse_solve(r)
         L = self.levels[l]
+        in_tail = (L.R + 1) * ((L.C + 7) // 8 * 8) <= self.TAIL_MAX_DP
+        nu = self.nu_tail if in_tail else self.nu
         z = np.zeros_like(r)
-        L.gs_half(z, r, L.red); L.gs_half(z, r, L.black)
+        for _ in range(nu):
+            L.gs_half(z, r, L.red); L.gs_half(z, r, L.black)
         d = r - L.apply(z); d[~L.mask] = 0
         z = z + prolong(self.vcycle(restrict(d), l + 1), r.shape)
         z[~L.mask] = 0
-        L.gs_half(z, r, L.black); L.gs_half(z, r, L.red)
+        for _ in range(nu):
+            L.gs_half(z, r, L.black); L.gs_half(z, r, L.red)
         return z
 
 
-def pcg(a, N, tol=1e-12, maxit=1000, coarse_sweeps=8):
-    g = GMG(a, N, coarse_sweeps)
+def pcg(a, N, tol=1e-12, maxit=1000, coarse_sweeps=8, nu=1, nu_tail=2):
+    g = GMG(a, N, coarse_sweeps, nu, nu_tail)
     L = g.levels[0]
     b = np.zeros((L.R + 1, L.C + 1)); b[1:-1, 1:-1] = 1.0 / N ** 2
     x = np.zeros_like(b); r = b.copy()

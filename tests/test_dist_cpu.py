@@ -1,0 +1,83 @@
+"""Host-side logic of the multi-GPU path on CPU: gloo backend, world_size 2 (rendezvous on 127.0.0.1)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from romhighcontrast_b200 import dist as rd
+
+
+def test_shard_and_column_bounds():
+    for K, w in [(10, 1), (10, 3), (100000, 8), (7, 8)]:
+        b = rd.shard_bounds(K, w)
+        assert b[0] == 0 and b[-1] == K and all(x <= y for x, y in zip(b, b[1:]))
+        assert max(np.diff(b)) - min(np.diff(b)) <= 1
+    for Dp, w in [(65792, 8), (65792, 3), (272, 2), (16770 // 8 * 8, 5)]:
+        cb = rd.column_bounds(Dp, w)
+        assert cb[0] == 0 and cb[-1] == Dp and all(c % 8 == 0 for c in cb)
+
+
+def test_merge_argmax_is_np_argmax():
+    rng = np.random.default_rng(0)
+    for trial in range(200):
+        K = int(rng.integers(1, 40))
+        v = rng.integers(0, 4, K).astype(float)          # many ties
+        if trial % 5 == 0:
+            v[rng.integers(0, K)] = np.nan
+        w = int(rng.integers(1, 6))
+        b = rd.shard_bounds(K, w)
+        vals, idxs = [], []
+        for r in range(w):
+            seg = v[b[r]:b[r + 1]]
+            if len(seg) == 0:
+                vals.append(0.0); idxs.append(-1)
+            else:
+                j = int(np.argmax(seg))
+                vals.append(seg[j]); idxs.append(b[r] + j)
+        _, gi, owner = rd.merge_argmax(vals, idxs)
+        assert gi == int(np.argmax(v))
+        assert b[owner] <= gi < b[owner + 1]
+
+
+def _worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # greedy argmax exchange: a tie across ranks must resolve to the lowest global index
+        K = 11
+        v = np.array([1.0, 3.0, 2.0, 3.0, 0.0, 3.0, 1.0, 3.0, 2.0, 0.5, 3.0])
+        sl = rd.local_slice(K)
+        seg = v[sl]
+        j = int(np.argmax(seg))
+        val, gi, owner = rd.global_argmax(seg[j], sl.start + j)
+        assert (val, gi, owner) == (3.0, 1, 0), (val, gi, owner)
+        row = torch.full((5,), float(rank))
+        rd.broadcast_from(row, 1)
+        assert torch.equal(row, torch.ones(5))
+        # K-sharded -> D-sharded transpose, then column all_gather must reproduce the full matrix
+        Kt, Dp = 9, 48
+        full = torch.arange(Kt * Dp, dtype=torch.float64).reshape(Kt, Dp)
+        b = rd.shard_bounds(Kt, world)
+        counts = [b[r + 1] - b[r] for r in range(world)]
+        Xs = rd.k_to_d_shards(full[b[rank]:b[rank + 1]].clone(), counts)
+        cb = rd.column_bounds(Dp, world)
+        assert torch.equal(Xs, full[:, cb[rank]:cb[rank + 1]])
+        # partial Gram + all_reduce == full Gram (the POD exchange), small dense check on CPU tensors
+        G = Xs @ Xs.T
+        dist.all_reduce(G)
+        assert torch.allclose(G, full @ full.T)
+        back = rd.all_gather_cols(Xs[:3].contiguous(), Dp)
+        assert torch.equal(back, full[:3])
+        open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_collectives_gloo(tmp_path):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()

@@ -12,7 +12,7 @@ from conftest import golden, relerr
 pytestmark = pytest.mark.gpu
 
 GEOS = [((2, 2), 8), ((3, 2), 4), ((4, 4), 16), ((2, 3), 6), ((3, 3), 5), ((1, 3), 8), ((2, 2), 32), ((3, 3), 43),
-        ((4, 4), 20)]
+        ((4, 4), 20), ((2, 4), 64), ((8, 8), 16)]
 
 
 @pytest.fixture(scope="module")
@@ -67,26 +67,31 @@ def test_pack_unpack_apply_norms(torch_mod, geo, N):
     np.testing.assert_allclose(en, ref, rtol=1e-12)
 
 
+@pytest.mark.parametrize("nu", [1, 2, 3])
 @pytest.mark.parametrize("geo,N", GEOS)
-def test_precond_matches_twin(torch_mod, geo, N):
+def test_precond_matches_twin(torch_mod, geo, N, nu):
     from gmg_twin import GMG
     eng = make_engine(geo, N)
+    eng.set_option("nu", nu)
+    eng.set_option("nu_tail", nu)
     K = 3
     y = rand_y(geo, K, seed=2)
     rng = np.random.default_rng(3)
     Rr = rng.standard_normal((K, eng.D))
     z = eng.unpad(eng.precond(eng.params(y), eng.pad(Rr))).cpu().numpy()
     for k in range(K):
-        tw = GMG(y[k], N)
+        tw = GMG(y[k], N, nu=nu, nu_tail=nu)
         zt = tw.vcycle(grid_of(eng, Rr[k]))[1:-1, 1:-1].ravel()
         assert relerr(z[k], zt) < 1e-9, (geo, N, k, relerr(z[k], zt))
 
 
 @pytest.mark.parametrize("geo,N", GEOS)
-def test_solve_matches_oracle(torch_mod, geo, N):
+@pytest.mark.parametrize("strip_kb", [100, 48, 227])
+def test_solve_matches_oracle(torch_mod, geo, N, strip_kb):
     from oracle import FEMOracle
     from gmg_twin import pcg
     eng = make_engine(geo, N)
+    eng.set_option("strip_kb", strip_kb)
     o = FEMOracle(geo, N)
     K = 7
     y = rand_y(geo, K, seed=4)
