@@ -43,7 +43,7 @@ int romhc_create(int nrb, int ncb, int N, int device, romhc_handle* out);
 int romhc_destroy(romhc_handle h);
 /* options: "rtol" (PCG tolerance on sqrt(r.z / r0.z0), default 1e-12), "maxit", "coarse_sweeps",
  * "workspace_gb", "check_every", "min_check_iter", "nu" / "nu_tail" (Gauss-Seidel sweeps of the V(nu,nu) cycle,
- * default nu = 1, nu_tail = 2), "strip_kb" (shared memory per strip CTA, default 100), "profile" */
+ * default nu = 1, nu_tail = 2), "strip_kb" (shared memory per strip CTA, default 113 = two CTAs per SM), "threads" (256 / 512 per strip CTA), "profile" */
 int romhc_set_option(romhc_handle h, const char* name, double value);
 /* info[0..15] = D, Dp, P, R, C, nlevels, tail_level, coarse_D, coarse_direct, nrb, ncb, N, 0... */
 int romhc_get_info(romhc_handle h, int64_t* info16);

@@ -193,11 +193,143 @@ k_reduced_solve(const double* __restrict__ y, int nb, const double* __restrict__
     }
 }
 
+// ---- thread-per-system variant (n <= 24): the packed lower triangle of every system lives in shared memory as
+// M[entry][thread] (consecutive threads -> consecutive banks: conflict free), so 32 systems per warp advance in
+// lock step with no synchronisation at all; the reduced operators are read as warp-uniform (broadcast) double2's.
+#define TPS_MAXN 24
+#define TPS_QCHUNK 16
+__global__ void __launch_bounds__(128)
+k_reduced_solve_tps(const double* __restrict__ y, int nb, const double* __restrict__ Ahat, const double* __restrict__ rhs,
+                    int rhs_per_system, int n, int64_t K, double* __restrict__ C, int* __restrict__ info, int npkp) {
+    extern __shared__ __align__(16) double sm[];
+    const int NT = blockDim.x, t = threadIdx.x;
+    const int npk = n * (n + 1) / 2;
+    double* Apk = sm;                                  // nb x npkp  (npkp = npk rounded up to even)
+    double* M = sm + size_t(nb) * npkp;                // npkp x NT
+    for (int idx = t; idx < nb * npkp; idx += NT) {
+        const int q = idx / npkp, e = idx % npkp;
+        double v = 0.0;
+        if (e < npk) {
+            int i = int((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+            while (i * (i + 1) / 2 > e) --i;
+            while ((i + 1) * (i + 2) / 2 <= e) ++i;
+            v = Ahat[(size_t(q) * n + i) * n + (e - i * (i + 1) / 2)];
+        }
+        Apk[idx] = v;
+    }
+    __syncthreads();
+    double* Mt = M + t;
+#define MM(e) Mt[(e) * NT]
+    for (int64_t k = int64_t(blockIdx.x) * NT + t; k < K; k += int64_t(gridDim.x) * NT) {
+        // ---- assemble sum_q y_q Ahat_q ----
+        for (int q0 = 0; q0 < nb; q0 += TPS_QCHUNK) {
+            double yq[TPS_QCHUNK];
+#pragma unroll
+            for (int q = 0; q < TPS_QCHUNK; ++q) yq[q] = (q0 + q < nb) ? y[k * nb + q0 + q] : 0.0;
+            const double* Ab = Apk + size_t(q0) * npkp;
+            const int nq = min(TPS_QCHUNK, nb - q0);
+            for (int e = 0; e < npkp; e += 2) {
+                double a0 = 0.0, a1 = 0.0;
+                if (q0) { a0 = MM(e); a1 = MM(e + 1); }
+                if (nq == TPS_QCHUNK) {
+#pragma unroll
+                    for (int q = 0; q < TPS_QCHUNK; ++q) {
+                        const double2 v = *reinterpret_cast<const double2*>(Ab + q * npkp + e);
+                        a0 = fma(yq[q], v.x, a0);
+                        a1 = fma(yq[q], v.y, a1);
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < TPS_QCHUNK; ++q) {
+                        if (q < nq) {
+                            const double2 v = *reinterpret_cast<const double2*>(Ab + q * npkp + e);
+                            a0 = fma(yq[q], v.x, a0);
+                            a1 = fma(yq[q], v.y, a1);
+                        }
+                    }
+                }
+                MM(e) = a0; MM(e + 1) = a1;
+            }
+        }
+        // ---- Cholesky (right looking); the diagonal keeps 1 / L_kk ----
+        int bad = 0;
+        for (int kc = 0; kc < n; ++kc) {
+            const int ekk = kc * (kc + 1) / 2 + kc;
+            const double d = MM(ekk);
+            if (!(d > 0.0)) bad = 1;
+            const double ild = 1.0 / sqrt(d);
+            MM(ekk) = ild;
+            for (int i = kc + 1; i < n; ++i) MM(i * (i + 1) / 2 + kc) *= ild;
+            for (int j = kc + 1; j < n; ++j) {
+                const double ljk = MM(j * (j + 1) / 2 + kc);
+#pragma unroll 4
+                for (int i = j; i < n; ++i) {
+                    const int eij = i * (i + 1) / 2 + j;
+                    MM(eij) = fma(-MM(i * (i + 1) / 2 + kc), ljk, MM(eij));
+                }
+            }
+        }
+        // ---- L L^T c = rhs ----
+        double b[TPS_MAXN];
+        const double* rb = rhs + (rhs_per_system ? k * n : 0);
+#pragma unroll
+        for (int i = 0; i < TPS_MAXN; ++i) b[i] = (i < n) ? rb[i] : 0.0;
+#pragma unroll
+        for (int i = 0; i < TPS_MAXN; ++i) {
+            if (i < n) {
+                double v = b[i];
+#pragma unroll
+                for (int j = 0; j < i; ++j) v = fma(-MM(i * (i + 1) / 2 + j), b[j], v);
+                b[i] = v * MM(i * (i + 1) / 2 + i);
+            }
+        }
+#pragma unroll
+        for (int i = TPS_MAXN - 1; i >= 0; --i) {
+            if (i < n) {
+                double v = b[i];
+#pragma unroll
+                for (int j = i + 1; j < TPS_MAXN; ++j)
+                    if (j < n) v = fma(-MM(j * (j + 1) / 2 + i), b[j], v);
+                b[i] = v * MM(i * (i + 1) / 2 + i);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < TPS_MAXN; ++i)
+            if (i < n) C[k * n + i] = b[i];
+        if (info) info[k] = bad;
+    }
+#undef MM
+}
+
 int reduced_solve(const double* y, int nb, const double* Ahat, const double* rhs, int rhs_per_system, int n,
                   int64_t K, double* C, int* info, cudaStream_t st) {
     if (n < 1 || n > 64) { set_error("reduced_solve: n must be in [1, 64], got %d", n); return ROMHC_ERR_ARG; }
     if (K <= 0) return ROMHC_OK;
     const int npk = n * (n + 1) / 2;
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= TPS_MAXN) {
+        const int npkp = (npk + 1) & ~1;
+        const size_t tab = size_t(nb) * npkp * 8;
+        const size_t budget = 224 * 1024;
+        if (tab + size_t(32) * npkp * 8 <= budget) {
+            int nt = int((budget - tab) / (size_t(npkp) * 8));
+            nt = std::min(128, (nt / 32) * 32);
+            static bool conf = false;
+            if (!conf) {
+                CK(cudaFuncSetAttribute(k_reduced_solve_tps, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                conf = true;
+            }
+            const size_t smb = tab + size_t(nt) * npkp * 8;
+            const int per_sm = std::max<int>(1, int((227 * 1024) / (smb + 1024)));
+            const int64_t want = (K + nt - 1) / nt;
+            const int grid = int(std::min<int64_t>(want, int64_t(nsm) * per_sm));
+            ++g_launches; k_reduced_solve_tps<<<grid, nt, smb, st>>>(y, nb, Ahat, rhs, rhs_per_system, n, K, C, info, npkp);
+            CK(cudaGetLastError());
+            return ROMHC_OK;
+        }
+    }
     const size_t per_warp = size_t(npk + nb + 2) * 8;
     const size_t tab = size_t(nb) * npk * 8;
     const int in_smem = (tab + RS_WARPS * per_warp) <= 96 * 1024;
@@ -207,9 +339,6 @@ int reduced_solve(const double* y, int nb, const double* Ahat, const double* rhs
         CK(cudaFuncSetAttribute(k_reduced_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
-    int dev = 0, nsm = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     const int64_t want = (K + RS_WARPS - 1) / RS_WARPS;
     const int grid = int(std::min<int64_t>(want, int64_t(nsm) * 8));
     ++g_launches; k_reduced_solve<<<grid, RS_WARPS * 32, smb, st>>>(y, nb, Ahat, rhs, rhs_per_system, n, K, C, info, in_smem);

@@ -78,8 +78,8 @@ struct Context {
     bool coarse_direct = false;
     int coarse_sweeps = 8;
     int nu = 1, nu_tail = 2;   // red/black Gauss-Seidel sweeps before and after the coarse correction: V(nu, nu)
-    int strip_threads = 256;            // threads per strip CTA (256 or 512)
-    size_t strip_budget = 100 * 1024;   // shared memory per strip CTA (>= 2 CTAs per SM so TMA loads overlap compute)
+    int strip_threads = 512;            // threads per strip CTA (256 or 512)
+    size_t strip_budget = 113 * 1024;   // shared memory per strip CTA (>= 2 CTAs per SM so TMA loads overlap compute)
     TailParams tail;
     size_t tail_smem = 0;
     // PCG controls

@@ -25,16 +25,40 @@ namespace romhc {
 // tx, tx+TXW, ... and a contiguous chunk of the phase's rows, walking down the rows so that the stencil
 // weights (ColW) are updated incrementally.  color: -1 all points, 0 red ((r+c) even), 1 black.
 // ------------------------------------------------------------------------------------------------------
+// Per-CTA strip context: everything that needs an integer division is evaluated once per kernel --
+// rowq[i] = (row0 + i) / N in shared memory, the thread's first column's block indices in `w0`.
+struct StripCtx {
+    LevelGeo g;
+    const double* sa;
+    const int* rowq;     // block-row index of strip row i (rows below 0 clamp to 0)
+    int row0;            // first row covered by rowq
+    int tx, ty, TXW, lgTYW;
+    int bl0, br0;        // block columns left/right of vertex column tx
+};
+
+__device__ __forceinline__ void strip_ctx_init(StripCtx& sc, const LevelGeo& g, const double* sa, int* rowq, int row0,
+                                               int nrow, int tid, int nt) {
+    sc.g = g; sc.sa = sa; sc.rowq = rowq; sc.row0 = row0;
+    sc.tx = threadIdx.x; sc.ty = threadIdx.y; sc.TXW = blockDim.x; sc.lgTYW = __ffs(blockDim.y) - 1;
+    for (int i = tid; i < nrow; i += nt) rowq[i] = max(row0 + i, 0) / g.N;
+    const int c = max(sc.tx, 1);
+    sc.bl0 = (c - 1) / g.N; sc.br0 = c / g.N;
+}
+
+// thread <-> point mapping shared by all strip kernels: blockDim = (TXW, TYW) (powers of two); a thread owns columns
+// tx, tx+TXW, ... and a contiguous chunk of the phase's rows.  Rows between two horizontal subdomain interfaces share
+// their weights: one weight evaluation per segment, then a branch-free inner loop.
+// color: -1 all points, 0 red ((r+c) even), 1 black.
 template <bool NEED_W, typename F>
-__device__ __forceinline__ void for_points(const LevelGeo& g, const double* sa, int tx, int ty, int TXW, int TYW,
-                                           int rlo, int rhi, int color, F f) {
+__device__ __forceinline__ void for_points(const StripCtx& sc, int rlo, int rhi, int color, F f) {
+    const LevelGeo& g = sc.g;
     rlo = max(rlo, 1);
     rhi = min(rhi, g.R - 1);
     const int nrows = rhi - rlo + 1;
     if (nrows <= 0) return;
-    const int ch = (nrows + TYW - 1) / TYW;
-    const int my_lo = rlo + ty * ch, my_hi = min(my_lo + ch - 1, rhi);
-    for (int c = tx; c < g.C; c += TXW) {
+    const int ch = (nrows + (1 << sc.lgTYW) - 1) >> sc.lgTYW;
+    const int my_lo = rlo + sc.ty * ch, my_hi = min(my_lo + ch - 1, rhi);
+    for (int c = sc.tx; c < g.C; c += sc.TXW) {
         if (c < 1) continue;
         int r = my_lo, step = 1;
         if (color >= 0) { r += (my_lo + c + color) & 1; step = 2; }
@@ -44,9 +68,12 @@ __device__ __forceinline__ void for_points(const LevelGeo& g, const double* sa, 
             for (; r <= my_hi; r += step) f(r, c, w);
             continue;
         }
-        // rows between two horizontal subdomain interfaces share their weights: one weight evaluation per
-        // segment, then a branch-free inner loop
-        w.init(sa, g, c, r);
+        w.a = sc.sa; w.ncb = g.ncb; w.N = g.N;
+        if (c == sc.tx) { w.bl = sc.bl0; w.br = sc.br0; }
+        else { w.bl = (c - 1) / g.N; w.br = c / g.N; }
+        w.rb = sc.rowq[r - sc.row0];
+        w.rm = r - w.rb * g.N;
+        w.compute();
         for (;;) {
             const int seg_end = min(my_hi, (w.rm == 0) ? r : r + (g.N - 1 - w.rm));
             const int r0 = r;
@@ -67,11 +94,67 @@ __device__ __forceinline__ double offdiag_sum(const double* s, int i, int P, con
     return w.wW * s[i - 1] + w.wE * s[i + 1] + w.wN * s[i - P] + w.wS * s[i + P];
 }
 
+// One red or black Gauss-Seidel half sweep on rows [rlo, rhi] of a strip: z = (r + sum_nb w_nb z_nb) / diag on the
+// points of one colour (ZERO: zero initial guess, z = r / diag).  Z and Rr are strips with pitch P whose first rows
+// are zrow0 / rrow0.  Within a colour phase no written value is read (all neighbours have the other colour), so two
+// consecutive same-colour rows are loaded, relaxed and stored together (ILP 2; their shared neighbour row is read
+// once) and addresses advance by pointer increments.
+template <bool ZERO>
+__device__ __forceinline__ void gs_phase(const StripCtx& sc, double* __restrict__ Z, const double* __restrict__ Rr,
+                                         int zrow0, int rrow0, int P, int rlo, int rhi, int color) {
+    const LevelGeo& g = sc.g;
+    rlo = max(rlo, 1);
+    rhi = min(rhi, g.R - 1);
+    const int nrows = rhi - rlo + 1;
+    if (nrows <= 0) return;
+    const int ch = (nrows + (1 << sc.lgTYW) - 1) >> sc.lgTYW;
+    const int my_lo = rlo + sc.ty * ch, my_hi = min(my_lo + ch - 1, rhi);
+    const int inc = 2 * P;
+    for (int c = sc.tx; c < g.C; c += sc.TXW) {
+        if (c < 1) continue;
+        int r = my_lo + ((my_lo + c + color) & 1);
+        if (r > my_hi) continue;
+        ColW w;
+        w.a = sc.sa; w.ncb = g.ncb; w.N = g.N;
+        if (c == sc.tx) { w.bl = sc.bl0; w.br = sc.br0; }
+        else { w.bl = (c - 1) / g.N; w.br = c / g.N; }
+        w.rb = sc.rowq[r - sc.row0];
+        w.rm = r - w.rb * g.N;
+        w.compute();
+        double* zp = Z + (r - zrow0) * P + c;
+        const double* rp = Rr + (r - rrow0) * P + c;
+        for (;;) {
+            const int seg_end = min(my_hi, (w.rm == 0) ? r : r + (g.N - 1 - w.rm));
+            const int r0 = r;
+            if (ZERO) {
+                for (; r <= seg_end; r += 2, zp += inc, rp += inc) zp[0] = rp[0] * w.idg;
+            } else {
+                for (; r + 2 <= seg_end; r += 4, zp += 2 * inc, rp += 2 * inc) {
+                    const double ra = rp[0], rb2 = rp[inc];
+                    const double zW0 = zp[-1], zE0 = zp[1], zN0 = zp[-P], zM = zp[P];
+                    const double zW1 = zp[inc - 1], zE1 = zp[inc + 1], zS1 = zp[inc + P];
+                    const double v0 = (ra + (w.wW * zW0 + w.wE * zE0) + (w.wN * zN0 + w.wS * zM)) * w.idg;
+                    const double v1 = (rb2 + (w.wW * zW1 + w.wE * zE1) + (w.wN * zM + w.wS * zS1)) * w.idg;
+                    zp[0] = v0;
+                    zp[inc] = v1;
+                }
+                for (; r <= seg_end; r += 2, zp += inc, rp += inc)
+                    zp[0] = (rp[0] + (w.wW * zp[-1] + w.wE * zp[1]) + (w.wN * zp[-P] + w.wS * zp[P])) * w.idg;
+            }
+            if (r > my_hi) break;
+            w.rm += r - r0;
+            while (w.rm >= g.N) { w.rm -= g.N; ++w.rb; }
+            w.compute();
+        }
+    }
+}
+
 // dynamic smem carve-up helper (all kernels): [coef table | reduction scratch | mbarrier | data...]
 struct SmemHdr {
     double* sa;
     double* red;
     uint64_t* bar;
+    int* rowq;      // 768 ints: block index of every strip row (and, in the tail kernel, of every column)
     double* data;
 };
 __device__ __forceinline__ SmemHdr smem_carve(unsigned char* base, int nb) {
@@ -80,10 +163,11 @@ __device__ __forceinline__ SmemHdr smem_carve(unsigned char* base, int nb) {
     const int nbp = (nb + 7) & ~7;
     h.red = h.sa + nbp;
     h.bar = reinterpret_cast<uint64_t*>(h.red + 32);
-    h.data = h.red + 40;   // 64-byte aligned: (nbp + 40) * 8
+    h.rowq = reinterpret_cast<int*>(h.red + 40);
+    h.data = h.red + 40 + 384;   // 64-byte aligned: (nbp + 424) * 8
     return h;
 }
-static inline size_t smem_hdr_bytes(int nb) { return size_t(((nb + 7) & ~7) + 40) * 8; }
+static inline size_t smem_hdr_bytes(int nb) { return size_t(((nb + 7) & ~7) + 424) * 8; }
 
 // ======================================================================================================
 // simple element-wise kernels
@@ -130,13 +214,15 @@ k_apply(LevelGeo g, const double* __restrict__ y, const double* __restrict__ u, 
     const int y0 = blockIdx.x * TY;
     if (tid == 0) { mbar_init(h.bar, 1); mbar_fence_init(); }
     load_coef(h.sa, y, k, nb, tid, nt);
-    __syncthreads();
     const int row0 = y0 - 1, nrow = TY + 2;
+    StripCtx sc;
+    strip_ctx_init(sc, g, h.sa, h.rowq, row0, nrow, tid, nt);
+    __syncthreads();
     strip_load_issue(h.data, u + k * g.Dp, g, row0, row0 + nrow, h.bar, tid, nt);
     mbar_wait(h.bar, 0);
     __syncthreads();
     double* o = out + k * g.Dp;
-    for_points<true>(g, h.sa, threadIdx.x, threadIdx.y, blockDim.x, blockDim.y, y0, y0 + TY - 1, -1,
+    for_points<true>(sc, y0, y0 + TY - 1, -1,
                      [&](int r, int c, const ColW& w) {
                          o[size_t(r) * g.P + c] = apply_diff(h.data, (r - row0) * g.P + c, g.P, w);
                      });
@@ -157,6 +243,8 @@ k_energy(LevelGeo g, const double* __restrict__ y, const double* __restrict__ u,
     const int y0 = blockIdx.x * TY;
     const int row0 = y0, nrow = TY + 1;   // one halo row below (edges to the south)
     load_coef(h.sa, y, k, nb, tid, nt);
+    StripCtx sc;
+    strip_ctx_init(sc, g, h.sa, h.rowq, row0, nrow, tid, nt);
     double* ck = h.data;                   // nbasis coefficients, then the strip
     double* s = h.data + ((nbasis + 7) & ~7);
     for (int j = tid; j < nbasis; j += nt) ck[j] = coef[k * nbasis + j];
@@ -179,7 +267,7 @@ k_energy(LevelGeo g, const double* __restrict__ y, const double* __restrict__ u,
     __syncthreads();
     double acc = 0.0;
     if (mode == 0) {
-        for_points<true>(g, h.sa, threadIdx.x, threadIdx.y, blockDim.x, blockDim.y, y0, y0 + TY - 1, -1,
+        for_points<true>(sc, y0, y0 + TY - 1, -1,
                          [&](int r, int c, const ColW& w) {
                              const int i = (r - row0) * g.P + c;
                              const double v = s[i];
@@ -190,7 +278,7 @@ k_energy(LevelGeo g, const double* __restrict__ y, const double* __restrict__ u,
                              acc += e;
                          });
     } else {
-        for_points<false>(g, h.sa, threadIdx.x, threadIdx.y, blockDim.x, blockDim.y, y0, y0 + TY - 1, -1,
+        for_points<false>(sc, y0, y0 + TY - 1, -1,
                           [&](int r, int c, const ColW&) {
                               const double v = s[(r - row0) * g.P + c];
                               acc += v * v;
@@ -228,8 +316,10 @@ k_pcg_p_apply(LevelGeo g, const double* __restrict__ y, const double* __restrict
     const int y0 = blockIdx.x * TY;
     if (tid == 0) { mbar_init(h.bar, 1); mbar_fence_init(); }
     load_coef(h.sa, y, k, nb, tid, nt);
-    __syncthreads();
     const int row0 = y0 - 1, nrow = TY + 2, P = g.P;
+    StripCtx sc;
+    strip_ctx_init(sc, g, h.sa, h.rowq, row0, nrow, tid, nt);
+    __syncthreads();
     double* Zs = h.data;
     double* Ps = Zs + size_t(nrow) * P;
     if (tid == 0) {
@@ -258,7 +348,7 @@ k_pcg_p_apply(LevelGeo g, const double* __restrict__ y, const double* __restrict
     __syncthreads();
     if (tid == 0) { strip_store(p_out + k * g.Dp, Ps, g, row0, y0, y0 + TY); bulk_commit(); }
     double acc = 0.0;
-    for_points<true>(g, h.sa, threadIdx.x, threadIdx.y, blockDim.x, blockDim.y, y0, y0 + TY - 1, -1,
+    for_points<true>(sc, y0, y0 + TY - 1, -1,
                      [&](int r, int c, const ColW& w) {
                          const int i = (r - row0) * P + c;
                          acc = fma(Ps[i], apply_diff(Ps, i, P, w), acc);
@@ -280,8 +370,10 @@ k_pcg_update(LevelGeo g, const double* __restrict__ y, const double* __restrict_
     const int y0 = blockIdx.x * TY;
     if (tid == 0) { mbar_init(h.bar, 1); mbar_fence_init(); }
     load_coef(h.sa, y, k, nb, tid, nt);
-    __syncthreads();
     const int row0 = y0 - 1, nrow = TY + 2, P = g.P;
+    StripCtx sc;
+    strip_ctx_init(sc, g, h.sa, h.rowq, row0, nrow, tid, nt);
+    __syncthreads();
     double* Ps = h.data;
     double* Xs = Ps + size_t(nrow) * P;
     double* Rs = Xs + size_t(TY) * P;
@@ -295,7 +387,7 @@ k_pcg_update(LevelGeo g, const double* __restrict__ y, const double* __restrict_
     const double al = alpha[k];
     mbar_wait(h.bar, 0);
     __syncthreads();
-    for_points<true>(g, h.sa, threadIdx.x, threadIdx.y, blockDim.x, blockDim.y, y0, y0 + TY - 1, -1,
+    for_points<true>(sc, y0, y0 + TY - 1, -1,
                      [&](int rr, int c, const ColW& w) {
                          const int i = (rr - row0) * P + c, j = (rr - y0) * P + c;
                          const double Ap = apply_diff(Ps, i, P, w);
@@ -327,10 +419,12 @@ k_mg_down(LevelGeo g, LevelGeo gc, const double* __restrict__ y, const double* _
     const int y0 = blockIdx.x * TY;
     if (tid == 0) { mbar_init(h.bar, 1); mbar_fence_init(); }
     load_coef(h.sa, y, k, nb, tid, nt);
-    __syncthreads();
     // validity cone: every half sweep consumes one row on each side
     const int halo_top = has_coarse ? 2 * nu + 1 : 2 * nu - 1, halo_bot = has_coarse ? 2 * nu : 2 * nu - 1;
     const int row0 = y0 - halo_top, nrow = TY + halo_top + halo_bot, last = row0 + nrow - 1;
+    StripCtx sc;
+    strip_ctx_init(sc, g, h.sa, h.rowq, row0, nrow, tid, nt);
+    __syncthreads();
     const int P = g.P, Pc = gc.P;
     double* Rs = h.data;
     double* Zs = Rs + size_t(nrow) * P;
@@ -340,27 +434,22 @@ k_mg_down(LevelGeo g, LevelGeo gc, const double* __restrict__ y, const double* _
         strip_issue(Rs, r_in + k * g.Dp, g, row0, nrow, h.bar);
     }
     strip_zero_oob(Rs, g, row0, nrow, tid, nt);
-    for (int i = tid; i < nrow * P; i += nt) Zs[i] = 0.0;
-    if (has_coarse) for (int i = tid; i < (TY / 2) * Pc; i += nt) Cs[i] = 0.0;
+    {
+        double2* Z2 = reinterpret_cast<double2*>(Zs);
+        const double2 zero2 = make_double2(0.0, 0.0);
+        for (int i = tid; i < nrow * P / 2; i += nt) Z2[i] = zero2;
+        if (has_coarse) {
+            double2* C2 = reinterpret_cast<double2*>(Cs);
+            for (int i = tid; i < (TY / 2) * Pc / 2; i += nt) C2[i] = zero2;
+        }
+    }
     mbar_wait(h.bar, 0);
     __syncthreads();
     for (int s = 0; s < nu; ++s) {
-        if (s == 0) {
-            for_points<true>(g, h.sa, tx, ty, TXW, TYW, row0, last, 0, [&](int r, int c, const ColW& w) {
-                const int i = (r - row0) * P + c;
-                Zs[i] = Rs[i] * w.idg;
-            });
-        } else {
-            for_points<true>(g, h.sa, tx, ty, TXW, TYW, row0 + 2 * s, last - 2 * s, 0, [&](int r, int c, const ColW& w) {
-                const int i = (r - row0) * P + c;
-                Zs[i] = (Rs[i] + offdiag_sum(Zs, i, P, w)) * w.idg;
-            });
-        }
+        if (s == 0) gs_phase<true>(sc, Zs, Rs, row0, row0, P, row0, last, 0);
+        else        gs_phase<false>(sc, Zs, Rs, row0, row0, P, row0 + 2 * s, last - 2 * s, 0);
         __syncthreads();
-        for_points<true>(g, h.sa, tx, ty, TXW, TYW, row0 + 2 * s + 1, last - 2 * s - 1, 1, [&](int r, int c, const ColW& w) {
-            const int i = (r - row0) * P + c;
-            Zs[i] = (Rs[i] + offdiag_sum(Zs, i, P, w)) * w.idg;
-        });
+        gs_phase<false>(sc, Zs, Rs, row0, row0, P, row0 + 2 * s + 1, last - 2 * s - 1, 1);
         if (s == nu - 1) fence_proxy_async();
         __syncthreads();
     }
@@ -368,7 +457,7 @@ k_mg_down(LevelGeo g, LevelGeo gc, const double* __restrict__ y, const double* _
     if (has_coarse) {
         // residual after the last full sweep: zero on black points (just relaxed); on red points
         // d = r - diag z + sum_nb w_nb z_nb (kept in the r strip)
-        for_points<true>(g, h.sa, tx, ty, TXW, TYW, y0 - 1, y0 + TY - 1, 0, [&](int r, int c, const ColW& w) {
+        for_points<true>(sc, y0 - 1, y0 + TY - 1, 0, [&](int r, int c, const ColW& w) {
             const int i = (r - row0) * P + c;
             Rs[i] = (Rs[i] - w.dg * Zs[i]) + offdiag_sum(Zs, i, P, w);
         });
@@ -376,12 +465,11 @@ k_mg_down(LevelGeo g, LevelGeo gc, const double* __restrict__ y, const double* _
         // r_c(I,J) = d(2I,2J) + (d(2I-1,2J+1) + d(2I+1,2J-1)) / 2   (E/W/N/S neighbours are black: d = 0)
         const int Ib = y0 / 2;
         const int I_lo = max(Ib, 1), I_hi = min(Ib + TY / 2 - 1, gc.R - 1);
-        const int nJ = gc.C - 1, nI = I_hi - I_lo + 1;
-        for (int idx = tid; idx < nI * nJ; idx += nt) {
-            const int I = I_lo + idx / nJ, J = 1 + idx % nJ;
-            const int i = (2 * I - row0) * P + 2 * J;
-            Cs[(I - Ib) * Pc + J] = Rs[i] + 0.5 * (Rs[i - P + 1] + Rs[i + P - 1]);
-        }
+        for (int I = I_lo + ty; I <= I_hi; I += TYW)
+            for (int J = 1 + tx; J <= gc.C - 1; J += TXW) {
+                const int i = (2 * I - row0) * P + 2 * J;
+                Cs[(I - Ib) * Pc + J] = Rs[i] + 0.5 * (Rs[i - P + 1] + Rs[i + P - 1]);
+            }
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) { strip_store(rc_out + k * gc.Dp, Cs, gc, Ib, Ib, Ib + TY / 2); bulk_commit(); }
@@ -404,9 +492,11 @@ k_mg_up(LevelGeo g, LevelGeo gc, const double* __restrict__ y, const double* __r
     const int y0 = blockIdx.x * TY;
     if (tid == 0) { mbar_init(h.bar, 1); mbar_fence_init(); }
     load_coef(h.sa, y, k, nb, tid, nt);
-    __syncthreads();
     const int P = g.P, Pc = gc.P;
     const int row0 = y0 - 2 * nu, nrow = TY + 4 * nu, last = row0 + nrow - 1;
+    StripCtx sc;
+    strip_ctx_init(sc, g, h.sa, h.rowq, row0, nrow, tid, nt);
+    __syncthreads();
     const int rrow0 = row0 + 1, nrrow = nrow - 2;
     const int I0 = y0 / 2 - nu, nI = TY / 2 + 2 * nu + 1;
     double* Zs = h.data;
@@ -427,7 +517,7 @@ k_mg_up(LevelGeo g, LevelGeo gc, const double* __restrict__ y, const double* __r
     if (has_coarse) {
         // prolongation on red points: (even, even) copies the coarse vertex, (odd, odd) is the midpoint of the
         // coarse cell's anti-diagonal (I, J+1)-(I+1, J).  Black values are overwritten by the first half sweep.
-        for_points<false>(g, h.sa, tx, ty, TXW, TYW, row0, last, 0, [&](int rr, int c, const ColW&) {
+        for_points<false>(sc, row0, last, 0, [&](int rr, int c, const ColW&) {
             const int i = (rr - row0) * P + c;
             const int I = (rr >> 1) - I0, J = c >> 1;
             if (rr & 1) Zs[i] += 0.5 * (Es[I * Pc + J + 1] + Es[(I + 1) * Pc + J]);
@@ -436,22 +526,16 @@ k_mg_up(LevelGeo g, LevelGeo gc, const double* __restrict__ y, const double* __r
         __syncthreads();
     }
     for (int s = 0; s < nu; ++s) {
-        for_points<true>(g, h.sa, tx, ty, TXW, TYW, row0 + 2 * s + 1, last - 2 * s - 1, 1, [&](int rr, int c, const ColW& w) {
-            const int i = (rr - row0) * P + c;
-            Zs[i] = (Rs[i - P] + offdiag_sum(Zs, i, P, w)) * w.idg;     // Rs starts one row below Zs
-        });
+        gs_phase<false>(sc, Zs, Rs, row0, rrow0, P, row0 + 2 * s + 1, last - 2 * s - 1, 1);
         __syncthreads();
-        for_points<true>(g, h.sa, tx, ty, TXW, TYW, row0 + 2 * s + 2, last - 2 * s - 2, 0, [&](int rr, int c, const ColW& w) {
-            const int i = (rr - row0) * P + c;
-            Zs[i] = (Rs[i - P] + offdiag_sum(Zs, i, P, w)) * w.idg;
-        });
+        gs_phase<false>(sc, Zs, Rs, row0, rrow0, P, row0 + 2 * s + 2, last - 2 * s - 2, 0);
         if (s == nu - 1) fence_proxy_async();
         __syncthreads();
     }
     if (tid == 0) { strip_store(z_out + k * g.Dp, Zs, g, row0, y0, y0 + TY); bulk_commit(); }
     if (part_rz) {
         double acc = 0.0;
-        for_points<false>(g, h.sa, tx, ty, TXW, TYW, y0, y0 + TY - 1, -1, [&](int rr, int c, const ColW&) {
+        for_points<false>(sc, y0, y0 + TY - 1, -1, [&](int rr, int c, const ColW&) {
             const int i = (rr - row0) * P + c;
             acc = fma(Rs[i - P], Zs[i], acc);
         });
@@ -471,15 +555,25 @@ __device__ __forceinline__ void tail_map(const LevelGeo& g, int tid, int nt, int
     ty = tid / TXW;
 }
 
-__device__ __forceinline__ void tail_gs_half(const LevelGeo& g, const double* sa, double* z, const double* r,
-                                             int color, bool zero_guess, int tid, int nt) {
+// strip context of a whole tail level (rows 0..R); ends with a __syncthreads()
+__device__ __forceinline__ void tail_ctx(StripCtx& sc, const LevelGeo& g, const double* sa, int* rowq, int tid, int nt) {
     int tx, ty, TXW, TYW;
     tail_map(g, tid, nt, tx, ty, TXW, TYW);
-    const int P = g.P;
-    for_points<true>(g, sa, tx, ty, TXW, TYW, 1, g.R - 1, color, [&](int rr, int c, const ColW& w) {
-        const int i = rr * P + c;
-        z[i] = zero_guess ? r[i] * w.idg : (r[i] + offdiag_sum(z, i, P, w)) * w.idg;
-    });
+    sc.g = g; sc.sa = sa; sc.rowq = rowq; sc.row0 = 0;
+    sc.tx = tx; sc.ty = ty; sc.TXW = TXW; sc.lgTYW = __ffs(TYW) - 1;
+    __syncthreads();                       // previous users of rowq are done
+    for (int i = tid; i <= g.R; i += nt) rowq[i] = i / g.N;
+    for (int i = tid; i <= g.C; i += nt) rowq[g.R + 1 + i] = i / g.N;     // column table behind the row table
+    const int c = max(tx, 1);
+    sc.bl0 = (c - 1) / g.N; sc.br0 = c / g.N;
+    __syncthreads();
+}
+
+__device__ __forceinline__ void tail_gs_half(const StripCtx& sc, double* z, const double* r, int color,
+                                             bool zero_guess) {
+    const LevelGeo& g = sc.g;
+    if (zero_guess) gs_phase<true>(sc, z, r, 0, 0, g.P, 1, g.R - 1, color);
+    else            gs_phase<false>(sc, z, r, 0, 0, g.P, 1, g.R - 1, color);
     __syncthreads();
 }
 
@@ -526,30 +620,37 @@ k_mg_tail(TailParams tp, const double* __restrict__ y, const double* __restrict_
         double* r = S + tp.off_r[l];
         double* z = S + tp.off_z[l];
         double* rc = S + tp.off_r[l + 1];
+        StripCtx sc;
+        tail_ctx(sc, g, h.sa, h.rowq, tid, nt);
         for (int sw = 0; sw < tp.nu; ++sw) {
-            tail_gs_half(g, h.sa, z, r, 0, sw == 0, tid, nt);
-            tail_gs_half(g, h.sa, z, r, 1, false, tid, nt);
+            tail_gs_half(sc, z, r, 0, sw == 0);
+            tail_gs_half(sc, z, r, 1, false);
         }
         // restriction of the residual (zero on the just-relaxed black points), computed on the fly at the red points
-        const int nJ = gc.C - 1, nI = gc.R - 1, P = g.P;
-        for (int idx = tid; idx < nI * nJ; idx += nt) {
-            const int I = 1 + idx / nJ, J = 1 + idx % nJ;
-            double acc = 0.0;
+        const int P = g.P;
+        const int* rq = h.rowq;
+        const int* cq = h.rowq + g.R + 1;
+        const int TYWc = 1 << sc.lgTYW;
+        for (int I = 1 + sc.ty; I <= gc.R - 1; I += TYWc)
+            for (int J = 1 + sc.tx; J <= gc.C - 1; J += sc.TXW) {
+                double acc = 0.0;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const int rr = 2 * I + (q == 1 ? -1 : (q == 2 ? 1 : 0));
-                const int cc = 2 * J + (q == 1 ? 1 : (q == 2 ? -1 : 0));
-                if (rr >= 1 && rr <= g.R - 1 && cc >= 1 && cc <= g.C - 1) {
-                    double wW, wE, wN, wS;
-                    vertex_weights(h.sa, g, rr, cc, wW, wE, wN, wS);
-                    const int i = rr * P + cc;
-                    const double d = (r[i] - ((wW + wE) + (wN + wS)) * z[i]) +
-                                     (wW * z[i - 1] + wE * z[i + 1] + wN * z[i - P] + wS * z[i + P]);
-                    acc += (q == 0) ? d : 0.5 * d;
+                for (int q = 0; q < 3; ++q) {
+                    const int rr = 2 * I + (q == 1 ? -1 : (q == 2 ? 1 : 0));
+                    const int cc = 2 * J + (q == 1 ? 1 : (q == 2 ? -1 : 0));
+                    if (rr >= 1 && rr <= g.R - 1 && cc >= 1 && cc <= g.C - 1) {
+                        const int bu = rq[rr - 1], bd = rq[rr], bl = cq[cc - 1], br = cq[cc];
+                        const double aul = h.sa[bu * g.ncb + bl], aur = h.sa[bu * g.ncb + br];
+                        const double adl = h.sa[bd * g.ncb + bl], adr = h.sa[bd * g.ncb + br];
+                        const double wW = 0.5 * (aul + adl), wE = 0.5 * (aur + adr), wN = 0.5 * (aul + aur), wS = 0.5 * (adl + adr);
+                        const int i = rr * P + cc;
+                        const double d = (r[i] - ((wW + wE) + (wN + wS)) * z[i]) +
+                                         (wW * z[i - 1] + wE * z[i + 1] + wN * z[i - P] + wS * z[i + P]);
+                        acc += (q == 0) ? d : 0.5 * d;
+                    }
                 }
+                rc[I * gc.P + J] = acc;
             }
-            rc[I * gc.P + J] = acc;
-        }
         __syncthreads();
     }
     // ---- coarsest ----
@@ -587,13 +688,15 @@ k_mg_tail(TailParams tp, const double* __restrict__ y, const double* __restrict_
             }
             __syncthreads();
         } else {
+            StripCtx sc;
+            tail_ctx(sc, g, h.sa, h.rowq, tid, nt);
             for (int sw = 0; sw < tp.coarse_sweeps; ++sw) {
-                tail_gs_half(g, h.sa, z, r, 0, sw == 0, tid, nt);
-                tail_gs_half(g, h.sa, z, r, 1, false, tid, nt);
+                tail_gs_half(sc, z, r, 0, sw == 0);
+                tail_gs_half(sc, z, r, 1, false);
             }
             for (int sw = 0; sw < tp.coarse_sweeps; ++sw) {
-                tail_gs_half(g, h.sa, z, r, 1, false, tid, nt);
-                tail_gs_half(g, h.sa, z, r, 0, false, tid, nt);
+                tail_gs_half(sc, z, r, 1, false);
+                tail_gs_half(sc, z, r, 0, false);
             }
         }
     }
@@ -604,10 +707,10 @@ k_mg_tail(TailParams tp, const double* __restrict__ y, const double* __restrict_
         double* r = S + tp.off_r[l];
         double* z = S + tp.off_z[l];
         const double* e = S + tp.off_z[l + 1];
-        int tx, ty, TXW, TYW;
-        tail_map(g, tid, nt, tx, ty, TXW, TYW);
+        StripCtx sc;
+        tail_ctx(sc, g, h.sa, h.rowq, tid, nt);
         const int P = g.P, Pc = gc.P;
-        for_points<false>(g, h.sa, tx, ty, TXW, TYW, 1, g.R - 1, 0, [&](int rr, int c, const ColW&) {
+        for_points<false>(sc, 1, g.R - 1, 0, [&](int rr, int c, const ColW&) {
             const int i = rr * P + c;
             const int I = rr >> 1, J = c >> 1;
             if (rr & 1) z[i] += 0.5 * (e[I * Pc + J + 1] + e[(I + 1) * Pc + J]);
@@ -615,8 +718,8 @@ k_mg_tail(TailParams tp, const double* __restrict__ y, const double* __restrict_
         });
         __syncthreads();
         for (int sw = 0; sw < tp.nu; ++sw) {
-            tail_gs_half(g, h.sa, z, r, 1, false, tid, nt);
-            tail_gs_half(g, h.sa, z, r, 0, false, tid, nt);
+            tail_gs_half(sc, z, r, 1, false);
+            tail_gs_half(sc, z, r, 0, false);
         }
     }
     // ---- output ----

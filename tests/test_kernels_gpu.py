@@ -148,7 +148,8 @@ def test_solve_contrast_sweep_iterations(torch_mod):
             assert err < 1e-9
 
 
-@pytest.mark.parametrize("geo,N,n", [((3, 2), 4, 5), ((4, 4), 16, 20), ((2, 2), 32, 10), ((3, 3), 5, 7)])
+@pytest.mark.parametrize("geo,N,n", [((3, 2), 4, 5), ((4, 4), 16, 20), ((2, 2), 32, 10), ((3, 3), 5, 7), ((8, 8), 4, 20),
+                                     ((4, 4), 8, 1), ((4, 4), 8, 24)])
 def test_projection_and_reduced_solve(torch_mod, geo, N, n):
     from oracle import FEMOracle
     eng = make_engine(geo, N)
@@ -184,6 +185,35 @@ def test_projection_and_reduced_solve(torch_mod, geo, N, n):
     # reconstruction GEMM
     rec = eng.unpad(eng.gemm_nn(eng.dev(Cg), Phip)).cpu().numpy()
     assert relerr(rec, Cg @ Phi) < 1e-13
+
+
+@pytest.mark.parametrize("n,nb,K", [(1, 4, 100), (7, 16, 1000), (20, 16, 5000), (24, 9, 333), (25, 16, 500), (40, 4, 257),
+                                    (20, 64, 999), (12, 200, 100)])
+def test_reduced_solve_random_spd(torch_mod, n, nb, K):
+    """both reduced-solve kernels (thread-per-system n <= 24, warp-per-system above) against numpy.linalg.solve"""
+    torch = torch_mod
+    from romhighcontrast_b200 import _lib
+    import ctypes as C
+    rng = np.random.default_rng(n * 1000 + nb)
+    B = rng.standard_normal((nb, n, n))
+    Ahat = np.einsum("qij,qkj->qik", B, B) + 0.1 * np.eye(n)
+    y = 10 ** rng.uniform(0, 4, (K, nb))
+    rhs = rng.standard_normal(n)
+    rhs_k = rng.standard_normal((K, n))
+    dev = torch.device("cuda")
+    p = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+    yd, Ad = p(y), p(Ahat)
+    for r, per in ((rhs, 0), (rhs_k, 1)):
+        out = torch.empty(K, n, dtype=torch.float64, device=dev)
+        info = torch.empty(K, dtype=torch.int32, device=dev)
+        rd = p(r)
+        _lib.call("romhc_reduced_solve", C.c_void_p(yd.data_ptr()), nb, C.c_void_p(Ad.data_ptr()), C.c_void_p(rd.data_ptr()),
+                  per, n, K, C.c_void_p(out.data_ptr()), C.c_void_p(info.data_ptr()), None)
+        torch.cuda.synchronize()
+        Ak = np.einsum("kq,qij->kij", y, Ahat)
+        ref = np.linalg.solve(Ak, np.broadcast_to(r, (K, n))[..., None])[..., 0]
+        assert int(info.sum()) == 0
+        assert relerr(out.cpu().numpy(), ref) < 1e-9
 
 
 def test_reduced_solve_flags_indefinite(torch_mod):
@@ -268,3 +298,24 @@ def test_c_abi_rejects_bad_arguments(torch_mod):
     eng = Engine((2, 2), 4)
     with pytest.raises(_lib.RomhcError):
         eng.set_option("nonsense", 1.0)
+
+
+@pytest.mark.parametrize("K,D,n,decay", [(1500, 900, 10, 0.7), (2000, 3000, 20, 0.97)])
+def test_pod_iterative_eigensolver(torch_mod, K, D, n, decay):
+    """K > 1024 takes the Chebyshev-filtered subspace iteration; check against LAPACK on a slowly decaying spectrum"""
+    torch = torch_mod
+    from romhighcontrast_b200.pod import top_eigenpairs
+    eng = make_engine((2, 2), 4)
+    rng = np.random.default_rng(0)
+    r = min(K, D)
+    Uo = np.linalg.qr(rng.standard_normal((K, r)))[0]
+    Vo = np.linalg.qr(rng.standard_normal((D, r)))[0]
+    sv = decay ** np.arange(r) * 10.0
+    X = (Uo * sv) @ Vo.T
+    Xd = torch.as_tensor(X, device="cuda")
+    G = eng.gemm_nt(Xd, Xd, symmetric=True)
+    lam, V = top_eigenpairs(eng, G, n)
+    np.testing.assert_allclose(np.sqrt(lam.cpu().numpy()), sv[:n], rtol=1e-9)
+    Vn = V.cpu().numpy()
+    for i in range(n):
+        assert abs(abs(Vn[:, i] @ Uo[:, i]) - 1.0) < 1e-7, i
