@@ -152,6 +152,9 @@ def main():
     ap.add_argument("--nu", type=int, default=None, help="Gauss-Seidel sweeps of the V(nu,nu) cycle (tuning)")
     ap.add_argument("--nu-tail", type=int, default=None)
     ap.add_argument("--threads", type=int, default=None)
+    ap.add_argument("--tile", type=int, default=None, help="1: register-tiled multigrid kernels (default), 0: strip kernels")
+    ap.add_argument("--tile-ty", type=int, default=None)
+    ap.add_argument("--tile-prefetch", type=int, default=None)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -181,6 +184,12 @@ def main():
         eng.set_option("nu_tail", args.nu_tail)
     if args.threads:
         eng.set_option("threads", args.threads)
+    if args.tile is not None:
+        eng.set_option("tile", args.tile)
+    if args.tile_ty:
+        eng.set_option("tile_ty", args.tile_ty)
+    if args.tile_prefetch is not None:
+        eng.set_option("tile_prefetch", args.tile_prefetch)
     K = args.k_snap
     y_host = sample_params(K, seed=42 + rank)                   # this rank's shard of the training set
     y = eng.params(y_host)

@@ -1,0 +1,585 @@
+// Register-tiled multigrid strip kernels (the V-cycle's level-0/1 smoothers, restriction and prolongation).
+//
+// Same algorithm as k_mg_down / k_mg_up in solver.cu (red/black Gauss-Seidel V(nu,nu), P1 anti-diagonal transfers;
+// preconditioner of the batched PCG that replaces galerkin(), /root/reference/src/lib/SolutionsManagers.py:17-40),
+// different execution model: the shared-memory strip kernels spend ~120 instructions and ~15 shared-memory accesses
+// per grid point (ncu, profiles/), which caps them at ~45 % of the HBM roofline.  Here every thread owns a 4 x 4
+// tile of the strip in REGISTERS for the whole kernel (z and r: 32 doubles), loads it straight from global memory
+// with 128-bit coalesced loads, and only the tile's perimeter travels through shared memory between the red and the
+// black half sweeps.  The exchange buffers are laid out edge-by-edge (left/right columns: [row][column group],
+// top/bottom rows: [row group][j][column group]) so that every warp access is dense -- no bank conflicts and
+// ~1.7 shared-memory accesses per point update instead of ~5.5.
+//
+// Stencil weights come from a per-system table (k_weight_table): the P1 stiffness weights do not depend on the mesh
+// width, so one table of (2 nrb - 1) x (2 ncb - 1) vertex classes ("inside block b" / "on the interface b-1 | b" per
+// direction) serves every level; each CTA stages its system's table in shared memory with one TMA bulk copy.
+// Rows that are not interface rows use w_N = w_S = diag / 4 exactly, so a thread keeps only {w_W, w_E, 1/diag} / diag
+// of its four columns in registers; interface rows (one in N) take a general path that reads all weights from the table.
+#include "common.cuh"
+#include "romhc_internal.h"
+
+#include <algorithm>
+#include <vector>
+
+namespace romhc {
+
+#define TWD 8              // doubles per weight-table entry: {wW, wE, wN, wS} / diag, 1 / diag, diag, 0, 0
+#define TILE_MAXT 512      // largest CTA of the tile kernels: 4 warps per SM sub-partition -> 128 registers per thread
+
+// ---- per-system weight table ----------------------------------------------------------------------------------------
+// entry (rv, cv): rv even -> vertex row inside block row rv / 2, rv odd -> on the interface between block rows
+// (rv - 1) / 2 and (rv + 1) / 2; same for cv.  Entry nrv * ncv is all zeros (boundary / padding columns).
+__global__ void k_weight_table(const double* __restrict__ y, double* __restrict__ tab, int nrb, int ncb, int64_t K) {
+    const int64_t k = blockIdx.x;
+    if (k >= K) return;
+    const int nrv = 2 * nrb - 1, ncv = 2 * ncb - 1, ne = nrv * ncv;
+    const double* a = y + k * int64_t(nrb) * ncb;
+    for (int e = threadIdx.x; e <= ne; e += blockDim.x) {
+        double* o = tab + (k * int64_t(ne + 1) + e) * TWD;
+        if (e == ne) {
+            for (int i = 0; i < TWD; ++i) o[i] = 0.0;
+            continue;
+        }
+        const int rv = e / ncv, cv = e - rv * ncv;
+        const int bd = (rv + 1) >> 1, bu = bd - (rv & 1);
+        const int br = (cv + 1) >> 1, bl = br - (cv & 1);
+        const double aul = a[bu * ncb + bl], aur = a[bu * ncb + br];
+        const double adl = a[bd * ncb + bl], adr = a[bd * ncb + br];
+        const double dg = (aul + aur) + (adl + adr);
+        const double idg = 1.0 / dg;
+        o[0] = 0.5 * (aul + adl) * idg;
+        o[1] = 0.5 * (aur + adr) * idg;
+        o[2] = 0.5 * (aul + aur) * idg;
+        o[3] = 0.5 * (adl + adr) * idg;
+        o[4] = idg;
+        o[5] = dg;
+        o[6] = 0.0;
+        o[7] = 0.0;
+    }
+}
+
+struct TileArgs {
+    LevelGeo g, gc;
+    const int* rowv;      // vertex class of row rho (valid for rho in [-ROWV_PAD, R + ROWV_PAD]); -1 = not an interior row
+    const int* colv;      // vertex class of column c in [0, P); -1 = boundary / padding
+    const double* tab;    // weight tables, ntab entries per system
+    int ntab, ncv;
+    int TY, ns, nu, has_coarse;
+    int NR, halo_top;     // rows of the CTA's region, rows above the owned strip
+    int pf_dist;          // L2 prefetch distance in CTAs (= CTAs resident on the GPU at once); 0: off
+};
+
+// shared memory (doubles): [T: ntab * TWD][red: 32][mbarrier: 2][EL: NR * (CG + 2)][ER: same][ET: (NRG + 2) * 4 * CG][EB: same]
+static size_t tile_smem_bytes(int ntab, int NR, int CG) {
+    const int NRG = NR / 4;
+    return (size_t(ntab) * TWD + 34 + size_t(2) * NR * (CG + 2) + size_t(2) * (NRG + 2) * 4 * CG) * 8;
+}
+
+// 32-bit shared-window accesses: every address is one register plus a compile-time displacement
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ double2 lds_f64x2(uint32_t a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+
+// Per-thread state.  CGT > 0: column groups per CTA known at compile time (P = 4 CGT), all displacements are immediates.
+template <int CGT>
+struct TileThread {
+    uint32_t xl, xr;      // own slots of row 0 of the tile in EL / ER   ([4 ty][tx + 1])
+    uint32_t et, eb;      // own slots of column 0 of the tile in ET / EB ([(ty + 1) * 4][tx])
+    uint32_t T;           // weight table
+    int rt;               // 2 bits per tile row: 0 not an interior row, 1 fast (class == the tile's primary class), 2 general
+    int cg;               // column groups (runtime copy)
+    int rho0;
+    __device__ __forceinline__ int CG() const { return CGT > 0 ? CGT : cg; }
+    __device__ __forceinline__ int CGp() const { return CG() + 2; }
+};
+
+// weights of the thread's four columns on the rows of the tile's primary class (w_N = w_S = 1/4 there)
+template <bool NEED_DG>
+struct ColWeights {
+    double hW[4], hE[4], idg[4], dg[NEED_DG ? 4 : 1];
+};
+
+template <int CGT>
+__device__ __forceinline__ uint32_t tile_entry(const TileThread<CGT>& t, const TileArgs& a, int I, int j) {
+    const int rv = __ldg(a.rowv + t.rho0 + I);
+    const int cv = __ldg(a.colv + 4 * int(threadIdx.x) + j);
+    const int e = cv >= 0 ? rv * a.ncv + cv : a.ntab - 1;
+    return t.T + uint32_t(e) * (TWD * 8);
+}
+
+// mbarrier + TMA bulk copy of the system's weight table, shared-memory carve-up, zeroed rim of the exchange buffers,
+// row classification, primary-class weights
+template <int CGT, bool NEED_DG>
+__device__ __forceinline__ void tile_setup_thread(TileThread<CGT>& t, ColWeights<NEED_DG>& w, const TileArgs& a,
+                                                  unsigned char* smem_raw, int64_t k, int rho0, uint32_t& red_addr) {
+    const int CG = CGT > 0 ? CGT : int(blockDim.x), NRG = blockDim.y;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const uint32_t base = smem_u32(smem_raw);
+    const uint32_t red = base + uint32_t(a.ntab) * (TWD * 8);
+    const uint32_t bar = red + 32 * 8;
+    const uint32_t EL = red + 34 * 8;
+    const uint32_t ER = EL + uint32_t(a.NR) * (CG + 2) * 8;
+    const uint32_t ET = ER + uint32_t(a.NR) * (CG + 2) * 8;
+    const uint32_t EB = ET + uint32_t(NRG + 2) * 4 * CG * 8;
+    red_addr = red;
+    t.cg = CG; t.T = base; t.rho0 = rho0;
+    if (tx == 0 && ty == 0) {
+        uint64_t* b = reinterpret_cast<uint64_t*>(smem_raw + (bar - base));
+        mbar_init(b, 1);
+        mbar_fence_init();
+        const uint32_t bytes = uint32_t(a.ntab) * TWD * 8u;
+        mbar_expect_tx(b, bytes);
+        bulk_g2s(smem_raw, a.tab + k * int64_t(a.ntab) * TWD, bytes, b);
+    }
+    t.xl = EL + uint32_t((4 * ty) * (CG + 2) + tx + 1) * 8;
+    t.xr = ER + uint32_t((4 * ty) * (CG + 2) + tx + 1) * 8;
+    t.et = ET + uint32_t((ty + 1) * 4 * CG + tx) * 8;
+    t.eb = EB + uint32_t((ty + 1) * 4 * CG + tx) * 8;
+    const int CGp = CG + 2;
+    if (tx == 0) {
+#pragma unroll
+        for (int I = 0; I < 4; ++I) sts_f64(t.xr + (I * CGp - 1) * 8, 0.0);      // left of column group 0
+    }
+    if (tx == CG - 1) {
+#pragma unroll
+        for (int I = 0; I < 4; ++I) sts_f64(t.xl + (I * CGp + 1) * 8, 0.0);      // column P aliases (row + 1, 0) == 0
+    }
+    if (ty == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sts_f64(t.eb + (j - 4) * CG * 8, 0.0);       // above the region
+    }
+    if (ty == NRG - 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sts_f64(t.et + (j + 4) * CG * 8, 0.0);       // below the region
+    }
+    // row classes: the first non-interface interior row defines the primary class
+    int rv[4], prim = -1;
+#pragma unroll
+    for (int I = 0; I < 4; ++I) {
+        rv[I] = __ldg(a.rowv + rho0 + I);
+        if (prim < 0 && rv[I] >= 0 && !(rv[I] & 1)) prim = rv[I];
+    }
+    t.rt = 0;
+#pragma unroll
+    for (int I = 0; I < 4; ++I) t.rt |= (rv[I] < 0 ? 0 : (rv[I] == prim ? 1 : 2)) << (2 * I);
+    // the mbarrier must be initialised before anybody polls it; then wait for the table and fetch the
+    // primary-class weights of the four columns
+    __syncthreads();
+    {
+        uint64_t* b = reinterpret_cast<uint64_t*>(smem_raw + (bar - base));
+        mbar_wait(b, 0);
+    }
+    const int4 cv = __ldg(reinterpret_cast<const int4*>(a.colv) + tx);
+    const int cvs[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int e = (cvs[j] >= 0 && prim >= 0) ? prim * a.ncv + cvs[j] : a.ntab - 1;
+        const uint32_t p = t.T + uint32_t(e) * (TWD * 8);
+        const double2 u = lds_f64x2(p), v = lds_f64x2(p + 32);
+        w.hW[j] = u.x; w.hE[j] = u.y; w.idg[j] = v.x;
+        if (NEED_DG) w.dg[j] = v.y;
+    }
+}
+
+// publish the perimeter values of colour X (0 red: (row + col) even, 1 black) of the tile
+template <int X, int CGT>
+__device__ __forceinline__ void tile_publish(const double (&z)[4][4], const TileThread<CGT>& t) {
+    const int CG = t.CG(), CGp = t.CGp();
+#pragma unroll
+    for (int I = 0; I < 4; ++I) {
+        if (((I + X) & 1) == 0) sts_f64(t.xl + I * CGp * 8, z[I][0]);
+        else                    sts_f64(t.xr + I * CGp * 8, z[I][3]);
+    }
+    sts_f64(t.et + (X) * CG * 8, z[0][X]);
+    sts_f64(t.et + (X + 2) * CG * 8, z[0][X + 2]);
+    sts_f64(t.eb + (1 - X) * CG * 8, z[3][1 - X]);
+    sts_f64(t.eb + (3 - X) * CG * 8, z[3][3 - X]);
+}
+
+// One half sweep over the tile's points of colour X.  Rows in the halo are relaxed like all others: what they
+// produce beyond the validity cone (one row per half sweep) is never used.
+// MODE 0: Gauss-Seidel update z = (r + sum_nb w z_nb) / diag
+// MODE 1: residual d = r - diag z + sum_nb w z_nb, stored in place of z
+// MODE 2: first half sweep from a zero initial guess, z = r / diag (no neighbours)
+template <int X, int MODE, bool NEED_DG, int CGT>
+__device__ __forceinline__ void tile_phase(double (&z)[4][4], const double (&r)[4][4], const ColWeights<NEED_DG>& w,
+                                           const TileThread<CGT>& t, const TileArgs& a) {
+    const int CG = t.CG(), CGp = t.CGp();
+#pragma unroll
+    for (int I = 0; I < 4; ++I) {
+        const int jX = (I + X) & 1;
+        const int rtype = (t.rt >> (2 * I)) & 3;
+        if (rtype == 0) continue;
+        double zWh = 0.0, zEh = 0.0, zN[2] = {0.0, 0.0}, zS[2] = {0.0, 0.0};
+        if (MODE != 2) {
+            if (jX == 0) zWh = lds_f64(t.xr + (I * CGp - 1) * 8);
+            else         zEh = lds_f64(t.xl + (I * CGp + 1) * 8);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int j = jX + 2 * q;
+                zN[q] = (I > 0) ? z[I > 0 ? I - 1 : 0][j] : lds_f64(t.eb + (j - 4) * CG * 8);
+                zS[q] = (I < 3) ? z[I < 3 ? I + 1 : 3][j] : lds_f64(t.et + (j + 4) * CG * 8);
+            }
+        }
+        if (rtype == 1) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int j = jX + 2 * q;
+                if (MODE == 2) { z[I][j] = r[I][j] * w.idg[j]; continue; }
+                const double zW = (j > 0) ? z[I][j > 0 ? j - 1 : 0] : zWh;
+                const double zE = (j < 3) ? z[I][j < 3 ? j + 1 : 3] : zEh;
+                const double upd = fma(r[I][j], w.idg[j], fma(0.25, zN[q] + zS[q], fma(w.hW[j], zW, w.hE[j] * zE)));
+                z[I][j] = (MODE == 1) ? w.dg[NEED_DG ? j : 0] * (upd - z[I][j]) : upd;
+            }
+        } else {
+            // interface row (or a second block row inside the tile): all weights of every point from the table
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int j = jX + 2 * q;
+                const uint32_t p = tile_entry(t, a, I, j);
+                const double2 wv = lds_f64x2(p + 32);      // 1 / diag, diag
+                if (MODE == 2) { z[I][j] = r[I][j] * wv.x; continue; }
+                const double2 we = lds_f64x2(p), ns = lds_f64x2(p + 16);
+                const double zW = (j > 0) ? z[I][j > 0 ? j - 1 : 0] : zWh;
+                const double zE = (j < 3) ? z[I][j < 3 ? j + 1 : 3] : zEh;
+                const double upd = fma(r[I][j], wv.x, (we.x * zW + we.y * zE) + (ns.x * zN[q] + ns.y * zS[q]));
+                z[I][j] = (MODE == 1) ? wv.y * (upd - z[I][j]) : upd;
+            }
+        }
+    }
+}
+
+// One CTA per SM cannot overlap its own loads with its own arithmetic, so every CTA asks the L2 (cp.async.bulk.prefetch.L2,
+// fire and forget) for the operand rows of the CTA that will run on this SM slot next: CTA ids are scheduled in
+// linear order, the one `pf_dist` ahead starts when this one retires.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tile_prefetch_rows(const double* base, const LevelGeo& g, int64_t k, int row_lo, int nrow) {
+    const int lo = max(row_lo, 0), hi = min(row_lo + nrow, g.R + 1);
+    if (hi > lo) bulk_prefetch_l2(base + k * g.Dp + size_t(lo) * g.P, uint32_t(hi - lo) * uint32_t(g.P) * 8u);
+}
+
+__device__ __forceinline__ void tile_load_row(double (&v)[4], const double* row) {
+    const double2 a = *reinterpret_cast<const double2*>(row);
+    const double2 b = *reinterpret_cast<const double2*>(row + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void tile_store_row(double* row, const double (&v)[4]) {
+    *reinterpret_cast<double2*>(row) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2*>(row + 2) = make_double2(v[2], v[3]);
+}
+
+// ---- going down: z = nu RB-GS sweeps from 0; r_coarse = P^T (r - A z) ----------------------------------------------------
+template <int CGT>
+__global__ void __launch_bounds__(TILE_MAXT, 1)
+k_mgt_down(TileArgs a, const double* __restrict__ r_in, double* __restrict__ z_out, double* __restrict__ rc_out,
+           const int* __restrict__ active) {
+    const int64_t k = blockIdx.y;
+    if (!active[k]) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int P = CGT > 0 ? 4 * CGT : a.g.P;
+    const int R = a.g.R;
+    const int y0 = blockIdx.x * a.TY;
+    if (threadIdx.x == 0 && threadIdx.y == 1 && a.pf_dist > 0) {
+        const int64_t n = k * gridDim.x + blockIdx.x + a.pf_dist;
+        const int64_t kn = n / gridDim.x;
+        if (kn < gridDim.y && active[kn])
+            tile_prefetch_rows(r_in, a.g, kn, int(n - kn * gridDim.x) * a.TY - a.halo_top, a.NR);
+    }
+    const int rho0 = y0 - a.halo_top + 4 * int(threadIdx.y), c0 = 4 * int(threadIdx.x);
+    double z[4][4], r[4][4];
+    const double* rp = r_in + k * a.g.Dp + int64_t(rho0) * P + c0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { z[i][j] = 0.0; r[i][j] = 0.0; }
+        if (unsigned(rho0 + i) <= unsigned(R)) tile_load_row(r[i], rp + i * P);
+    }
+    TileThread<CGT> t;
+    ColWeights<true> w;
+    uint32_t red;
+    tile_setup_thread(t, w, a, smem_raw, k, rho0, red);
+    const int nu = a.nu;
+    tile_phase<0, 2, true>(z, r, w, t, a);
+    tile_publish<0>(z, t);
+    __syncthreads();
+    tile_phase<1, 0, true>(z, r, w, t, a);
+    tile_publish<1>(z, t);
+    __syncthreads();
+    for (int sw = 1; sw < nu; ++sw) {
+        tile_phase<0, 0, true>(z, r, w, t, a);
+        tile_publish<0>(z, t);
+        __syncthreads();
+        tile_phase<1, 0, true>(z, r, w, t, a);
+        tile_publish<1>(z, t);
+        __syncthreads();
+    }
+    double* zo = z_out + k * a.g.Dp + int64_t(rho0) * P + c0;
+    const int own_lo = y0 - rho0, own_hi = min(y0 + a.TY, R + 1) - rho0;     // owned tile rows: own_lo <= i < own_hi
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (i >= own_lo && i < own_hi) tile_store_row(zo + i * P, z[i]);
+    if (!a.has_coarse) return;
+    // residual on the red points (it vanishes on the just-relaxed black points), in place of z
+    tile_phase<0, 1, true>(z, r, w, t, a);
+    tile_publish<0>(z, t);
+    __syncthreads();
+    // r_c(I, J) = d(2I, 2J) + (d(2I-1, 2J+1) + d(2I+1, 2J-1)) / 2: tile-local (0,0), (0,2), (2,0), (2,2)
+    const LevelGeo& gc = a.gc;
+    const int CG = t.CG(), CGp = t.CGp();
+    const double dN31 = lds_f64(t.eb + (1 - 4) * CG * 8), dN33 = lds_f64(t.eb + (3 - 4) * CG * 8);
+    const double dW13 = lds_f64(t.xr + (1 * CGp - 1) * 8), dW33 = lds_f64(t.xr + (3 * CGp - 1) * 8);
+    double rc[2][2];
+    rc[0][0] = z[0][0] + 0.5 * (dN31 + dW13);
+    rc[0][1] = z[0][2] + 0.5 * (dN33 + z[1][1]);
+    rc[1][0] = z[2][0] + 0.5 * (z[1][1] + dW33);
+    rc[1][1] = z[2][2] + 0.5 * (z[1][3] + z[3][1]);
+    const int J0 = 2 * int(threadIdx.x);
+    const bool okJ0 = J0 >= 1 && J0 <= gc.C - 1, okJ1 = J0 + 1 <= gc.C - 1;
+    double* co = rc_out + k * gc.Dp + J0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int rho = rho0 + 2 * q;
+        const int I = rho >> 1;
+        if (rho >= y0 && rho < y0 + a.TY && I <= gc.R) {
+            const bool okI = I >= 1 && I <= gc.R - 1;
+            *reinterpret_cast<double2*>(co + size_t(I) * gc.P) =
+                make_double2(okI && okJ0 ? rc[q][0] : 0.0, okI && okJ1 ? rc[q][1] : 0.0);
+        }
+    }
+}
+
+// ---- going up: z += P e, nu BR-GS sweeps; optional r.z partials ----------------------------------------------------------
+template <int CGT>
+__global__ void __launch_bounds__(TILE_MAXT, 1)
+k_mgt_up(TileArgs a, const double* __restrict__ e_c, const double* __restrict__ z_in, const double* __restrict__ r_in,
+         double* __restrict__ z_out, const int* __restrict__ active, double* __restrict__ part_rz) {
+    const int64_t k = blockIdx.y;
+    if (!active[k]) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int P = CGT > 0 ? 4 * CGT : a.g.P;
+    const int R = a.g.R;
+    const int y0 = blockIdx.x * a.TY;
+    if (threadIdx.x == 0 && threadIdx.y == 1 && a.pf_dist > 0) {
+        const int64_t n = k * gridDim.x + blockIdx.x + a.pf_dist;
+        const int64_t kn = n / gridDim.x;
+        if (kn < gridDim.y && active[kn]) {
+            const int yn = int(n - kn * gridDim.x) * a.TY - a.halo_top;
+            tile_prefetch_rows(z_in, a.g, kn, yn, a.NR);
+            tile_prefetch_rows(r_in, a.g, kn, yn + 1, a.NR - 2);
+            if (a.has_coarse) tile_prefetch_rows(e_c, a.gc, kn, yn >> 1, a.NR / 2 + 1);
+        }
+    }
+    const int rho0 = y0 - a.halo_top + 4 * int(threadIdx.y), c0 = 4 * int(threadIdx.x);
+    double z[4][4], r[4][4];
+    const double* zp = z_in + k * a.g.Dp + int64_t(rho0) * P + c0;
+    const double* rp = r_in + k * a.g.Dp + int64_t(rho0) * P + c0;
+    const int NR = a.NR;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int lr = 4 * int(threadIdx.y) + i;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { z[i][j] = 0.0; r[i][j] = 0.0; }
+        if (unsigned(rho0 + i) <= unsigned(R)) {
+            tile_load_row(z[i], zp + i * P);
+            if (lr >= 1 && lr <= NR - 2) tile_load_row(r[i], rp + i * P);     // the outermost rows are never valid
+        }
+    }
+    double e[3][3];
+    if (a.has_coarse) {
+        const LevelGeo& gc = a.gc;
+        const int I0 = rho0 >> 1, J0 = 2 * int(threadIdx.x);
+        const double* es = e_c + k * gc.Dp + int64_t(I0) * gc.P + J0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            e[q][0] = e[q][1] = e[q][2] = 0.0;
+            if (unsigned(I0 + q) <= unsigned(gc.R)) {
+                const double2 v = *reinterpret_cast<const double2*>(es + q * gc.P);
+                e[q][0] = v.x; e[q][1] = v.y;
+                if (J0 + 2 < gc.P) e[q][2] = es[q * gc.P + 2];
+            }
+        }
+    }
+    TileThread<CGT> t;
+    ColWeights<false> w;
+    uint32_t red;
+    tile_setup_thread(t, w, a, smem_raw, k, rho0, red);
+    if (a.has_coarse) {
+        // prolongation on the red points: (even, even) copies the coarse vertex, (odd, odd) is the midpoint of the
+        // coarse cell's anti-diagonal (I, J+1)-(I+1, J).  Black values are overwritten by the first half sweep.
+        z[0][0] += e[0][0]; z[0][2] += e[0][1];
+        z[2][0] += e[1][0]; z[2][2] += e[1][1];
+        z[1][1] += 0.5 * (e[0][1] + e[1][0]); z[1][3] += 0.5 * (e[0][2] + e[1][1]);
+        z[3][1] += 0.5 * (e[1][1] + e[2][0]); z[3][3] += 0.5 * (e[1][2] + e[2][1]);
+    }
+    tile_publish<0>(z, t);
+    __syncthreads();
+    const int nu = a.nu;
+    for (int sw = 0; sw < nu; ++sw) {
+        tile_phase<1, 0, false>(z, r, w, t, a);
+        tile_publish<1>(z, t);
+        __syncthreads();
+        tile_phase<0, 0, false>(z, r, w, t, a);
+        if (sw + 1 < nu) {
+            tile_publish<0>(z, t);
+            __syncthreads();
+        }
+    }
+    double* zo = z_out + k * a.g.Dp + int64_t(rho0) * P + c0;
+    const int own_lo = y0 - rho0, own_hi = min(y0 + a.TY, R + 1) - rho0;
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (i >= own_lo && i < own_hi) {
+            tile_store_row(zo + i * P, z[i]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc = fma(r[i][j], z[i][j], acc);
+        }
+    }
+    if (part_rz) {
+        const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+        double* redp = reinterpret_cast<double*>(smem_raw + (red - smem_u32(smem_raw)));
+        const double tot = block_sum(acc, redp, tid, nt);
+        if (tid == 0) part_rz[k * a.ns + blockIdx.x] = tot;
+    }
+}
+
+// ======================================================================================================
+// host side
+// ======================================================================================================
+int Context::tile_setup() {
+    if (tile_ready) return ROMHC_OK;
+    tile_maxt_down = tile_maxt_up = TILE_MAXT;
+    const void* fns[] = {(const void*)k_mgt_down<64>, (const void*)k_mgt_down<32>, (const void*)k_mgt_down<0>,
+                         (const void*)k_mgt_up<64>,   (const void*)k_mgt_up<32>,   (const void*)k_mgt_up<0>};
+    for (int i = 0; i < 6; ++i) {
+        CK(cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        cudaFuncAttributes fa;
+        CK(cudaFuncGetAttributes(&fa, fns[i]));
+        int& m = i < 3 ? tile_maxt_down : tile_maxt_up;
+        m = std::min(m, fa.maxThreadsPerBlock);
+    }
+    // vertex-class tables of every level
+    for (int* p : tile_rowv) cudaFree(p);
+    for (int* p : tile_colv) cudaFree(p);
+    tile_rowv.clear(); tile_colv.clear();
+    auto vclass = [](int v, int n, int nblk) {
+        if (v < 1 || v > nblk * n - 1) return -1;
+        return (v % n) ? 2 * (v / n) : 2 * (v / n) - 1;
+    };
+    for (const LevelGeo& g : levels) {
+        std::vector<int> rv(g.R + 1 + 2 * ROMHC_ROWV_PAD), cv(g.P);
+        for (int i = 0; i < (int)rv.size(); ++i) rv[i] = vclass(i - ROMHC_ROWV_PAD, g.N, g.nrb);
+        for (int c = 0; c < g.P; ++c) cv[c] = vclass(c, g.N, g.ncb);
+        int *dr = nullptr, *dc = nullptr;
+        CK(cudaMalloc(&dr, rv.size() * sizeof(int)));
+        CK(cudaMalloc(&dc, cv.size() * sizeof(int)));
+        CK(cudaMemcpy(dr, rv.data(), rv.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dc, cv.data(), cv.size() * sizeof(int), cudaMemcpyHostToDevice));
+        tile_rowv.push_back(dr); tile_colv.push_back(dc);
+    }
+    tile_ready = true;
+    return ROMHC_OK;
+}
+
+// CTAs of `func` resident on the whole GPU (the distance, in CTA ids, to the CTA that takes this one's slot next)
+int Context::tile_pf_dist(const void* func, int threads, size_t smem) {
+    if (!tile_prefetch) return 0;
+    int per_sm = 1, nsm = 148;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, threads, smem) != cudaSuccess) per_sm = 1;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+    return std::max(1, per_sm) * nsm;
+}
+
+int Context::tile_ntab() const { return (2 * nrb - 1) * (2 * ncb - 1) + 1; }
+
+int Context::tile_weight_table(const double* y, int Kc, cudaStream_t st) {
+    ++g_launches; k_weight_table<<<Kc, 64, 0, st>>>(y, ws.wtab, nrb, ncb, Kc);
+    CK(cudaGetLastError());
+    return ROMHC_OK;
+}
+
+// can the tile kernels run level l?  (column groups per CTA, register budget, shared memory)
+bool Context::tile_level_ok(int l) const {
+    if (!use_tile) return false;
+    const LevelGeo& g = levels[l];
+    const int CG = g.P / 4;
+    const int maxt = std::min(tile_maxt_down, tile_maxt_up);
+    const int nrg_min = (2 + 4 * nu + 2 + 3) / 4;      // TY = 2 in the down kernel
+    if (CG * nrg_min > maxt || CG > 128) return false;
+    return true;
+}
+
+// strip height (even) and region rows (a multiple of 4, the tile height): the tallest region whose CTA fits the
+// thread budget, capped by tile_ty_cap and by the grid height
+static void tile_pick_ty(const LevelGeo& g, int extra_rows, int maxt, int cap, int* TY_out, int* NR_out) {
+    const int CG = g.P / 4;
+    const int nrg = std::max(1, std::min(maxt / CG, 16));
+    int TY = 4 * nrg - extra_rows;
+    TY = std::min(TY, cap);
+    TY = std::max(TY & ~1, 2);
+    const int ns = (g.R + TY - 1) / TY;                  // strips needed at the tallest height ...
+    TY = std::min(TY, (((g.R + ns - 1) / ns) + 1) & ~1);  // ... then balance the rows over them
+    *TY_out = TY;
+    *NR_out = ((TY + extra_rows + 3) / 4) * 4;
+}
+
+int Context::tile_down(int l, const double* y, int Kc, cudaStream_t st) {
+    (void)y;
+    const int L = int(levels.size()) - 1;
+    TileArgs a;
+    a.g = levels[l];
+    a.has_coarse = l < L ? 1 : 0;
+    a.gc = a.has_coarse ? levels[l + 1] : levels[l];
+    a.rowv = tile_rowv[l] + ROMHC_ROWV_PAD; a.colv = tile_colv[l];
+    a.tab = ws.wtab; a.ntab = tile_ntab(); a.ncv = 2 * ncb - 1;
+    a.nu = nu;
+    a.halo_top = 2 * nu + 2;
+    tile_pick_ty(a.g, 4 * nu + 2, tile_maxt_down, tile_ty_cap, &a.TY, &a.NR);
+    a.ns = (a.g.R + a.TY - 1) / a.TY;
+    const int CG = a.g.P / 4;
+    const size_t sm = tile_smem_bytes(a.ntab, a.NR, CG);
+    if (sm > 227 * 1024) { set_error("tile kernels: shared memory"); return ROMHC_ERR_ARG; }
+    auto fn = CG == 64 ? k_mgt_down<64> : (CG == 32 ? k_mgt_down<32> : k_mgt_down<0>);
+    a.pf_dist = tile_pf_dist((const void*)fn, CG * (a.NR / 4), sm);
+    ++g_launches;
+    fn<<<dim3(a.ns, Kc), dim3(CG, a.NR / 4), sm, st>>>(a, ws.r[l], ws.za[l], a.has_coarse ? ws.r[l + 1] : nullptr, ws.active);
+    return ROMHC_OK;
+}
+
+int Context::tile_up(int l, const double* y, int Kc, const double* e, double* part_rz, int* ns_out, cudaStream_t st) {
+    (void)y;
+    const int L = int(levels.size()) - 1;
+    TileArgs a;
+    a.g = levels[l];
+    a.has_coarse = l < L ? 1 : 0;
+    a.gc = a.has_coarse ? levels[l + 1] : levels[l];
+    a.rowv = tile_rowv[l] + ROMHC_ROWV_PAD; a.colv = tile_colv[l];
+    a.tab = ws.wtab; a.ntab = tile_ntab(); a.ncv = 2 * ncb - 1;
+    a.nu = nu;
+    a.halo_top = 2 * nu;
+    tile_pick_ty(a.g, 4 * nu, tile_maxt_up, tile_ty_cap, &a.TY, &a.NR);
+    a.ns = (a.g.R + a.TY - 1) / a.TY;
+    const int CG = a.g.P / 4;
+    const size_t sm = tile_smem_bytes(a.ntab, a.NR, CG);
+    if (sm > 227 * 1024) { set_error("tile kernels: shared memory"); return ROMHC_ERR_ARG; }
+    auto fn = CG == 64 ? k_mgt_up<64> : (CG == 32 ? k_mgt_up<32> : k_mgt_up<0>);
+    a.pf_dist = tile_pf_dist((const void*)fn, CG * (a.NR / 4), sm);
+    ++g_launches;
+    fn<<<dim3(a.ns, Kc), dim3(CG, a.NR / 4), sm, st>>>(a, e, ws.za[l], ws.r[l], ws.zb[l], ws.active, part_rz);
+    *ns_out = a.ns;
+    return ROMHC_OK;
+}
+
+}  // namespace romhc

@@ -12,6 +12,7 @@
 #define ROMHC_ERR_CUDA 2
 #define ROMHC_ERR_NUMERIC 3   // singular / non-SPD system (reference: numpy.linalg.LinAlgError)
 #define ROMHC_ERR_NOTCONVERGED 4
+#define ROMHC_ROWV_PAD 64      // rows of padding on both sides of the tile kernels' row-class tables
 
 namespace romhc {
 
@@ -38,6 +39,7 @@ struct SolveWorkspace {
     std::vector<double*> r, za, zb;   // per level
     double* p[2];
     double* cfac;
+    double* wtab;                     // per-system stencil weight tables of the tile kernels (mgtile.cu)
     double *part_pAp, *part_rz;
     int np;
     double *alpha, *beta, *rz, *rz0, *relres;
@@ -78,6 +80,12 @@ struct Context {
     bool coarse_direct = false;
     int coarse_sweeps = 8;
     int nu = 1, nu_tail = 2;   // red/black Gauss-Seidel sweeps before and after the coarse correction: V(nu, nu)
+    bool use_tile = true;               // register-tiled multigrid kernels (mgtile.cu) where the level fits
+    int tile_ty_cap = 64;               // largest strip height of the tile kernels
+    bool tile_prefetch = true;          // L2 prefetch of the next CTA's operand rows
+    bool tile_ready = false;
+    int tile_maxt_down = 0, tile_maxt_up = 0;
+    std::vector<int*> tile_rowv, tile_colv;   // per level: vertex class of every row / column (device)
     int strip_threads = 512;            // threads per strip CTA (256 or 512)
     size_t strip_budget = 113 * 1024;   // shared memory per strip CTA (>= 2 CTAs per SM so TMA loads overlap compute)
     TailParams tail;
@@ -128,6 +136,15 @@ struct Context {
     int solve(const double* y, int64_t K, double* x, int* iters_out, double* relres_out, cudaStream_t st,
               SolveStats* stats);
     int precond(const double* y, const double* r, double* z, int64_t K, cudaStream_t st);
+
+    // mgtile.cu
+    int tile_setup();
+    int tile_ntab() const;
+    int tile_pf_dist(const void* func, int threads, size_t smem);
+    bool tile_level_ok(int l) const;
+    int tile_weight_table(const double* y, int Kc, cudaStream_t st);
+    int tile_down(int l, const double* y, int Kc, cudaStream_t st);
+    int tile_up(int l, const double* y, int Kc, const double* e, double* part_rz, int* ns_out, cudaStream_t st);
 
     // reduced.cu
     int project_operators(const double* basis, int n, double* Ahat, double* bhat, cudaStream_t st);

@@ -934,6 +934,7 @@ int Context::configure_kernels() {
     CK(cudaFuncSetAttribute(k_mg_up, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
     CK(cudaFuncSetAttribute(k_mg_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
     CK(cudaFuncSetAttribute(k_coarse_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    { int rc = tile_setup(); if (rc) return rc; }
     kernels_configured = true;
     return ROMHC_OK;
 }
@@ -996,6 +997,7 @@ size_t Context::solve_bytes_per_system() const {
     d += size_t(levels[0].Dp) * 5;                           // r, p0, p1, zA, zB  (x is the caller's output)
     for (int l = 1; l <= L && l <= tail_level; ++l) d += size_t(levels[l].Dp) * 3;   // r_l, zA_l, zB_l
     if (coarse_direct) d += size_t(coarse_D) * coarse_LD;
+    d += size_t(tile_ntab()) * 8;
     d += 64 + 4 * size_t((levels[0].R + 1) / 2);              // scalars + partials (upper bound)
     return d * 8;
 }
@@ -1027,6 +1029,7 @@ int Context::ensure_solve_ws(int64_t Kc) {
     }
     const size_t o_p0 = take(size_t(Kc) * levels[0].Dp), o_p1 = take(size_t(Kc) * levels[0].Dp);
     const size_t o_fac = coarse_direct ? take(size_t(Kc) * coarse_D * coarse_LD) : 0;
+    const size_t o_tab = take(size_t(Kc) * tile_ntab() * 8);
     const int np = std::max(1, (levels[0].R + 1) / 2 + 1);
     const size_t o_pp = take(size_t(Kc) * np), o_pr = take(size_t(Kc) * np);
     const size_t o_sc = take(size_t(Kc) * 6);
@@ -1038,6 +1041,7 @@ int Context::ensure_solve_ws(int64_t Kc) {
     for (int l = 0; l <= top; ++l) { ws.r[l] = b + o_r[l]; ws.za[l] = b + o_za[l]; ws.zb[l] = b + o_zb[l]; }
     ws.p[0] = b + o_p0; ws.p[1] = b + o_p1;
     ws.cfac = coarse_direct ? b + o_fac : nullptr;
+    ws.wtab = b + o_tab;
     ws.part_pAp = b + o_pp; ws.part_rz = b + o_pr; ws.np = np;
     ws.alpha = b + o_sc; ws.beta = ws.alpha + Kc; ws.rz = ws.beta + Kc; ws.rz0 = ws.rz + Kc; ws.relres = ws.rz0 + Kc;
     ws.active = (int*)(b + o_int); ws.iters = ws.active + Kc;
@@ -1060,6 +1064,12 @@ int Context::vcycle(const double* y, int Kc, cudaStream_t st, const double** z_r
         const LevelGeo& g = levels[l];
         const bool has_c = l < L;
         const LevelGeo& gc = has_c ? levels[l + 1] : g;
+        if (tile_level_ok(l)) {
+            prof_begin(PROF_DOWN0 + std::min(l, 1), st);
+            int rc = tile_down(l, y, Kc, st); if (rc) return rc;
+            prof_end(st);
+            continue;
+        }
         dim3 block; strip_block(g, block, strip_threads);
         const int halo = has_c ? 4 * nu + 1 : 4 * nu - 2;
         auto bytes = [&](int TY) { return hdr + size_t(2) * (TY + halo) * g.P * 8 + (has_c ? size_t(TY / 2) * gc.P * 8 : 0); };
@@ -1090,6 +1100,14 @@ int Context::vcycle(const double* y, int Kc, cudaStream_t st, const double** z_r
         const int ns = (g.R + TY - 1) / TY;
         // coarse correction comes from the level below: its post-smoothed zb, or za if that level is the tail's top
         const double* e = has_c ? ((l + 1 < nstrip_levels) ? ws.zb[l + 1] : ws.za[l + 1]) : nullptr;
+        if (tile_level_ok(l)) {
+            prof_begin(PROF_UP0 + std::min(l, 1), st);
+            int ns_t = 1;
+            int rc = tile_up(l, y, Kc, e, l == 0 ? ws.part_rz : nullptr, &ns_t, st); if (rc) return rc;
+            prof_end(st);
+            if (l == 0) *np_rz = ns_t;
+            continue;
+        }
         prof_begin(PROF_UP0 + std::min(l, 1), st);
         ++g_launches; k_mg_up<<<dim3(ns, Kc), block, bytes(TY), st>>>(g, gc, y, e, ws.za[l], ws.r[l], ws.zb[l], ws.active,
                                                         l == 0 ? ws.part_rz : nullptr, TY, ns, has_c ? 1 : 0, nu);
@@ -1127,6 +1145,7 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
         const size_t sm = smem_hdr_bytes(nb) + size_t(coarse_D) * coarse_LD * 8;
         ++g_launches; k_coarse_factor<<<Kc, 64, sm, st>>>(gl, y, ws.cfac, coarse_D, coarse_LD, ws_flags + 0);
     }
+    { int rc2 = tile_weight_table(y, Kc, st); if (rc2) return rc2; }
     const size_t hdr = smem_hdr_bytes(nb);
     auto bytes_p = [&](int TY) { return hdr + size_t(2) * (TY + 2) * g.P * 8; };
     auto bytes_u = [&](int TY) { return hdr + size_t(3 * TY + 2) * g.P * 8; };
@@ -1216,6 +1235,7 @@ int Context::precond(const double* y, const double* r, double* z, int64_t K, cud
         const size_t sm = smem_hdr_bytes(nrb * ncb) + size_t(coarse_D) * coarse_LD * 8;
         ++g_launches; k_coarse_factor<<<Kc, 64, sm, st>>>(gl, y, ws.cfac, coarse_D, coarse_LD, ws_flags + 0);
     }
+    rc = tile_weight_table(y, Kc, st); if (rc) return rc;
     const double* zr = nullptr; int np = 1;
     rc = vcycle(y, Kc, st, &zr, &np); if (rc) return rc;
     CK(cudaMemcpyAsync(z, zr, size_t(Kc) * g.Dp * 8, cudaMemcpyDeviceToDevice, st));

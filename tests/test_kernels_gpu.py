@@ -67,11 +67,14 @@ def test_pack_unpack_apply_norms(torch_mod, geo, N):
     np.testing.assert_allclose(en, ref, rtol=1e-12)
 
 
+@pytest.mark.parametrize("tile", [1, 0])
 @pytest.mark.parametrize("nu", [1, 2, 3])
 @pytest.mark.parametrize("geo,N", GEOS)
-def test_precond_matches_twin(torch_mod, geo, N, nu):
+def test_precond_matches_twin(torch_mod, geo, N, nu, tile):
+    """one V-cycle of both kernel families (tile=1: register-tiled mgtile.cu, tile=0: shared-memory strips)"""
     from gmg_twin import GMG
     eng = make_engine(geo, N)
+    eng.set_option("tile", tile)
     eng.set_option("nu", nu)
     eng.set_option("nu_tail", nu)
     K = 3
@@ -86,12 +89,14 @@ def test_precond_matches_twin(torch_mod, geo, N, nu):
 
 
 @pytest.mark.parametrize("geo,N", GEOS)
-@pytest.mark.parametrize("strip_kb", [100, 48, 227])
-def test_solve_matches_oracle(torch_mod, geo, N, strip_kb):
+@pytest.mark.parametrize("strip_kb,tile,tile_ty", [(100, 1, 32), (100, 1, 6), (100, 0, 32), (48, 0, 32), (227, 0, 32)])
+def test_solve_matches_oracle(torch_mod, geo, N, strip_kb, tile, tile_ty):
     from oracle import FEMOracle
     from gmg_twin import pcg
     eng = make_engine(geo, N)
     eng.set_option("strip_kb", strip_kb)
+    eng.set_option("tile", tile)
+    eng.set_option("tile_ty", tile_ty)
     o = FEMOracle(geo, N)
     K = 7
     y = rand_y(geo, K, seed=4)
