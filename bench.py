@@ -155,6 +155,7 @@ def main():
     ap.add_argument("--tile", type=int, default=None, help="1: register-tiled multigrid kernels (default), 0: strip kernels")
     ap.add_argument("--tile-ty", type=int, default=None)
     ap.add_argument("--tile-prefetch", type=int, default=None)
+    ap.add_argument("--tile-persistent", type=int, default=None)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -190,6 +191,8 @@ def main():
         eng.set_option("tile_ty", args.tile_ty)
     if args.tile_prefetch is not None:
         eng.set_option("tile_prefetch", args.tile_prefetch)
+    if args.tile_persistent is not None:
+        eng.set_option("tile_persistent", args.tile_persistent)
     K = args.k_snap
     y_host = sample_params(K, seed=42 + rank)                   # this rank's shard of the training set
     y = eng.params(y_host)

@@ -30,6 +30,8 @@ void Context::release() {
     for (int* p : tile_rowv) cudaFree(p);
     for (int* p : tile_colv) cudaFree(p);
     tile_rowv.clear(); tile_colv.clear(); tile_ready = false; kernels_configured = false;
+    for (auto& kv : tile_rinfo_cache) cudaFree(kv.second);
+    tile_rinfo_cache.clear();
     scratch = nullptr; ws_base = nullptr; ws_flags = nullptr; h_flags = nullptr;
     scratch_bytes = 0; ws_K = 0;
     free_host_stage();
@@ -133,6 +135,7 @@ int romhc_set_option(romhc_handle h, const char* name, double value) {
     else if (!strcmp(name, "nu")) { c->nu = std::max(1, std::min(4, (int)value)); }
     else if (!strcmp(name, "nu_tail")) { c->nu_tail = std::max(1, std::min(8, (int)value)); c->build_levels(); }
     else if (!strcmp(name, "tile")) c->use_tile = value != 0.0;
+    else if (!strcmp(name, "tile_persistent")) c->tile_persistent = value != 0.0;
     else if (!strcmp(name, "tile_prefetch")) c->tile_prefetch = value != 0.0;
     else if (!strcmp(name, "tile_ty")) c->tile_ty_cap = std::max(4, std::min(64, ((int)value) & ~3));
     else if (!strcmp(name, "threads")) c->strip_threads = ((int)value >= 512) ? 512 : 256;

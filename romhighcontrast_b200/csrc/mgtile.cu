@@ -19,6 +19,8 @@
 #include "romhc_internal.h"
 
 #include <algorithm>
+#include <array>
+#include <map>
 #include <vector>
 
 namespace romhc {
@@ -67,6 +69,7 @@ struct TileArgs {
     int TY, ns, nu, has_coarse;
     int NR, halo_top;     // rows of the CTA's region, rows above the owned strip
     int pf_dist;          // L2 prefetch distance in CTAs (= CTAs resident on the GPU at once); 0: off
+    const int* rinfo;     // persistent kernels: per (strip, row group) row types (2 bits per row) | primary class << 8
 };
 
 // shared memory (doubles): [T: ntab * TWD][red: 32][mbarrier: 2][EL: NR * (CG + 2)][ER: same][ET: (NRG + 2) * 4 * CG][EB: same]
@@ -455,6 +458,468 @@ k_mgt_up(TileArgs a, const double* __restrict__ e_c, const double* __restrict__ 
     }
 }
 
+// =====================================================================================================
+// Persistent, TMA-pipelined variants.  One CTA per SM walks over the work items (system, strip) round robin.  While
+// item i is relaxed in registers, the operand rows of item i+1 (z, r, the coarse correction, the weight table) are
+// already in flight: 1-D TMA bulk copies into a shared-memory staging area, signalled by one mbarrier.  At the top of
+// an item every thread moves its tile from the staging area into registers, a __syncthreads() frees the area and the
+// next item's copies are issued.  The register tile is what makes a single staging buffer enough.
+// Tiles whose four rows are interior rows of one vertex class (all but the boundary / interface tiles; the flag is
+// warp uniform) run straight-line code: eight independent updates per half sweep, no branches.
+// Staging layout (doubles): [T0][T1][red 32][mbarrier 2][EL][ER][ET][EB][Rs: NR rows][Zs: NR rows][Es: NR/2+1 coarse rows]
+// =====================================================================================================
+struct TileStage {
+    uint32_t T0, tb, red, bar, colv, rinfo, ex, Zs, Rs, Es;
+};
+// doubles reserved in front of the exchange buffers: two weight tables, 2 x 32 reduction slots, mbarrier, the
+// column-class table (P ints) and the row-info table (ns * NRG ints)
+static __host__ __device__ __forceinline__ uint32_t tile_stage_head(int ntab, int P, int nrinfo) {
+    return uint32_t(2 * ntab * TWD + 64 + 2 + (P + 1) / 2 + (nrinfo + 1) / 2 + 1) & ~1u;
+}
+__device__ __forceinline__ TileStage tile_stage_carve(uint32_t base, const TileArgs& a, int CG, int NRG, bool with_z) {
+    TileStage s;
+    s.tb = uint32_t(a.ntab) * (TWD * 8);
+    s.T0 = base;
+    s.red = base + 2 * s.tb;
+    s.bar = s.red + 64 * 8;
+    s.colv = s.bar + 16;
+    s.rinfo = s.colv + uint32_t((4 * CG + 1) / 2) * 8;
+    s.ex = base + tile_stage_head(a.ntab, 4 * CG, a.ns * NRG) * 8;
+    const uint32_t exb = (uint32_t(2) * a.NR * (CG + 2) + uint32_t(2) * (NRG + 2) * 4 * CG) * 8;
+    const uint32_t strip = uint32_t(a.NR) * (4 * CG) * 8;
+    s.Rs = s.ex + exb;
+    s.Zs = s.Rs + strip;
+    s.Es = s.Zs + (with_z ? strip : 0);
+    return s;
+}
+static size_t tile_stage_bytes(int ntab, int NR, int CG, int ns, bool with_z, int e_rows, int Pc) {
+    const int NRG = NR / 4;
+    return (size_t(tile_stage_head(ntab, 4 * CG, ns * NRG)) + size_t(2) * NR * (CG + 2) + size_t(2) * (NRG + 2) * 4 * CG +
+            size_t(with_z ? 2 : 1) * NR * 4 * CG + size_t(e_rows) * Pc) * 8;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ int4 lds_s32x4(uint32_t a) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+// all threads: copy the column-class and row-info tables into shared memory (once per CTA)
+__device__ __forceinline__ void tile_stage_tables(const TileStage& s, const TileArgs& a, int P, int nrinfo) {
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+    for (int i = tid; i < P; i += nt)
+        asm volatile("st.shared.s32 [%0], %1;" ::"r"(s.colv + i * 4), "r"(__ldg(a.colv + i)) : "memory");
+    for (int i = tid; i < nrinfo; i += nt)
+        asm volatile("st.shared.s32 [%0], %1;" ::"r"(s.rinfo + i * 4), "r"(__ldg(a.rinfo + i)) : "memory");
+}
+
+// one-time per-thread setup of the exchange-buffer addresses and the zero rim
+template <int CGT>
+__device__ __forceinline__ void tile_exchange_init(TileThread<CGT>& t, const TileArgs& a, uint32_t ex) {
+    const int CG = CGT > 0 ? CGT : int(blockDim.x), NRG = blockDim.y;
+    const int tx = threadIdx.x, ty = threadIdx.y, CGp = CG + 2;
+    const uint32_t EL = ex;
+    const uint32_t ER = EL + uint32_t(a.NR) * CGp * 8;
+    const uint32_t ET = ER + uint32_t(a.NR) * CGp * 8;
+    const uint32_t EB = ET + uint32_t(NRG + 2) * 4 * CG * 8;
+    t.cg = CG;
+    t.xl = EL + uint32_t((4 * ty) * CGp + tx + 1) * 8;
+    t.xr = ER + uint32_t((4 * ty) * CGp + tx + 1) * 8;
+    t.et = ET + uint32_t((ty + 1) * 4 * CG + tx) * 8;
+    t.eb = EB + uint32_t((ty + 1) * 4 * CG + tx) * 8;
+    if (tx == 0) {
+#pragma unroll
+        for (int I = 0; I < 4; ++I) sts_f64(t.xr + (I * CGp - 1) * 8, 0.0);
+    }
+    if (tx == CG - 1) {
+#pragma unroll
+        for (int I = 0; I < 4; ++I) sts_f64(t.xl + (I * CGp + 1) * 8, 0.0);
+    }
+    if (ty == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sts_f64(t.eb + (j - 4) * CG * 8, 0.0);
+    }
+    if (ty == NRG - 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sts_f64(t.et + (j + 4) * CG * 8, 0.0);
+    }
+}
+
+// per-item: primary-class weights of the thread's four columns (table already in shared memory).
+// rinfo = (row types, 2 bits per row) | primary class << 8, precomputed on the host per (strip, row group).
+template <int CGT, bool NEED_DG>
+__device__ __forceinline__ void tile_item_init(TileThread<CGT>& t, ColWeights<NEED_DG>& w, const TileArgs& a, uint32_t T,
+                                               int rho0, int rinfo, uint32_t colv_s) {
+    t.T = T; t.rho0 = rho0;
+    t.rt = rinfo & 0xff;
+    const int prim = rinfo >> 8;          // -1: no fast row in this tile
+    const int4 cv = lds_s32x4(colv_s + threadIdx.x * 16);
+    const int cvs[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int e = (cvs[j] >= 0 && prim >= 0) ? prim * a.ncv + cvs[j] : a.ntab - 1;
+        const uint32_t p = T + uint32_t(e) * (TWD * 8);
+        const double2 u = lds_f64x2(p), v = lds_f64x2(p + 32);
+        w.hW[j] = u.x; w.hE[j] = u.y; w.idg[j] = v.x;
+        if (NEED_DG) w.dg[j] = v.y;
+    }
+}
+
+__device__ __forceinline__ void tile_lds_row(double (&v)[4], uint32_t addr) {
+    const double2 a = lds_f64x2(addr), b = lds_f64x2(addr + 16);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+// straight-line half sweep for a tile whose four rows all have the primary class (t.rt == 0x55)
+template <int X, int MODE, bool NEED_DG, int CGT>
+__device__ __forceinline__ void tile_phase_fast(double (&z)[4][4], const double (&r)[4][4], const ColWeights<NEED_DG>& w,
+                                                const TileThread<CGT>& t) {
+    const int CG = t.CG(), CGp = t.CGp();
+    if (MODE == 2) {
+#pragma unroll
+        for (int I = 0; I < 4; ++I)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int j = ((I + X) & 1) + 2 * q;
+                z[I][j] = r[I][j] * w.idg[j];
+            }
+        return;
+    }
+    double hx[4], zN0[2], zS3[2];
+#pragma unroll
+    for (int I = 0; I < 4; ++I)
+        hx[I] = (((I + X) & 1) == 0) ? lds_f64(t.xr + (I * CGp - 1) * 8) : lds_f64(t.xl + (I * CGp + 1) * 8);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        zN0[q] = lds_f64(t.eb + ((X & 1) + 2 * q - 4) * CG * 8);
+        zS3[q] = lds_f64(t.et + (((3 + X) & 1) + 2 * q + 4) * CG * 8);
+    }
+    double upd[4][2];
+#pragma unroll
+    for (int I = 0; I < 4; ++I)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int j = ((I + X) & 1) + 2 * q;
+            const double zW = (j > 0) ? z[I][j > 0 ? j - 1 : 0] : hx[I];
+            const double zE = (j < 3) ? z[I][j < 3 ? j + 1 : 3] : hx[I];
+            const double zN = (I > 0) ? z[I > 0 ? I - 1 : 0][j] : zN0[q];
+            const double zS = (I < 3) ? z[I < 3 ? I + 1 : 3][j] : zS3[q];
+            upd[I][q] = fma(r[I][j], w.idg[j], fma(0.25, zN + zS, fma(w.hW[j], zW, w.hE[j] * zE)));
+        }
+#pragma unroll
+    for (int I = 0; I < 4; ++I)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int j = ((I + X) & 1) + 2 * q;
+            z[I][j] = (MODE == 1) ? w.dg[NEED_DG ? j : 0] * (upd[I][q] - z[I][j]) : upd[I][q];
+        }
+}
+
+template <int X, int MODE, bool NEED_DG, int CGT>
+__device__ __forceinline__ void tile_phase_any(double (&z)[4][4], const double (&r)[4][4], const ColWeights<NEED_DG>& w,
+                                               const TileThread<CGT>& t, const TileArgs& a) {
+    if (t.rt == 0x55) tile_phase_fast<X, MODE, NEED_DG, CGT>(z, r, w, t);
+    else              tile_phase<X, MODE, NEED_DG, CGT>(z, r, w, t, a);
+}
+
+// one thread: TMA bulk copy of rows [row0, row0 + nrow) (clamped to the grid) of one system into a staging strip
+// whose first row is stage_row0; returns nothing, the byte count is computed by tile_rows_bytes
+__device__ __forceinline__ uint32_t tile_rows_bytes(int row0, int nrow, int R, int P) {
+    const int lo = max(row0, 0), hi = min(row0 + nrow, R + 1);
+    return hi > lo ? uint32_t(hi - lo) * uint32_t(P) * 8u : 0u;
+}
+__device__ __forceinline__ void tile_tma(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tile_tma_rows(uint32_t dst, const double* gsys, int P, int R, int row0, int nrow,
+                                              int stage_row0, uint32_t bar) {
+    const int lo = max(row0, 0), hi = min(row0 + nrow, R + 1);
+    if (hi > lo)
+        tile_tma(dst + uint32_t(lo - stage_row0) * uint32_t(P) * 8u, gsys + size_t(lo) * P,
+                 uint32_t(hi - lo) * uint32_t(P) * 8u, bar);
+}
+
+// round-robin walk over the (system, strip) items of the active systems
+struct TileWalk {
+    int k, strip, K, ns, dk, ds;
+    const int* active;
+    __device__ __forceinline__ void init(int K_, int ns_, const int* act) {
+        K = K_; ns = ns_; active = act;
+        dk = int(gridDim.x) / ns; ds = int(gridDim.x) - dk * ns;
+        k = int(blockIdx.x) / ns; strip = int(blockIdx.x) - k * ns;
+        skip();
+    }
+    __device__ __forceinline__ void skip() { while (k < K && !active[k]) step(); }
+    __device__ __forceinline__ void step() {
+        k += dk; strip += ds;
+        if (strip >= ns) { strip -= ns; ++k; }
+    }
+    __device__ __forceinline__ void next() { step(); skip(); }
+    __device__ __forceinline__ bool valid() const { return k < K; }
+    // split form of next(): step() + flag() early (the load overlaps the item), settle() when the successor is needed
+    __device__ __forceinline__ int flag() const { return k < K ? active[k] : 1; }
+    __device__ __forceinline__ void settle(int f) { if (!f) { step(); skip(); } }
+};
+
+template <int CGT>
+__global__ void __launch_bounds__(TILE_MAXT, 1)
+k_mgp_down(TileArgs a, const double* __restrict__ r_in, double* __restrict__ z_out, double* __restrict__ rc_out,
+           const int* __restrict__ active, int K) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int CG = CGT > 0 ? CGT : int(blockDim.x), NRG = blockDim.y;
+    const int P = 4 * CG, R = a.g.R;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const bool leader = tx == 0 && ty == 0;
+    const uint32_t base = smem_u32(smem_raw);
+    const TileStage s = tile_stage_carve(base, a, CG, NRG, false);
+    TileThread<CGT> t;
+    tile_exchange_init(t, a, s.ex);
+    tile_stage_tables(s, a, P, a.ns * NRG);
+    if (leader) {
+        mbar_init(reinterpret_cast<uint64_t*>(smem_raw + (s.bar - base)), 1);
+        mbar_fence_init();
+    }
+    auto issue = [&](const TileWalk& wk, int stage) {
+        const int row0 = wk.strip * a.TY - a.halo_top;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s.bar),
+                     "r"(s.tb + tile_rows_bytes(row0, a.NR, R, P)) : "memory");
+        tile_tma(s.T0 + stage * s.tb, a.tab + int64_t(wk.k) * a.ntab * TWD, s.tb, s.bar);
+        tile_tma_rows(s.Rs, r_in + int64_t(wk.k) * a.g.Dp, P, R, row0, a.NR, row0, s.bar);
+    };
+    __syncthreads();
+    TileWalk wk;
+    wk.init(K, a.ns, active);
+    if (leader && wk.valid()) issue(wk, 0);
+    uint32_t phase = 0;
+    int stage = 0;
+    const int nu = a.nu;
+    const int CGp = CG + 2;
+    const uint32_t rs_own = s.Rs + uint32_t((4 * ty) * P + 4 * tx) * 8;
+    while (wk.valid()) {
+        const int k = wk.k, y0 = wk.strip * a.TY;
+        const int rho0 = y0 - a.halo_top + 4 * ty;
+        TileWalk nx = wk;
+        nx.step();
+        const int nflag = nx.flag();                       // in flight while this item is set up
+        const int rinfo = lds_s32(s.rinfo + (wk.strip * NRG + ty) * 4);
+        mbar_wait(reinterpret_cast<uint64_t*>(smem_raw + (s.bar - base)), phase);
+        phase ^= 1u;
+        double z[4][4], r[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) z[i][j] = 0.0;
+        if ((rinfo & 0xff) == 0x55) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tile_lds_row(r[i], rs_own + i * P * 8);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) r[i][j] = 0.0;
+                if (unsigned(rho0 + i) <= unsigned(R)) tile_lds_row(r[i], rs_own + i * P * 8);
+            }
+        }
+        ColWeights<true> w;
+        tile_item_init(t, w, a, s.T0 + stage * s.tb, rho0, rinfo, s.colv);
+        __syncthreads();                                   // everybody has left the staging strip
+        nx.settle(nflag);
+        if (leader && nx.valid()) issue(nx, stage ^ 1);
+        tile_phase_any<0, 2, true>(z, r, w, t, a);
+        tile_publish<0>(z, t);
+        __syncthreads();
+        tile_phase_any<1, 0, true>(z, r, w, t, a);
+        tile_publish<1>(z, t);
+        __syncthreads();
+        for (int sw = 1; sw < nu; ++sw) {
+            tile_phase_any<0, 0, true>(z, r, w, t, a);
+            tile_publish<0>(z, t);
+            __syncthreads();
+            tile_phase_any<1, 0, true>(z, r, w, t, a);
+            tile_publish<1>(z, t);
+            __syncthreads();
+        }
+        double* zo = z_out + int64_t(k) * a.g.Dp + int64_t(rho0) * P + 4 * tx;
+        const int own_lo = y0 - rho0, own_hi = min(y0 + a.TY, R + 1) - rho0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i >= own_lo && i < own_hi) tile_store_row(zo + i * P, z[i]);
+        if (a.has_coarse) {
+            tile_phase_any<0, 1, true>(z, r, w, t, a);
+            tile_publish<0>(z, t);
+            __syncthreads();
+            const LevelGeo& gc = a.gc;
+            const double dN31 = lds_f64(t.eb + (1 - 4) * CG * 8), dN33 = lds_f64(t.eb + (3 - 4) * CG * 8);
+            const double dW13 = lds_f64(t.xr + (1 * CGp - 1) * 8), dW33 = lds_f64(t.xr + (3 * CGp - 1) * 8);
+            double rc[2][2];
+            rc[0][0] = z[0][0] + 0.5 * (dN31 + dW13);
+            rc[0][1] = z[0][2] + 0.5 * (dN33 + z[1][1]);
+            rc[1][0] = z[2][0] + 0.5 * (z[1][1] + dW33);
+            rc[1][1] = z[2][2] + 0.5 * (z[1][3] + z[3][1]);
+            const int J0 = 2 * tx;
+            const bool okJ0 = J0 >= 1 && J0 <= gc.C - 1, okJ1 = J0 + 1 <= gc.C - 1;
+            double* co = rc_out + int64_t(k) * gc.Dp + J0;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int rho = rho0 + 2 * q;
+                const int I = rho >> 1;
+                if (rho >= y0 && rho < y0 + a.TY && I <= gc.R) {
+                    const bool okI = I >= 1 && I <= gc.R - 1;
+                    *reinterpret_cast<double2*>(co + size_t(I) * gc.P) =
+                        make_double2(okI && okJ0 ? rc[q][0] : 0.0, okI && okJ1 ? rc[q][1] : 0.0);
+                }
+            }
+        }
+        // no barrier here: the next item writes exchange slots only after its own staging barrier
+        wk = nx;
+        stage ^= 1;
+    }
+}
+
+template <int CGT>
+__global__ void __launch_bounds__(TILE_MAXT, 1)
+k_mgp_up(TileArgs a, const double* __restrict__ e_c, const double* __restrict__ z_in, const double* __restrict__ r_in,
+         double* __restrict__ z_out, const int* __restrict__ active, double* __restrict__ part_rz, int K) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int CG = CGT > 0 ? CGT : int(blockDim.x), NRG = blockDim.y;
+    const int P = 4 * CG, R = a.g.R, NR = a.NR;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const bool leader = tx == 0 && ty == 0;
+    const uint32_t base = smem_u32(smem_raw);
+    const TileStage s = tile_stage_carve(base, a, CG, NRG, true);
+    TileThread<CGT> t;
+    tile_exchange_init(t, a, s.ex);
+    tile_stage_tables(s, a, P, a.ns * NRG);
+    if (leader) {
+        mbar_init(reinterpret_cast<uint64_t*>(smem_raw + (s.bar - base)), 1);
+        mbar_fence_init();
+    }
+    const int Pc = a.gc.P, Rc = a.gc.R;
+    auto issue = [&](const TileWalk& wk, int stage) {
+        const int row0 = wk.strip * a.TY - a.halo_top;
+        uint32_t tot = s.tb + 2u * tile_rows_bytes(row0, NR, R, P);
+        if (a.has_coarse) tot += tile_rows_bytes(row0 >> 1, NR / 2 + 1, Rc, Pc);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s.bar), "r"(tot) : "memory");
+        tile_tma(s.T0 + stage * s.tb, a.tab + int64_t(wk.k) * a.ntab * TWD, s.tb, s.bar);
+        tile_tma_rows(s.Zs, z_in + int64_t(wk.k) * a.g.Dp, P, R, row0, NR, row0, s.bar);
+        tile_tma_rows(s.Rs, r_in + int64_t(wk.k) * a.g.Dp, P, R, row0, NR, row0, s.bar);
+        if (a.has_coarse) tile_tma_rows(s.Es, e_c + int64_t(wk.k) * a.gc.Dp, Pc, Rc, row0 >> 1, NR / 2 + 1, row0 >> 1, s.bar);
+    };
+    __syncthreads();
+    TileWalk wk;
+    wk.init(K, a.ns, active);
+    if (leader && wk.valid()) issue(wk, 0);
+    uint32_t phase = 0;
+    int stage = 0;
+    const int nu = a.nu;
+    const uint32_t own = uint32_t((4 * ty) * P + 4 * tx) * 8;
+    const uint32_t es_own = s.Es + uint32_t((2 * ty) * Pc + 2 * tx) * 8;
+    const int tid = ty * int(blockDim.x) + tx, nwarps = (int(blockDim.x * blockDim.y) + 31) >> 5;
+    int64_t prev_slot = -1;                                // part_rz slot of the previous item (its reduction is deferred)
+    while (wk.valid()) {
+        const int k = wk.k, strip = wk.strip;
+        const int y0 = strip * a.TY;
+        const int rho0 = y0 - a.halo_top + 4 * ty;
+        TileWalk nx = wk;
+        nx.step();
+        const int nflag = nx.flag();
+        const int rinfo = lds_s32(s.rinfo + (strip * NRG + ty) * 4);
+        mbar_wait(reinterpret_cast<uint64_t*>(smem_raw + (s.bar - base)), phase);
+        phase ^= 1u;
+        double z[4][4], r[4][4];
+        if ((rinfo & 0xff) == 0x55) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                tile_lds_row(z[i], s.Zs + own + i * P * 8);
+                tile_lds_row(r[i], s.Rs + own + i * P * 8);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { z[i][j] = 0.0; r[i][j] = 0.0; }
+                if (unsigned(rho0 + i) <= unsigned(R)) {
+                    tile_lds_row(z[i], s.Zs + own + i * P * 8);
+                    tile_lds_row(r[i], s.Rs + own + i * P * 8);
+                }
+            }
+        }
+        if (a.has_coarse) {
+            // prolongation on the red points (see k_mgt_up); the staging strip's coarse row 2 ty is row (rho0 >> 1)
+            const int I0 = rho0 >> 1, J0 = 2 * tx;
+            double e[3][3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                e[q][0] = e[q][1] = e[q][2] = 0.0;
+                if (unsigned(I0 + q) <= unsigned(Rc)) {
+                    const uint32_t ea = es_own + q * Pc * 8;
+                    const double2 v = lds_f64x2(ea);
+                    e[q][0] = v.x; e[q][1] = v.y;
+                    if (J0 + 2 < Pc) e[q][2] = lds_f64(ea + 16);
+                }
+            }
+            z[0][0] += e[0][0]; z[0][2] += e[0][1];
+            z[2][0] += e[1][0]; z[2][2] += e[1][1];
+            z[1][1] += 0.5 * (e[0][1] + e[1][0]); z[1][3] += 0.5 * (e[0][2] + e[1][1]);
+            z[3][1] += 0.5 * (e[1][1] + e[2][0]); z[3][3] += 0.5 * (e[1][2] + e[2][1]);
+        }
+        ColWeights<false> w;
+        tile_item_init(t, w, a, s.T0 + stage * s.tb, rho0, rinfo, s.colv);
+        tile_publish<0>(z, t);
+        __syncthreads();                                   // staging strip free, red perimeter visible
+        nx.settle(nflag);
+        if (leader && nx.valid()) issue(nx, stage ^ 1);
+        if (part_rz && prev_slot >= 0 && tid < 32) {
+            // deferred deterministic reduction of the previous item's per-warp r.z partials (other parity)
+            double v = tid < nwarps ? lds_f64(s.red + ((stage ^ 1) * 32 + tid) * 8) : 0.0;
+            v = warp_sum(v);
+            if (tid == 0) part_rz[prev_slot] = v;
+        }
+        for (int sw = 0; sw < nu; ++sw) {
+            tile_phase_any<1, 0, false>(z, r, w, t, a);
+            tile_publish<1>(z, t);
+            __syncthreads();
+            tile_phase_any<0, 0, false>(z, r, w, t, a);
+            if (sw + 1 < nu) {
+                tile_publish<0>(z, t);
+                __syncthreads();
+            }
+        }
+        double* zo = z_out + int64_t(k) * a.g.Dp + int64_t(rho0) * P + 4 * tx;
+        const int own_lo = y0 - rho0, own_hi = min(y0 + a.TY, R + 1) - rho0;
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (i >= own_lo && i < own_hi) {
+                tile_store_row(zo + i * P, z[i]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc = fma(r[i][j], z[i][j], acc);
+            }
+        }
+        if (part_rz) {
+            acc = warp_sum(acc);
+            if ((tid & 31) == 0) sts_f64(s.red + (stage * 32 + (tid >> 5)) * 8, acc);
+            prev_slot = int64_t(k) * a.ns + strip;
+        }
+        // no barrier here: the next item's staging barrier orders the exchange-buffer and reduction-slot reuse
+        wk = nx;
+        stage ^= 1;
+    }
+    if (part_rz && prev_slot >= 0) {
+        __syncthreads();
+        if (tid < 32) {
+            double v = tid < nwarps ? lds_f64(s.red + ((stage ^ 1) * 32 + tid) * 8) : 0.0;
+            v = warp_sum(v);
+            if (tid == 0) part_rz[prev_slot] = v;
+        }
+    }
+}
+
 // ======================================================================================================
 // host side
 // ======================================================================================================
@@ -470,6 +935,16 @@ int Context::tile_setup() {
         int& m = i < 3 ? tile_maxt_down : tile_maxt_up;
         m = std::min(m, fa.maxThreadsPerBlock);
     }
+    const void* pfns[] = {(const void*)k_mgp_down<64>, (const void*)k_mgp_down<32>, (const void*)k_mgp_down<0>,
+                          (const void*)k_mgp_up<64>,   (const void*)k_mgp_up<32>,   (const void*)k_mgp_up<0>};
+    for (int i = 0; i < 6; ++i) {
+        CK(cudaFuncSetAttribute(pfns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        cudaFuncAttributes fa;
+        CK(cudaFuncGetAttributes(&fa, pfns[i]));
+        int& m = i < 3 ? tile_maxt_down : tile_maxt_up;
+        m = std::min(m, fa.maxThreadsPerBlock);
+    }
+    CK(cudaDeviceGetAttribute(&tile_nsm, cudaDevAttrMultiProcessorCount, device));
     // vertex-class tables of every level
     for (int* p : tile_rowv) cudaFree(p);
     for (int* p : tile_colv) cudaFree(p);
@@ -500,6 +975,37 @@ int Context::tile_pf_dist(const void* func, int threads, size_t smem) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, threads, smem) != cudaSuccess) per_sm = 1;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
     return std::max(1, per_sm) * nsm;
+}
+
+// per (strip, row group): row types of the tile rows (2 bits each: 0 not interior, 1 primary class, 2 other) and the
+// primary class (the first non-interface interior row's), cached per (level, strip height, halo, region rows)
+const int* Context::tile_rinfo(int l, int TY, int halo_top, int NR) {
+    const std::array<int, 4> key{l, TY, halo_top, NR};
+    auto it = tile_rinfo_cache.find(key);
+    if (it != tile_rinfo_cache.end()) return it->second;
+    const LevelGeo& g = levels[l];
+    auto vclass = [&](int v) {
+        if (v < 1 || v > g.R - 1) return -1;
+        return (v % g.N) ? 2 * (v / g.N) : 2 * (v / g.N) - 1;
+    };
+    const int ns = (g.R + TY - 1) / TY, NRG = NR / 4;
+    std::vector<int> tab(size_t(ns) * NRG);
+    for (int s = 0; s < ns; ++s)
+        for (int ty = 0; ty < NRG; ++ty) {
+            const int rho0 = s * TY - halo_top + 4 * ty;
+            int rv[4], prim = -1, rt = 0;
+            for (int i = 0; i < 4; ++i) {
+                rv[i] = vclass(rho0 + i);
+                if (prim < 0 && rv[i] >= 0 && !(rv[i] & 1)) prim = rv[i];
+            }
+            for (int i = 0; i < 4; ++i) rt |= (rv[i] < 0 ? 0 : (rv[i] == prim ? 1 : 2)) << (2 * i);
+            tab[size_t(s) * NRG + ty] = (prim * 256) | rt;
+        }
+    int* d = nullptr;
+    if (cudaMalloc(&d, tab.size() * sizeof(int)) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+    tile_rinfo_cache[key] = d;
+    return d;
 }
 
 int Context::tile_ntab() const { return (2 * nrb - 1) * (2 * ncb - 1) + 1; }
@@ -546,9 +1052,28 @@ int Context::tile_down(int l, const double* y, int Kc, cudaStream_t st) {
     a.tab = ws.wtab; a.ntab = tile_ntab(); a.ncv = 2 * ncb - 1;
     a.nu = nu;
     a.halo_top = 2 * nu + 2;
+    a.pf_dist = 0; a.rinfo = nullptr;
+    const int CG = a.g.P / 4;
+    if (tile_persistent) {
+        for (int cap = tile_ty_cap; cap >= 2; cap -= 2) {
+            tile_pick_ty(a.g, 4 * nu + 2, tile_maxt_down, cap, &a.TY, &a.NR);
+            a.ns = (a.g.R + a.TY - 1) / a.TY;
+            if (tile_stage_bytes(a.ntab, a.NR, CG, a.ns, false, 0, 0) <= 227 * 1024) break;
+        }
+        const size_t sm = tile_stage_bytes(a.ntab, a.NR, CG, a.ns, false, 0, 0);
+        if (sm <= 227 * 1024) {
+            a.ns = (a.g.R + a.TY - 1) / a.TY;
+            const int grid = int(std::min<int64_t>(tile_nsm, int64_t(Kc) * a.ns));
+            auto fn = CG == 64 ? k_mgp_down<64> : (CG == 32 ? k_mgp_down<32> : k_mgp_down<0>);
+            a.rinfo = tile_rinfo(l, a.TY, a.halo_top, a.NR);
+            if (!a.rinfo) { set_error("tile kernels: row-info table allocation failed"); return ROMHC_ERR_CUDA; }
+            ++g_launches;
+            fn<<<grid, dim3(CG, a.NR / 4), sm, st>>>(a, ws.r[l], ws.za[l], a.has_coarse ? ws.r[l + 1] : nullptr, ws.active, Kc);
+            return ROMHC_OK;
+        }
+    }
     tile_pick_ty(a.g, 4 * nu + 2, tile_maxt_down, tile_ty_cap, &a.TY, &a.NR);
     a.ns = (a.g.R + a.TY - 1) / a.TY;
-    const int CG = a.g.P / 4;
     const size_t sm = tile_smem_bytes(a.ntab, a.NR, CG);
     if (sm > 227 * 1024) { set_error("tile kernels: shared memory"); return ROMHC_ERR_ARG; }
     auto fn = CG == 64 ? k_mgt_down<64> : (CG == 32 ? k_mgt_down<32> : k_mgt_down<0>);
@@ -569,9 +1094,29 @@ int Context::tile_up(int l, const double* y, int Kc, const double* e, double* pa
     a.tab = ws.wtab; a.ntab = tile_ntab(); a.ncv = 2 * ncb - 1;
     a.nu = nu;
     a.halo_top = 2 * nu;
+    a.pf_dist = 0; a.rinfo = nullptr;
+    const int CG = a.g.P / 4;
+    if (tile_persistent) {
+        auto bytes = [&]() { return tile_stage_bytes(a.ntab, a.NR, CG, (a.g.R + a.TY - 1) / a.TY, true, a.has_coarse ? a.NR / 2 + 1 : 0, a.gc.P); };
+        for (int cap = tile_ty_cap; cap >= 2; cap -= 2) {
+            tile_pick_ty(a.g, 4 * nu, tile_maxt_up, cap, &a.TY, &a.NR);
+            if (bytes() <= 227 * 1024) break;
+        }
+        const size_t sm = bytes();
+        if (sm <= 227 * 1024) {
+            a.ns = (a.g.R + a.TY - 1) / a.TY;
+            const int grid = int(std::min<int64_t>(tile_nsm, int64_t(Kc) * a.ns));
+            auto fn = CG == 64 ? k_mgp_up<64> : (CG == 32 ? k_mgp_up<32> : k_mgp_up<0>);
+            a.rinfo = tile_rinfo(l, a.TY, a.halo_top, a.NR);
+            if (!a.rinfo) { set_error("tile kernels: row-info table allocation failed"); return ROMHC_ERR_CUDA; }
+            ++g_launches;
+            fn<<<grid, dim3(CG, a.NR / 4), sm, st>>>(a, e, ws.za[l], ws.r[l], ws.zb[l], ws.active, part_rz, Kc);
+            *ns_out = a.ns;
+            return ROMHC_OK;
+        }
+    }
     tile_pick_ty(a.g, 4 * nu, tile_maxt_up, tile_ty_cap, &a.TY, &a.NR);
     a.ns = (a.g.R + a.TY - 1) / a.TY;
-    const int CG = a.g.P / 4;
     const size_t sm = tile_smem_bytes(a.ntab, a.NR, CG);
     if (sm > 227 * 1024) { set_error("tile kernels: shared memory"); return ROMHC_ERR_ARG; }
     auto fn = CG == 64 ? k_mgt_up<64> : (CG == 32 ? k_mgt_up<32> : k_mgt_up<0>);

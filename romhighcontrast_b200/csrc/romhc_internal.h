@@ -2,7 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <array>
 #include <atomic>
+#include <map>
 #include <vector>
 
 #include "common.cuh"
@@ -82,7 +84,10 @@ struct Context {
     int nu = 1, nu_tail = 2;   // red/black Gauss-Seidel sweeps before and after the coarse correction: V(nu, nu)
     bool use_tile = true;               // register-tiled multigrid kernels (mgtile.cu) where the level fits
     int tile_ty_cap = 64;               // largest strip height of the tile kernels
-    bool tile_prefetch = true;          // L2 prefetch of the next CTA's operand rows
+    bool tile_prefetch = true;          // L2 prefetch of the next CTA's operand rows (non-persistent tile kernels)
+    bool tile_persistent = true;        // persistent, TMA-pipelined tile kernels (one CTA per SM)
+    int tile_nsm = 148;
+    std::map<std::array<int, 4>, int*> tile_rinfo_cache;   // (level, TY, halo, NR) -> device row-info table
     bool tile_ready = false;
     int tile_maxt_down = 0, tile_maxt_up = 0;
     std::vector<int*> tile_rowv, tile_colv;   // per level: vertex class of every row / column (device)
@@ -140,6 +145,7 @@ struct Context {
     // mgtile.cu
     int tile_setup();
     int tile_ntab() const;
+    const int* tile_rinfo(int l, int TY, int halo_top, int NR);
     int tile_pf_dist(const void* func, int threads, size_t smem);
     bool tile_level_ok(int l) const;
     int tile_weight_table(const double* y, int Kc, cudaStream_t st);

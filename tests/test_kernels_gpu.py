@@ -67,14 +67,16 @@ def test_pack_unpack_apply_norms(torch_mod, geo, N):
     np.testing.assert_allclose(en, ref, rtol=1e-12)
 
 
-@pytest.mark.parametrize("tile", [1, 0])
+@pytest.mark.parametrize("tile", [2, 1, 0])
 @pytest.mark.parametrize("nu", [1, 2, 3])
 @pytest.mark.parametrize("geo,N", GEOS)
 def test_precond_matches_twin(torch_mod, geo, N, nu, tile):
-    """one V-cycle of both kernel families (tile=1: register-tiled mgtile.cu, tile=0: shared-memory strips)"""
+    """one V-cycle of every kernel family (tile=2: persistent TMA-pipelined register tiles, 1: one CTA per strip
+    register tiles, 0: shared-memory strips)"""
     from gmg_twin import GMG
     eng = make_engine(geo, N)
-    eng.set_option("tile", tile)
+    eng.set_option("tile", min(tile, 1))
+    eng.set_option("tile_persistent", 1 if tile == 2 else 0)
     eng.set_option("nu", nu)
     eng.set_option("nu_tail", nu)
     K = 3
@@ -89,13 +91,15 @@ def test_precond_matches_twin(torch_mod, geo, N, nu, tile):
 
 
 @pytest.mark.parametrize("geo,N", GEOS)
-@pytest.mark.parametrize("strip_kb,tile,tile_ty", [(100, 1, 32), (100, 1, 6), (100, 0, 32), (48, 0, 32), (227, 0, 32)])
+@pytest.mark.parametrize("strip_kb,tile,tile_ty", [(100, 2, 64), (100, 2, 6), (100, 1, 32), (100, 1, 6), (100, 0, 32),
+                                                   (48, 0, 32), (227, 0, 32)])
 def test_solve_matches_oracle(torch_mod, geo, N, strip_kb, tile, tile_ty):
     from oracle import FEMOracle
     from gmg_twin import pcg
     eng = make_engine(geo, N)
     eng.set_option("strip_kb", strip_kb)
-    eng.set_option("tile", tile)
+    eng.set_option("tile", min(tile, 1))
+    eng.set_option("tile_persistent", 1 if tile == 2 else 0)
     eng.set_option("tile_ty", tile_ty)
     o = FEMOracle(geo, N)
     K = 7
