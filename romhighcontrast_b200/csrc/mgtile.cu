@@ -273,14 +273,12 @@ __device__ __forceinline__ void tile_prefetch_rows(const double* base, const Lev
     if (hi > lo) bulk_prefetch_l2(base + k * g.Dp + size_t(lo) * g.P, uint32_t(hi - lo) * uint32_t(g.P) * 8u);
 }
 
+// a tile row is one 32-byte sector: 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256)
 __device__ __forceinline__ void tile_load_row(double (&v)[4], const double* row) {
-    const double2 a = *reinterpret_cast<const double2*>(row);
-    const double2 b = *reinterpret_cast<const double2*>(row + 2);
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(row));
 }
 __device__ __forceinline__ void tile_store_row(double* row, const double (&v)[4]) {
-    *reinterpret_cast<double2*>(row) = make_double2(v[0], v[1]);
-    *reinterpret_cast<double2*>(row + 2) = make_double2(v[2], v[3]);
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(row), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
 }
 
 // ---- going down: z = nu RB-GS sweeps from 0; r_coarse = P^T (r - A z) ----------------------------------------------------
@@ -874,11 +872,13 @@ k_mgp_up(TileArgs a, const double* __restrict__ e_c, const double* __restrict__ 
         __syncthreads();                                   // staging strip free, red perimeter visible
         nx.settle(nflag);
         if (leader && nx.valid()) issue(nx, stage ^ 1);
-        if (part_rz && prev_slot >= 0 && tid < 32) {
-            // deferred deterministic reduction of the previous item's per-warp r.z partials (other parity)
-            double v = tid < nwarps ? lds_f64(s.red + ((stage ^ 1) * 32 + tid) * 8) : 0.0;
+        if (part_rz && prev_slot >= 0 && (tid >> 5) == nwarps - 1) {
+            // deferred deterministic reduction of the previous item's per-warp r.z partials (other parity), on the
+            // last warp: the first one is busy issuing the copies
+            const int l = tid & 31;
+            double v = l < nwarps ? lds_f64(s.red + ((stage ^ 1) * 32 + l) * 8) : 0.0;
             v = warp_sum(v);
-            if (tid == 0) part_rz[prev_slot] = v;
+            if (l == 0) part_rz[prev_slot] = v;
         }
         for (int sw = 0; sw < nu; ++sw) {
             tile_phase_any<1, 0, false>(z, r, w, t, a);
@@ -892,16 +892,16 @@ k_mgp_up(TileArgs a, const double* __restrict__ e_c, const double* __restrict__ 
         }
         double* zo = z_out + int64_t(k) * a.g.Dp + int64_t(rho0) * P + 4 * tx;
         const int own_lo = y0 - rho0, own_hi = min(y0 + a.TY, R + 1) - rho0;
-        double acc = 0.0;
+        double acc4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (i >= own_lo && i < own_hi) {
                 tile_store_row(zo + i * P, z[i]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc = fma(r[i][j], z[i][j], acc);
+                acc4[i] = fma(r[i][0], z[i][0], r[i][1] * z[i][1]) + fma(r[i][2], z[i][2], r[i][3] * z[i][3]);
             }
         }
         if (part_rz) {
+            double acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
             acc = warp_sum(acc);
             if ((tid & 31) == 0) sts_f64(s.red + (stage * 32 + (tid >> 5)) * 8, acc);
             prev_slot = int64_t(k) * a.ns + strip;
