@@ -45,6 +45,9 @@ void Context::free_host_stage() {
         if (hstage.copied[i]) cudaEventDestroy(hstage.copied[i]);
         hstage.done[i] = hstage.copied[i] = nullptr;
     }
+    if (hstage.it_pin) cudaFreeHost(hstage.it_pin);
+    if (hstage.rel_pin) cudaFreeHost(hstage.rel_pin);
+    hstage.it_pin = nullptr; hstage.rel_pin = nullptr; hstage.pin_cap = 0;
     if (hstage.compute) cudaStreamDestroy(hstage.compute);
     if (hstage.copy) cudaStreamDestroy(hstage.copy);
     hstage.compute = hstage.copy = nullptr;
@@ -262,6 +265,14 @@ int romhc_generate_solutions_host(romhc_handle h, const double* y_host, int64_t 
     int rc = c->ensure_host_stage(chunk);
     if (rc) return rc;
     HostStage& s = c->hstage;
+    if (K > s.pin_cap) {
+        if (s.it_pin) cudaFreeHost(s.it_pin);
+        if (s.rel_pin) cudaFreeHost(s.rel_pin);
+        s.it_pin = nullptr; s.rel_pin = nullptr; s.pin_cap = 0;
+        CK(cudaMallocHost((void**)&s.it_pin, size_t(K) * 4));
+        CK(cudaMallocHost((void**)&s.rel_pin, size_t(K) * 8));
+        s.pin_cap = K;
+    }
     int64_t nchunk = 0;
     for (int64_t k0 = 0; k0 < K; k0 += chunk, ++nchunk) {
         const int64_t kc = std::min<int64_t>(chunk, K - k0);
@@ -275,12 +286,18 @@ int romhc_generate_solutions_host(romhc_handle h, const double* y_host, int64_t 
         CK(cudaEventRecord(s.done[slot], s.compute));
         CK(cudaStreamWaitEvent(s.copy, s.done[slot], 0));
         CK(cudaMemcpyAsync(U_host + k0 * D, s.u[slot], size_t(kc) * D * 8, cudaMemcpyDeviceToHost, s.copy));
-        if (iters_host) CK(cudaMemcpyAsync(iters_host + k0, s.it[slot], size_t(kc) * 4, cudaMemcpyDeviceToHost, s.copy));
-        if (relres_host) CK(cudaMemcpyAsync(relres_host + k0, s.rel[slot], size_t(kc) * 8, cudaMemcpyDeviceToHost, s.copy));
+        // per-system statistics go to pinned staging first: a D2H copy into the caller's (usually pageable) arrays would
+        // block the host behind the big solution copy and serialise the pipeline
+        if (iters_host) CK(cudaMemcpyAsync(s.it_pin + k0, s.it[slot], size_t(kc) * 4, cudaMemcpyDeviceToHost, s.copy));
+        if (relres_host) CK(cudaMemcpyAsync(s.rel_pin + k0, s.rel[slot], size_t(kc) * 8, cudaMemcpyDeviceToHost, s.copy));
         CK(cudaEventRecord(s.copied[slot], s.copy));
     }
     CK(cudaStreamSynchronize(s.copy));
     CK(cudaStreamSynchronize(s.compute));
+    if (rc == ROMHC_OK) {
+        if (iters_host) memcpy(iters_host, s.it_pin, size_t(K) * 4);
+        if (relres_host) memcpy(relres_host, s.rel_pin, size_t(K) * 8);
+    }
     return rc;
 }
 

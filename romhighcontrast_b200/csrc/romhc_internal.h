@@ -71,6 +71,9 @@ struct HostStage {
     cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
     cudaStream_t compute = nullptr, copy = nullptr;
     int64_t cap = 0;
+    int* it_pin = nullptr;        // pinned staging of the per-system statistics (whole batch)
+    double* rel_pin = nullptr;
+    int64_t pin_cap = 0;
 };
 
 struct Context {
@@ -109,7 +112,8 @@ struct Context {
     size_t ws_bytes = 0;
     SolveWorkspace ws;
     int* ws_flags = nullptr;
-    int* h_flags = nullptr;
+    int* h_flags = nullptr;     // mapped pinned host memory
+    int* d_hflags = nullptr;    // its device address
     // per-kernel timing (option "profile")
     bool prof_on = false, prof_window = false;
     std::vector<ProfEvent> prof_events;

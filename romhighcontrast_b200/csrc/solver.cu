@@ -181,6 +181,13 @@ __global__ void k_fill_interior(LevelGeo g, double* v, double value, int64_t K) 
     for (int c = 1 + threadIdx.x; c < g.C; c += blockDim.x) p[c] = value;
 }
 
+__global__ void k_fill_int(int* v, int value, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = value;
+}
+// one int from device memory to mapped pinned host memory
+__global__ void k_post_flag(const int* __restrict__ src, volatile int* dst) { *dst = *src; __threadfence_system(); }
+
 // compact (K, D) <-> padded (K, Dp)
 __global__ void k_pack(LevelGeo g, const double* __restrict__ compact, double* __restrict__ padded, int64_t K) {
     const int64_t row = blockIdx.x;
@@ -1047,7 +1054,10 @@ int Context::ensure_solve_ws(int64_t Kc) {
     ws.active = (int*)(b + o_int); ws.iters = ws.active + Kc;
     if (!ws_flags) {
         CK(cudaMalloc(&ws_flags, 64 * sizeof(int)));
-        CK(cudaMallocHost(&h_flags, 64 * sizeof(int)));
+        // mapped pinned memory: convergence flags reach the host by a kernel's posted write, never through the D2H
+        // copy engine (which the host-buffer entry point keeps busy with gigabytes of solutions)
+        CK(cudaHostAlloc((void**)&h_flags, 64 * sizeof(int), cudaHostAllocMapped));
+        CK(cudaHostGetDevicePointer((void**)&d_hflags, h_flags, 0));
     }
     ws_K = Kc;
     ws_bytes = off * 8;
@@ -1133,11 +1143,7 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
     CK(cudaMemsetAsync(ws.p[0], 0, size_t(Kc) * g.Dp * 8, st));
     CK(cudaMemsetAsync(ws.p[1], 0, size_t(Kc) * g.Dp * 8, st));
     ++g_launches; k_fill_interior<<<(unsigned)(int64_t(Kc) * (g.R - 1)), 128, 0, st>>>(g, ws.r[0], 1.0 / (double(N) * double(N)), Kc);
-    {
-        std::vector<int> ones(Kc, 1);
-        CK(cudaMemcpyAsync(ws.active, ones.data(), size_t(Kc) * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));
-    }
+    ++g_launches; k_fill_int<<<(Kc + 255) / 256, 256, 0, st>>>(ws.active, 1, Kc);
     CK(cudaMemsetAsync(ws.iters, 0, size_t(Kc) * 4, st));
     CK(cudaMemsetAsync(ws_flags, 0, 64 * sizeof(int), st));
     if (coarse_direct) {
@@ -1181,12 +1187,12 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
                                           it, tol2, ctr, ws_flags + 0);
         ++total_launch_iters;
         if (it >= min_check_iter && ((it - min_check_iter) % check_every == 0 || it == maxit)) {
-            CK(cudaMemcpyAsync(h_flags, ctr, sizeof(int), cudaMemcpyDeviceToHost, st));
+            ++g_launches; k_post_flag<<<1, 1, 0, st>>>(ctr, d_hflags);
             CK(cudaStreamSynchronize(st));
             if (h_flags[0] == 0) break;
         }
     }
-    CK(cudaMemcpyAsync(h_flags, ws_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ++g_launches; k_post_flag<<<1, 1, 0, st>>>(ws_flags, d_hflags);
     if (iters_out) CK(cudaMemcpyAsync(iters_out, ws.iters, size_t(Kc) * 4, cudaMemcpyDeviceToDevice, st));
     if (relres_out) CK(cudaMemcpyAsync(relres_out, ws.relres, size_t(Kc) * 8, cudaMemcpyDeviceToDevice, st));
     CK(cudaStreamSynchronize(st));
@@ -1225,9 +1231,7 @@ int Context::precond(const double* y, const double* r, double* z, int64_t K, cud
     const int Kc = int(K);
     const LevelGeo& g = levels[0];
     rc = ensure_solve_ws(Kc); if (rc) return rc;
-    std::vector<int> ones(Kc, 1);
-    CK(cudaMemcpyAsync(ws.active, ones.data(), size_t(Kc) * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));
+    ++g_launches; k_fill_int<<<(Kc + 255) / 256, 256, 0, st>>>(ws.active, 1, Kc);
     CK(cudaMemcpyAsync(ws.r[0], r, size_t(Kc) * g.Dp * 8, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemsetAsync(ws_flags, 0, 64 * sizeof(int), st));
     if (coarse_direct) {
