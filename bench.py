@@ -279,8 +279,19 @@ def main():
     dom = max(per_kind, key=lambda k: k["avg_ms"]) if per_kind else None
     roofline = None
     if dom:
+        # DRAM bytes per launch of the same kernel from the committed ncu pass (same workload, K = 10000); null otherwise
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_dram_traffic_k10000.json")))
+            ncu_name = {"k_mg_down(l0)": "k_mgp_down(l0)", "k_mg_down(l>=1)": "k_mgp_down(l>=1)", "k_mg_up(l0)": "k_mgp_up(l0)",
+                        "k_mg_up(l>=1)": "k_mgp_up(l>=1)"}.get(dom["kernel"], dom["kernel"])
+            if tr.get("K") == K and ncu_name in tr["kernels"] and all(v is None for v in (args.strip_kb, args.nu, args.tile, args.tile_ty)):
+                traffic = tr["kernels"][ncu_name]["dram_bytes_per_launch"] / 1e9
+        except Exception:
+            traffic = None
         roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["GBps"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": dom["GBps"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": dom["GBps"] / hbm_peak, "traffic": traffic, "traffic_unit": "GB per launch (ncu dram__bytes_read+write)",
+                    "algorithmic_GB_per_launch": dom["algorithmic_GB"], "peak_source": peak_src,
                     "whole_iteration_GBps": sum(k["algorithmic_GB"] for k in per_kind) / (tot_ms * 1e-3)}
 
     secondary = {}
