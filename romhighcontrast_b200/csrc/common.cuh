@@ -14,7 +14,8 @@
 #define ROMHC_MAX_BLOCKS 256      // nrb * ncb
 #define ROMHC_MAX_LEVELS 12
 #define ROMHC_DIRECT_MAX 64       // coarsest level solved by dense Cholesky up to this many DOFs
-#define ROMHC_TAIL_MAX_DP 4352    // levels with Dp <= this run inside the one-CTA-per-system tail kernel
+#define ROMHC_TAIL_MAX_DP 4352    // levels with Dp <= this are smoothed nu_tail times (and may run inside the tail kernel)
+#define ROMHC_DEEP_TAIL_MAX_DP 1100   // the tail kernel proper starts at the first level this small (if the coarsest is)
 
 struct LevelGeo {
     int nrb, ncb;   // subdomain blocks (rows, cols)

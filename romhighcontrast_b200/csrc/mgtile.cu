@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "romhc_internal.h"
 
+#include <string.h>
 #include <algorithm>
 #include <array>
 #include <map>
@@ -89,12 +90,17 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t a) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
     return v;
 }
+__device__ __forceinline__ int lds_s32(uint32_t a) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
 __device__ __forceinline__ void sts_f64(uint32_t a, double v) {
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
 
 // Per-thread state.  CGT > 0: column groups per CTA known at compile time (P = 4 CGT), all displacements are immediates.
-template <int CGT>
+template <int CGT, bool CLS_SMEM = false>
 struct TileThread {
     uint32_t xl, xr;      // own slots of row 0 of the tile in EL / ER   ([4 ty][tx + 1])
     uint32_t et, eb;      // own slots of column 0 of the tile in ET / EB ([(ty + 1) * 4][tx])
@@ -102,6 +108,11 @@ struct TileThread {
     int rt;               // 2 bits per tile row: 0 not an interior row, 1 fast (class == the tile's primary class), 2 general
     int cg;               // column groups (runtime copy)
     int rho0;
+    int tx;               // column group of this thread
+    // vertex class + 1 of the tile's rows / columns, 16 bits each (0: not interior): in registers, or (CLS_SMEM, the
+    // persistent kernels) read from the row-info / column-class tables in shared memory when a general row needs them
+    uint32_t rvp[CLS_SMEM ? 1 : 2], cep[CLS_SMEM ? 1 : 2];
+    uint32_t ri_s, cv_s;  // CLS_SMEM: shared addresses of {rinfo, rvp0, rvp1} of this (strip, row group) and of the int4 column classes
     __device__ __forceinline__ int CG() const { return CGT > 0 ? CGT : cg; }
     __device__ __forceinline__ int CGp() const { return CG() + 2; }
 };
@@ -112,12 +123,25 @@ struct ColWeights {
     double hW[4], hE[4], idg[4], dg[NEED_DG ? 4 : 1];
 };
 
-template <int CGT>
-__device__ __forceinline__ uint32_t tile_entry(const TileThread<CGT>& t, const TileArgs& a, int I, int j) {
-    const int rv = __ldg(a.rowv + t.rho0 + I);
-    const int cv = __ldg(a.colv + 4 * int(threadIdx.x) + j);
+template <int CGT, bool CS>
+__device__ __forceinline__ uint32_t tile_entry(const TileThread<CGT, CS>& t, const TileArgs& a, int I, int j) {
+    int rv, cv;
+    if (CS) {
+        rv = int((uint32_t(lds_s32(t.ri_s + 4 + 4 * (I >> 1))) >> (16 * (I & 1))) & 0xffffu) - 1;
+        cv = lds_s32(t.cv_s + 4 * j);
+    } else {
+        rv = int((t.rvp[CS ? 0 : (I >> 1)] >> (16 * (I & 1))) & 0xffffu) - 1;
+        cv = int((t.cep[CS ? 0 : (j >> 1)] >> (16 * (j & 1))) & 0xffffu) - 1;
+    }
     const int e = cv >= 0 ? rv * a.ncv + cv : a.ntab - 1;
     return t.T + uint32_t(e) * (TWD * 8);
+}
+template <int CGT>
+__device__ __forceinline__ void tile_pack_classes(TileThread<CGT>& t, const int (&rv)[4], const int (&cv)[4]) {
+    t.rvp[0] = uint32_t(rv[0] + 1) | (uint32_t(rv[1] + 1) << 16);
+    t.rvp[1] = uint32_t(rv[2] + 1) | (uint32_t(rv[3] + 1) << 16);
+    t.cep[0] = uint32_t(cv[0] + 1) | (uint32_t(cv[1] + 1) << 16);
+    t.cep[1] = uint32_t(cv[2] + 1) | (uint32_t(cv[3] + 1) << 16);
 }
 
 // mbarrier + TMA bulk copy of the system's weight table, shared-memory carve-up, zeroed rim of the exchange buffers,
@@ -135,7 +159,7 @@ __device__ __forceinline__ void tile_setup_thread(TileThread<CGT>& t, ColWeights
     const uint32_t ET = ER + uint32_t(a.NR) * (CG + 2) * 8;
     const uint32_t EB = ET + uint32_t(NRG + 2) * 4 * CG * 8;
     red_addr = red;
-    t.cg = CG; t.T = base; t.rho0 = rho0;
+    t.cg = CG; t.T = base; t.rho0 = rho0; t.tx = tx;
     if (tx == 0 && ty == 0) {
         uint64_t* b = reinterpret_cast<uint64_t*>(smem_raw + (bar - base));
         mbar_init(b, 1);
@@ -184,6 +208,7 @@ __device__ __forceinline__ void tile_setup_thread(TileThread<CGT>& t, ColWeights
     }
     const int4 cv = __ldg(reinterpret_cast<const int4*>(a.colv) + tx);
     const int cvs[4] = {cv.x, cv.y, cv.z, cv.w};
+    tile_pack_classes(t, rv, cvs);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int e = (cvs[j] >= 0 && prim >= 0) ? prim * a.ncv + cvs[j] : a.ntab - 1;
@@ -195,8 +220,8 @@ __device__ __forceinline__ void tile_setup_thread(TileThread<CGT>& t, ColWeights
 }
 
 // publish the perimeter values of colour X (0 red: (row + col) even, 1 black) of the tile
-template <int X, int CGT>
-__device__ __forceinline__ void tile_publish(const double (&z)[4][4], const TileThread<CGT>& t) {
+template <int X, int CGT, bool CS>
+__device__ __forceinline__ void tile_publish(const double (&z)[4][4], const TileThread<CGT, CS>& t) {
     const int CG = t.CG(), CGp = t.CGp();
 #pragma unroll
     for (int I = 0; I < 4; ++I) {
@@ -214,9 +239,9 @@ __device__ __forceinline__ void tile_publish(const double (&z)[4][4], const Tile
 // MODE 0: Gauss-Seidel update z = (r + sum_nb w z_nb) / diag
 // MODE 1: residual d = r - diag z + sum_nb w z_nb, stored in place of z
 // MODE 2: first half sweep from a zero initial guess, z = r / diag (no neighbours)
-template <int X, int MODE, bool NEED_DG, int CGT>
+template <int X, int MODE, bool NEED_DG, int CGT, bool CS>
 __device__ __forceinline__ void tile_phase(double (&z)[4][4], const double (&r)[4][4], const ColWeights<NEED_DG>& w,
-                                           const TileThread<CGT>& t, const TileArgs& a) {
+                                           const TileThread<CGT, CS>& t, const TileArgs& a) {
     const int CG = t.CG(), CGp = t.CGp();
 #pragma unroll
     for (int I = 0; I < 4; ++I) {
@@ -482,7 +507,7 @@ __device__ __forceinline__ TileStage tile_stage_carve(uint32_t base, const TileA
     s.bar = s.red + 64 * 8;
     s.colv = s.bar + 16;
     s.rinfo = s.colv + uint32_t((4 * CG + 1) / 2) * 8;
-    s.ex = base + tile_stage_head(a.ntab, 4 * CG, a.ns * NRG) * 8;
+    s.ex = base + tile_stage_head(a.ntab, 4 * CG, 3 * a.ns * NRG) * 8;
     const uint32_t exb = (uint32_t(2) * a.NR * (CG + 2) + uint32_t(2) * (NRG + 2) * 4 * CG) * 8;
     const uint32_t strip = uint32_t(a.NR) * (4 * CG) * 8;
     s.Rs = s.ex + exb;
@@ -492,13 +517,8 @@ __device__ __forceinline__ TileStage tile_stage_carve(uint32_t base, const TileA
 }
 static size_t tile_stage_bytes(int ntab, int NR, int CG, int ns, bool with_z, int e_rows, int Pc) {
     const int NRG = NR / 4;
-    return (size_t(tile_stage_head(ntab, 4 * CG, ns * NRG)) + size_t(2) * NR * (CG + 2) + size_t(2) * (NRG + 2) * 4 * CG +
+    return (size_t(tile_stage_head(ntab, 4 * CG, 3 * ns * NRG)) + size_t(2) * NR * (CG + 2) + size_t(2) * (NRG + 2) * 4 * CG +
             size_t(with_z ? 2 : 1) * NR * 4 * CG + size_t(e_rows) * Pc) * 8;
-}
-__device__ __forceinline__ int lds_s32(uint32_t a) {
-    int v;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
 }
 __device__ __forceinline__ int4 lds_s32x4(uint32_t a) {
     int4 v;
@@ -516,14 +536,14 @@ __device__ __forceinline__ void tile_stage_tables(const TileStage& s, const Tile
 
 // one-time per-thread setup of the exchange-buffer addresses and the zero rim
 template <int CGT>
-__device__ __forceinline__ void tile_exchange_init(TileThread<CGT>& t, const TileArgs& a, uint32_t ex) {
+__device__ __forceinline__ void tile_exchange_init(TileThread<CGT, true>& t, const TileArgs& a, uint32_t ex) {
     const int CG = CGT > 0 ? CGT : int(blockDim.x), NRG = blockDim.y;
     const int tx = threadIdx.x, ty = threadIdx.y, CGp = CG + 2;
     const uint32_t EL = ex;
     const uint32_t ER = EL + uint32_t(a.NR) * CGp * 8;
     const uint32_t ET = ER + uint32_t(a.NR) * CGp * 8;
     const uint32_t EB = ET + uint32_t(NRG + 2) * 4 * CG * 8;
-    t.cg = CG;
+    t.cg = CG; t.tx = tx;
     t.xl = EL + uint32_t((4 * ty) * CGp + tx + 1) * 8;
     t.xr = ER + uint32_t((4 * ty) * CGp + tx + 1) * 8;
     t.et = ET + uint32_t((ty + 1) * 4 * CG + tx) * 8;
@@ -549,12 +569,13 @@ __device__ __forceinline__ void tile_exchange_init(TileThread<CGT>& t, const Til
 // per-item: primary-class weights of the thread's four columns (table already in shared memory).
 // rinfo = (row types, 2 bits per row) | primary class << 8, precomputed on the host per (strip, row group).
 template <int CGT, bool NEED_DG>
-__device__ __forceinline__ void tile_item_init(TileThread<CGT>& t, ColWeights<NEED_DG>& w, const TileArgs& a, uint32_t T,
-                                               int rho0, int rinfo, uint32_t colv_s) {
+__device__ __forceinline__ void tile_item_init(TileThread<CGT, true>& t, ColWeights<NEED_DG>& w, const TileArgs& a, uint32_t T,
+                                               int rho0, int rinfo, uint32_t ri_s, uint32_t colv_s) {
     t.T = T; t.rho0 = rho0;
     t.rt = rinfo & 0xff;
+    t.ri_s = ri_s; t.cv_s = colv_s + threadIdx.x * 16;
     const int prim = rinfo >> 8;          // -1: no fast row in this tile
-    const int4 cv = lds_s32x4(colv_s + threadIdx.x * 16);
+    const int4 cv = lds_s32x4(t.cv_s);
     const int cvs[4] = {cv.x, cv.y, cv.z, cv.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -572,9 +593,9 @@ __device__ __forceinline__ void tile_lds_row(double (&v)[4], uint32_t addr) {
 }
 
 // straight-line half sweep for a tile whose four rows all have the primary class (t.rt == 0x55)
-template <int X, int MODE, bool NEED_DG, int CGT>
+template <int X, int MODE, bool NEED_DG, int CGT, bool CS>
 __device__ __forceinline__ void tile_phase_fast(double (&z)[4][4], const double (&r)[4][4], const ColWeights<NEED_DG>& w,
-                                                const TileThread<CGT>& t) {
+                                                const TileThread<CGT, CS>& t) {
     const int CG = t.CG(), CGp = t.CGp();
     if (MODE == 2) {
 #pragma unroll
@@ -616,11 +637,11 @@ __device__ __forceinline__ void tile_phase_fast(double (&z)[4][4], const double 
         }
 }
 
-template <int X, int MODE, bool NEED_DG, int CGT>
+template <int X, int MODE, bool NEED_DG, int CGT, bool CS>
 __device__ __forceinline__ void tile_phase_any(double (&z)[4][4], const double (&r)[4][4], const ColWeights<NEED_DG>& w,
-                                               const TileThread<CGT>& t, const TileArgs& a) {
-    if (t.rt == 0x55) tile_phase_fast<X, MODE, NEED_DG, CGT>(z, r, w, t);
-    else              tile_phase<X, MODE, NEED_DG, CGT>(z, r, w, t, a);
+                                               const TileThread<CGT, CS>& t, const TileArgs& a) {
+    if (t.rt == 0x55) tile_phase_fast<X, MODE, NEED_DG>(z, r, w, t);
+    else              tile_phase<X, MODE, NEED_DG>(z, r, w, t, a);
 }
 
 // one thread: TMA bulk copy of rows [row0, row0 + nrow) (clamped to the grid) of one system into a staging strip
@@ -675,9 +696,9 @@ k_mgp_down(TileArgs a, const double* __restrict__ r_in, double* __restrict__ z_o
     const bool leader = tx == 0 && ty == 0;
     const uint32_t base = smem_u32(smem_raw);
     const TileStage s = tile_stage_carve(base, a, CG, NRG, false);
-    TileThread<CGT> t;
+    TileThread<CGT, true> t;
     tile_exchange_init(t, a, s.ex);
-    tile_stage_tables(s, a, P, a.ns * NRG);
+    tile_stage_tables(s, a, P, 3 * a.ns * NRG);
     if (leader) {
         mbar_init(reinterpret_cast<uint64_t*>(smem_raw + (s.bar - base)), 1);
         mbar_fence_init();
@@ -704,7 +725,8 @@ k_mgp_down(TileArgs a, const double* __restrict__ r_in, double* __restrict__ z_o
         TileWalk nx = wk;
         nx.step();
         const int nflag = nx.flag();                       // in flight while this item is set up
-        const int rinfo = lds_s32(s.rinfo + (wk.strip * NRG + ty) * 4);
+        const uint32_t ri = s.rinfo + (wk.strip * NRG + ty) * 12;
+        const int rinfo = lds_s32(ri);
         mbar_wait(reinterpret_cast<uint64_t*>(smem_raw + (s.bar - base)), phase);
         phase ^= 1u;
         double z[4][4], r[4][4];
@@ -724,7 +746,7 @@ k_mgp_down(TileArgs a, const double* __restrict__ r_in, double* __restrict__ z_o
             }
         }
         ColWeights<true> w;
-        tile_item_init(t, w, a, s.T0 + stage * s.tb, rho0, rinfo, s.colv);
+        tile_item_init(t, w, a, s.T0 + stage * s.tb, rho0, rinfo, ri, s.colv);
         __syncthreads();                                   // everybody has left the staging strip
         nx.settle(nflag);
         if (leader && nx.valid()) issue(nx, stage ^ 1);
@@ -790,9 +812,9 @@ k_mgp_up(TileArgs a, const double* __restrict__ e_c, const double* __restrict__ 
     const bool leader = tx == 0 && ty == 0;
     const uint32_t base = smem_u32(smem_raw);
     const TileStage s = tile_stage_carve(base, a, CG, NRG, true);
-    TileThread<CGT> t;
+    TileThread<CGT, true> t;
     tile_exchange_init(t, a, s.ex);
-    tile_stage_tables(s, a, P, a.ns * NRG);
+    tile_stage_tables(s, a, P, 3 * a.ns * NRG);
     if (leader) {
         mbar_init(reinterpret_cast<uint64_t*>(smem_raw + (s.bar - base)), 1);
         mbar_fence_init();
@@ -826,7 +848,8 @@ k_mgp_up(TileArgs a, const double* __restrict__ e_c, const double* __restrict__ 
         TileWalk nx = wk;
         nx.step();
         const int nflag = nx.flag();
-        const int rinfo = lds_s32(s.rinfo + (strip * NRG + ty) * 4);
+        const uint32_t ri = s.rinfo + (strip * NRG + ty) * 12;
+        const int rinfo = lds_s32(ri);
         mbar_wait(reinterpret_cast<uint64_t*>(smem_raw + (s.bar - base)), phase);
         phase ^= 1u;
         double z[4][4], r[4][4];
@@ -867,7 +890,7 @@ k_mgp_up(TileArgs a, const double* __restrict__ e_c, const double* __restrict__ 
             z[3][1] += 0.5 * (e[1][1] + e[2][0]); z[3][3] += 0.5 * (e[1][2] + e[2][1]);
         }
         ColWeights<false> w;
-        tile_item_init(t, w, a, s.T0 + stage * s.tb, rho0, rinfo, s.colv);
+        tile_item_init(t, w, a, s.T0 + stage * s.tb, rho0, rinfo, ri, s.colv);
         tile_publish<0>(z, t);
         __syncthreads();                                   // staging strip free, red perimeter visible
         nx.settle(nflag);
@@ -920,6 +943,336 @@ k_mgp_up(TileArgs a, const double* __restrict__ e_c, const double* __restrict__ 
     }
 }
 
+// =====================================================================================================
+// Multigrid tail on register tiles: every level with <= ROMHC_TAIL_MAX_DP padded vertices of ONE system, handled by one
+// CTA.  The level being relaxed lives in registers (4 x 4 tile per thread, as above), the other levels wait in
+// shared memory as plain padded arrays.  Replaces k_mg_tail (solver.cu), which spent ~90 instructions per point update
+// in generic shared-memory loops.
+// Shared memory (doubles): [T][red 32][mbarrier 2][exchange buffers of the finest tail level][z_l, r_l arrays][factor]
+// =====================================================================================================
+struct TailTileArgs {
+    int nlev;
+    LevelGeo geo[ROMHC_MAX_LEVELS];
+    const int* rowv[ROMHC_MAX_LEVELS];
+    const int* colv[ROMHC_MAX_LEVELS];
+    int off_z[ROMHC_MAX_LEVELS], off_r[ROMHC_MAX_LEVELS];   // doubles from the start of shared memory; off_r[0] < 0 if unused
+    int off_ex, off_fac, n_doubles;
+    const double* tab;
+    int ntab, ncv;
+    int direct, DL, LD, coarse_sweeps, nu;
+};
+
+// per-level thread setup: tile coordinates, exchange addresses + zero rim, row types, primary-class weights
+template <bool NEED_DG>
+__device__ __forceinline__ bool tail_level_enter(TileThread<0>& t, ColWeights<NEED_DG>& w, TileArgs& a, const TailTileArgs& p,
+                                                 int li, uint32_t base, int tid) {
+    const LevelGeo& g = p.geo[li];
+    const int CG = g.P / 4, NRG = (g.R + 3) / 4, CGp = CG + 2;
+    const int ty = tid / CG, tx = tid - ty * CG;
+    const bool act = ty < NRG;
+    a.rowv = p.rowv[li]; a.colv = p.colv[li]; a.ncv = p.ncv; a.ntab = p.ntab;
+    const int NR = 4 * NRG;
+    const uint32_t EL = base + uint32_t(p.off_ex) * 8;
+    const uint32_t ER = EL + uint32_t(NR) * CGp * 8;
+    const uint32_t ET = ER + uint32_t(NR) * CGp * 8;
+    const uint32_t EB = ET + uint32_t(NRG + 2) * 4 * CG * 8;
+    t.cg = CG; t.tx = tx; t.T = base; t.rho0 = 4 * ty; t.rt = 0;
+    t.xl = EL + uint32_t((4 * ty) * CGp + tx + 1) * 8;
+    t.xr = ER + uint32_t((4 * ty) * CGp + tx + 1) * 8;
+    t.et = ET + uint32_t((ty + 1) * 4 * CG + tx) * 8;
+    t.eb = EB + uint32_t((ty + 1) * 4 * CG + tx) * 8;
+    if (!act) return false;
+    if (tx == 0) {
+#pragma unroll
+        for (int I = 0; I < 4; ++I) sts_f64(t.xr + (I * CGp - 1) * 8, 0.0);
+    }
+    if (tx == CG - 1) {
+#pragma unroll
+        for (int I = 0; I < 4; ++I) sts_f64(t.xl + (I * CGp + 1) * 8, 0.0);
+    }
+    if (ty == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sts_f64(t.eb + (j - 4) * CG * 8, 0.0);
+    }
+    if (ty == NRG - 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sts_f64(t.et + (j + 4) * CG * 8, 0.0);
+    }
+    int rv[4], prim = -1;
+#pragma unroll
+    for (int I = 0; I < 4; ++I) {
+        rv[I] = __ldg(a.rowv + 4 * ty + I);
+        if (prim < 0 && rv[I] >= 0 && !(rv[I] & 1)) prim = rv[I];
+    }
+#pragma unroll
+    for (int I = 0; I < 4; ++I) t.rt |= (rv[I] < 0 ? 0 : (rv[I] == prim ? 1 : 2)) << (2 * I);
+    const int4 cv = __ldg(reinterpret_cast<const int4*>(a.colv) + tx);
+    const int cvs[4] = {cv.x, cv.y, cv.z, cv.w};
+    tile_pack_classes(t, rv, cvs);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int e = (cvs[j] >= 0 && prim >= 0) ? prim * a.ncv + cvs[j] : a.ntab - 1;
+        const uint32_t q = t.T + uint32_t(e) * (TWD * 8);
+        const double2 u = lds_f64x2(q), v = lds_f64x2(q + 32);
+        w.hW[j] = u.x; w.hE[j] = u.y; w.idg[j] = v.x;
+        if (NEED_DG) w.dg[j] = v.y;
+    }
+    return true;
+}
+
+// tile <-> padded array in shared memory (rows 0..R only)
+__device__ __forceinline__ void tail_tile_load(double (&v)[4][4], uint32_t arr, const LevelGeo& g, int rho0, int tx) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (rho0 + i <= g.R) tile_lds_row(v[i], arr + uint32_t((rho0 + i) * g.P + 4 * tx) * 8);
+        else { v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.0; }
+    }
+}
+__device__ __forceinline__ void tail_tile_store(uint32_t arr, const double (&v)[4][4], const LevelGeo& g, int rho0, int tx) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (rho0 + i <= g.R) {
+            const uint32_t a = arr + uint32_t((rho0 + i) * g.P + 4 * tx) * 8;
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v[i][0]), "d"(v[i][1]) : "memory");
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a + 16), "d"(v[i][2]), "d"(v[i][3]) : "memory");
+        }
+}
+__device__ __forceinline__ void tail_tile_load_global(double (&v)[4][4], const double* gsys, const LevelGeo& g, int rho0,
+                                                      int tx) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (rho0 + i <= g.R) tile_load_row(v[i], gsys + size_t(rho0 + i) * g.P + 4 * tx);
+        else { v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.0; }
+    }
+}
+
+__global__ void __launch_bounds__(256, 2)
+k_mgt_tail(TailTileArgs p, const double* __restrict__ r_in, double* __restrict__ z_out, const double* __restrict__ cfac,
+           const int* __restrict__ active, double* __restrict__ part_rz) {
+    const int64_t k = blockIdx.x;
+    if (!active[k]) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t base = smem_u32(smem_raw);
+    double* S = reinterpret_cast<double*>(smem_raw);
+    double* redp = S + size_t(p.ntab) * TWD;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(redp + 32);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        const uint32_t bytes = uint32_t(p.ntab) * TWD * 8u;
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(S, p.tab + k * int64_t(p.ntab) * TWD, bytes, bar);
+    }
+    // level arrays start out as zeros (boundary and padding slots stay zero for ever)
+    for (int i = p.off_ex + tid; i < p.off_fac; i += nt) S[i] = 0.0;
+    if (p.direct) {
+        const double* src = cfac + k * size_t(p.DL) * p.LD;
+        double* F = S + p.off_fac;
+        for (int i = tid; i < p.DL * p.LD; i += nt) F[i] = src[i];
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+    const int last = p.nlev - 1;
+    const double* rg = r_in + k * p.geo[0].Dp;
+    TileThread<0> t;
+    TileArgs a;
+    double z[4][4], r[4][4];
+    // ---- down ----
+    for (int li = 0; li < last; ++li) {
+        const LevelGeo& g = p.geo[li];
+        const LevelGeo& gc = p.geo[li + 1];
+        ColWeights<true> w;
+        const bool act = tail_level_enter(t, w, a, p, li, base, tid);
+        if (act) {
+            if (li == 0) tail_tile_load_global(r, rg, g, t.rho0, t.tx);
+            else         tail_tile_load(r, base + uint32_t(p.off_r[li]) * 8, g, t.rho0, t.tx);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) z[i][j] = 0.0;
+        }
+        for (int sw = 0; sw < p.nu; ++sw) {
+            if (act) {
+                if (sw == 0) tile_phase_any<0, 2, true>(z, r, w, t, a);
+                else         tile_phase_any<0, 0, true>(z, r, w, t, a);
+                tile_publish<0>(z, t);
+            }
+            __syncthreads();
+            if (act) {
+                tile_phase_any<1, 0, true>(z, r, w, t, a);
+                tile_publish<1>(z, t);
+            }
+            __syncthreads();
+        }
+        if (act) {
+            tail_tile_store(base + uint32_t(p.off_z[li]) * 8, z, g, t.rho0, t.tx);
+            tile_phase_any<0, 1, true>(z, r, w, t, a);
+            tile_publish<0>(z, t);
+        }
+        __syncthreads();
+        if (act) {
+            const int CG = t.cg, CGp = CG + 2;
+            const double dN31 = lds_f64(t.eb + (1 - 4) * CG * 8), dN33 = lds_f64(t.eb + (3 - 4) * CG * 8);
+            const double dW13 = lds_f64(t.xr + (1 * CGp - 1) * 8), dW33 = lds_f64(t.xr + (3 * CGp - 1) * 8);
+            double rc[2][2];
+            rc[0][0] = z[0][0] + 0.5 * (dN31 + dW13);
+            rc[0][1] = z[0][2] + 0.5 * (dN33 + z[1][1]);
+            rc[1][0] = z[2][0] + 0.5 * (z[1][1] + dW33);
+            rc[1][1] = z[2][2] + 0.5 * (z[1][3] + z[3][1]);
+            const int J0 = 2 * t.tx;
+            const bool okJ0 = J0 >= 1 && J0 <= gc.C - 1, okJ1 = J0 + 1 <= gc.C - 1;
+            double* co = S + p.off_r[li + 1] + J0;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int I = (t.rho0 >> 1) + q;
+                if (I <= gc.R) {
+                    const bool okI = I >= 1 && I <= gc.R - 1;
+                    co[size_t(I) * gc.P] = okI && okJ0 ? rc[q][0] : 0.0;
+                    co[size_t(I) * gc.P + 1] = okI && okJ1 ? rc[q][1] : 0.0;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // ---- coarsest ----
+    {
+        const LevelGeo& g = p.geo[last];
+        double* rs = S + p.off_r[last];
+        double* zs = S + p.off_z[last];
+        if (last == 0) {
+            for (int i = tid; i < g.Dp; i += nt) rs[i] = rg[i];
+            __syncthreads();
+        }
+        if (p.direct) {
+            // L L^T z = r with the packed factor (diagonal stores 1 / L_ii); warp 0, lanes own rows lane, lane+32
+            if (tid < 32) {
+                const int D = p.DL, LD = p.LD, W = g.C - 1;
+                const double* F = S + p.off_fac;
+                const int j0 = tid, j1 = tid + 32;
+                double b0 = 0.0, b1 = 0.0;
+                if (j0 < D) b0 = rs[(1 + j0 / W) * g.P + 1 + j0 % W];
+                if (j1 < D) b1 = rs[(1 + j1 / W) * g.P + 1 + j1 % W];
+                for (int i = 0; i < D; ++i) {
+                    const double bi = __shfl_sync(0xffffffffu, i < 32 ? b0 : b1, i & 31);
+                    const double yi = bi * F[i * LD + i];
+                    if (j0 == i) b0 = yi;
+                    if (j1 == i) b1 = yi;
+                    if (j0 > i && j0 < D) b0 = fma(-F[j0 * LD + i], yi, b0);
+                    if (j1 > i && j1 < D) b1 = fma(-F[j1 * LD + i], yi, b1);
+                }
+                for (int i = D - 1; i >= 0; --i) {
+                    const double bi = __shfl_sync(0xffffffffu, i < 32 ? b0 : b1, i & 31);
+                    const double xi = bi * F[i * LD + i];
+                    if (j0 == i) b0 = xi;
+                    if (j1 == i) b1 = xi;
+                    if (j0 < i) b0 = fma(-F[i * LD + j0], xi, b0);
+                    if (j1 < i) b1 = fma(-F[i * LD + j1], xi, b1);
+                }
+                if (j0 < D) zs[(1 + j0 / W) * g.P + 1 + j0 % W] = b0;
+                if (j1 < D) zs[(1 + j1 / W) * g.P + 1 + j1 % W] = b1;
+            }
+            __syncthreads();
+        } else {
+            ColWeights<false> w;
+            const bool act = tail_level_enter(t, w, a, p, last, base, tid);
+            if (act) {
+                tail_tile_load(r, base + uint32_t(p.off_r[last]) * 8, g, t.rho0, t.tx);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) z[i][j] = 0.0;
+            }
+            for (int sw = 0; sw < p.coarse_sweeps; ++sw) {
+                if (act) {
+                    if (sw == 0) tile_phase_any<0, 2, false>(z, r, w, t, a);
+                    else         tile_phase_any<0, 0, false>(z, r, w, t, a);
+                    tile_publish<0>(z, t);
+                }
+                __syncthreads();
+                if (act) { tile_phase_any<1, 0, false>(z, r, w, t, a); tile_publish<1>(z, t); }
+                __syncthreads();
+            }
+            for (int sw = 0; sw < p.coarse_sweeps; ++sw) {
+                if (act) { tile_phase_any<1, 0, false>(z, r, w, t, a); tile_publish<1>(z, t); }
+                __syncthreads();
+                if (act) { tile_phase_any<0, 0, false>(z, r, w, t, a); tile_publish<0>(z, t); }
+                __syncthreads();
+            }
+            if (act) tail_tile_store(base + uint32_t(p.off_z[last]) * 8, z, g, t.rho0, t.tx);
+            __syncthreads();
+        }
+    }
+    // ---- up ----
+    double acc = 0.0;
+    for (int li = last - 1; li >= 0; --li) {
+        const LevelGeo& g = p.geo[li];
+        const LevelGeo& gc = p.geo[li + 1];
+        ColWeights<false> w;
+        const bool act = tail_level_enter(t, w, a, p, li, base, tid);
+        if (act) {
+            tail_tile_load(z, base + uint32_t(p.off_z[li]) * 8, g, t.rho0, t.tx);
+            if (li == 0) tail_tile_load_global(r, rg, g, t.rho0, t.tx);
+            else         tail_tile_load(r, base + uint32_t(p.off_r[li]) * 8, g, t.rho0, t.tx);
+            const int I0 = t.rho0 >> 1, J0 = 2 * t.tx;
+            const uint32_t es = base + uint32_t(p.off_z[li + 1] + I0 * gc.P + J0) * 8;
+            double e[3][3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                e[q][0] = e[q][1] = e[q][2] = 0.0;
+                if (I0 + q <= gc.R) {
+                    const double2 v = lds_f64x2(es + q * gc.P * 8);
+                    e[q][0] = v.x; e[q][1] = v.y;
+                    if (J0 + 2 < gc.P) e[q][2] = lds_f64(es + q * gc.P * 8 + 16);
+                }
+            }
+            z[0][0] += e[0][0]; z[0][2] += e[0][1];
+            z[2][0] += e[1][0]; z[2][2] += e[1][1];
+            z[1][1] += 0.5 * (e[0][1] + e[1][0]); z[1][3] += 0.5 * (e[0][2] + e[1][1]);
+            z[3][1] += 0.5 * (e[1][1] + e[2][0]); z[3][3] += 0.5 * (e[1][2] + e[2][1]);
+            tile_publish<0>(z, t);
+        }
+        __syncthreads();
+        for (int sw = 0; sw < p.nu; ++sw) {
+            if (act) { tile_phase_any<1, 0, false>(z, r, w, t, a); tile_publish<1>(z, t); }
+            __syncthreads();
+            if (act) {
+                tile_phase_any<0, 0, false>(z, r, w, t, a);
+                if (sw + 1 < p.nu) tile_publish<0>(z, t);
+            }
+            if (sw + 1 < p.nu) __syncthreads();
+        }
+        if (li > 0) {
+            if (act) tail_tile_store(base + uint32_t(p.off_z[li]) * 8, z, g, t.rho0, t.tx);
+            __syncthreads();
+        } else if (act) {
+            double* zo = z_out + k * g.Dp;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (t.rho0 + i <= g.R) {
+                    tile_store_row(zo + size_t(t.rho0 + i) * g.P + 4 * t.tx, z[i]);
+                    acc += fma(r[i][0], z[i][0], r[i][1] * z[i][1]) + fma(r[i][2], z[i][2], r[i][3] * z[i][3]);
+                }
+        }
+    }
+    if (last == 0) {
+        // the whole hierarchy is the coarsest level: the solution sits in the shared-memory array
+        const LevelGeo& g = p.geo[0];
+        const double* zs = S + p.off_z[0];
+        const double* rs = S + p.off_r[0];
+        double* zo = z_out + k * g.Dp;
+        for (int i = tid; i < g.Dp; i += nt) {
+            const double v = zs[i];
+            zo[i] = v;
+            acc = fma(rs[i], v, acc);
+        }
+    }
+    if (part_rz) {
+        const double tot = block_sum(acc, redp, tid, nt);
+        if (tid == 0) part_rz[k] = tot;
+    }
+}
+
 // ======================================================================================================
 // host side
 // ======================================================================================================
@@ -935,16 +1288,17 @@ int Context::tile_setup() {
         int& m = i < 3 ? tile_maxt_down : tile_maxt_up;
         m = std::min(m, fa.maxThreadsPerBlock);
     }
-    const void* pfns[] = {(const void*)k_mgp_down<64>, (const void*)k_mgp_down<32>, (const void*)k_mgp_down<0>,
-                          (const void*)k_mgp_up<64>,   (const void*)k_mgp_up<32>,   (const void*)k_mgp_up<0>};
-    for (int i = 0; i < 6; ++i) {
+    const void* pfns[] = {(const void*)k_mgp_down<64>, (const void*)k_mgp_down<32>, (const void*)k_mgp_down<16>, (const void*)k_mgp_down<0>,
+                          (const void*)k_mgp_up<64>,   (const void*)k_mgp_up<32>,   (const void*)k_mgp_up<16>,   (const void*)k_mgp_up<0>};
+    for (int i = 0; i < 8; ++i) {
         CK(cudaFuncSetAttribute(pfns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         cudaFuncAttributes fa;
         CK(cudaFuncGetAttributes(&fa, pfns[i]));
-        int& m = i < 3 ? tile_maxt_down : tile_maxt_up;
+        int& m = i < 4 ? tile_maxt_down : tile_maxt_up;
         m = std::min(m, fa.maxThreadsPerBlock);
     }
     CK(cudaDeviceGetAttribute(&tile_nsm, cudaDevAttrMultiProcessorCount, device));
+    CK(cudaFuncSetAttribute(k_mgt_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     // vertex-class tables of every level
     for (int* p : tile_rowv) cudaFree(p);
     for (int* p : tile_colv) cudaFree(p);
@@ -989,7 +1343,7 @@ const int* Context::tile_rinfo(int l, int TY, int halo_top, int NR) {
         return (v % g.N) ? 2 * (v / g.N) : 2 * (v / g.N) - 1;
     };
     const int ns = (g.R + TY - 1) / TY, NRG = NR / 4;
-    std::vector<int> tab(size_t(ns) * NRG);
+    std::vector<int> tab(size_t(ns) * NRG * 3);
     for (int s = 0; s < ns; ++s)
         for (int ty = 0; ty < NRG; ++ty) {
             const int rho0 = s * TY - halo_top + 4 * ty;
@@ -999,13 +1353,23 @@ const int* Context::tile_rinfo(int l, int TY, int halo_top, int NR) {
                 if (prim < 0 && rv[i] >= 0 && !(rv[i] & 1)) prim = rv[i];
             }
             for (int i = 0; i < 4; ++i) rt |= (rv[i] < 0 ? 0 : (rv[i] == prim ? 1 : 2)) << (2 * i);
-            tab[size_t(s) * NRG + ty] = (prim * 256) | rt;
+            int* o = &tab[(size_t(s) * NRG + ty) * 3];
+            o[0] = (prim * 256) | rt;
+            o[1] = int(unsigned(rv[0] + 1) | (unsigned(rv[1] + 1) << 16));
+            o[2] = int(unsigned(rv[2] + 1) | (unsigned(rv[3] + 1) << 16));
         }
     int* d = nullptr;
     if (cudaMalloc(&d, tab.size() * sizeof(int)) != cudaSuccess) return nullptr;
     if (cudaMemcpy(d, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
     tile_rinfo_cache[key] = d;
     return d;
+}
+
+// grid of a persistent kernel: every CTA slot of the GPU (SMs x resident CTAs per SM), at most one CTA per item
+int Context::tile_persistent_grid(const void* func, int threads, size_t smem, int64_t items) {
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return int(std::min<int64_t>(int64_t(tile_nsm) * per_sm, items));
 }
 
 int Context::tile_ntab() const { return (2 * nrb - 1) * (2 * ncb - 1) + 1; }
@@ -1016,12 +1380,52 @@ int Context::tile_weight_table(const double* y, int Kc, cudaStream_t st) {
     return ROMHC_OK;
 }
 
+// multigrid tail on register tiles; returns ROMHC_ERR_ARG if the configuration does not fit (caller falls back)
+int Context::tile_tail(const double* y, int Kc, double* part_rz, cudaStream_t st) {
+    (void)y;
+    const int L = int(levels.size()) - 1;
+    TailTileArgs p;
+    memset(&p, 0, sizeof(p));
+    p.nlev = L - tail_level + 1;
+    p.tab = ws.wtab; p.ntab = tile_ntab(); p.ncv = 2 * ncb - 1;
+    p.direct = coarse_direct ? 1 : 0; p.DL = coarse_D; p.LD = coarse_LD; p.coarse_sweeps = coarse_sweeps; p.nu = nu_tail;
+    const LevelGeo& g0 = levels[tail_level];
+    const int CG0 = g0.P / 4, NRG0 = (g0.R + 3) / 4;
+    int threads = ((CG0 * NRG0 + 31) / 32) * 32;
+    int off = p.ntab * TWD + 34;
+    p.off_ex = off;
+    int exmax = 0;
+    for (int l = 0; l < p.nlev; ++l) {
+        const LevelGeo& g = levels[tail_level + l];
+        const int CG = g.P / 4, NRG = (g.R + 3) / 4;
+        exmax = std::max(exmax, 2 * 4 * NRG * (CG + 2) + 2 * (NRG + 2) * 4 * CG);
+        threads = std::max(threads, ((CG * NRG + 31) / 32) * 32);
+    }
+    off += exmax;
+    for (int l = 0; l < p.nlev; ++l) {
+        p.geo[l] = levels[tail_level + l];
+        p.rowv[l] = tile_rowv[tail_level + l] + ROMHC_ROWV_PAD;
+        p.colv[l] = tile_colv[tail_level + l];
+        p.off_z[l] = off; off += p.geo[l].Dp;
+        if (l > 0 || p.nlev == 1) { p.off_r[l] = off; off += p.geo[l].Dp; } else p.off_r[l] = -1;
+    }
+    p.off_fac = off;
+    if (coarse_direct) off += coarse_D * coarse_LD;
+    p.n_doubles = off;
+    const size_t sm = size_t(off) * 8;
+    if (threads > 256 || sm > 227 * 1024) return ROMHC_ERR_ARG;
+    ++g_launches;
+    k_mgt_tail<<<Kc, threads, sm, st>>>(p, ws.r[tail_level], ws.za[tail_level], ws.cfac, ws.active, part_rz);
+    return ROMHC_OK;
+}
+
 // can the tile kernels run level l?  (column groups per CTA, register budget, shared memory)
 bool Context::tile_level_ok(int l) const {
     if (!use_tile) return false;
     const LevelGeo& g = levels[l];
     const int CG = g.P / 4;
     const int maxt = std::min(tile_maxt_down, tile_maxt_up);
+    const int nu = nu_of(l);
     const int nrg_min = (2 + 4 * nu + 2 + 3) / 4;      // TY = 2 in the down kernel
     if (CG * nrg_min > maxt || CG > 128) return false;
     return true;
@@ -1050,6 +1454,7 @@ int Context::tile_down(int l, const double* y, int Kc, cudaStream_t st) {
     a.gc = a.has_coarse ? levels[l + 1] : levels[l];
     a.rowv = tile_rowv[l] + ROMHC_ROWV_PAD; a.colv = tile_colv[l];
     a.tab = ws.wtab; a.ntab = tile_ntab(); a.ncv = 2 * ncb - 1;
+    const int nu = nu_of(l);
     a.nu = nu;
     a.halo_top = 2 * nu + 2;
     a.pf_dist = 0; a.rinfo = nullptr;
@@ -1063,10 +1468,10 @@ int Context::tile_down(int l, const double* y, int Kc, cudaStream_t st) {
         const size_t sm = tile_stage_bytes(a.ntab, a.NR, CG, a.ns, false, 0, 0);
         if (sm <= 227 * 1024) {
             a.ns = (a.g.R + a.TY - 1) / a.TY;
-            const int grid = int(std::min<int64_t>(tile_nsm, int64_t(Kc) * a.ns));
-            auto fn = CG == 64 ? k_mgp_down<64> : (CG == 32 ? k_mgp_down<32> : k_mgp_down<0>);
+            auto fn = CG == 64 ? k_mgp_down<64> : (CG == 32 ? k_mgp_down<32> : (CG == 16 ? k_mgp_down<16> : k_mgp_down<0>));
             a.rinfo = tile_rinfo(l, a.TY, a.halo_top, a.NR);
             if (!a.rinfo) { set_error("tile kernels: row-info table allocation failed"); return ROMHC_ERR_CUDA; }
+            const int grid = tile_persistent_grid((const void*)fn, CG * (a.NR / 4), sm, int64_t(Kc) * a.ns);
             ++g_launches;
             fn<<<grid, dim3(CG, a.NR / 4), sm, st>>>(a, ws.r[l], ws.za[l], a.has_coarse ? ws.r[l + 1] : nullptr, ws.active, Kc);
             return ROMHC_OK;
@@ -1092,6 +1497,7 @@ int Context::tile_up(int l, const double* y, int Kc, const double* e, double* pa
     a.gc = a.has_coarse ? levels[l + 1] : levels[l];
     a.rowv = tile_rowv[l] + ROMHC_ROWV_PAD; a.colv = tile_colv[l];
     a.tab = ws.wtab; a.ntab = tile_ntab(); a.ncv = 2 * ncb - 1;
+    const int nu = nu_of(l);
     a.nu = nu;
     a.halo_top = 2 * nu;
     a.pf_dist = 0; a.rinfo = nullptr;
@@ -1105,10 +1511,10 @@ int Context::tile_up(int l, const double* y, int Kc, const double* e, double* pa
         const size_t sm = bytes();
         if (sm <= 227 * 1024) {
             a.ns = (a.g.R + a.TY - 1) / a.TY;
-            const int grid = int(std::min<int64_t>(tile_nsm, int64_t(Kc) * a.ns));
-            auto fn = CG == 64 ? k_mgp_up<64> : (CG == 32 ? k_mgp_up<32> : k_mgp_up<0>);
+            auto fn = CG == 64 ? k_mgp_up<64> : (CG == 32 ? k_mgp_up<32> : (CG == 16 ? k_mgp_up<16> : k_mgp_up<0>));
             a.rinfo = tile_rinfo(l, a.TY, a.halo_top, a.NR);
             if (!a.rinfo) { set_error("tile kernels: row-info table allocation failed"); return ROMHC_ERR_CUDA; }
+            const int grid = tile_persistent_grid((const void*)fn, CG * (a.NR / 4), sm, int64_t(Kc) * a.ns);
             ++g_launches;
             fn<<<grid, dim3(CG, a.NR / 4), sm, st>>>(a, e, ws.za[l], ws.r[l], ws.zb[l], ws.active, part_rz, Kc);
             *ns_out = a.ns;

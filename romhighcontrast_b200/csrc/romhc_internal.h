@@ -81,6 +81,8 @@ struct Context {
     // multigrid hierarchy
     std::vector<LevelGeo> levels;
     int tail_level = 0;        // first level handled by the tail kernel (levels.size() if none)
+    int smooth_tail_level = 0; // first level smoothed nu_tail times
+    int nu_of(int l) const { return l >= smooth_tail_level ? nu_tail : nu; }
     int coarse_D = 0, coarse_LD = 1;
     bool coarse_direct = false;
     int coarse_sweeps = 8;
@@ -149,10 +151,12 @@ struct Context {
     // mgtile.cu
     int tile_setup();
     int tile_ntab() const;
+    int tile_persistent_grid(const void* func, int threads, size_t smem, int64_t items);
     const int* tile_rinfo(int l, int TY, int halo_top, int NR);
     int tile_pf_dist(const void* func, int threads, size_t smem);
     bool tile_level_ok(int l) const;
     int tile_weight_table(const double* y, int Kc, cudaStream_t st);
+    int tile_tail(const double* y, int Kc, double* part_rz, cudaStream_t st);
     int tile_down(int l, const double* y, int Kc, cudaStream_t st);
     int tile_up(int l, const double* y, int Kc, const double* e, double* part_rz, int* ns_out, cudaStream_t st);
 

@@ -884,6 +884,13 @@ int Context::build_levels() {
     tail_level = L + 1;
     for (int l = 0; l <= L; ++l)
         if (levels[l].Dp <= ROMHC_TAIL_MAX_DP) { tail_level = l; break; }
+    // levels from `smooth_tail_level` on are smoothed nu_tail times (the algorithm, mirrored by tests/gmg_twin.py); the
+    // one-CTA-per-system tail KERNEL starts deeper when the coarsest level is small enough: the levels in between
+    // (e.g. the 65 x 64 grid of the 256^2 hierarchy) keep more SMs busy in the batched strip kernels
+    smooth_tail_level = tail_level;
+    if (levels[L].Dp <= ROMHC_DEEP_TAIL_MAX_DP)
+        for (int l = tail_level; l <= L; ++l)
+            if (levels[l].Dp <= ROMHC_DEEP_TAIL_MAX_DP) { tail_level = l; break; }
     const LevelGeo& gl = levels[L];
     coarse_D = (gl.R - 1) * (gl.C - 1);
     coarse_direct = (tail_level <= L) && coarse_D <= ROMHC_DIRECT_MAX;
@@ -1081,6 +1088,7 @@ int Context::vcycle(const double* y, int Kc, cudaStream_t st, const double** z_r
             continue;
         }
         dim3 block; strip_block(g, block, strip_threads);
+        const int nu = nu_of(l);
         const int halo = has_c ? 4 * nu + 1 : 4 * nu - 2;
         auto bytes = [&](int TY) { return hdr + size_t(2) * (TY + halo) * g.P * 8 + (has_c ? size_t(TY / 2) * gc.P * 8 : 0); };
         const int TY = pick_ty_fn(g, strip_budget, bytes);
@@ -1093,8 +1101,11 @@ int Context::vcycle(const double* y, int Kc, cudaStream_t st, const double** z_r
     }
     if (tail_level <= L) {
         prof_begin(PROF_TAIL, st);
-        ++g_launches; k_mg_tail<<<Kc, 256, tail_smem, st>>>(tail, y, ws.r[tail_level], ws.za[tail_level], ws.cfac, ws.active,
-                                              tail_level == 0 ? ws.part_rz : nullptr);
+        int rc_t = use_tile ? tile_tail(y, Kc, tail_level == 0 ? ws.part_rz : nullptr, st) : ROMHC_ERR_ARG;
+        if (rc_t != ROMHC_OK) {
+            ++g_launches; k_mg_tail<<<Kc, 256, tail_smem, st>>>(tail, y, ws.r[tail_level], ws.za[tail_level], ws.cfac, ws.active,
+                                                  tail_level == 0 ? ws.part_rz : nullptr);
+        }
         prof_end(st);
     }
     for (int l = nstrip_levels - 1; l >= 0; --l) {
@@ -1102,6 +1113,7 @@ int Context::vcycle(const double* y, int Kc, cudaStream_t st, const double** z_r
         const bool has_c = l < L;
         const LevelGeo& gc = has_c ? levels[l + 1] : g;
         dim3 block; strip_block(g, block, strip_threads);
+        const int nu = nu_of(l);
         auto bytes = [&](int TY) {
             return hdr + size_t(2 * TY + 8 * nu - 2) * g.P * 8 + (has_c ? size_t(TY / 2 + 2 * nu + 1) * gc.P * 8 : 0);
         };
