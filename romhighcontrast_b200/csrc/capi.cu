@@ -136,6 +136,7 @@ int romhc_set_option(romhc_handle h, const char* name, double value) {
     else if (!strcmp(name, "maxit")) c->maxit = (int)value;
     else if (!strcmp(name, "coarse_sweeps")) { c->coarse_sweeps = std::max(1, (int)value); c->build_levels(); }
     else if (!strcmp(name, "nu")) { c->nu = std::max(1, std::min(4, (int)value)); }
+    else if (!strcmp(name, "nu_mid")) { c->nu_mid = std::max(0, std::min(4, (int)value)); }
     else if (!strcmp(name, "nu_tail")) { c->nu_tail = std::max(1, std::min(8, (int)value)); c->build_levels(); }
     else if (!strcmp(name, "tile")) c->use_tile = value != 0.0;
     else if (!strcmp(name, "tile_persistent")) c->tile_persistent = value != 0.0;

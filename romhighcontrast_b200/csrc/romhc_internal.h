@@ -82,11 +82,14 @@ struct Context {
     std::vector<LevelGeo> levels;
     int tail_level = 0;        // first level handled by the tail kernel (levels.size() if none)
     int smooth_tail_level = 0; // first level smoothed nu_tail times
-    int nu_of(int l) const { return l >= smooth_tail_level ? nu_tail : nu; }
+    int nu_of(int l) const { return l >= smooth_tail_level ? nu_tail : (l == 0 || nu_mid <= 0 ? nu : nu_mid); }
     int coarse_D = 0, coarse_LD = 1;
     bool coarse_direct = false;
     int coarse_sweeps = 8;
-    int nu = 1, nu_tail = 2;   // red/black Gauss-Seidel sweeps before and after the coarse correction: V(nu, nu)
+    // red/black Gauss-Seidel sweeps before and after the coarse correction, V(nu, nu): nu on the finest level, nu_mid on
+    // the other levels handled by the batched kernels (0: same as nu), nu_tail on the small levels (Dp <= ROMHC_TAIL_MAX_DP)
+    // defaults from a sweep on the 256^2 / 10k-system workload (profiles/README.md): V(2,2) / V(3,3) / V(4,4)
+    int nu = 2, nu_mid = 3, nu_tail = 4;
     bool use_tile = true;               // register-tiled multigrid kernels (mgtile.cu) where the level fits
     int tile_ty_cap = 64;               // largest strip height of the tile kernels
     bool tile_prefetch = true;          // L2 prefetch of the next CTA's operand rows (non-persistent tile kernels)

@@ -1,7 +1,8 @@
 """numpy twin of the CUDA GMG-PCG algorithm (romhighcontrast_b200/csrc/solver.cu) on the full vertex grid.
 
 Test infrastructure: used to check single kernels (stencil apply, one V-cycle, iteration counts)
-at sizes where running it takes milliseconds.  Same algorithm, different code: red/black GS V(1,1),
+at sizes where running it takes milliseconds.  Same algorithm, different code: red/black GS V(nu,nu) with
+nu = 2 / 3 / 4 sweeps on the finest / intermediate / small levels (the library defaults),
 P1 anti-diagonal transfers, rediscretised coarse operators, dense coarsest solve, difference-form apply.
 """
 import numpy as np
@@ -82,9 +83,9 @@ class GMG:
     DIRECT_MAX = 64
     TAIL_MAX_DP = 4352
 
-    def __init__(self, a, N, coarse_sweeps=8, nu=1, nu_tail=2):
+    def __init__(self, a, N, coarse_sweeps=8, nu=2, nu_tail=4, nu_mid=3):
         a = np.asarray(a, float)
-        self.nu, self.nu_tail = nu, nu_tail
+        self.nu, self.nu_tail, self.nu_mid = nu, nu_tail, (nu_mid or nu)
         nrb, ncb = a.shape
         self.levels = []
         n = N
@@ -116,7 +117,7 @@ class GMG:
         if self.direct:
             z[1:-1, 1:-1] = np.linalg.solve(self.coarse_matrix, r[1:-1, 1:-1].ravel()).reshape(L.R - 1, L.C - 1)
             return z
-        sweeps = self.nu if self.smooth_only else self.coarse_sweeps
+        sweeps = (self.nu if len(self.levels) == 1 else self.nu_mid) if self.smooth_only else self.coarse_sweeps
         for _ in range(sweeps):
             L.gs_half(z, r, L.red); L.gs_half(z, r, L.black)
         for _ in range(sweeps):
@@ -128,7 +129,7 @@ class GMG:
             return self.coarse_solve(r)
         L = self.levels[l]
         in_tail = (L.R + 1) * ((L.C + 7) // 8 * 8) <= self.TAIL_MAX_DP
-        nu = self.nu_tail if in_tail else self.nu
+        nu = self.nu_tail if in_tail else (self.nu if l == 0 else self.nu_mid)
         z = np.zeros_like(r)
         for _ in range(nu):
             L.gs_half(z, r, L.red); L.gs_half(z, r, L.black)
@@ -140,8 +141,8 @@ class GMG:
         return z
 
 
-def pcg(a, N, tol=1e-12, maxit=1000, coarse_sweeps=8, nu=1, nu_tail=2):
-    g = GMG(a, N, coarse_sweeps, nu, nu_tail)
+def pcg(a, N, tol=1e-12, maxit=1000, coarse_sweeps=8, nu=2, nu_tail=4, nu_mid=3):
+    g = GMG(a, N, coarse_sweeps, nu, nu_tail, nu_mid)
     L = g.levels[0]
     b = np.zeros((L.R + 1, L.C + 1)); b[1:-1, 1:-1] = 1.0 / N ** 2
     x = np.zeros_like(b); r = b.copy()

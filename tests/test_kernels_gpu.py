@@ -78,6 +78,7 @@ def test_precond_matches_twin(torch_mod, geo, N, nu, tile):
     eng.set_option("tile", min(tile, 1))
     eng.set_option("tile_persistent", 1 if tile == 2 else 0)
     eng.set_option("nu", nu)
+    eng.set_option("nu_mid", nu)
     eng.set_option("nu_tail", nu)
     K = 3
     y = rand_y(geo, K, seed=2)
@@ -85,7 +86,7 @@ def test_precond_matches_twin(torch_mod, geo, N, nu, tile):
     Rr = rng.standard_normal((K, eng.D))
     z = eng.unpad(eng.precond(eng.params(y), eng.pad(Rr))).cpu().numpy()
     for k in range(K):
-        tw = GMG(y[k], N, nu=nu, nu_tail=nu)
+        tw = GMG(y[k], N, nu=nu, nu_tail=nu, nu_mid=nu)
         zt = tw.vcycle(grid_of(eng, Rr[k]))[1:-1, 1:-1].ravel()
         assert relerr(z[k], zt) < 1e-9, (geo, N, k, relerr(z[k], zt))
 
