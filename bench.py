@@ -274,6 +274,8 @@ def main():
         if pn[i] > 0:
             avg_ms = pms[i] / pn[i]
             streams = KIND_STREAMS[i]
+            if nm == "k_mg_tail":
+                streams = 2.0 / 4.0 ** eng.tail_level            # reads r, writes z of its first level
             if nm.endswith("(l>=1)") and pn[2] > 0:
                 nl = max(1, int(round(pn[i] / pn[2])))          # levels 1..nl share this kind: mean bytes per launch
                 streams = KIND_STREAMS[i] * sum(4.0 ** -(l - 1) for l in range(1, nl + 1)) / nl

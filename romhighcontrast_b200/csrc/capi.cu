@@ -146,6 +146,7 @@ int romhc_set_option(romhc_handle h, const char* name, double value) {
     else if (!strcmp(name, "strip_kb")) c->strip_budget = (size_t)std::max(16.0, std::min(227.0, value)) * 1024;
     else if (!strcmp(name, "workspace_gb")) c->ws_budget_bytes = (size_t)(value * double(1 << 30));
     else if (!strcmp(name, "profile")) { c->prof_on = value != 0.0; for (int i = 0; i < PROF_NKIND; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; } }
+    else if (!strcmp(name, "host_chunks")) c->host_chunks = std::max(1, std::min(64, (int)value));
     else if (!strcmp(name, "check_every")) c->check_every = std::max(1, (int)value);
     else if (!strcmp(name, "min_check_iter")) c->min_check_iter = std::max(1, (int)value);
     else { set_error("unknown option '%s'", name); return ROMHC_ERR_ARG; }
@@ -262,7 +263,7 @@ int romhc_generate_solutions_host(romhc_handle h, const double* y_host, int64_t 
     // (compute stream).  Staging buffers persist in the context.
     const size_t per = 2 * size_t(g.Dp + D) * 8 + c->solve_bytes_per_system();
     int64_t chunk = std::max<int64_t>(1, std::min<int64_t>({(int64_t)(c->ws_budget_bytes / per), (int64_t)32768, K}));
-    if (K >= 4096) chunk = std::min<int64_t>(chunk, (K + 3) / 4);
+    if (K >= 4096) chunk = std::min<int64_t>(chunk, (K + c->host_chunks - 1) / c->host_chunks);
     int rc = c->ensure_host_stage(chunk);
     if (rc) return rc;
     HostStage& s = c->hstage;

@@ -108,6 +108,7 @@ struct Context {
     int maxit = 1000;
     int min_check_iter = 8, check_every = 2;
     size_t ws_budget_bytes = size_t(48) << 30;
+    int host_chunks = 4;       // pipeline depth of the host-buffer entry point for large batches
     // state
     bool kernels_configured = false;
     void* scratch = nullptr;

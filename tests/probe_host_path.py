@@ -16,11 +16,11 @@ y=bench.sample_params(K,42)
 U=torch.empty((K,eng.D),dtype=torch.float64).pin_memory().numpy()
 yp=np.ascontiguousarray(y.reshape(K,-1))
 eng.generate_solutions_host(yp,out=U)
-for ws in [48, 12, 6]:
-    eng.set_option("workspace_gb", ws)
+for ws in [4, 6, 8, 12]:
+    eng.set_option("host_chunks", ws)
     eng.generate_solutions_host(yp,out=U)
     torch.cuda.synchronize(); t=time.perf_counter(); eng.generate_solutions_host(yp,out=U); torch.cuda.synchronize(); dt=time.perf_counter()-t
-    print('workspace_gb',ws,'e2e ms',dt*1e3, K/dt)
+    print('host_chunks',ws,'e2e ms',dt*1e3, K/dt)
 yd=eng.params(y); x=eng.empty(K,eng.Dp)
 eng.set_option("workspace_gb", 48)
 for k in [10000,2500,1250]:
