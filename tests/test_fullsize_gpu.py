@@ -1,0 +1,112 @@
+"""GPU parity at BASELINE.json's full mesh size through size-independent properties (the oracle only spot-checks).
+
+configs[2]: (4,4) subdomains, N = 64 (256 x 256 cells, D = 65 025), contrast 10^U(0,6).  Tolerances: 1e-9 relative
+(north_star) on anything compared with the oracle; the algebraic identities are checked to the accuracy the PCG
+stopping rule (rtol 1e-12 on the preconditioned residual) implies.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GEO, N = (4, 4), 64
+
+
+def sample(K, seed):
+    return 10 ** np.random.default_rng(seed).uniform(0, 6, (K,) + GEO)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from romhighcontrast_b200.engine import Engine
+    return Engine(GEO, N)
+
+
+def test_snapshots_full_size_identities(eng):
+    import torch
+    from oracle import FEMOracle
+    K = 4096
+    y = sample(K, 42)
+    yd = eng.params(y)
+    x, iters, relres = eng.solve(yd)
+    assert eng.last_solve_stats["status"] == 0
+    assert int(iters.max()) <= 30 and int(iters.min()) >= 5
+    assert float(relres.max()) <= 1e-12 * 1.0000001
+    # true residual b - A(y) u, b = 1 / N^2 on the interior vertices (SolutionsManagers.py:177-185).  With contrast
+    # 1e6 the Euclidean norm of the residual is dominated by the stiff blocks (entries of A up to 4e6), so the
+    # scale-free measure is the Jacobi-scaled one: |r_i| / diag_i relative to max |u|
+    b = eng.pad(np.full((1, eng.D), 1.0 / N ** 2))
+    res = b - eng.apply(yd, x)
+    sub = slice(0, 64)
+    kc = np.kron(y[sub], np.ones((1, N, N)))                               # cell coefficients (64, R, C)
+    kp = np.pad(kc, ((0, 0), (1, 1), (1, 1)))
+    diag = (kp[:, :-1, :-1] + kp[:, :-1, 1:] + kp[:, 1:, :-1] + kp[:, 1:, 1:])[:, 1:-1, 1:-1].reshape(64, -1)
+    r_sub = eng.unpad(res[sub]).cpu().numpy()
+    u_sub = eng.unpad(x[sub]).cpu().numpy()
+    scaled = np.abs(r_sub / diag).max(axis=1) / np.abs(u_sub).max(axis=1)
+    assert scaled.max() < 1e-11, scaled.max()
+    rel = torch.linalg.vector_norm(res, dim=1) / torch.linalg.vector_norm(b)
+    assert float(rel.max()) < 1e-6, float(rel.max())
+    # energy identity u^T A u = b^T u
+    en2 = eng.energy_norm(yd, x) ** 2
+    bu = (x * b).sum(dim=1)
+    assert float(((en2 - bu).abs() / bu).max()) < 1e-10
+    # scaling: A(s y) = s A(y)  =>  u(s y) = u(y) / s, exactly representable for s = 4
+    sel = slice(0, 512)
+    x4, _, _ = eng.solve(eng.params(4.0 * y[sel]))
+    d = torch.linalg.vector_norm(4.0 * x4 - x[sel], dim=1) / torch.linalg.vector_norm(x[sel], dim=1)
+    assert float(d.max()) < 1e-10
+    # oracle spot check (sparse LU restatement of the reference)
+    pick = [0, K // 2, K - 1]
+    Uo = FEMOracle(GEO, N).generate_solutions(y[pick])
+    U = eng.unpad(x[pick]).cpu().numpy()
+    err = np.linalg.norm(U - Uo, axis=1) / np.linalg.norm(Uo, axis=1)
+    assert err.max() < 1e-9, err
+
+
+def test_host_entry_full_size_matches_resident(eng):
+    """chunked, pipelined host-buffer entry point == device-resident solve, bit for bit (same kernels, same order)"""
+    K = 4100                                   # > 4096: exercises the multi-chunk pipeline and a ragged last chunk
+    y = sample(K, 7)
+    U_host, iters, relres = eng.generate_solutions_host(y, return_stats=True)
+    x, it_d, rel_d = eng.solve(eng.params(y))
+    np.testing.assert_array_equal(U_host, eng.unpad(x).cpu().numpy())
+    np.testing.assert_array_equal(iters, it_d.cpu().numpy())
+    np.testing.assert_array_equal(relres, rel_d.cpu().numpy())
+
+
+def test_gram_and_online_stage_full_size(eng):
+    import torch
+    K, n = 2048, 20
+    y = sample(K, 3)
+    x, _, _ = eng.solve(eng.params(y))
+    # centred Gram on the DMMA path: symmetric, trace = sum of squared row norms, sub-block equals a torch fp64 product
+    mean = eng.column_mean(x)
+    Xc = x - mean[None, :]
+    G = eng.gemm_nt(Xc, Xc, symmetric=True)
+    assert torch.equal(G, G.T)
+    tr = float(torch.trace(G)); ref = float((Xc * Xc).sum())
+    assert abs(tr - ref) <= 1e-12 * ref
+    blk = Xc[:192] @ Xc[:64].T
+    assert float((G[:192, :64] - blk).abs().max()) <= 1e-12 * float(blk.abs().max())
+    # POD basis from the top eigenpairs, then 200k online reduced Galerkin solves: the reduced residual vanishes
+    from romhighcontrast_b200.pod import top_eigenpairs
+    lam, V = top_eigenpairs(eng, G, n)
+    Phi = (eng.gemm_tn(V, Xc) / torch.sqrt(lam)[:, None]).contiguous()
+    gram_phi = Phi @ Phi.T
+    assert float((gram_phi - torch.eye(n, dtype=torch.float64, device=Phi.device)).abs().max()) < 1e-9
+    Ahat, bhat = eng.project_operators(Phi)
+    Ko = 200000
+    yo = sample(Ko, 43)
+    C = eng.reduced_solve(eng.params(yo), Ahat, bhat)
+    idx = np.random.default_rng(0).choice(Ko, 300, replace=False)
+    Ah, bh, Ch = Ahat.cpu().numpy(), bhat.cpu().numpy(), C.cpu().numpy()
+    for k in idx:
+        A = np.einsum("q,qij->ij", yo[k].ravel(), Ah)
+        r = A @ Ch[k] - bh
+        assert np.linalg.norm(r) <= 1e-10 * np.linalg.norm(bh)
+    # scaling property of the reduced problem: c(2 y) = c(y) / 2
+    C2 = eng.reduced_solve(eng.params(2.0 * yo[:1000]), Ahat, bhat)
+    assert float((2.0 * C2 - C[:1000]).abs().max()) <= 1e-12 * float(C[:1000].abs().max())
