@@ -375,11 +375,16 @@ def run_secondary(eng, x, y, K, args, world, rank, barrier, ev):
         barrier(); e0.record(); dist.all_reduce(G); e1.record(); torch.cuda.synchronize()
         out["gram_allreduce_ms"] = e0.elapsed_time(e1)
     from romhighcontrast_b200.pod import top_eigenpairs
-    t0 = time.perf_counter()
-    lam, V = top_eigenpairs(eng, G, n)
-    comps = eng.gemm_tn(V, X) / torch.sqrt(lam)[:, None]
-    torch.cuda.synchronize()
-    out["pod_eig_backproject_ms"] = 1e3 * (time.perf_counter() - t0)
+    pod_ms = []
+    for _ in range(3):       # the first pass pays torch's one-time cuSOLVER initialisation (QR of the Lanczos blocks)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lam, V = top_eigenpairs(eng, G, n)
+        comps = eng.gemm_tn(V, X) / torch.sqrt(lam)[:, None]
+        torch.cuda.synchronize()
+        pod_ms.append(1e3 * (time.perf_counter() - t0))
+    out["pod_eig_backproject_ms"] = min(pod_ms[1:])
+    out["pod_eig_backproject_first_call_ms"] = pod_ms[0]
     out["pod_singular_values_head"] = [float(v) for v in torch.sqrt(lam)[:5].cpu()]
     # online stage: reduced operators once, then k_online reduced Galerkin solves
     Ahat, bhat = eng.project_operators(comps.contiguous())
