@@ -157,6 +157,7 @@ def main():
     ap.add_argument("--tile-ty", type=int, default=None)
     ap.add_argument("--tile-prefetch", type=int, default=None)
     ap.add_argument("--tile-persistent", type=int, default=None)
+    ap.add_argument("--fused", type=int, default=None, help="1: PCG update fused into the finest going-down kernel (default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -196,6 +197,8 @@ def main():
         eng.set_option("tile_prefetch", args.tile_prefetch)
     if args.tile_persistent is not None:
         eng.set_option("tile_persistent", args.tile_persistent)
+    if args.fused is not None:
+        eng.set_option("fused", args.fused)
     K = args.k_snap
     y_host = sample_params(K, seed=42 + rank)                   # this rank's shard of the training set
     y = eng.params(y_host)
@@ -274,6 +277,9 @@ def main():
         if pn[i] > 0:
             avg_ms = pms[i] / pn[i]
             streams = KIND_STREAMS[i]
+            if nm == "k_mg_down(l0)" and pn[1] == 0:
+                streams += 4.0                                    # fused with the PCG update: R p, x; W x, r on top
+                nm = "k_mg_update_down(l0)"
             if nm == "k_mg_tail":
                 streams = 2.0 / 4.0 ** eng.tail_level            # reads r, writes z of its first level
             if nm.endswith("(l>=1)") and pn[2] > 0:

@@ -801,6 +801,195 @@ k_mgp_down(TileArgs a, const double* __restrict__ r_in, double* __restrict__ z_o
     }
 }
 
+// ---- PCG update fused into the going-down kernel of the finest level --------------------------------------------------
+// x += alpha p ; r -= alpha A p ; then exactly k_mgp_down on the new residual.  The residual never makes the round trip
+// through HBM between the two steps (one stream of 7.25 saved, and one launch), at the price of recomputing A p on the
+// halo rows of the region.  Neighbouring strips read the OLD residual on their halo rows, so the new one goes to a second
+// buffer (the host swaps the two after the launch).  A p is evaluated in difference form, sum_nb w_nb (p - p_nb), like k_pcg_update; the
+// neighbours outside the tile are read straight from the staged p strip (no exchange round needed).
+// Region rows: r_new is valid on local rows [1, NR - 2], the smoother's validity cone starts from there.
+template <bool GENERAL, int CGT>
+__device__ __forceinline__ void tile_apply_row(double (&r)[4][4], const double (&p)[4][4], const ColWeights<true>& w,
+                                               const TileThread<CGT, true>& t, const TileArgs& a, int I, double nalpha,
+                                               double pWh, double pEh, const double (&pN)[4], const double (&pS)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const double pc = p[I][j];
+        const double pW = (j > 0) ? p[I][j > 0 ? j - 1 : 0] : pWh;
+        const double pE = (j < 3) ? p[I][j < 3 ? j + 1 : 3] : pEh;
+        if (GENERAL) {
+            const uint32_t q = tile_entry(t, a, I, j);
+            const double2 we = lds_f64x2(q), ns = lds_f64x2(q + 16), wv = lds_f64x2(q + 32);
+            const double s = (we.x * (pc - pW) + we.y * (pc - pE)) + (ns.x * (pc - pN[j]) + ns.y * (pc - pS[j]));
+            r[I][j] = fma(nalpha * wv.y, s, r[I][j]);
+        } else {
+            const double s = fma(0.25, (pc - pN[j]) + (pc - pS[j]), fma(w.hW[j], pc - pW, w.hE[j] * (pc - pE)));
+            r[I][j] = fma(nalpha * w.dg[j], s, r[I][j]);
+        }
+    }
+}
+
+template <int CGT>
+__global__ void __launch_bounds__(TILE_MAXT, 1)
+k_mgp_update_down(TileArgs a, const double* __restrict__ p_in, double* __restrict__ x_io, const double* __restrict__ r_in,
+                  double* __restrict__ r_out, const double* __restrict__ alpha, double* __restrict__ z_out, double* __restrict__ rc_out,
+                  const int* __restrict__ active, int K) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int CG = CGT > 0 ? CGT : int(blockDim.x), NRG = blockDim.y;
+    const int P = 4 * CG, R = a.g.R, NR = a.NR;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const bool leader = tx == 0 && ty == 0;
+    const uint32_t base = smem_u32(smem_raw);
+    const TileStage s = tile_stage_carve(base, a, CG, NRG, true);          // Zs holds the p strip
+    TileThread<CGT, true> t;
+    tile_exchange_init(t, a, s.ex);
+    tile_stage_tables(s, a, P, 3 * a.ns * NRG);
+    if (leader) {
+        mbar_init(reinterpret_cast<uint64_t*>(smem_raw + (s.bar - base)), 1);
+        mbar_fence_init();
+    }
+    auto issue = [&](const TileWalk& wk, int stage) {
+        const int row0 = wk.strip * a.TY - a.halo_top;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s.bar),
+                     "r"(s.tb + 2u * tile_rows_bytes(row0, NR, R, P)) : "memory");
+        tile_tma(s.T0 + stage * s.tb, a.tab + int64_t(wk.k) * a.ntab * TWD, s.tb, s.bar);
+        tile_tma_rows(s.Zs, p_in + int64_t(wk.k) * a.g.Dp, P, R, row0, NR, row0, s.bar);
+        tile_tma_rows(s.Rs, r_in + int64_t(wk.k) * a.g.Dp, P, R, row0, NR, row0, s.bar);
+        tile_prefetch_rows(x_io, a.g, wk.k, wk.strip * a.TY, a.TY);       // x is read straight from global: warm the L2
+    };
+    __syncthreads();
+    TileWalk wk;
+    wk.init(K, a.ns, active);
+    if (leader && wk.valid()) issue(wk, 0);
+    uint32_t phase = 0;
+    int stage = 0;
+    const int nu = a.nu;
+    const int CGp = CG + 2;
+    const uint32_t own = uint32_t((4 * ty) * P + 4 * tx) * 8;
+    while (wk.valid()) {
+        const int k = wk.k, y0 = wk.strip * a.TY;
+        const int rho0 = y0 - a.halo_top + 4 * ty;
+        TileWalk nx = wk;
+        nx.step();
+        const int nflag = nx.flag();
+        const uint32_t ri = s.rinfo + (wk.strip * NRG + ty) * 12;
+        const int rinfo = lds_s32(ri);
+        const double al = __ldg(alpha + k);
+        const int own_lo = y0 - rho0, own_hi = min(y0 + a.TY, R + 1) - rho0;   // owned tile rows: own_lo <= i < own_hi
+        const int64_t goff = int64_t(k) * a.g.Dp + int64_t(rho0) * P + 4 * tx;
+        double z[4][4], r[4][4];                                             // z holds p until the residual is updated
+#pragma unroll
+        for (int i = 0; i < 4; ++i)                                           // x rows: in flight during the staging wait
+            if (i >= own_lo && i < own_hi) tile_load_row(r[i], x_io + goff + i * P);
+        mbar_wait(reinterpret_cast<uint64_t*>(smem_raw + (s.bar - base)), phase);
+        phase ^= 1u;
+        const bool all_rows = (rinfo & 0xff) == 0x55;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (all_rows || unsigned(rho0 + i) <= unsigned(R)) tile_lds_row(z[i], s.Zs + own + i * P * 8);
+            else { z[i][0] = z[i][1] = z[i][2] = z[i][3] = 0.0; }
+        }
+        // x += alpha p on the owned rows
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i >= own_lo && i < own_hi) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) r[i][j] = fma(al, z[i][j], r[i][j]);
+                tile_store_row(x_io + goff + i * P, r[i]);
+            }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (all_rows || unsigned(rho0 + i) <= unsigned(R)) tile_lds_row(r[i], s.Rs + own + i * P * 8);
+            else { r[i][0] = r[i][1] = r[i][2] = r[i][3] = 0.0; }
+        }
+        ColWeights<true> w;
+        tile_item_init(t, w, a, s.T0 + stage * s.tb, rho0, rinfo, ri, s.colv);
+        // r -= alpha A p; neighbours of the tile from the staged p strip (rows outside the region: zero, those region
+        // rows are outside the validity cone anyway)
+        {
+            const uint32_t pb = s.Zs + own;
+            double pN[4], pS[4];
+            if (ty > 0) tile_lds_row(pN, pb - P * 8); else { pN[0] = pN[1] = pN[2] = pN[3] = 0.0; }
+#pragma unroll
+            for (int I = 0; I < 4; ++I) {
+                const int rtype = (t.rt >> (2 * I)) & 3;
+                if (I == 3) {
+                    if (ty < NRG - 1) tile_lds_row(pS, pb + 4 * P * 8); else { pS[0] = pS[1] = pS[2] = pS[3] = 0.0; }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) pS[j] = z[I + 1 < 4 ? I + 1 : 3][j];
+                }
+                if (I > 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) pN[j] = z[I > 0 ? I - 1 : 0][j];
+                }
+                if (rtype != 0) {
+                    const double pWh = lds_f64(pb + I * P * 8 - 8), pEh = lds_f64(pb + I * P * 8 + 32);
+                    if (rtype == 1) tile_apply_row<false>(r, z, w, t, a, I, -al, pWh, pEh, pN, pS);
+                    else            tile_apply_row<true>(r, z, w, t, a, I, -al, pWh, pEh, pN, pS);
+                }
+            }
+        }
+        double* ro = r_out + goff;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i >= own_lo && i < own_hi) tile_store_row(ro + i * P, r[i]);
+        __syncthreads();                                   // everybody has left the staging strips
+        nx.settle(nflag);
+        if (leader && nx.valid()) issue(nx, stage ^ 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) z[i][j] = 0.0;
+        tile_phase_any<0, 2, true>(z, r, w, t, a);
+        tile_publish<0>(z, t);
+        __syncthreads();
+        tile_phase_any<1, 0, true>(z, r, w, t, a);
+        tile_publish<1>(z, t);
+        __syncthreads();
+        for (int sw = 1; sw < nu; ++sw) {
+            tile_phase_any<0, 0, true>(z, r, w, t, a);
+            tile_publish<0>(z, t);
+            __syncthreads();
+            tile_phase_any<1, 0, true>(z, r, w, t, a);
+            tile_publish<1>(z, t);
+            __syncthreads();
+        }
+        double* zo = z_out + goff;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i >= own_lo && i < own_hi) tile_store_row(zo + i * P, z[i]);
+        if (a.has_coarse) {
+            tile_phase_any<0, 1, true>(z, r, w, t, a);
+            tile_publish<0>(z, t);
+            __syncthreads();
+            const LevelGeo& gc = a.gc;
+            const double dN31 = lds_f64(t.eb + (1 - 4) * CG * 8), dN33 = lds_f64(t.eb + (3 - 4) * CG * 8);
+            const double dW13 = lds_f64(t.xr + (1 * CGp - 1) * 8), dW33 = lds_f64(t.xr + (3 * CGp - 1) * 8);
+            double rc[2][2];
+            rc[0][0] = z[0][0] + 0.5 * (dN31 + dW13);
+            rc[0][1] = z[0][2] + 0.5 * (dN33 + z[1][1]);
+            rc[1][0] = z[2][0] + 0.5 * (z[1][1] + dW33);
+            rc[1][1] = z[2][2] + 0.5 * (z[1][3] + z[3][1]);
+            const int J0 = 2 * tx;
+            const bool okJ0 = J0 >= 1 && J0 <= gc.C - 1, okJ1 = J0 + 1 <= gc.C - 1;
+            double* co = rc_out + int64_t(k) * gc.Dp + J0;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int rho = rho0 + 2 * q;
+                const int I = rho >> 1;
+                if (rho >= y0 && rho < y0 + a.TY && I <= gc.R) {
+                    const bool okI = I >= 1 && I <= gc.R - 1;
+                    *reinterpret_cast<double2*>(co + size_t(I) * gc.P) =
+                        make_double2(okI && okJ0 ? rc[q][0] : 0.0, okI && okJ1 ? rc[q][1] : 0.0);
+                }
+            }
+        }
+        wk = nx;
+        stage ^= 1;
+    }
+}
+
 template <int CGT>
 __global__ void __launch_bounds__(TILE_MAXT, 1)
 k_mgp_up(TileArgs a, const double* __restrict__ e_c, const double* __restrict__ z_in, const double* __restrict__ r_in,
@@ -1288,6 +1477,14 @@ int Context::tile_setup() {
         int& m = i < 3 ? tile_maxt_down : tile_maxt_up;
         m = std::min(m, fa.maxThreadsPerBlock);
     }
+    const void* ffns[] = {(const void*)k_mgp_update_down<64>, (const void*)k_mgp_update_down<32>,
+                          (const void*)k_mgp_update_down<16>, (const void*)k_mgp_update_down<0>};
+    for (int i = 0; i < 4; ++i) {
+        CK(cudaFuncSetAttribute(ffns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        cudaFuncAttributes fa;
+        CK(cudaFuncGetAttributes(&fa, ffns[i]));
+        tile_maxt_down = std::min(tile_maxt_down, fa.maxThreadsPerBlock);
+    }
     const void* pfns[] = {(const void*)k_mgp_down<64>, (const void*)k_mgp_down<32>, (const void*)k_mgp_down<16>, (const void*)k_mgp_down<0>,
                           (const void*)k_mgp_up<64>,   (const void*)k_mgp_up<32>,   (const void*)k_mgp_up<16>,   (const void*)k_mgp_up<0>};
     for (int i = 0; i < 8; ++i) {
@@ -1485,6 +1682,43 @@ int Context::tile_down(int l, const double* y, int Kc, cudaStream_t st) {
     a.pf_dist = tile_pf_dist((const void*)fn, CG * (a.NR / 4), sm);
     ++g_launches;
     fn<<<dim3(a.ns, Kc), dim3(CG, a.NR / 4), sm, st>>>(a, ws.r[l], ws.za[l], a.has_coarse ? ws.r[l + 1] : nullptr, ws.active);
+    return ROMHC_OK;
+}
+
+// x += alpha p, r -= alpha A p and the going-down kernel of level l in one launch (persistent tile kernels only);
+// returns ROMHC_ERR_ARG if the configuration does not fit (the caller then runs the two kernels separately)
+int Context::tile_update_down(int l, int Kc, const double* p, double* x, const double* alpha, cudaStream_t st) {
+    const int L = int(levels.size()) - 1;
+    if (!tile_persistent || !use_fused) return ROMHC_ERR_ARG;
+    TileArgs a;
+    a.g = levels[l];
+    a.has_coarse = l < L ? 1 : 0;
+    a.gc = a.has_coarse ? levels[l + 1] : levels[l];
+    a.rowv = tile_rowv[l] + ROMHC_ROWV_PAD; a.colv = tile_colv[l];
+    a.tab = ws.wtab; a.ntab = tile_ntab(); a.ncv = 2 * ncb - 1;
+    const int nu = nu_of(l);
+    a.nu = nu;
+    a.halo_top = 2 * nu + 2;
+    a.pf_dist = 0; a.rinfo = nullptr;
+    const int CG = a.g.P / 4;
+    auto bytes = [&]() { return tile_stage_bytes(a.ntab, a.NR, CG, (a.g.R + a.TY - 1) / a.TY, true, 0, 0); };
+    for (int cap = tile_ty_cap; cap >= 2; cap -= 2) {
+        tile_pick_ty(a.g, 4 * nu + 3, tile_maxt_down, cap, &a.TY, &a.NR);
+        if (bytes() <= 227 * 1024) break;
+    }
+    const size_t sm = bytes();
+    if (sm > 227 * 1024 || a.NR < 4 * nu + 6) return ROMHC_ERR_ARG;
+    a.ns = (a.g.R + a.TY - 1) / a.TY;
+    auto fn = CG == 64 ? k_mgp_update_down<64> : (CG == 32 ? k_mgp_update_down<32> : (CG == 16 ? k_mgp_update_down<16> : k_mgp_update_down<0>));
+    a.rinfo = tile_rinfo(l, a.TY, a.halo_top, a.NR);
+    if (!a.rinfo) { set_error("tile kernels: row-info table allocation failed"); return ROMHC_ERR_CUDA; }
+    const int grid = tile_persistent_grid((const void*)fn, CG * (a.NR / 4), sm, int64_t(Kc) * a.ns);
+    ++g_launches;
+    if (l != 0) return ROMHC_ERR_ARG;
+    // systems that are no longer active keep their (converged) residual in the old buffer: nobody reads it again
+    fn<<<grid, dim3(CG, a.NR / 4), sm, st>>>(a, p, x, ws.r[0], ws.r_alt, alpha, ws.za[0], a.has_coarse ? ws.r[1] : nullptr,
+                                             ws.active, Kc);
+    std::swap(ws.r[0], ws.r_alt);
     return ROMHC_OK;
 }
 

@@ -40,6 +40,7 @@ struct SolveStats {
 struct SolveWorkspace {
     std::vector<double*> r, za, zb;   // per level
     double* p[2];
+    double* r_alt;                    // the fused update kernel writes the new residual here, then the two swap
     double* cfac;
     double* wtab;                     // per-system stencil weight tables of the tile kernels (mgtile.cu)
     double *part_pAp, *part_rz;
@@ -94,6 +95,7 @@ struct Context {
     int tile_ty_cap = 64;               // largest strip height of the tile kernels
     bool tile_prefetch = true;          // L2 prefetch of the next CTA's operand rows (non-persistent tile kernels)
     bool tile_persistent = true;        // persistent, TMA-pipelined tile kernels (one CTA per SM)
+    bool use_fused = true;              // PCG update fused into the finest level's going-down kernel
     int tile_nsm = 148;
     std::map<std::array<int, 4>, int*> tile_rinfo_cache;   // (level, TY, halo, NR) -> device row-info table
     bool tile_ready = false;
@@ -127,6 +129,7 @@ struct Context {
     long long prof_n[PROF_NKIND] = {0, 0, 0, 0, 0, 0, 0};
     void prof_begin(int kind, cudaStream_t st);
     void prof_end(cudaStream_t st);
+    void prof_cancel();
     void prof_collect();
 
     int build_levels();
@@ -145,12 +148,16 @@ struct Context {
                int64_t K, int mode, int take_sqrt, cudaStream_t st);
     int pack(const double* compact, double* padded, int64_t K, cudaStream_t st);
     int unpack(const double* padded, double* compact, int64_t K, cudaStream_t st);
-    int vcycle(const double* y, int Kc, cudaStream_t st, const double** z_result, int* np_rz);
+    // fuse_p != nullptr: the PCG update x += alpha p, r -= alpha A p is still pending and may be fused into level 0
+    // (*fused tells the caller whether it was)
+    int vcycle(const double* y, int Kc, cudaStream_t st, const double** z_result, int* np_rz,
+               const double* fuse_p = nullptr, double* fuse_x = nullptr, const double* fuse_alpha = nullptr);
     int solve_chunk(const double* y, int Kc, double* x, int* iters_out, double* relres_out, cudaStream_t st,
                     SolveStats* stats);
     int solve(const double* y, int64_t K, double* x, int* iters_out, double* relres_out, cudaStream_t st,
               SolveStats* stats);
     int precond(const double* y, const double* r, double* z, int64_t K, cudaStream_t st);
+    int pcg_update(const double* y, int Kc, const double* p, double* x, const double* alpha, cudaStream_t st);
 
     // mgtile.cu
     int tile_setup();
@@ -161,6 +168,7 @@ struct Context {
     bool tile_level_ok(int l) const;
     int tile_weight_table(const double* y, int Kc, cudaStream_t st);
     int tile_tail(const double* y, int Kc, double* part_rz, cudaStream_t st);
+    int tile_update_down(int l, int Kc, const double* p, double* x, const double* alpha, cudaStream_t st);
     int tile_down(int l, const double* y, int Kc, cudaStream_t st);
     int tile_up(int l, const double* y, int Kc, const double* e, double* part_rz, int* ns_out, cudaStream_t st);
 

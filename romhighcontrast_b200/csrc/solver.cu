@@ -841,6 +841,11 @@ void Context::prof_begin(int kind, cudaStream_t st) {
     cudaEventRecord(a, st);
     prof_events.push_back({kind, a, b});
 }
+void Context::prof_cancel() {
+    if (!prof_on || !prof_window || prof_events.empty()) return;
+    cudaEventDestroy(prof_events.back().a); cudaEventDestroy(prof_events.back().b);
+    prof_events.pop_back();
+}
 void Context::prof_end(cudaStream_t st) {
     if (!prof_on || !prof_window || prof_events.empty()) return;
     cudaEventRecord(prof_events.back().b, st);
@@ -1008,7 +1013,7 @@ int Context::unpack(const double* padded, double* compact, int64_t K, cudaStream
 size_t Context::solve_bytes_per_system() const {
     size_t d = 0;
     const int L = int(levels.size()) - 1;
-    d += size_t(levels[0].Dp) * 5;                           // r, p0, p1, zA, zB  (x is the caller's output)
+    d += size_t(levels[0].Dp) * 6;                           // r, r', p0, p1, zA, zB  (x is the caller's output)
     for (int l = 1; l <= L && l <= tail_level; ++l) d += size_t(levels[l].Dp) * 3;   // r_l, zA_l, zB_l
     if (coarse_direct) d += size_t(coarse_D) * coarse_LD;
     d += size_t(tile_ntab()) * 8;
@@ -1042,6 +1047,7 @@ int Context::ensure_solve_ws(int64_t Kc) {
         o_zb[l] = (l < nlev_strip) ? take(size_t(Kc) * levels[l].Dp) : o_za[l];
     }
     const size_t o_p0 = take(size_t(Kc) * levels[0].Dp), o_p1 = take(size_t(Kc) * levels[0].Dp);
+    const size_t o_ralt = take(size_t(Kc) * levels[0].Dp);     // second residual buffer of the fused update kernel
     const size_t o_fac = coarse_direct ? take(size_t(Kc) * coarse_D * coarse_LD) : 0;
     const size_t o_tab = take(size_t(Kc) * tile_ntab() * 8);
     const int np = std::max(1, (levels[0].R + 1) / 2 + 1);
@@ -1054,6 +1060,7 @@ int Context::ensure_solve_ws(int64_t Kc) {
     ws.r.assign(L + 2, nullptr); ws.za.assign(L + 2, nullptr); ws.zb.assign(L + 2, nullptr);
     for (int l = 0; l <= top; ++l) { ws.r[l] = b + o_r[l]; ws.za[l] = b + o_za[l]; ws.zb[l] = b + o_zb[l]; }
     ws.p[0] = b + o_p0; ws.p[1] = b + o_p1;
+    ws.r_alt = b + o_ralt;
     ws.cfac = coarse_direct ? b + o_fac : nullptr;
     ws.wtab = b + o_tab;
     ws.part_pAp = b + o_pp; ws.part_rz = b + o_pr; ws.np = np;
@@ -1071,16 +1078,45 @@ int Context::ensure_solve_ws(int64_t Kc) {
     return ROMHC_OK;
 }
 
+// x += alpha p, r -= alpha A p on the finest level (streaming strip kernel)
+int Context::pcg_update(const double* y, int Kc, const double* p, double* x, const double* alpha, cudaStream_t st) {
+    const LevelGeo& g = levels[0];
+    const size_t hdr = smem_hdr_bytes(nrb * ncb);
+    auto bytes_u = [&](int TY) { return hdr + size_t(3 * TY + 2) * g.P * 8; };
+    const int TYu = pick_ty_fn(g, strip_budget, bytes_u);
+    if (bytes_u(TYu) > SMEM_MAX) { set_error("mesh too wide for the PCG strip kernels (C = %d)", g.C); return ROMHC_ERR_ARG; }
+    const int nsu = (g.R + TYu - 1) / TYu;
+    dim3 block; strip_block(g, block, strip_threads);
+    prof_begin(PROF_UPDATE, st);
+    ++g_launches; k_pcg_update<<<dim3(nsu, Kc), block, bytes_u(TYu), st>>>(g, y, p, x, ws.r[0], alpha, ws.active, TYu);
+    prof_end(st);
+    CK(cudaGetLastError());
+    return ROMHC_OK;
+}
+
 // one V-cycle: z_0 (ws.zb[0] or ws.za[0] when the tail starts at level 0) = M r_0; writes r.z partials
-int Context::vcycle(const double* y, int Kc, cudaStream_t st, const double** z_result, int* np_rz) {
+int Context::vcycle(const double* y, int Kc, cudaStream_t st, const double** z_result, int* np_rz, const double* fuse_p,
+                    double* fuse_x, const double* fuse_alpha) {
     const int L = int(levels.size()) - 1;
     const int nb = nrb * ncb;
     const int nstrip_levels = std::min(tail_level, L + 1);
     const size_t hdr = smem_hdr_bytes(nb);
+    if (fuse_p && nstrip_levels == 0) {       // the whole hierarchy lives in the tail kernel: plain update first
+        const int rc_u = pcg_update(y, Kc, fuse_p, fuse_x, fuse_alpha, st); if (rc_u) return rc_u;
+    }
     for (int l = 0; l < nstrip_levels; ++l) {
         const LevelGeo& g = levels[l];
         const bool has_c = l < L;
         const LevelGeo& gc = has_c ? levels[l + 1] : g;
+        if (l == 0 && fuse_p) {
+            // pending PCG update: fused into the tile kernel if possible, else the streaming update kernel first
+            prof_begin(PROF_DOWN0, st);
+            const int rc_f = tile_level_ok(0) ? tile_update_down(0, Kc, fuse_p, fuse_x, fuse_alpha, st) : ROMHC_ERR_ARG;
+            if (rc_f == ROMHC_OK) { prof_end(st); continue; }
+            prof_cancel();
+            if (rc_f != ROMHC_ERR_ARG) return rc_f;
+            const int rc_u = pcg_update(y, Kc, fuse_p, fuse_x, fuse_alpha, st); if (rc_u) return rc_u;
+        }
         if (tile_level_ok(l)) {
             prof_begin(PROF_DOWN0 + std::min(l, 1), st);
             int rc = tile_down(l, y, Kc, st); if (rc) return rc;
@@ -1189,10 +1225,7 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
         prof_end(st);
         cur ^= 1;
         ++g_launches; k_scalar_alpha<<<gs, 128, 0, st>>>(Kc, nsp, ws.part_pAp, ws.rz, ws.alpha, ws.active, ws_flags + 0);
-        prof_begin(PROF_UPDATE, st);
-        ++g_launches; k_pcg_update<<<dim3(nsu, Kc), block, bytes_u(TYu), st>>>(g, y, ws.p[cur], x, ws.r[0], ws.alpha, ws.active, TYu);
-        prof_end(st);
-        rc = vcycle(y, Kc, st, &z, &np_rz); if (rc) return rc;
+        rc = vcycle(y, Kc, st, &z, &np_rz, ws.p[cur], x, ws.alpha); if (rc) return rc;
         int* ctr = n_active + 1 + (it % 32);
         CK(cudaMemsetAsync(ctr, 0, sizeof(int), st));
         ++g_launches; k_scalar_beta<<<gs, 128, 0, st>>>(Kc, np_rz, ws.part_rz, ws.rz, ws.rz0, ws.beta, ws.active, ws.iters, ws.relres,
