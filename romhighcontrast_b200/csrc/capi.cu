@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <atomic>
 #include <new>
+#include <vector>
 
 namespace romhc {
 
@@ -35,6 +36,7 @@ void Context::release() {
     scratch = nullptr; ws_base = nullptr; ws_flags = nullptr; h_flags = nullptr;
     scratch_bytes = 0; ws_K = 0;
     free_host_stage();
+    for (int i = 0; i < 5; ++i) { if (rg_buf[i]) cudaFree(rg_buf[i]); rg_buf[i] = nullptr; rg_cap[i] = 0; }
 }
 
 void Context::free_host_stage() {
@@ -52,6 +54,18 @@ void Context::free_host_stage() {
     if (hstage.copy) cudaStreamDestroy(hstage.copy);
     hstage.compute = hstage.copy = nullptr;
     hstage.cap = 0;
+}
+
+int Context::ensure_pinned_stats(int64_t K) {
+    HostStage& s = hstage;
+    if (K <= s.pin_cap) return ROMHC_OK;
+    if (s.it_pin) cudaFreeHost(s.it_pin);
+    if (s.rel_pin) cudaFreeHost(s.rel_pin);
+    s.it_pin = nullptr; s.rel_pin = nullptr; s.pin_cap = 0;
+    CK(cudaMallocHost((void**)&s.it_pin, size_t(K) * 4));
+    CK(cudaMallocHost((void**)&s.rel_pin, size_t(K) * 8));
+    s.pin_cap = K;
+    return ROMHC_OK;
 }
 
 int Context::ensure_host_stage(int64_t chunk) {
@@ -268,14 +282,8 @@ int romhc_generate_solutions_host(romhc_handle h, const double* y_host, int64_t 
     int rc = c->ensure_host_stage(chunk);
     if (rc) return rc;
     HostStage& s = c->hstage;
-    if (K > s.pin_cap) {
-        if (s.it_pin) cudaFreeHost(s.it_pin);
-        if (s.rel_pin) cudaFreeHost(s.rel_pin);
-        s.it_pin = nullptr; s.rel_pin = nullptr; s.pin_cap = 0;
-        CK(cudaMallocHost((void**)&s.it_pin, size_t(K) * 4));
-        CK(cudaMallocHost((void**)&s.rel_pin, size_t(K) * 8));
-        s.pin_cap = K;
-    }
+    rc = c->ensure_pinned_stats(K);
+    if (rc) return rc;
     int64_t nchunk = 0;
     for (int64_t k0 = 0; k0 < K; k0 += chunk, ++nchunk) {
         const int64_t kc = std::min<int64_t>(chunk, K - k0);
@@ -304,32 +312,56 @@ int romhc_generate_solutions_host(romhc_handle h, const double* y_host, int64_t 
     return rc;
 }
 
-#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_error("%s: %s", #call, cudaGetErrorString(e_)); cleanup(); return ROMHC_ERR_CUDA; } } while (0)
 int romhc_reduced_galerkin_host(romhc_handle h, const double* y_host, const double* Ahat_host, const double* bhat_host,
                                 int n, int64_t K, double* C_host, int* info_host) {
     CHECK_H(h);
     if (K <= 0) return ROMHC_OK;
     Context* c = H(h);
     const int nb = c->nrb * c->ncb;
-    double *y_d = nullptr, *A_d = nullptr, *b_d = nullptr, *C_d = nullptr;
-    int* info_d = nullptr;
+    // device staging persists in the context (grow only): repeated online batches pay no allocation
+    const size_t need[5] = {size_t(K) * nb * 8, size_t(nb) * n * n * 8, size_t(n) * 8, size_t(K) * n * 8, size_t(K) * 4};
+    for (int i = 0; i < 5; ++i)
+        if (need[i] > c->rg_cap[i]) {
+            if (c->rg_buf[i]) cudaFree(c->rg_buf[i]);
+            c->rg_buf[i] = nullptr; c->rg_cap[i] = 0;
+            CK(cudaMalloc(&c->rg_buf[i], need[i]));
+            c->rg_cap[i] = need[i];
+        }
+    double* y_d = (double*)c->rg_buf[0]; double* A_d = (double*)c->rg_buf[1]; double* b_d = (double*)c->rg_buf[2];
+    double* C_d = (double*)c->rg_buf[3]; int* info_d = (int*)c->rg_buf[4];
     cudaStream_t st = 0;
-    auto cleanup = [&]() { cudaFree(y_d); cudaFree(A_d); cudaFree(b_d); cudaFree(C_d); cudaFree(info_d); };
-    CKC(cudaMalloc(&y_d, size_t(K) * nb * 8));
-    CKC(cudaMalloc(&A_d, size_t(nb) * n * n * 8));
-    CKC(cudaMalloc(&b_d, size_t(n) * 8));
-    CKC(cudaMalloc(&C_d, size_t(K) * n * 8));
-    CKC(cudaMalloc(&info_d, size_t(K) * 4));
-    CKC(cudaMemcpyAsync(y_d, y_host, size_t(K) * nb * 8, cudaMemcpyHostToDevice, st));
-    CKC(cudaMemcpyAsync(A_d, Ahat_host, size_t(nb) * n * n * 8, cudaMemcpyHostToDevice, st));
-    CKC(cudaMemcpyAsync(b_d, bhat_host, size_t(n) * 8, cudaMemcpyHostToDevice, st));
-    int rc = reduced_solve(y_d, nb, A_d, b_d, 0, n, K, C_d, info_d, st);
-    if (rc == ROMHC_OK) {
-        CKC(cudaMemcpyAsync(C_host, C_d, size_t(K) * n * 8, cudaMemcpyDeviceToHost, st));
-        if (info_host) CKC(cudaMemcpyAsync(info_host, info_d, size_t(K) * 4, cudaMemcpyDeviceToHost, st));
-        CKC(cudaStreamSynchronize(st));
+    CK(cudaMemcpyAsync(A_d, Ahat_host, need[1], cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b_d, bhat_host, need[2], cudaMemcpyHostToDevice, st));
+    // chunks: the H2D copy of chunk i+1 and the D2H copy of chunk i-1 ride on the copy engines while chunk i is solved
+    // (they only overlap when the caller's buffers are pinned; pageable buffers serialise, still correct)
+    const int64_t chunk = std::max<int64_t>(1 << 16, (K + 7) / 8);
+    if (!c->hstage.compute) {
+        CK(cudaStreamCreateWithFlags(&c->hstage.compute, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->hstage.copy, cudaStreamNonBlocking));
     }
-    cleanup();
+    cudaStream_t s_in = c->hstage.copy, s_run = c->hstage.compute;
+    { const int rcp = c->ensure_pinned_stats(K); if (rcp) return rcp; }
+    CK(cudaStreamSynchronize(st));
+    std::vector<cudaEvent_t> ev;
+    int rc = ROMHC_OK;
+    for (int64_t k0 = 0; k0 < K && rc == ROMHC_OK; k0 += chunk) {
+        const int64_t kc = std::min<int64_t>(chunk, K - k0);
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ev.push_back(e);
+        CK(cudaMemcpyAsync(y_d + k0 * nb, y_host + k0 * nb, size_t(kc) * nb * 8, cudaMemcpyHostToDevice, s_in));
+        CK(cudaEventRecord(e, s_in));
+        CK(cudaStreamWaitEvent(s_run, e, 0));
+        rc = reduced_solve(y_d + k0 * nb, nb, A_d, b_d, 0, n, kc, C_d + k0 * n, info_d + k0, s_run);
+        if (rc != ROMHC_OK) break;
+        CK(cudaMemcpyAsync(C_host + k0 * n, C_d + k0 * n, size_t(kc) * n * 8, cudaMemcpyDeviceToHost, s_run));
+        if (info_host) CK(cudaMemcpyAsync(c->hstage.it_pin + k0, info_d + k0, size_t(kc) * 4, cudaMemcpyDeviceToHost, s_run));
+    }
+    cudaStreamSynchronize(s_in);
+    cudaStreamSynchronize(s_run);
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    if (rc == ROMHC_OK && info_host) memcpy(info_host, c->hstage.it_pin, size_t(K) * 4);
+    if (rc == ROMHC_OK) CK(cudaGetLastError());
     return rc;
 }
 

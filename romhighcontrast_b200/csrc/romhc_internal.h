@@ -139,7 +139,10 @@ struct Context {
     size_t solve_bytes_per_system() const;
     void release();
     HostStage hstage;
+    void* rg_buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // staging of romhc_reduced_galerkin_host
+    size_t rg_cap[5] = {0, 0, 0, 0, 0};
     int ensure_host_stage(int64_t chunk);
+    int ensure_pinned_stats(int64_t K);
     void free_host_stage();
 
     // solver.cu

@@ -221,12 +221,12 @@ class Engine:
             else C.c_void_p(U.data_ptr()), iters.ctypes.data_as(C.c_void_p), relres.ctypes.data_as(C.c_void_p)))
         return (U, iters, relres) if return_stats else U
 
-    def reduced_galerkin_host(self, y_host, Ahat_host, bhat_host):
+    def reduced_galerkin_host(self, y_host, Ahat_host, bhat_host, out=None):
         y = np.ascontiguousarray(np.asarray(y_host, dtype=np.float64).reshape(-1, self.nb))
         A = np.ascontiguousarray(np.asarray(Ahat_host, dtype=np.float64))
         b = np.ascontiguousarray(np.asarray(bhat_host, dtype=np.float64))
         K, n = y.shape[0], b.shape[0]
-        Cc = np.empty((K, n))
+        Cc = np.empty((K, n)) if out is None else out          # pass pinned memory to let the copies overlap the solves
         info = np.empty(K, dtype=np.int32)
         _lib.check(self.lib.romhc_reduced_galerkin_host(
             self.handle, y.ctypes.data_as(C.c_void_p), A.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), n, K,
