@@ -284,9 +284,15 @@ int romhc_generate_solutions_host(romhc_handle h, const double* y_host, int64_t 
     HostStage& s = c->hstage;
     rc = c->ensure_pinned_stats(K);
     if (rc) return rc;
-    int64_t nchunk = 0;
-    for (int64_t k0 = 0; k0 < K; k0 += chunk, ++nchunk) {
-        const int64_t kc = std::min<int64_t>(chunk, K - k0);
+    // Chunk schedule: full chunks first, then halved ones -- only the LAST chunk's D2H copy is exposed (nothing left
+    // to overlap it with), so it should be small; chunks below ~600 systems would under-fill the persistent kernels.
+    int64_t nchunk = 0, kc_next = chunk;
+    const int64_t small = std::max<int64_t>(512, chunk / 4);
+    for (int64_t k0 = 0; k0 < K; ++nchunk) {
+        const int64_t left = K - k0;
+        int64_t kc = std::min<int64_t>(kc_next, left);
+        if (K >= 4096 && left <= chunk + small && left > small) kc = std::max<int64_t>(small, (left + 1) / 2);
+        if (left - kc < small / 2) kc = left;                  // no tiny remainder
         const int slot = int(nchunk & 1);
         if (nchunk >= 2) CK(cudaStreamWaitEvent(s.compute, s.copied[slot], 0));
         CK(cudaMemcpyAsync(s.y[slot], y_host + k0 * nb, size_t(kc) * nb * 8, cudaMemcpyHostToDevice, s.compute));
@@ -302,6 +308,7 @@ int romhc_generate_solutions_host(romhc_handle h, const double* y_host, int64_t 
         if (iters_host) CK(cudaMemcpyAsync(s.it_pin + k0, s.it[slot], size_t(kc) * 4, cudaMemcpyDeviceToHost, s.copy));
         if (relres_host) CK(cudaMemcpyAsync(s.rel_pin + k0, s.rel[slot], size_t(kc) * 8, cudaMemcpyDeviceToHost, s.copy));
         CK(cudaEventRecord(s.copied[slot], s.copy));
+        k0 += kc;
     }
     CK(cudaStreamSynchronize(s.copy));
     CK(cudaStreamSynchronize(s.compute));
