@@ -91,6 +91,11 @@ int romhc_error_norm(romhc_handle h, const double* U_pad_dev, const double* coef
  * stats4 (optional, host): {iterations launched (sum over chunks), chunks, status bits, workspace bytes}. */
 int romhc_solve(romhc_handle h, const double* y_dev, int64_t K, double* x_pad_dev, int* iters_dev, double* relres_dev,
                 void* stream, int64_t* stats4);
+/* same solver with caller-supplied right-hand sides rhs_pad_dev (K, Dp) (padded layout, zeros outside the interior);
+ * y_dev == NULL solves with a == 1, i.e. A_1 u = f: the H10 Riesz representers the reference leaves unimplemented
+ * (generate_riesz(norm="h10"), SolutionsManagers.py:78-84) are m such solves with point-evaluation functionals. */
+int romhc_solve_rhs(romhc_handle h, const double* y_dev, const double* rhs_pad_dev, int64_t K, double* x_pad_dev,
+                    int* iters_dev, double* relres_dev, void* stream, int64_t* stats4);
 /* z = M r: one application of the multigrid preconditioner (test hook) */
 int romhc_precond(romhc_handle h, const double* y_dev, const double* r_pad_dev, double* z_pad_dev, int64_t K,
                   void* stream);

@@ -50,6 +50,7 @@ SIGNATURES = {
     "romhc_l2_norm": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "romhc_error_norm": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp, _vp]),
     "romhc_solve": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, C.POINTER(_i64)]),
+    "romhc_solve_rhs": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, C.POINTER(_i64)]),
     "romhc_precond": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "romhc_project_operators": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "romhc_reduced_solve": (_i, [_vp, _i, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp]),

@@ -226,6 +226,15 @@ int romhc_solve(romhc_handle h, const double* y, int64_t K, double* x, int* iter
     if (stats4) { stats4[0] = s.launched_iterations; stats4[1] = s.chunks; stats4[2] = s.status; stats4[3] = (int64_t)H(h)->ws_bytes; }
     return rc;
 }
+int romhc_solve_rhs(romhc_handle h, const double* y, const double* rhs, int64_t K, double* x, int* iters, double* relres,
+                    void* st, int64_t* stats4) {
+    CHECK_H(h);
+    if (!rhs) { set_error("solve_rhs: rhs is null"); return ROMHC_ERR_ARG; }
+    SolveStats s{0, 0, 0};
+    const int rc = H(h)->solve(y, K, x, iters, relres, ST(st), &s, rhs);
+    if (stats4) { stats4[0] = s.launched_iterations; stats4[1] = s.chunks; stats4[2] = s.status; stats4[3] = (int64_t)H(h)->ws_bytes; }
+    return rc;
+}
 int romhc_precond(romhc_handle h, const double* y, const double* r, double* z, int64_t K, void* st) {
     CHECK_H(h); return H(h)->precond(y, r, z, K, ST(st));
 }

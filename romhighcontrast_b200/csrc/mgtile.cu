@@ -36,7 +36,7 @@ __global__ void k_weight_table(const double* __restrict__ y, double* __restrict_
     const int64_t k = blockIdx.x;
     if (k >= K) return;
     const int nrv = 2 * nrb - 1, ncv = 2 * ncb - 1, ne = nrv * ncv;
-    const double* a = y + k * int64_t(nrb) * ncb;
+    const double* a = y ? y + k * int64_t(nrb) * ncb : nullptr;      // y == nullptr: a == 1 (the H10 operator A_1)
     for (int e = threadIdx.x; e <= ne; e += blockDim.x) {
         double* o = tab + (k * int64_t(ne + 1) + e) * TWD;
         if (e == ne) {
@@ -46,8 +46,8 @@ __global__ void k_weight_table(const double* __restrict__ y, double* __restrict_
         const int rv = e / ncv, cv = e - rv * ncv;
         const int bd = (rv + 1) >> 1, bu = bd - (rv & 1);
         const int br = (cv + 1) >> 1, bl = br - (cv & 1);
-        const double aul = a[bu * ncb + bl], aur = a[bu * ncb + br];
-        const double adl = a[bd * ncb + bl], adr = a[bd * ncb + br];
+        const double aul = a ? a[bu * ncb + bl] : 1.0, aur = a ? a[bu * ncb + br] : 1.0;
+        const double adl = a ? a[bd * ncb + bl] : 1.0, adr = a ? a[bd * ncb + br] : 1.0;
         const double dg = (aul + aur) + (adl + adr);
         const double idg = 1.0 / dg;
         o[0] = 0.5 * (aul + adl) * idg;

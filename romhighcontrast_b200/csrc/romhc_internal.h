@@ -156,9 +156,9 @@ struct Context {
     int vcycle(const double* y, int Kc, cudaStream_t st, const double** z_result, int* np_rz,
                const double* fuse_p = nullptr, double* fuse_x = nullptr, const double* fuse_alpha = nullptr);
     int solve_chunk(const double* y, int Kc, double* x, int* iters_out, double* relres_out, cudaStream_t st,
-                    SolveStats* stats);
+                    SolveStats* stats, const double* rhs = nullptr);
     int solve(const double* y, int64_t K, double* x, int* iters_out, double* relres_out, cudaStream_t st,
-              SolveStats* stats);
+              SolveStats* stats, const double* rhs = nullptr);
     int precond(const double* y, const double* r, double* z, int64_t K, cudaStream_t st);
     int pcg_update(const double* y, int Kc, const double* p, double* x, const double* alpha, cudaStream_t st);
 

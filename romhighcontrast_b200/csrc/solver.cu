@@ -1180,17 +1180,18 @@ int Context::vcycle(const double* y, int Kc, cudaStream_t st, const double** z_r
 
 // Solve A(y_k) u_k = b for Kc systems; x (padded, Kc*Dp) is written.  y: device (Kc, nb).
 int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, double* relres_out, cudaStream_t st,
-                         SolveStats* stats) {
+                         SolveStats* stats, const double* rhs) {
     const LevelGeo& g = levels[0];
     const int nb = nrb * ncb;
     int rc = ensure_solve_ws(Kc); if (rc) return rc;
     dim3 block; strip_block(g, block, strip_threads);
     // x = 0, r = b, active = 1
     CK(cudaMemsetAsync(x, 0, size_t(Kc) * g.Dp * 8, st));
-    CK(cudaMemsetAsync(ws.r[0], 0, size_t(Kc) * g.Dp * 8, st));
+    if (rhs) CK(cudaMemcpyAsync(ws.r[0], rhs, size_t(Kc) * g.Dp * 8, cudaMemcpyDeviceToDevice, st));
+    else     CK(cudaMemsetAsync(ws.r[0], 0, size_t(Kc) * g.Dp * 8, st));
     CK(cudaMemsetAsync(ws.p[0], 0, size_t(Kc) * g.Dp * 8, st));
     CK(cudaMemsetAsync(ws.p[1], 0, size_t(Kc) * g.Dp * 8, st));
-    ++g_launches; k_fill_interior<<<(unsigned)(int64_t(Kc) * (g.R - 1)), 128, 0, st>>>(g, ws.r[0], 1.0 / (double(N) * double(N)), Kc);
+    if (!rhs) { ++g_launches; k_fill_interior<<<(unsigned)(int64_t(Kc) * (g.R - 1)), 128, 0, st>>>(g, ws.r[0], 1.0 / (double(N) * double(N)), Kc); }
     ++g_launches; k_fill_int<<<(Kc + 255) / 256, 256, 0, st>>>(ws.active, 1, Kc);
     CK(cudaMemsetAsync(ws.iters, 0, size_t(Kc) * 4, st));
     CK(cudaMemsetAsync(ws_flags, 0, 64 * sizeof(int), st));
@@ -1253,7 +1254,7 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
 }
 
 int Context::solve(const double* y, int64_t K, double* x, int* iters_out, double* relres_out, cudaStream_t st,
-                   SolveStats* stats) {
+                   SolveStats* stats, const double* rhs) {
     int rc = configure_kernels(); if (rc) return rc;
     if (tail_smem > 227 * 1024) { set_error("tail kernel needs %zu B of shared memory", tail_smem); return ROMHC_ERR_ARG; }
     const size_t per = solve_bytes_per_system();
@@ -1262,8 +1263,8 @@ int Context::solve(const double* y, int64_t K, double* x, int* iters_out, double
     if (stats) { stats->launched_iterations = 0; stats->chunks = 0; stats->status = 0; }
     for (int64_t k0 = 0; k0 < K; k0 += chunk) {
         const int kc = int(std::min<int64_t>(chunk, K - k0));
-        rc = solve_chunk(y + k0 * nrb * ncb, kc, x + k0 * levels[0].Dp, iters_out ? iters_out + k0 : nullptr,
-                         relres_out ? relres_out + k0 : nullptr, st, stats);
+        rc = solve_chunk(y ? y + k0 * nrb * ncb : nullptr, kc, x + k0 * levels[0].Dp, iters_out ? iters_out + k0 : nullptr,
+                         relres_out ? relres_out + k0 : nullptr, st, stats, rhs ? rhs + k0 * levels[0].Dp : nullptr);
         if (rc) return rc;
     }
     return ROMHC_OK;

@@ -112,15 +112,23 @@ class Engine:
         return out
 
     # ---- K1 --------------------------------------------------------------------------------------------
-    def solve(self, y, out=None):
-        """Batched snapshot solves; y (K, nb) device -> (x_pad (K, Dp), iters (K,), relres (K,))."""
-        K = y.shape[0]
+    def solve(self, y, out=None, rhs=None):
+        """Batched snapshot solves; y (K, nb) device -> (x_pad (K, Dp), iters (K,), relres (K,)).
+
+        rhs (K, Dp) padded device tensor: caller-supplied right-hand sides (default: the reference's load vector
+        b = 1 / N^2); with rhs given, y may be None (a == 1: the H10 operator A_1)."""
+        K = y.shape[0] if y is not None else rhs.shape[0]
         x = self.empty(K, self.Dp) if out is None else out
         iters = self.empty(K, dtype=torch.int32)
         relres = self.empty(K)
         stats = (C.c_int64 * 4)()
-        _lib.check(self.lib.romhc_solve(self.handle, _ptr(y), K, _ptr(x), _ptr(iters), _ptr(relres), self.stream(),
-                                        stats))
+        if rhs is None:
+            _lib.check(self.lib.romhc_solve(self.handle, _ptr(y), K, _ptr(x), _ptr(iters), _ptr(relres), self.stream(),
+                                            stats))
+        else:
+            assert rhs.shape == (K, self.Dp)
+            _lib.check(self.lib.romhc_solve_rhs(self.handle, _ptr(y), _ptr(rhs), K, _ptr(x), _ptr(iters), _ptr(relres),
+                                                self.stream(), stats))
         self.last_solve_stats = {"launched_iterations": int(stats[0]), "chunks": int(stats[1]),
                                  "status": int(stats[2]), "workspace_bytes": int(stats[3])}
         return x, iters, relres

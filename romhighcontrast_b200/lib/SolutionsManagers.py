@@ -141,6 +141,20 @@ class SolutionsManager:
             raise Exception("Not implemented.")                        # reference :86
 
     # ---- reduced Galerkin ---------------------------------------------------------------------------------------------
+    def generate_riesz_h10(self, x, a=None):
+        """Extension (the reference stubs this out at :78-84): Riesz representers of the point
+        evaluations at x (m, 2) with respect to the H10 inner product u^T A_1 v, shape (m, D): row j solves
+        A_1 w_j = l_j with l_j[i] = phi_i(x_j).  `a` (nrb, ncb) selects the energy inner product of A(a) instead.
+        m batched GMG-PCG solves on the device with point-functional right-hand sides."""
+        eng = self._engine_()
+        L = self._interpolation_matrix(np.asarray(x, dtype=np.float64))            # (m, D) point functionals
+        y = None
+        if a is not None:
+            y = eng.params(np.broadcast_to(np.asarray(a, dtype=np.float64), (L.shape[0],) + tuple(self.blocks_geometry)))
+        w, iters, relres = eng.solve(y, rhs=eng.pad(L))
+        self.last_solver_report = {"iterations": iters.cpu().numpy(), "relative_residual": relres.cpu().numpy()}
+        return eng.unpad(w).cpu().numpy()
+
     def generate_fm_solutions(self, a: Union[np.ndarray, List[np.ndarray]], coefficients_rom: List[np.ndarray], *,
                               return_coefs=False):
         """Galerkin projection onto span(coefficients_rom) for every parameter (reference :88-106)."""

@@ -196,3 +196,31 @@ def test_pbdw_and_large_batch_online_stage():
     # the corrected state interpolates the data up to the conditioning of R R^T
     inv = rb.parameter_estimation_inverse(c)
     assert inv.shape == (K, 4, 4)
+
+
+def test_riesz_h10_extension():
+    """H10 Riesz representers (the reference raises 'Not implemented.'): <w_j, v>_{A_1} = v(x_j) for every v, and the
+    representers equal the sparse direct solution of A_1 w = l_j; the energy variant uses A(a)."""
+    from lib.SolutionsManagers import SolutionsManagerFEM
+    from oracle import FEMOracle
+    import scipy.sparse.linalg as spla
+    geo, N = (3, 2), 16
+    sm = SolutionsManagerFEM(geo, N)
+    o = FEMOracle(geo, N)
+    rng = np.random.default_rng(3)
+    pts = np.column_stack([rng.uniform(*sm.x_domain, 7), rng.uniform(*sm.y_domain, 7)])
+    with pytest.raises(Exception, match="Not implemented"):
+        sm.generate_riesz(pts, norm="h10")                      # the reference-compatible entry point is untouched
+    W = sm.generate_riesz_h10(pts)
+    assert W.shape == (7, sm.vspace_dim)
+    V = rng.standard_normal((5, sm.vspace_dim))
+    lhs = V @ (o.A1 @ W.T)                                      # (5, 7) inner products
+    rhs = sm.evaluate_solutions(pts, V)                         # (5, 7) point values
+    assert relerr(lhs, rhs) < 1e-10
+    Lmat = sm.generate_riesz(pts, norm="l2")                    # (7, D) point functionals
+    Wo = spla.splu(o.A1.tocsc()).solve(Lmat.T).T
+    assert relerr(W, Wo) < 1e-9
+    a = 10 ** rng.uniform(0, 4, geo)
+    Wa = sm.generate_riesz_h10(pts, a=a)
+    Wao = spla.splu(o.matrix(a).tocsc()).solve(Lmat.T).T
+    assert relerr(Wa, Wao) < 1e-9
