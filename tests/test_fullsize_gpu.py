@@ -110,3 +110,33 @@ def test_gram_and_online_stage_full_size(eng):
     # scaling property of the reduced problem: c(2 y) = c(y) / 2
     C2 = eng.reduced_solve(eng.params(2.0 * yo[:1000]), Ahat, bhat)
     assert float((2.0 * C2 - C[:1000]).abs().max()) <= 1e-12 * float(C[:1000].abs().max())
+
+
+def test_config1_greedy_and_pca_parity_at_full_size():
+    """BASELINE configs[1]: (3,3) subdomains, 128 x 128 interior nodes (N = 43: prime, single-level solver), 1000 samples,
+    contrast up to 1e6, n = 20: both greedy criteria pick the oracle's index sequence, PCA singular values agree."""
+    from lib.ReducedBasis import ReducedBasisGreedy, ReducedBasisPCA, GREEDY_FOR_GALERKIN, GREEDY_FOR_H10
+    from lib.SolutionsManagers import SolutionsManagerFEM
+    from oracle import FEMOracle
+    from oracle.rb import greedy_build, pca_components
+    geo, Nb, K, n = (3, 3), 43, 1000, 20
+    y = 10 ** np.random.default_rng(42).uniform(0, 6, (K,) + geo)
+    sm = SolutionsManagerFEM(geo, Nb, method="lsqsparse")
+    U = sm.generate_solutions(y)
+    o = FEMOracle(geo, Nb)
+    Uo = o.generate_solutions(y[:8])
+    assert (np.linalg.norm(U[:8] - Uo, axis=1) / np.linalg.norm(Uo, axis=1)).max() < 1e-9
+    h1 = sm.H10norm(U)
+    np.testing.assert_allclose(h1, o.H10norm(U), rtol=1e-12)
+    for crit in (GREEDY_FOR_GALERKIN, GREEDY_FOR_H10):
+        rb = ReducedBasisGreedy(greedy_for=crit).build(n=n, sm=sm, solutions2train=U, a2train=y, solutions2train_h1norm=h1)
+        _, _, picked, trace = greedy_build(o, n, U, y, o.H10norm(U), greedy_for=crit, return_trace=True)
+        for step, (a_, b_) in enumerate(zip(picked, rb.selected_indices)):
+            top = np.sort(trace[step])[-2:]
+            gap = (top[1] - top[0]) / top[1]
+            assert a_ == b_ or gap < 1e-9, (crit, step, a_, b_, gap)     # bit-identical wherever the gap exceeds 1e-9
+            if a_ != b_:
+                break
+    rbp = ReducedBasisPCA().build(n=n, sm=sm, solutions2train=U, a2train=y)
+    _, so, _ = pca_components(U, n)
+    assert np.max(np.abs(np.asarray(rbp.singular_values_) - so) / so) < 1e-9
