@@ -74,12 +74,12 @@ class BaseReducedBasis:
         return sm.project_solutions(true_solutions, self.basis, **kwargs)                # reference :62-63
 
     def state_estimation(self, sm: SolutionsManager, measurement_points: np.ndarray, measurements: np.ndarray,
-                         return_coefs=False):
+                         return_coefs=False, *, reconstruct=True):
         """Least-squares fit of the basis to point measurements (reference :65-70).
 
         The (m, n) collocation matrix is factorised once on the host (np.linalg.lstsq against the identity gives its
         pseudo-inverse with the same gelsd/rcond=-1 semantics); applying it to the K measurement vectors and
-        reconstructing c^T basis are device GEMMs."""
+        reconstructing c^T basis are device GEMMs.  Additive keyword `reconstruct=False` returns only c (n, K)."""
         eng = sm._engine_()
         rb_evaluations_in_points = sm.evaluate_solutions(measurement_points, self.basis)           # (n, m)
         Z = np.asarray(measurements, dtype=np.float64)
@@ -87,6 +87,8 @@ class BaseReducedBasis:
         pinv = np.linalg.lstsq(rb_evaluations_in_points.T, np.eye(m), rcond=-1)[0]                # (n, m)
         Zd = eng.dev(Z.reshape(-1, m))
         c_dev = eng.gemm_nt(eng.dev(pinv), Zd)                                                    # (n, K)
+        if not reconstruct:            # large observation batches: (K, D) fields would not fit; coefficients only
+            return c_dev.cpu().numpy()
         basis_pad = sm._pad_rows(self.basis)
         est = eng.unpad(eng.gemm_nn(c_dev.T.contiguous(), basis_pad))                              # c^T basis
         solution_estimations = est.cpu().numpy()

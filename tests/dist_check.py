@@ -25,7 +25,9 @@ def main():
     from romhighcontrast_b200.lib.ReducedBasis import ReducedBasisGreedy, GREEDY_FOR_GALERKIN, GREEDY_FOR_H10
     from romhighcontrast_b200.lib.SolutionsManagers import SolutionsManagerFEM
     from romhighcontrast_b200.pod import pca_components
-    geo, N, K, n = (3, 3), 16, 203, 8
+    # default: a small ragged case; DIST_CHECK_CASE=config4 runs the geometry of BASELINE configs[4] ((8,8) subdomains,
+    # 512 x 512 cells) at a reduced training-set size
+    geo, N, K, n = ((8, 8), 64, 1024, 10) if os.environ.get("DIST_CHECK_CASE") == "config4" else ((3, 3), 16, 203, 8)
     y = 10 ** np.random.default_rng(5).uniform(0, 6, (K,) + geo)
     sm = SolutionsManagerFEM(geo, N)
     eng = sm._engine_()
