@@ -1,0 +1,14 @@
+"""Probe (not a test): the fp64 DMMA Gram kernel alone (K = 10 000 snapshots of the 256^2 mesh), for ncu."""
+import sys, torch
+sys.path.insert(0, '.')
+from romhighcontrast_b200.engine import Engine
+eng = Engine((4, 4), 64)
+K = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
+X = torch.randn(K, eng.Dp, dtype=torch.float64, device='cuda')
+for _ in range(2):
+    G = eng.gemm_nt(X, X, symmetric=True)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); G = eng.gemm_nt(X, X, symmetric=True); e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1)
+print(f"K={K}: {ms:.2f} ms, {K * (K + 1) * eng.D / ms / 1e9:.2f} TFLOP/s (triangle, algorithmic D)")
