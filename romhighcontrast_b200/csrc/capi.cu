@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <atomic>
 #include <new>
+#include <thread>
 #include <vector>
 
 namespace romhc {
@@ -47,6 +48,10 @@ void Context::free_host_stage() {
         if (hstage.copied[i]) cudaEventDestroy(hstage.copied[i]);
         hstage.done[i] = hstage.copied[i] = nullptr;
     }
+    for (int i = 0; i < 2; ++i) { if (hstage.bounce[i]) cudaFreeHost(hstage.bounce[i]); hstage.bounce[i] = nullptr; }
+    hstage.bounce_cap = 0;
+    if (hstage.copy2) cudaStreamDestroy(hstage.copy2);
+    hstage.copy2 = nullptr;
     if (hstage.it_pin) cudaFreeHost(hstage.it_pin);
     if (hstage.rel_pin) cudaFreeHost(hstage.rel_pin);
     hstage.it_pin = nullptr; hstage.rel_pin = nullptr; hstage.pin_cap = 0;
@@ -275,6 +280,25 @@ int romhc_estimator(const double* c, int64_t K, int n, const double* ab, int nb,
 int romhc_argmax(const double* v, int64_t K, int64_t* idx, double* val, void* st) { return argmax_first(v, K, idx, val, ST(st)); }
 
 // ---- host-buffer entry points --------------------------------------------------------------------------------------------
+// Pageable destinations: a device-to-host copy into pageable memory blocks the calling thread behind the whole copy and
+// would serialise the pipeline, so the solutions go to pinned bounce buffers first and a stream-ordered host callback
+// moves them on with a few threads while the next chunk is being solved.
+struct HostCopyTask { const char* src; char* dst; size_t bytes; int nthreads; };
+static void CUDART_CB host_copy_callback(void* p) {
+    HostCopyTask* t = static_cast<HostCopyTask*>(p);
+    const int nt = std::max(1, t->nthreads);
+    const size_t per = ((t->bytes + nt - 1) / nt + 4095) & ~size_t(4095);
+    std::vector<std::thread> th;
+    for (int i = 1; i < nt; ++i) {
+        const size_t o = per * i;
+        if (o >= t->bytes) break;
+        th.emplace_back([=]() { memcpy(t->dst + o, t->src + o, std::min(per, t->bytes - o)); });
+    }
+    memcpy(t->dst, t->src, std::min(per, t->bytes));
+    for (auto& x : th) x.join();
+    delete t;
+}
+
 int romhc_generate_solutions_host(romhc_handle h, const double* y_host, int64_t K, double* U_host, int* iters_host,
                                   double* relres_host) {
     CHECK_H(h);
@@ -293,6 +317,25 @@ int romhc_generate_solutions_host(romhc_handle h, const double* y_host, int64_t 
     HostStage& s = c->hstage;
     rc = c->ensure_pinned_stats(K);
     if (rc) return rc;
+    // is the destination pinned (or managed)?  cudaPointerGetAttributes reports plain malloc memory as unregistered
+    bool pinned_dst = false;
+    {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, U_host) == cudaSuccess)
+            pinned_dst = at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+        cudaGetLastError();
+    }
+    if (!pinned_dst) {
+        const size_t need = size_t(chunk) * D * 8;
+        if (need > s.bounce_cap) {
+            for (int i = 0; i < 2; ++i) { if (s.bounce[i]) cudaFreeHost(s.bounce[i]); s.bounce[i] = nullptr; }
+            s.bounce_cap = 0;
+            for (int i = 0; i < 2; ++i) CK(cudaMallocHost((void**)&s.bounce[i], need));
+            s.bounce_cap = need;
+        }
+        if (!s.copy2) CK(cudaStreamCreateWithFlags(&s.copy2, cudaStreamNonBlocking));
+    }
+    const int copy_threads = std::max(1, std::min(8, int(std::thread::hardware_concurrency()) / 2));
     // Chunk schedule: full chunks first, then halved ones -- only the LAST chunk's D2H copy is exposed (nothing left
     // to overlap it with), so it should be small; chunks below ~600 systems would under-fill the persistent kernels.
     int64_t nchunk = 0, kc_next = chunk;
@@ -310,16 +353,28 @@ int romhc_generate_solutions_host(romhc_handle h, const double* y_host, int64_t 
         rc = c->unpack(s.x[slot], s.u[slot], kc, s.compute);
         if (rc) break;
         CK(cudaEventRecord(s.done[slot], s.compute));
-        CK(cudaStreamWaitEvent(s.copy, s.done[slot], 0));
-        CK(cudaMemcpyAsync(U_host + k0 * D, s.u[slot], size_t(kc) * D * 8, cudaMemcpyDeviceToHost, s.copy));
+        // pageable destination: slot 0 and slot 1 use different copy streams so that the callback of one chunk and the
+        // D2H copy of the next run side by side
+        cudaStream_t cs = (!pinned_dst && slot) ? s.copy2 : s.copy;
+        CK(cudaStreamWaitEvent(cs, s.done[slot], 0));
+        if (pinned_dst) {
+            CK(cudaMemcpyAsync(U_host + k0 * D, s.u[slot], size_t(kc) * D * 8, cudaMemcpyDeviceToHost, cs));
+        } else {
+            CK(cudaMemcpyAsync(s.bounce[slot], s.u[slot], size_t(kc) * D * 8, cudaMemcpyDeviceToHost, cs));
+        }
         // per-system statistics go to pinned staging first: a D2H copy into the caller's (usually pageable) arrays would
         // block the host behind the big solution copy and serialise the pipeline
-        if (iters_host) CK(cudaMemcpyAsync(s.it_pin + k0, s.it[slot], size_t(kc) * 4, cudaMemcpyDeviceToHost, s.copy));
-        if (relres_host) CK(cudaMemcpyAsync(s.rel_pin + k0, s.rel[slot], size_t(kc) * 8, cudaMemcpyDeviceToHost, s.copy));
-        CK(cudaEventRecord(s.copied[slot], s.copy));
+        if (iters_host) CK(cudaMemcpyAsync(s.it_pin + k0, s.it[slot], size_t(kc) * 4, cudaMemcpyDeviceToHost, cs));
+        if (relres_host) CK(cudaMemcpyAsync(s.rel_pin + k0, s.rel[slot], size_t(kc) * 8, cudaMemcpyDeviceToHost, cs));
+        CK(cudaEventRecord(s.copied[slot], cs));
+        if (!pinned_dst) {
+            HostCopyTask* t = new HostCopyTask{(const char*)s.bounce[slot], (char*)(U_host + k0 * D), size_t(kc) * D * 8, copy_threads};
+            CK(cudaLaunchHostFunc(cs, host_copy_callback, t));
+        }
         k0 += kc;
     }
     CK(cudaStreamSynchronize(s.copy));
+    if (s.copy2) CK(cudaStreamSynchronize(s.copy2));
     CK(cudaStreamSynchronize(s.compute));
     if (rc == ROMHC_OK) {
         if (iters_host) memcpy(iters_host, s.it_pin, size_t(K) * 4);

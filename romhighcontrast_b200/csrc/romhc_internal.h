@@ -75,6 +75,9 @@ struct HostStage {
     int* it_pin = nullptr;        // pinned staging of the per-system statistics (whole batch)
     double* rel_pin = nullptr;
     int64_t pin_cap = 0;
+    double* bounce[2] = {nullptr, nullptr};   // pinned bounce buffers for pageable destinations
+    size_t bounce_cap = 0;
+    cudaStream_t copy2 = nullptr;
 };
 
 struct Context {

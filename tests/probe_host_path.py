@@ -21,6 +21,11 @@ for ws in [4, 6, 8, 12]:
     eng.generate_solutions_host(yp,out=U)
     torch.cuda.synchronize(); t=time.perf_counter(); eng.generate_solutions_host(yp,out=U); torch.cuda.synchronize(); dt=time.perf_counter()-t
     print('host_chunks',ws,'e2e ms',dt*1e3, K/dt)
+Upg=np.empty((K,eng.D))
+eng.set_option("host_chunks", 4)
+for rep in range(3):
+    torch.cuda.synchronize(); t=time.perf_counter(); eng.generate_solutions_host(yp,out=Upg); torch.cuda.synchronize(); dt=time.perf_counter()-t
+    print('pageable destination e2e ms',dt*1e3, K/dt, 'equal to pinned result:', bool(np.array_equal(Upg,U)))
 yd=eng.params(y); x=eng.empty(K,eng.Dp)
 eng.set_option("workspace_gb", 48)
 for k in [10000,2500,1250]:
