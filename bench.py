@@ -255,6 +255,22 @@ def main():
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_val = world * K / float(t_e2e.item())
     clocks = sampler.stop()
+    # the same through the reference-facing class API (numpy in, fresh pageable numpy out): src.lib mirror -> C ABI
+    api_val = None
+    try:
+        from lib.SolutionsManagers import SolutionsManagerFEM
+        sm = SolutionsManagerFEM(GEO, NPB, method="lsqsparse")
+        sm.generate_solutions(y_host[:256])
+        sm.generate_solutions(y_host)                               # first full call allocates the pinned bounce buffers
+        t0 = time.perf_counter()
+        U_api = sm.generate_solutions(y_host)
+        t_api = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_api, op=dist.ReduceOp.MAX)
+        api_val = world * K / float(t_api.item())
+        del U_api, sm
+    except MemoryError:
+        api_val = None
 
     # ---- parity spot check of what was just timed (sub-sample against the CPU oracle) ------------------------------
     parity = None
@@ -332,7 +348,9 @@ def main():
                        "parity_rel_l2_vs_oracle": parity},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": int(y_np.nbytes),
-                    "d2h_bytes_per_step": int(U_np.nbytes + K * 12)},
+                    "d2h_bytes_per_step": int(U_np.nbytes + K * 12),
+                    "path": "romhc_generate_solutions_host (C ABI), pinned host buffers",
+                    "class_api_value": api_val, "class_api_path": "SolutionsManagerFEM.generate_solutions: numpy in, fresh numpy out"},
             "gpu_launches": int(launches),
             "roofline": roofline, "kernels": per_kind, "cpu_baseline": cpu, "secondary": secondary,
         }
