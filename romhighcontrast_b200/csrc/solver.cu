@@ -1217,7 +1217,7 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
     ++g_launches; k_scalar_beta<<<gs, 128, 0, st>>>(Kc, np_rz, ws.part_rz, ws.rz, ws.rz0, ws.beta, ws.active, ws.iters, ws.relres, 0,
                                       tol2, n_active, ws_flags + 0);
     int it = 0, cur = 0;
-    int total_launch_iters = 0;
+    int total_launch_iters = 0, still_active = -1;
     for (it = 1; it <= maxit; ++it) {
         prof_window = (it <= min_check_iter);
         prof_begin(PROF_PAPPLY, st);
@@ -1232,10 +1232,11 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
         ++g_launches; k_scalar_beta<<<gs, 128, 0, st>>>(Kc, np_rz, ws.part_rz, ws.rz, ws.rz0, ws.beta, ws.active, ws.iters, ws.relres,
                                           it, tol2, ctr, ws_flags + 0);
         ++total_launch_iters;
-        if (it >= min_check_iter && ((it - min_check_iter) % check_every == 0 || it == maxit)) {
+        if ((it >= min_check_iter && (it - min_check_iter) % check_every == 0) || it == maxit) {
             ++g_launches; k_post_flag<<<1, 1, 0, st>>>(ctr, d_hflags);
             CK(cudaStreamSynchronize(st));
-            if (h_flags[0] == 0) break;
+            still_active = h_flags[0];
+            if (still_active == 0) break;
         }
     }
     ++g_launches; k_post_flag<<<1, 1, 0, st>>>(ws_flags, d_hflags);
@@ -1250,6 +1251,11 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
         stats->status |= h_flags[0];
     }
     if (h_flags[0] & 1) { set_error("coarse Cholesky hit a non-positive pivot (coefficients must be > 0)"); return ROMHC_ERR_NUMERIC; }
+    if (still_active > 0) {            // the loop ran into maxit: never hand back unconverged solutions silently
+        if (stats) stats->status |= 8;
+        set_error("PCG: %d of %d systems did not reach rtol = %.3g within maxit = %d iterations", still_active, Kc, rtol, maxit);
+        return ROMHC_ERR_NOTCONVERGED;
+    }
     return ROMHC_OK;
 }
 

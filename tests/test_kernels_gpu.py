@@ -298,6 +298,18 @@ def test_evaluate_estimators_argmax(torch_mod):
     assert eng.argmax(eng.dev(v))[0] == int(np.argmax(v)) == 200000
 
 
+def test_solver_reports_non_convergence(torch_mod):
+    """maxit too small: the C ABI returns ROMHC_ERR_NOTCONVERGED instead of handing back inaccurate snapshots"""
+    from romhighcontrast_b200 import _lib
+    eng = make_engine((4, 4), 16)
+    eng.set_option("maxit", 3)
+    with pytest.raises(_lib.RomhcError, match="did not reach rtol"):
+        eng.solve(eng.params(rand_y((4, 4), 5, seed=9)))
+    eng.set_option("maxit", 1000)
+    _, iters, relres = eng.solve(eng.params(rand_y((4, 4), 5, seed=9)))
+    assert float(relres.max()) <= 1e-12 * 1.0000001
+
+
 def test_c_abi_rejects_bad_arguments(torch_mod):
     from romhighcontrast_b200 import _lib
     from romhighcontrast_b200.engine import Engine
