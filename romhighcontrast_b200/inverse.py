@@ -1,0 +1,112 @@
+"""Notebook-level inverse-problem methods on the device.
+
+The reference defines these only inside `src/notebooks/InverseProblemPipeline.ipynb` (cells 35, 44, 52), as functions of
+a global `sm`.  Here they take `sm` explicitly; names and argument meaning follow the notebook:
+
+* cell 52  `state_estimation_fitting_method_least_squares`, `pbdw_correction`, `state_estimation_fitting_method_pbdw`,
+           `state_estimation_fitting_method_weighted_least_squares`
+* cell 44  `inverse_christoffel_function`, `measurements_sampling_method_optimal`
+* cell 35  `reduced_basis_generator_greedy` (the notebook's l2 / H10 greedy: least-squares residual, argmax)
+
+Every O(K D) operation (point evaluation, reconstruction c^T basis, Riesz correction, residual norms) runs through the
+C ABI (`romhc_evaluate`, `romhc_gemm_nn`, `romhc_energy_norm`, ...); the (m, n) collocation systems are factorised on
+the host with the same LAPACK call the notebook uses (`np.linalg.lstsq(..., rcond=-1)`).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .lib.ReducedBasis import orthonormalize_base
+
+
+def _basis_array(reduced_basis):
+    return np.ascontiguousarray(np.asarray(reduced_basis, dtype=np.float64)).reshape(len(reduced_basis), -1)
+
+
+def _ls_coefficients(sm, measurement_points, measurements, basis, weights=None):
+    """c (n, K) minimising || W (E^T c - z) || for every measurement vector z (rows of `measurements`)."""
+    eng = sm._engine_()
+    E = sm.evaluate_solutions(measurement_points, basis)                    # (n, m)
+    m = E.shape[1]
+    A = E.T if weights is None else E.T * weights[:, None]
+    pinv = np.linalg.lstsq(A, np.eye(m), rcond=-1)[0]                         # (n, m): x = pinv @ (W z)
+    if weights is not None:
+        pinv = pinv * weights[None, :]
+    Z = eng.dev(np.asarray(measurements, dtype=np.float64).reshape(-1, m))
+    return eng.gemm_nt(eng.dev(pinv), Z)                                     # (n, K) device
+
+
+def state_estimation_fitting_method_least_squares(sm, measurement_points, measurements, reduced_basis, **kwargs):
+    """cell 52: least-squares fit of the basis to the point values, returns the (K, D) approximations."""
+    eng = sm._engine_()
+    basis = _basis_array(reduced_basis)
+    c = _ls_coefficients(sm, measurement_points, measurements, basis)
+    return eng.unpad(eng.gemm_nn(c.T.contiguous(), sm._pad_rows(basis))).cpu().numpy()
+
+
+def pbdw_correction(sm, measurement_points, measurements, approximate_solutions, **kwargs):
+    """cell 52: u* = v + z R^T - (v R) R^T with the l2 Riesz representers R = evaluate(points, eye(D)) (D, m).
+
+    v R is the point evaluation of v, so no D x m matrix-matrix product is needed for it; the correction
+    (z - v R) R^T is one (K, m) x (m, D) product with the (m, D) interpolation matrix."""
+    eng = sm._engine_()
+    V = sm._pad_rows(np.asarray(approximate_solutions, dtype=np.float64))
+    Z = eng.dev(np.asarray(measurements, dtype=np.float64).reshape(V.shape[0], -1))
+    Rt = sm._pad_rows(sm.generate_riesz(measurement_points, norm="l2"))     # (m, Dp)
+    diff = (Z - eng.evaluate(measurement_points, V)).contiguous()            # (K, m)
+    return eng.unpad(V + eng.gemm_nn(diff, Rt)).cpu().numpy()
+
+
+def state_estimation_fitting_method_pbdw(sm, measurement_points, measurements, reduced_basis, **kwargs):
+    v = state_estimation_fitting_method_least_squares(sm, measurement_points, measurements, reduced_basis)
+    return pbdw_correction(sm, measurement_points, measurements, v)
+
+
+def inverse_christoffel_function(basis, sm, measurement_points):
+    """cell 44: sum of squares of the ORTHONORMALISED basis functions at the points, shape (m,)."""
+    q = orthonormalize_base(_basis_array(basis))
+    vals = sm.evaluate_solutions(measurement_points, q)                      # (n, m)
+    return np.sum(vals ** 2, axis=0)
+
+
+def state_estimation_fitting_method_weighted_least_squares(sm, measurement_points, measurements, reduced_basis, **kwargs):
+    """cell 52: the same least squares with rows weighted by 1 / inverse_christoffel_function."""
+    eng = sm._engine_()
+    basis = _basis_array(reduced_basis)
+    weights = 1.0 / inverse_christoffel_function(basis, sm, measurement_points)
+    c = _ls_coefficients(sm, measurement_points, measurements, basis, weights=weights)
+    return eng.unpad(eng.gemm_nn(c.T.contiguous(), sm._pad_rows(basis))).cpu().numpy()
+
+
+def measurements_sampling_method_optimal(number_of_measures, xlim, ylim, basis, sm, seed=42, discretization=5, **kwargs):
+    """cell 44: sample measurement points from the density given by the inverse Christoffel function on a grid."""
+    np.random.seed(seed)
+    n_per_dim = int(discretization * np.sqrt(number_of_measures))
+    x, y = np.meshgrid(*[np.linspace(*xlim, num=n_per_dim), np.linspace(*ylim, num=n_per_dim)])
+    pts = np.concatenate([x.reshape((-1, 1)), y.reshape((-1, 1))], axis=1)
+    weights = inverse_christoffel_function(basis, sm, pts)
+    weights /= np.sum(weights)
+    return pts[np.random.choice(len(pts), size=number_of_measures, p=weights, replace=False)]
+
+
+def reduced_basis_generator_greedy(sm, solutions_offline, number_of_reduced_base_elements, norm="l2"):
+    """cell 35: start from the snapshot of largest norm; then repeatedly add the snapshot with the largest norm of its
+    Euclidean least-squares residual against the current basis (np.argmax: first maximum).  Returns (basis, indices).
+
+    The residual S - (S B^+) B is formed on the device; its norms come from the stencil-energy / l2 kernels."""
+    if norm not in ("l2", "h10"):
+        raise Exception(f"Norm {norm} not implemented.")
+    eng = sm._engine_()
+    S_host = np.asarray(solutions_offline, dtype=np.float64)
+    S = sm._pad_rows(S_host)                                                  # (K, Dp) device
+    f_norm = eng.l2_norm if norm == "l2" else eng.h10_norm
+    picked = [int(np.argmax(f_norm(S).cpu().numpy()))]
+    for _ in range(1, number_of_reduced_base_elements):
+        B = S[picked].contiguous()                                            # (n, Dp)
+        G = eng.gemm_nt(B, B).cpu().numpy()                                  # (n, n) Gram of the basis
+        rhs = eng.gemm_nt(B, S)                                               # (n, K)
+        X = torch.as_tensor(np.linalg.lstsq(G, np.eye(len(picked)), rcond=None)[0], device=S.device) @ rhs
+        resid = S - eng.gemm_nn(X.T.contiguous(), B)
+        picked.append(int(np.argmax(f_norm(resid).cpu().numpy())))
+    return [S_host[i] for i in picked], picked

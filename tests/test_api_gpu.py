@@ -224,3 +224,55 @@ def test_riesz_h10_extension():
     Wa = sm.generate_riesz_h10(pts, a=a)
     Wao = spla.splu(o.matrix(a).tocsc()).solve(Lmat.T).T
     assert relerr(Wa, Wao) < 1e-9
+
+
+def test_notebook_inverse_methods():
+    """romhighcontrast_b200.inverse vs direct numpy restatements of InverseProblemPipeline.ipynb cells 35 / 44 / 52 run
+    on the CPU oracle (same snapshots, same points)."""
+    from lib.SolutionsManagers import SolutionsManagerFEM
+    from lib.ReducedBasis import orthonormalize_base
+    from oracle import FEMOracle
+    from romhighcontrast_b200 import inverse as inv
+    geo, N, K, n, m = (2, 2), 10, 60, 5, 30
+    sm = SolutionsManagerFEM(geo, N)
+    o = FEMOracle(geo, N)
+    rng = np.random.default_rng(12)
+    y = 10 ** rng.uniform(0, 3, (K,) + geo)
+    U = sm.generate_solutions(y)
+    pts = np.column_stack([rng.uniform(*sm.x_domain, m), rng.uniform(*sm.y_domain, m)])
+    Z = o.evaluate_solutions(pts, U)
+    # cell 35: notebook greedy, both norms
+    for norm, f in (("l2", o.l2norm), ("h10", o.H10norm)):
+        basis = [U[int(np.argmax(f(U), axis=0))]]
+        idx = [int(np.argmax(f(U), axis=0))]
+        for _ in range(1, n):
+            x = np.linalg.lstsq(np.transpose(basis), np.transpose(U), rcond=None)[0]
+            nxt = int(np.argmax(f((np.transpose(U) - np.transpose(basis) @ x).T)))
+            basis.append(U[nxt]); idx.append(nxt)
+        got, gidx = inv.reduced_basis_generator_greedy(sm, U, n, norm=norm)
+        assert gidx == idx, (norm, gidx, idx)
+        np.testing.assert_array_equal(np.asarray(got), np.asarray(basis))
+    rb = basis
+    # cell 52: least squares, PBDW, weighted least squares
+    E = o.evaluate_solutions(pts, rb)
+    ls = (np.linalg.lstsq(E.T, Z.T, rcond=-1)[0]).T @ np.array(rb)
+    assert relerr(inv.state_estimation_fitting_method_least_squares(sm, pts, Z, rb), ls) < 1e-9
+    R = o.evaluate_solutions(points=pts, solutions=np.eye(o.vspace_dim))        # (D, m)
+    pb = ls + Z @ R.T - (ls @ R) @ R.T
+    assert relerr(inv.pbdw_correction(sm, pts, Z, ls), pb) < 1e-9
+    assert relerr(inv.state_estimation_fitting_method_pbdw(sm, pts, Z, rb), pb) < 1e-9
+    w = np.sum(o.evaluate_solutions(pts, orthonormalize_base(np.asarray(rb))) ** 2, axis=0)
+    np.testing.assert_allclose(inv.inverse_christoffel_function(rb, sm, pts), w, rtol=1e-10)
+    wl = 1 / w
+    wls = (np.linalg.lstsq(E.T * wl[:, None], Z.T * wl[:, None], rcond=-1)[0]).T @ np.array(rb)
+    assert relerr(inv.state_estimation_fitting_method_weighted_least_squares(sm, pts, Z, rb), wls) < 1e-9
+    # cell 44: optimal sampling draws the same points (same seed, same density up to rounding)
+    p1 = inv.measurements_sampling_method_optimal(8, sm.x_domain, sm.y_domain, rb, sm, seed=3)
+    np.random.seed(3)
+    npd = int(5 * np.sqrt(8))
+    gx, gy = np.meshgrid(np.linspace(*sm.x_domain, num=npd), np.linspace(*sm.y_domain, num=npd))
+    gp = np.concatenate([gx.reshape((-1, 1)), gy.reshape((-1, 1))], axis=1)
+    ww = np.sum(o.evaluate_solutions(gp, orthonormalize_base(np.asarray(rb))) ** 2, axis=0)
+    ww /= ww.sum()
+    p2 = gp[np.random.choice(len(gp), size=8, p=ww, replace=False)]
+    np.testing.assert_allclose(p1, p2)
