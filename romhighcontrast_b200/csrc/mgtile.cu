@@ -1646,6 +1646,7 @@ int Context::tile_down(int l, const double* y, int Kc, cudaStream_t st) {
     (void)y;
     const int L = int(levels.size()) - 1;
     TileArgs a;
+    memset(&a, 0, sizeof(a));
     a.g = levels[l];
     a.has_coarse = l < L ? 1 : 0;
     a.gc = a.has_coarse ? levels[l + 1] : levels[l];
@@ -1691,6 +1692,7 @@ int Context::tile_update_down(int l, int Kc, const double* p, double* x, const d
     const int L = int(levels.size()) - 1;
     if (!tile_persistent || !use_fused) return ROMHC_ERR_ARG;
     TileArgs a;
+    memset(&a, 0, sizeof(a));
     a.g = levels[l];
     a.has_coarse = l < L ? 1 : 0;
     a.gc = a.has_coarse ? levels[l + 1] : levels[l];
@@ -1726,6 +1728,7 @@ int Context::tile_up(int l, const double* y, int Kc, const double* e, double* pa
     (void)y;
     const int L = int(levels.size()) - 1;
     TileArgs a;
+    memset(&a, 0, sizeof(a));
     a.g = levels[l];
     a.has_coarse = l < L ? 1 : 0;
     a.gc = a.has_coarse ? levels[l + 1] : levels[l];

@@ -1203,10 +1203,9 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
     { int rc2 = tile_weight_table(y, Kc, st); if (rc2) return rc2; }
     const size_t hdr = smem_hdr_bytes(nb);
     auto bytes_p = [&](int TY) { return hdr + size_t(2) * (TY + 2) * g.P * 8; };
-    auto bytes_u = [&](int TY) { return hdr + size_t(3 * TY + 2) * g.P * 8; };
-    const int TYp = pick_ty_fn(g, strip_budget, bytes_p), TYu = pick_ty_fn(g, strip_budget, bytes_u);
-    if (bytes_p(TYp) > SMEM_MAX || bytes_u(TYu) > SMEM_MAX) { set_error("mesh too wide for the PCG strip kernels (C = %d)", g.C); return ROMHC_ERR_ARG; }
-    const int nsp = (g.R + TYp - 1) / TYp, nsu = (g.R + TYu - 1) / TYu;
+    const int TYp = pick_ty_fn(g, strip_budget, bytes_p);
+    if (bytes_p(TYp) > SMEM_MAX) { set_error("mesh too wide for the PCG strip kernels (C = %d)", g.C); return ROMHC_ERR_ARG; }
+    const int nsp = (g.R + TYp - 1) / TYp;
     const int gs = (Kc + 127) / 128;
     const double* z = nullptr;
     int np_rz = 1;
