@@ -298,6 +298,23 @@ def test_evaluate_estimators_argmax(torch_mod):
     assert eng.argmax(eng.dev(v))[0] == int(np.argmax(v)) == 200000
 
 
+@pytest.mark.parametrize("K", [1, 2, 40000])
+def test_solve_batch_sizes(torch_mod, K):
+    """a single system, and more systems than one solver chunk (32768) / one persistent grid"""
+    from oracle import FEMOracle
+    geo, N = (2, 2), 8
+    eng = make_engine(geo, N)
+    y = rand_y(geo, K, seed=21)
+    x, iters, relres = eng.solve(eng.params(y))
+    assert float(relres.max()) <= 1e-12 * 1.0000001
+    if K > 32768:
+        assert eng.last_solve_stats["chunks"] >= 2
+    pick = sorted({0, K // 2, K - 1, min(K - 1, 32768)})
+    Uo = FEMOracle(geo, N).generate_solutions(y[pick])
+    U = eng.unpad(x[pick]).cpu().numpy()
+    assert relerr(U, Uo) < 1e-9
+
+
 def test_solver_reports_non_convergence(torch_mod):
     """maxit too small: the C ABI returns ROMHC_ERR_NOTCONVERGED instead of handing back inaccurate snapshots"""
     from romhighcontrast_b200 import _lib
