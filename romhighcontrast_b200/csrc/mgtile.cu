@@ -587,9 +587,15 @@ __device__ __forceinline__ void tile_item_init(TileThread<CGT, true>& t, ColWeig
     }
 }
 
+// Thread tx reads the 32 bytes at base + 32 tx with two 128-bit loads.  The hardware serves a 128-bit shared load per
+// quarter warp: its eight 16-byte pieces must fall into eight different 16-byte bank groups, which a stride of 32 bytes
+// does not give (lanes 0 and 4 collide, ...).  Lanes 4..7 of every quarter therefore fetch their two halves in the
+// opposite order: conflict free (the timeline probe showed the plain version spending 2400 of ~10 000 cycles per item
+// in this copy).
 __device__ __forceinline__ void tile_lds_row(double (&v)[4], uint32_t addr) {
-    const double2 a = lds_f64x2(addr), b = lds_f64x2(addr + 16);
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    const uint32_t h = (threadIdx.x & 4u) << 2;           // 0 or 16
+    const double2 a = lds_f64x2(addr + h), b = lds_f64x2(addr + (h ^ 16u));
+    v[0] = h ? b.x : a.x; v[1] = h ? b.y : a.y; v[2] = h ? a.x : b.x; v[3] = h ? a.y : b.y;
 }
 
 // straight-line half sweep for a tile whose four rows all have the primary class (t.rt == 0x55)
@@ -684,7 +690,6 @@ struct TileWalk {
     __device__ __forceinline__ int flag() const { return k < K ? active[k] : 1; }
     __device__ __forceinline__ void settle(int f) { if (!f) { step(); skip(); } }
 };
-
 template <int CGT>
 __global__ void __launch_bounds__(TILE_MAXT, 1)
 k_mgp_down(TileArgs a, const double* __restrict__ r_in, double* __restrict__ z_out, double* __restrict__ rc_out,
@@ -703,17 +708,22 @@ k_mgp_down(TileArgs a, const double* __restrict__ r_in, double* __restrict__ z_o
         mbar_init(reinterpret_cast<uint64_t*>(smem_raw + (s.bar - base)), 1);
         mbar_fence_init();
     }
-    auto issue = [&](const TileWalk& wk, int stage) {
+    // the copies of one item are issued by different warps (part 0: expected byte count + weight table, part 1: r strip)
+    auto issue = [&](const TileWalk& wk, int stage, int parts) {
         const int row0 = wk.strip * a.TY - a.halo_top;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s.bar),
-                     "r"(s.tb + tile_rows_bytes(row0, a.NR, R, P)) : "memory");
-        tile_tma(s.T0 + stage * s.tb, a.tab + int64_t(wk.k) * a.ntab * TWD, s.tb, s.bar);
-        tile_tma_rows(s.Rs, r_in + int64_t(wk.k) * a.g.Dp, P, R, row0, a.NR, row0, s.bar);
+        if (parts & 1) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s.bar),
+                         "r"(s.tb + tile_rows_bytes(row0, a.NR, R, P)) : "memory");
+            tile_tma(s.T0 + stage * s.tb, a.tab + int64_t(wk.k) * a.ntab * TWD, s.tb, s.bar);
+        }
+        if (parts & 2) tile_tma_rows(s.Rs, r_in + int64_t(wk.k) * a.g.Dp, P, R, row0, a.NR, row0, s.bar);
     };
+    const int tid_ = ty * int(blockDim.x) + tx, nt_ = int(blockDim.x * blockDim.y);
+    const int my_parts = (tid_ == 0 ? 1 : 0) | (tid_ == (nt_ > 32 ? 32 : 0) ? 2 : 0);
     __syncthreads();
     TileWalk wk;
     wk.init(K, a.ns, active);
-    if (leader && wk.valid()) issue(wk, 0);
+    if (my_parts && wk.valid()) issue(wk, 0, my_parts);
     uint32_t phase = 0;
     int stage = 0;
     const int nu = a.nu;
@@ -749,7 +759,7 @@ k_mgp_down(TileArgs a, const double* __restrict__ r_in, double* __restrict__ z_o
         tile_item_init(t, w, a, s.T0 + stage * s.tb, rho0, rinfo, ri, s.colv);
         __syncthreads();                                   // everybody has left the staging strip
         nx.settle(nflag);
-        if (leader && nx.valid()) issue(nx, stage ^ 1);
+        if (my_parts && nx.valid()) issue(nx, stage ^ 1, my_parts);
         tile_phase_any<0, 2, true>(z, r, w, t, a);
         tile_publish<0>(z, t);
         __syncthreads();
@@ -848,19 +858,25 @@ k_mgp_update_down(TileArgs a, const double* __restrict__ p_in, double* __restric
         mbar_init(reinterpret_cast<uint64_t*>(smem_raw + (s.bar - base)), 1);
         mbar_fence_init();
     }
-    auto issue = [&](const TileWalk& wk, int stage) {
+    // the copies of one item are issued by different warps (part 0: expected byte count, weight table, p strip;
+    // part 1: r strip; part 2: L2 prefetch of the x rows, which are read straight from global memory)
+    auto issue = [&](const TileWalk& wk, int stage, int parts) {
         const int row0 = wk.strip * a.TY - a.halo_top;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s.bar),
-                     "r"(s.tb + 2u * tile_rows_bytes(row0, NR, R, P)) : "memory");
-        tile_tma(s.T0 + stage * s.tb, a.tab + int64_t(wk.k) * a.ntab * TWD, s.tb, s.bar);
-        tile_tma_rows(s.Zs, p_in + int64_t(wk.k) * a.g.Dp, P, R, row0, NR, row0, s.bar);
-        tile_tma_rows(s.Rs, r_in + int64_t(wk.k) * a.g.Dp, P, R, row0, NR, row0, s.bar);
-        tile_prefetch_rows(x_io, a.g, wk.k, wk.strip * a.TY, a.TY);       // x is read straight from global: warm the L2
+        if (parts & 1) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s.bar),
+                         "r"(s.tb + 2u * tile_rows_bytes(row0, NR, R, P)) : "memory");
+            tile_tma(s.T0 + stage * s.tb, a.tab + int64_t(wk.k) * a.ntab * TWD, s.tb, s.bar);
+            tile_tma_rows(s.Zs, p_in + int64_t(wk.k) * a.g.Dp, P, R, row0, NR, row0, s.bar);
+        }
+        if (parts & 2) tile_tma_rows(s.Rs, r_in + int64_t(wk.k) * a.g.Dp, P, R, row0, NR, row0, s.bar);
+        if (parts & 4) tile_prefetch_rows(x_io, a.g, wk.k, wk.strip * a.TY, a.TY);
     };
+    const int tid_ = ty * int(blockDim.x) + tx, nt_ = int(blockDim.x * blockDim.y);
+    const int my_parts = (tid_ == 0 ? 1 : 0) | (tid_ == (nt_ > 32 ? 32 : 0) ? 2 : 0) | (tid_ == (nt_ > 64 ? 64 : 0) ? 4 : 0);
     __syncthreads();
     TileWalk wk;
     wk.init(K, a.ns, active);
-    if (leader && wk.valid()) issue(wk, 0);
+    if (my_parts && wk.valid()) issue(wk, 0, my_parts);
     uint32_t phase = 0;
     int stage = 0;
     const int nu = a.nu;
@@ -871,7 +887,7 @@ k_mgp_update_down(TileArgs a, const double* __restrict__ p_in, double* __restric
         const int rho0 = y0 - a.halo_top + 4 * ty;
         TileWalk nx = wk;
         nx.step();
-        const int nflag = nx.flag();
+        const int nflag = nx.flag();                       // in flight while this item is set up
         const uint32_t ri = s.rinfo + (wk.strip * NRG + ty) * 12;
         const int rinfo = lds_s32(ri);
         const double al = __ldg(alpha + k);
@@ -936,7 +952,7 @@ k_mgp_update_down(TileArgs a, const double* __restrict__ p_in, double* __restric
             if (i >= own_lo && i < own_hi) tile_store_row(ro + i * P, r[i]);
         __syncthreads();                                   // everybody has left the staging strips
         nx.settle(nflag);
-        if (leader && nx.valid()) issue(nx, stage ^ 1);
+        if (my_parts && nx.valid()) issue(nx, stage ^ 1, my_parts);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -1009,26 +1025,35 @@ k_mgp_up(TileArgs a, const double* __restrict__ e_c, const double* __restrict__ 
         mbar_fence_init();
     }
     const int Pc = a.gc.P, Rc = a.gc.R;
-    auto issue = [&](const TileWalk& wk, int stage) {
+    // the copies of one item are issued by different warps (part 0: expected byte count, weight table, z strip;
+    // part 1: r strip; part 2: coarse correction strip)
+    auto issue = [&](const TileWalk& wk, int stage, int parts) {
         const int row0 = wk.strip * a.TY - a.halo_top;
-        uint32_t tot = s.tb + 2u * tile_rows_bytes(row0, NR, R, P);
-        if (a.has_coarse) tot += tile_rows_bytes(row0 >> 1, NR / 2 + 1, Rc, Pc);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s.bar), "r"(tot) : "memory");
-        tile_tma(s.T0 + stage * s.tb, a.tab + int64_t(wk.k) * a.ntab * TWD, s.tb, s.bar);
-        tile_tma_rows(s.Zs, z_in + int64_t(wk.k) * a.g.Dp, P, R, row0, NR, row0, s.bar);
-        tile_tma_rows(s.Rs, r_in + int64_t(wk.k) * a.g.Dp, P, R, row0, NR, row0, s.bar);
-        if (a.has_coarse) tile_tma_rows(s.Es, e_c + int64_t(wk.k) * a.gc.Dp, Pc, Rc, row0 >> 1, NR / 2 + 1, row0 >> 1, s.bar);
+        if (parts & 1) {
+            uint32_t tot = s.tb + 2u * tile_rows_bytes(row0, NR, R, P);
+            if (a.has_coarse) tot += tile_rows_bytes(row0 >> 1, NR / 2 + 1, Rc, Pc);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s.bar), "r"(tot) : "memory");
+            tile_tma(s.T0 + stage * s.tb, a.tab + int64_t(wk.k) * a.ntab * TWD, s.tb, s.bar);
+        }
+        if (parts & 8) tile_tma_rows(s.Zs, z_in + int64_t(wk.k) * a.g.Dp, P, R, row0, NR, row0, s.bar);
+        if (parts & 2) tile_tma_rows(s.Rs, r_in + int64_t(wk.k) * a.g.Dp, P, R, row0, NR, row0, s.bar);
+        if ((parts & 4) && a.has_coarse)
+            tile_tma_rows(s.Es, e_c + int64_t(wk.k) * a.gc.Dp, Pc, Rc, row0 >> 1, NR / 2 + 1, row0 >> 1, s.bar);
     };
     __syncthreads();
     TileWalk wk;
     wk.init(K, a.ns, active);
-    if (leader && wk.valid()) issue(wk, 0);
+    const int tid = ty * int(blockDim.x) + tx, nwarps = (int(blockDim.x * blockDim.y) + 31) >> 5;
+    const int nt_ = int(blockDim.x * blockDim.y);
+    // one bulk copy per issuing warp: issuing a copy costs the thread several hundred cycles (timeline probe)
+    const int my_parts = (tid == 0 ? 1 : 0) | (tid == (nt_ > 32 ? 32 : 0) ? 2 : 0) | (tid == (nt_ > 64 ? 64 : 0) ? 4 : 0) |
+                         (tid == (nt_ > 96 ? 96 : 0) ? 8 : 0);
+    if (my_parts && wk.valid()) issue(wk, 0, my_parts);
     uint32_t phase = 0;
     int stage = 0;
     const int nu = a.nu;
     const uint32_t own = uint32_t((4 * ty) * P + 4 * tx) * 8;
     const uint32_t es_own = s.Es + uint32_t((2 * ty) * Pc + 2 * tx) * 8;
-    const int tid = ty * int(blockDim.x) + tx, nwarps = (int(blockDim.x * blockDim.y) + 31) >> 5;
     int64_t prev_slot = -1;                                // part_rz slot of the previous item (its reduction is deferred)
     while (wk.valid()) {
         const int k = wk.k, strip = wk.strip;
@@ -1036,7 +1061,7 @@ k_mgp_up(TileArgs a, const double* __restrict__ e_c, const double* __restrict__ 
         const int rho0 = y0 - a.halo_top + 4 * ty;
         TileWalk nx = wk;
         nx.step();
-        const int nflag = nx.flag();
+        const int nflag = nx.flag();                       // in flight while this item is set up
         const uint32_t ri = s.rinfo + (strip * NRG + ty) * 12;
         const int rinfo = lds_s32(ri);
         mbar_wait(reinterpret_cast<uint64_t*>(smem_raw + (s.bar - base)), phase);
@@ -1083,7 +1108,7 @@ k_mgp_up(TileArgs a, const double* __restrict__ e_c, const double* __restrict__ 
         tile_publish<0>(z, t);
         __syncthreads();                                   // staging strip free, red perimeter visible
         nx.settle(nflag);
-        if (leader && nx.valid()) issue(nx, stage ^ 1);
+        if (my_parts && nx.valid()) issue(nx, stage ^ 1, my_parts);
         if (part_rz && prev_slot >= 0 && (tid >> 5) == nwarps - 1) {
             // deferred deterministic reduction of the previous item's per-warp r.z partials (other parity), on the
             // last warp: the first one is busy issuing the copies
