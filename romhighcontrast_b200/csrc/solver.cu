@@ -1188,9 +1188,10 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
     // x = 0, r = b, active = 1
     CK(cudaMemsetAsync(x, 0, size_t(Kc) * g.Dp * 8, st));
     if (rhs) CK(cudaMemcpyAsync(ws.r[0], rhs, size_t(Kc) * g.Dp * 8, cudaMemcpyDeviceToDevice, st));
-    else     CK(cudaMemsetAsync(ws.r[0], 0, size_t(Kc) * g.Dp * 8, st));
+    // r: k_fill_interior rewrites every interior slot below, boundary and padding slots of the workspace are zero since
+    // its allocation (the kernels only ever store zeros there).  p[1] is written by the first k_pcg_p_apply before it is
+    // read; p[0] is multiplied by beta = 0 there, so it must be finite: cleared.
     CK(cudaMemsetAsync(ws.p[0], 0, size_t(Kc) * g.Dp * 8, st));
-    CK(cudaMemsetAsync(ws.p[1], 0, size_t(Kc) * g.Dp * 8, st));
     if (!rhs) { ++g_launches; k_fill_interior<<<(unsigned)(int64_t(Kc) * (g.R - 1)), 128, 0, st>>>(g, ws.r[0], 1.0 / (double(N) * double(N)), Kc); }
     ++g_launches; k_fill_int<<<(Kc + 255) / 256, 256, 0, st>>>(ws.active, 1, Kc);
     CK(cudaMemsetAsync(ws.iters, 0, size_t(Kc) * 4, st));
