@@ -12,6 +12,7 @@
 #include <vector>
 
 namespace romhc {
+extern int g_gram_variant;
 
 static thread_local char g_err[1024] = "";
 std::atomic<long long> g_launches{0};
@@ -158,6 +159,7 @@ int romhc_set_option(romhc_handle h, const char* name, double value) {
     else if (!strcmp(name, "nu_mid")) { c->nu_mid = std::max(0, std::min(4, (int)value)); }
     else if (!strcmp(name, "nu_tail")) { c->nu_tail = std::max(1, std::min(8, (int)value)); c->build_levels(); }
     else if (!strcmp(name, "tile")) c->use_tile = value != 0.0;
+    else if (!strcmp(name, "gram_variant")) romhc::g_gram_variant = (int)value;
     else if (!strcmp(name, "fused")) c->use_fused = value != 0.0;
     else if (!strcmp(name, "tile_persistent")) c->tile_persistent = value != 0.0;
     else if (!strcmp(name, "tile_prefetch")) c->tile_prefetch = value != 0.0;
