@@ -42,10 +42,13 @@ const char* romhc_last_error(void);
 int romhc_create(int nrb, int ncb, int N, int device, romhc_handle* out);
 int romhc_destroy(romhc_handle h);
 /* options: "rtol" (PCG tolerance on sqrt(r.z / r0.z0), default 1e-12), "maxit", "coarse_sweeps",
- * "workspace_gb", "check_every", "min_check_iter", "nu" / "nu_tail" (Gauss-Seidel sweeps of the V(nu,nu) cycle,
- * default nu = 1, nu_tail = 2), "strip_kb" (shared memory per strip CTA, default 113 = two CTAs per SM), "threads" (256 / 512 per strip CTA), "profile" */
+ * "workspace_gb", "check_every", "min_check_iter", "nu" / "nu_mid" / "nu_tail" (Gauss-Seidel sweeps of the V(nu,nu) cycle on the
+ * finest / intermediate / small levels, defaults 2 / 3 / 4), "strip_kb" (shared memory per strip CTA, default 113 = two
+ * CTAs per SM), "threads" (256 / 512 per strip CTA), "profile", "bridge" (1: non-nested transfer to a power-of-two
+ * hierarchy when N has an odd factor, default; 0: stop coarsening at the odd level) */
 int romhc_set_option(romhc_handle h, const char* name, double value);
-/* info[0..15] = D, Dp, P, R, C, nlevels, tail_level, coarse_D, coarse_direct, nrb, ncb, N, 0... */
+/* info[0..15] = D, Dp, P, R, C, nlevels, tail_level, coarse_D, coarse_direct, nrb, ncb, N, workspace bytes per system,
+ * tail kernel shared memory, bridge_level (-1: none), cells per subdomain below the bridge */
 int romhc_get_info(romhc_handle h, int64_t* info16);
 /* with option "profile" = 1: accumulated CUDA-event time (ms) and launch count per solver kernel over the first
  * min_check_iter PCG iterations of every solve (all systems active there).  Index: 0 k_pcg_p_apply, 1 k_pcg_update,

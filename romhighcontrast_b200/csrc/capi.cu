@@ -159,6 +159,20 @@ int romhc_set_option(romhc_handle h, const char* name, double value) {
     else if (!strcmp(name, "nu_mid")) { c->nu_mid = std::max(0, std::min(4, (int)value)); }
     else if (!strcmp(name, "nu_tail")) { c->nu_tail = std::max(1, std::min(8, (int)value)); c->build_levels(); }
     else if (!strcmp(name, "tile")) c->use_tile = value != 0.0;
+    else if (!strcmp(name, "bridge")) {
+        // the hierarchy changes: drop everything sized by it (workspace, vertex-class and row-info tables)
+        cudaSetDevice(c->device);
+        cudaDeviceSynchronize();
+        c->use_bridge = value != 0.0;
+        if (c->ws_base) cudaFree(c->ws_base);
+        c->ws_base = nullptr; c->ws_K = 0;
+        for (int* q : c->tile_rowv) cudaFree(q);
+        for (int* q : c->tile_colv) cudaFree(q);
+        c->tile_rowv.clear(); c->tile_colv.clear(); c->tile_ready = false; c->kernels_configured = false;
+        for (auto& kv : c->tile_rinfo_cache) cudaFree(kv.second);
+        c->tile_rinfo_cache.clear();
+        c->build_levels();
+    }
     else if (!strcmp(name, "gram_variant")) romhc::g_gram_variant = (int)value;
     else if (!strcmp(name, "fused")) c->use_fused = value != 0.0;
     else if (!strcmp(name, "tile_persistent")) c->tile_persistent = value != 0.0;
@@ -183,7 +197,8 @@ int romhc_get_info(romhc_handle h, int64_t* info) {
     info[0] = int64_t(g.R - 1) * (g.C - 1); info[1] = g.Dp; info[2] = g.P; info[3] = g.R; info[4] = g.C;
     info[5] = (int64_t)c->levels.size(); info[6] = c->tail_level; info[7] = c->coarse_D; info[8] = c->coarse_direct;
     info[9] = c->nrb; info[10] = c->ncb; info[11] = c->N; info[12] = (int64_t)c->solve_bytes_per_system();
-    info[13] = (int64_t)c->tail_smem;
+    info[13] = (int64_t)c->tail_smem; info[14] = c->bridge_level;
+    info[15] = c->bridge_level >= 0 ? c->levels[c->bridge_level + 1].N : 0;
     return ROMHC_OK;
 }
 

@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "romhc_internal.h"
 
+#include <stdio.h>
 #include <string.h>
 #include <algorithm>
 #include <array>
@@ -1581,8 +1582,13 @@ const int* Context::tile_rinfo(int l, int TY, int halo_top, int NR) {
             o[2] = int(unsigned(rv[2] + 1) | (unsigned(rv[3] + 1) << 16));
         }
     int* d = nullptr;
-    if (cudaMalloc(&d, tab.size() * sizeof(int)) != cudaSuccess) return nullptr;
-    if (cudaMemcpy(d, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+    cudaError_t e = cudaMalloc(&d, tab.size() * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(d, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess || !d) {
+        fprintf(stderr, "tile_rinfo(l=%d, TY=%d, halo=%d, NR=%d): %zu ints: %s\n", l, TY, halo_top, NR, tab.size(), cudaGetErrorString(e));
+        if (d) cudaFree(d);
+        return nullptr;
+    }
     tile_rinfo_cache[key] = d;
     return d;
 }
@@ -1669,11 +1675,10 @@ static void tile_pick_ty(const LevelGeo& g, int extra_rows, int maxt, int cap, i
 
 int Context::tile_down(int l, const double* y, int Kc, cudaStream_t st) {
     (void)y;
-    const int L = int(levels.size()) - 1;
     TileArgs a;
     memset(&a, 0, sizeof(a));
     a.g = levels[l];
-    a.has_coarse = l < L ? 1 : 0;
+    a.has_coarse = fused_coarse(l) ? 1 : 0;
     a.gc = a.has_coarse ? levels[l + 1] : levels[l];
     a.rowv = tile_rowv[l] + ROMHC_ROWV_PAD; a.colv = tile_colv[l];
     a.tab = ws.wtab; a.ntab = tile_ntab(); a.ncv = 2 * ncb - 1;
@@ -1714,12 +1719,11 @@ int Context::tile_down(int l, const double* y, int Kc, cudaStream_t st) {
 // x += alpha p, r -= alpha A p and the going-down kernel of level l in one launch (persistent tile kernels only);
 // returns ROMHC_ERR_ARG if the configuration does not fit (the caller then runs the two kernels separately)
 int Context::tile_update_down(int l, int Kc, const double* p, double* x, const double* alpha, cudaStream_t st) {
-    const int L = int(levels.size()) - 1;
     if (!tile_persistent || !use_fused) return ROMHC_ERR_ARG;
     TileArgs a;
     memset(&a, 0, sizeof(a));
     a.g = levels[l];
-    a.has_coarse = l < L ? 1 : 0;
+    a.has_coarse = fused_coarse(l) ? 1 : 0;
     a.gc = a.has_coarse ? levels[l + 1] : levels[l];
     a.rowv = tile_rowv[l] + ROMHC_ROWV_PAD; a.colv = tile_colv[l];
     a.tab = ws.wtab; a.ntab = tile_ntab(); a.ncv = 2 * ncb - 1;
@@ -1728,7 +1732,9 @@ int Context::tile_update_down(int l, int Kc, const double* p, double* x, const d
     a.halo_top = 2 * nu + 2;
     a.pf_dist = 0; a.rinfo = nullptr;
     const int CG = a.g.P / 4;
-    auto bytes = [&]() { return tile_stage_bytes(a.ntab, a.NR, CG, (a.g.R + a.TY - 1) / a.TY, true, 0, 0); };
+    // + 16: the east neighbour of the region's last point is read one element past the p strip (value unused: that
+    // row lies outside the validity cone, but the address must stay inside the CTA's shared-memory window)
+    auto bytes = [&]() { return tile_stage_bytes(a.ntab, a.NR, CG, (a.g.R + a.TY - 1) / a.TY, true, 0, 0) + 16; };
     for (int cap = tile_ty_cap; cap >= 2; cap -= 2) {
         tile_pick_ty(a.g, 4 * nu + 3, tile_maxt_down, cap, &a.TY, &a.NR);
         if (bytes() <= 227 * 1024) break;
@@ -1751,11 +1757,10 @@ int Context::tile_update_down(int l, int Kc, const double* p, double* x, const d
 
 int Context::tile_up(int l, const double* y, int Kc, const double* e, double* part_rz, int* ns_out, cudaStream_t st) {
     (void)y;
-    const int L = int(levels.size()) - 1;
     TileArgs a;
     memset(&a, 0, sizeof(a));
     a.g = levels[l];
-    a.has_coarse = l < L ? 1 : 0;
+    a.has_coarse = fused_coarse(l) ? 1 : 0;
     a.gc = a.has_coarse ? levels[l + 1] : levels[l];
     a.rowv = tile_rowv[l] + ROMHC_ROWV_PAD; a.colv = tile_colv[l];
     a.tab = ws.wtab; a.ntab = tile_ntab(); a.ncv = 2 * ncb - 1;

@@ -62,7 +62,7 @@ struct TailParams {
     int nu;                           // smoothing sweeps per level inside the tail
 };
 
-enum ProfKind { PROF_PAPPLY = 0, PROF_UPDATE, PROF_DOWN0, PROF_DOWN1, PROF_TAIL, PROF_UP0, PROF_UP1, PROF_NKIND };
+enum ProfKind { PROF_PAPPLY = 0, PROF_UPDATE, PROF_DOWN0, PROF_DOWN1, PROF_TAIL, PROF_UP0, PROF_UP1, PROF_BRIDGE, PROF_NKIND };
 struct ProfEvent { int kind; cudaEvent_t a, b; };
 
 // persistent staging of the host-buffer entry point (double buffered: compute stream + copy stream)
@@ -87,6 +87,12 @@ struct Context {
     int tail_level = 0;        // first level handled by the tail kernel (levels.size() if none)
     int smooth_tail_level = 0; // first level smoothed nu_tail times
     int nu_of(int l) const { return l >= smooth_tail_level ? nu_tail : (l == 0 || nu_mid <= 0 ? nu : nu_mid); }
+    // Non-nested transfer ("bridge"): when halving the cells per subdomain gets stuck on an odd count whose grid is too
+    // large for the dense coarsest solve, level `bridge_level` hands over to a power-of-two hierarchy through bilinear
+    // interpolation inside each subdomain (k_bridge_restrict / k_bridge_prolong); -1: every transfer is nested
+    int bridge_level = -1;
+    bool use_bridge = true;
+    bool fused_coarse(int l) const { return l + 1 < int(levels.size()) && l != bridge_level; }
     int coarse_D = 0, coarse_LD = 1;
     bool coarse_direct = false;
     int coarse_sweeps = 8;
@@ -128,8 +134,8 @@ struct Context {
     // per-kernel timing (option "profile")
     bool prof_on = false, prof_window = false;
     std::vector<ProfEvent> prof_events;
-    double prof_ms[PROF_NKIND] = {0, 0, 0, 0, 0, 0, 0};
-    long long prof_n[PROF_NKIND] = {0, 0, 0, 0, 0, 0, 0};
+    double prof_ms[PROF_NKIND] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_n[PROF_NKIND] = {0, 0, 0, 0, 0, 0, 0, 0};
     void prof_begin(int kind, cudaStream_t st);
     void prof_end(cudaStream_t st);
     void prof_cancel();
@@ -164,6 +170,8 @@ struct Context {
               SolveStats* stats, const double* rhs = nullptr);
     int precond(const double* y, const double* r, double* z, int64_t K, cudaStream_t st);
     int pcg_update(const double* y, int Kc, const double* p, double* x, const double* alpha, cudaStream_t st);
+    int bridge_restrict(int l, const double* y, int Kc, cudaStream_t st);
+    int bridge_prolong(int l, const double* e, int Kc, cudaStream_t st);
 
     // mgtile.cu
     int tile_setup();

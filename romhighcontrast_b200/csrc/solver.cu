@@ -14,6 +14,7 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
@@ -552,8 +553,106 @@ k_mg_up(LevelGeo g, LevelGeo gc, const double* __restrict__ y, const double* __r
     if (tid == 0) bulk_wait_all();
 }
 
-// ---- multigrid tail: levels T..L of one system entirely in shared memory (one CTA per system) --------------------
+// ---- non-nested transfer between a level with Nf cells per subdomain and a power-of-two level with Nc ----------------
+// Interpolation: bilinear inside each subdomain (its edges are grid lines of both meshes, so no interpolation crosses a
+// coefficient jump); 1-D weight of coarse vertex I at fine vertex i = max(0, Nf - |i Nc - I Nf|) / Nf, the coarse hat
+// function.  Restriction is the exact transpose, so the V-cycle stays symmetric.  As in the nested kernels only RED
+// fine points take part: the residual vanishes on the black points just relaxed, and the first half sweep on the way
+// up overwrites the black points from their red neighbours.
+//
+// rc = P^T (r - A z): grid (bands, K); a CTA owns TB coarse rows and stages the fine rows under their hat functions.
+__global__ void __launch_bounds__(256)
+k_bridge_restrict(LevelGeo g, LevelGeo gc, const double* __restrict__ y, const double* __restrict__ r_in,
+                  const double* __restrict__ z_in, double* __restrict__ rc_out, const int* __restrict__ active, int TB) {
+    const int64_t k = blockIdx.y;
+    if (!active[k]) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int nb = g.nrb * g.ncb;
+    SmemHdr h = smem_carve(smem_raw, nb);
+    const int tx = threadIdx.x, ty = threadIdx.y, TXW = blockDim.x, TYW = blockDim.y;
+    const int tid = ty * TXW + tx, nt = TXW * TYW;
+    const int Nf = g.N, Nc = gc.N;
+    const int I0 = 1 + blockIdx.x * TB, I1 = min(I0 + TB - 1, gc.R - 1);
+    // fine rows i with (I0 - 1) Nf < i Nc < (I1 + 1) Nf
+    const int i_lo = max(((I0 - 1) * Nf) / Nc + 1, 1), i_hi = min(((I1 + 1) * Nf - 1) / Nc, g.R - 1);
+    const int row0 = i_lo - 1, nrow = i_hi - i_lo + 3;          // z strip: one more row on each side
+    if (tid == 0) { mbar_init(h.bar, 1); mbar_fence_init(); }
+    load_coef(h.sa, y, k, nb, tid, nt);
+    StripCtx sc;
+    strip_ctx_init(sc, g, h.sa, h.rowq, row0, nrow, tid, nt);
+    __syncthreads();
+    const int P = g.P;
+    double* Zs = h.data;
+    double* Rs = Zs + size_t(nrow) * P;                         // same row origin; first and last row unused
+    if (tid == 0) {
+        mbar_expect_tx(h.bar, strip_tx_bytes(g, row0, nrow) + strip_tx_bytes(g, i_lo, nrow - 2));
+        strip_issue(Zs, z_in + k * g.Dp, g, row0, nrow, h.bar);
+        strip_issue(Rs + P, r_in + k * g.Dp, g, i_lo, nrow - 2, h.bar);
+    }
+    mbar_wait(h.bar, 0);
+    __syncthreads();
+    for_points<true>(sc, i_lo, i_hi, 0, [&](int r, int c, const ColW& w) {
+        const int i = (r - row0) * P + c;
+        Rs[i] = (Rs[i] - w.dg * Zs[i]) + offdiag_sum(Zs, i, P, w);
+    });
+    __syncthreads();
+    const double inv = 1.0 / double(Nf);
+    double* out = rc_out + k * gc.Dp;
+    for (int I = I0 + ty; I <= I1; I += TYW) {
+        const int ia = max(((I - 1) * Nf) / Nc + 1, 1), ib = min(((I + 1) * Nf - 1) / Nc, g.R - 1);
+        for (int J = 1 + tx; J <= gc.C - 1; J += TXW) {
+            const int ja = max(((J - 1) * Nf) / Nc + 1, 1), jb = min(((J + 1) * Nf - 1) / Nc, g.C - 1);
+            double acc = 0.0;
+            for (int i = ia; i <= ib; ++i) {
+                const double* row = Rs + (i - row0) * P;
+                double racc = 0.0;
+                for (int j = ja + ((i + ja) & 1); j <= jb; j += 2)
+                    racc = fma(double(Nf - abs(j * Nc - J * Nf)), row[j], racc);
+                acc = fma(double(Nf - abs(i * Nc - I * Nf)) * inv, racc, acc);
+            }
+            out[size_t(I) * gc.P + J] = acc * inv;
+        }
+    }
+}
 
+// z += P e on the red fine points: grid (row bands, K); per-column coarse index / weight tables in shared memory.
+__global__ void __launch_bounds__(256)
+k_bridge_prolong(LevelGeo g, LevelGeo gc, const double* __restrict__ e_c, double* __restrict__ z,
+                 const int* __restrict__ active, int TR) {
+    const int64_t k = blockIdx.y;
+    if (!active[k]) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* colw = reinterpret_cast<double*>(smem_raw);
+    int* colq = reinterpret_cast<int*>(colw + g.P);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int Nf = g.N, Nc = gc.N, Pc = gc.P;
+    const double inv = 1.0 / double(Nf);
+    for (int j = tid; j < g.C; j += nt) {                      // C <= P: both tables hold P entries
+        const int q = min((j * Nc) / Nf, gc.C - 1);
+        colq[j] = q;
+        colw[j] = double(j * Nc - q * Nf) * inv;
+    }
+    __syncthreads();
+    const int r0 = 1 + blockIdx.x * TR, r1 = min(r0 + TR - 1, g.R - 1);
+    const double* e = e_c + k * gc.Dp;
+    double* zs = z + k * g.Dp;
+    const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    for (int r = r0 + warp; r <= r1; r += nw) {
+        const int qy = min((r * Nc) / Nf, gc.R - 1);
+        const double wy = double(r * Nc - qy * Nf) * inv;
+        const double* e0 = e + size_t(qy) * Pc;
+        const double* e1 = e0 + Pc;
+        double* zr = zs + size_t(r) * g.P;
+        for (int c = 2 - (r & 1) + 2 * lane; c <= g.C - 1; c += 64) {   // (r + c) even, c >= 1
+            const int q = colq[c];
+            const double wx = colw[c];
+            const double lo = fma(wx, e0[q + 1] - e0[q], e0[q]), hi = fma(wx, e1[q + 1] - e1[q], e1[q]);
+            zr[c] += fma(wy, hi - lo, lo);
+        }
+    }
+}
+
+// ---- multigrid tail: levels T..L of one system entirely in shared memory (one CTA per system) --------------------
 __device__ __forceinline__ void tail_map(const LevelGeo& g, int tid, int nt, int& tx, int& ty, int& TXW, int& TYW) {
     TXW = 1;
     while (TXW < g.C && TXW < nt) TXW <<= 1;
@@ -876,15 +975,36 @@ static int pick_ty(const LevelGeo& g, int extra_rows, size_t extra_bytes, size_t
 
 int Context::build_levels() {
     levels.clear();
-    int n = N;
-    for (;;) {
-        levels.push_back(make_level(nrb, ncb, n));
-        if (n % 2 != 0) break;
-        const int nn = n / 2;
-        if (nrb * nn < 2 || ncb * nn < 2) break;
-        if ((int)levels.size() >= ROMHC_MAX_LEVELS) break;
-        n = nn;
+    bridge_level = -1;
+    std::vector<int> chain{N};
+    auto halve = [&]() {
+        for (;;) {
+            const int n = chain.back();
+            if (n % 2 != 0 || nrb * (n / 2) < 2 || ncb * (n / 2) < 2 || (int)chain.size() >= ROMHC_MAX_LEVELS) return;
+            chain.push_back(n / 2);
+        }
+    };
+    halve();
+    {
+        // stuck on an odd count with a coarsest grid the dense solve cannot take: continue from the deepest batched
+        // level on a power-of-two hierarchy (ratio >= 1.5) through the non-nested transfer kernels
+        const int n = chain.back();
+        if (use_bridge && n % 2 != 0 && n >= 3 && (nrb * n - 1) * (ncb * n - 1) > ROMHC_DIRECT_MAX &&
+            (int)chain.size() < ROMHC_MAX_LEVELS) {
+            int j = -1;
+            for (int i = 0; i < (int)chain.size(); ++i)
+                if (make_level(nrb, ncb, chain[i]).Dp > ROMHC_TAIL_MAX_DP) j = i;
+            if (j >= 0) {
+                int nc = 1;
+                while (3 * (2 * nc) <= 2 * chain[j]) nc *= 2;
+                chain.resize(j + 1);
+                chain.push_back(nc);
+                bridge_level = j;
+                halve();
+            }
+        }
     }
+    for (int n : chain) levels.push_back(make_level(nrb, ncb, n));
     const int L = int(levels.size()) - 1;
     tail_level = L + 1;
     for (int l = 0; l <= L; ++l)
@@ -952,6 +1072,7 @@ int Context::configure_kernels() {
     CK(cudaFuncSetAttribute(k_mg_down, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
     CK(cudaFuncSetAttribute(k_mg_up, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
     CK(cudaFuncSetAttribute(k_mg_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    CK(cudaFuncSetAttribute(k_bridge_restrict, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
     CK(cudaFuncSetAttribute(k_coarse_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
     { int rc = tile_setup(); if (rc) return rc; }
     kernels_configured = true;
@@ -1095,6 +1216,45 @@ int Context::pcg_update(const double* y, int Kc, const double* p, double* x, con
 }
 
 // one V-cycle: z_0 (ws.zb[0] or ws.za[0] when the tail starts at level 0) = M r_0; writes r.z partials
+// non-nested transfers of level l = bridge_level (kernels above): r_{l+1} = P^T (r_l - A z_l), z_l += P e
+int Context::bridge_restrict(int l, const double* y, int Kc, cudaStream_t st) {
+    const LevelGeo& g = levels[l];
+    const LevelGeo& gc = levels[l + 1];
+    const size_t hdr = smem_hdr_bytes(nrb * ncb);
+    auto bytes = [&](int TB) { return hdr + size_t(2) * (((TB + 1) * g.N) / gc.N + 3) * g.P * 8; };
+    int TB = 16;
+    while (TB > 1 && bytes(TB) > strip_budget) TB /= 2;
+    if (bytes(TB) > SMEM_MAX) { set_error("mesh too wide for the non-nested restriction (C = %d)", g.C); return ROMHC_ERR_ARG; }
+    dim3 block; strip_block(g, block, 256);
+    prof_begin(PROF_BRIDGE, st);
+    ++g_launches;
+    k_bridge_restrict<<<dim3((gc.R - 1 + TB - 1) / TB, Kc), block, bytes(TB), st>>>(g, gc, y, ws.r[l], ws.za[l], ws.r[l + 1],
+                                                                                    ws.active, TB);
+    prof_end(st);
+    return ROMHC_OK;
+}
+
+int Context::bridge_prolong(int l, const double* e, int Kc, cudaStream_t st) {
+    const LevelGeo& g = levels[l];
+    const LevelGeo& gc = levels[l + 1];
+    const int TR = 32;
+    prof_begin(PROF_BRIDGE, st);
+    ++g_launches;
+    k_bridge_prolong<<<dim3((g.R - 1 + TR - 1) / TR, Kc), 256, size_t(g.P) * 12, st>>>(g, gc, e, ws.za[l], ws.active, TR);
+    prof_end(st);
+    return ROMHC_OK;
+}
+
+// ROMHC_DEBUG_SYNC=1: synchronise after every V-cycle launch and name the kernel that failed
+static int dbg_sync(const char* what, int l, cudaStream_t st) {
+    static const bool on = getenv("ROMHC_DEBUG_SYNC") != nullptr;
+    if (!on) return ROMHC_OK;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("%s (level %d): %s", what, l, cudaGetErrorString(e)); fprintf(stderr, "%s (level %d): %s\n", what, l, cudaGetErrorString(e)); return ROMHC_ERR_CUDA; }
+    return ROMHC_OK;
+}
+
 int Context::vcycle(const double* y, int Kc, cudaStream_t st, const double** z_result, int* np_rz, const double* fuse_p,
                     double* fuse_x, const double* fuse_alpha) {
     const int L = int(levels.size()) - 1;
@@ -1106,21 +1266,29 @@ int Context::vcycle(const double* y, int Kc, cudaStream_t st, const double** z_r
     }
     for (int l = 0; l < nstrip_levels; ++l) {
         const LevelGeo& g = levels[l];
-        const bool has_c = l < L;
+        const bool has_c = fused_coarse(l);
         const LevelGeo& gc = has_c ? levels[l + 1] : g;
+        bool done = false;
         if (l == 0 && fuse_p) {
             // pending PCG update: fused into the tile kernel if possible, else the streaming update kernel first
             prof_begin(PROF_DOWN0, st);
             const int rc_f = tile_level_ok(0) ? tile_update_down(0, Kc, fuse_p, fuse_x, fuse_alpha, st) : ROMHC_ERR_ARG;
-            if (rc_f == ROMHC_OK) { prof_end(st); continue; }
-            prof_cancel();
-            if (rc_f != ROMHC_ERR_ARG) return rc_f;
-            const int rc_u = pcg_update(y, Kc, fuse_p, fuse_x, fuse_alpha, st); if (rc_u) return rc_u;
+            if (rc_f == ROMHC_OK) { prof_end(st); done = true; }
+            else {
+                prof_cancel();
+                if (rc_f != ROMHC_ERR_ARG) return rc_f;
+                const int rc_u = pcg_update(y, Kc, fuse_p, fuse_x, fuse_alpha, st); if (rc_u) return rc_u;
+            }
         }
-        if (tile_level_ok(l)) {
+        if (!done && tile_level_ok(l)) {
             prof_begin(PROF_DOWN0 + std::min(l, 1), st);
             int rc = tile_down(l, y, Kc, st); if (rc) return rc;
             prof_end(st);
+            done = true;
+        }
+        if (done) {
+            { int rc = dbg_sync("tile down", l, st); if (rc) return rc; }
+            if (l == bridge_level) { int rc = bridge_restrict(l, y, Kc, st); if (rc) return rc; rc = dbg_sync("bridge restrict", l, st); if (rc) return rc; }
             continue;
         }
         dim3 block; strip_block(g, block, strip_threads);
@@ -1134,6 +1302,7 @@ int Context::vcycle(const double* y, int Kc, cudaStream_t st, const double** z_r
         ++g_launches; k_mg_down<<<dim3(ns, Kc), block, bytes(TY), st>>>(g, gc, y, ws.r[l], ws.za[l], has_c ? ws.r[l + 1] : nullptr,
                                                           ws.active, TY, has_c ? 1 : 0, nu);
         prof_end(st);
+        if (l == bridge_level) { int rc = bridge_restrict(l, y, Kc, st); if (rc) return rc; }
     }
     if (tail_level <= L) {
         prof_begin(PROF_TAIL, st);
@@ -1143,27 +1312,31 @@ int Context::vcycle(const double* y, int Kc, cudaStream_t st, const double** z_r
                                                   tail_level == 0 ? ws.part_rz : nullptr);
         }
         prof_end(st);
+        { int rc = dbg_sync("tail", tail_level, st); if (rc) return rc; }
     }
     for (int l = nstrip_levels - 1; l >= 0; --l) {
         const LevelGeo& g = levels[l];
-        const bool has_c = l < L;
+        const bool has_c = fused_coarse(l);
         const LevelGeo& gc = has_c ? levels[l + 1] : g;
         dim3 block; strip_block(g, block, strip_threads);
         const int nu = nu_of(l);
+        // coarse correction comes from the level below: its post-smoothed zb, or za if that level is the tail's top
+        const double* e_below = l < L ? ((l + 1 < nstrip_levels) ? ws.zb[l + 1] : ws.za[l + 1]) : nullptr;
+        if (l == bridge_level) { int rc = bridge_prolong(l, e_below, Kc, st); if (rc) return rc; rc = dbg_sync("bridge prolong", l, st); if (rc) return rc; }
         auto bytes = [&](int TY) {
             return hdr + size_t(2 * TY + 8 * nu - 2) * g.P * 8 + (has_c ? size_t(TY / 2 + 2 * nu + 1) * gc.P * 8 : 0);
         };
         const int TY = pick_ty_fn(g, strip_budget, bytes);
         if (bytes(TY) > SMEM_MAX) { set_error("mesh too wide for the multigrid strip kernels (C = %d)", g.C); return ROMHC_ERR_ARG; }
         const int ns = (g.R + TY - 1) / TY;
-        // coarse correction comes from the level below: its post-smoothed zb, or za if that level is the tail's top
-        const double* e = has_c ? ((l + 1 < nstrip_levels) ? ws.zb[l + 1] : ws.za[l + 1]) : nullptr;
+        const double* e = has_c ? e_below : nullptr;
         if (tile_level_ok(l)) {
             prof_begin(PROF_UP0 + std::min(l, 1), st);
             int ns_t = 1;
             int rc = tile_up(l, y, Kc, e, l == 0 ? ws.part_rz : nullptr, &ns_t, st); if (rc) return rc;
             prof_end(st);
             if (l == 0) *np_rz = ns_t;
+            { int rc2 = dbg_sync("tile up", l, st); if (rc2) return rc2; }
             continue;
         }
         prof_begin(PROF_UP0 + std::min(l, 1), st);

@@ -35,7 +35,8 @@ class Engine:
         info = (C.c_int64 * 16)()
         _lib.check(self.lib.romhc_get_info(self.handle, info))
         (self.D, self.Dp, self.P, self.R, self.C, self.nlevels, self.tail_level, self.coarse_D, self.coarse_direct,
-         self.nrb, self.ncb, self.N, self.solve_bytes_per_system, self.tail_smem) = [int(v) for v in info[:14]]
+         self.nrb, self.ncb, self.N, self.solve_bytes_per_system, self.tail_smem, self.bridge_level,
+         self.bridge_N) = [int(v) for v in info[:16]]
         self.nb = nrb * ncb
         self.last_solve_stats = None
 

@@ -4,6 +4,10 @@ Test infrastructure: used to check single kernels (stencil apply, one V-cycle, i
 at sizes where running it takes milliseconds.  Same algorithm, different code: red/black GS V(nu,nu) with
 nu = 2 / 3 / 4 sweeps on the finest / intermediate / small levels (the library defaults),
 P1 anti-diagonal transfers, rediscretised coarse operators, dense coarsest solve, difference-form apply.
+When halving the cells per subdomain gets stuck on an odd count with a coarsest grid too large for the dense solve
+(N = 43: 129 x 129 cells), the deepest batched level hands over to a power-of-two hierarchy through a NON-NESTED
+transfer: bilinear interpolation inside each subdomain (block interfaces are grid lines of both meshes), its
+transpose as restriction (`coarsening_chain`, `bridge_matrix`).
 """
 import numpy as np
 
@@ -79,24 +83,56 @@ def prolong(e, shape):
     return z
 
 
-class GMG:
-    DIRECT_MAX = 64
-    TAIL_MAX_DP = 4352
+DIRECT_MAX = 64
+TAIL_MAX_DP = 4352
+MAX_LEVELS = 12
 
-    def __init__(self, a, N, coarse_sweeps=8, nu=2, nu_tail=4, nu_mid=3):
+
+def coarsening_chain(nrb, ncb, N, bridge=True):
+    """Cells per subdomain on every level and the index of the level whose transfer to the next one is non-nested
+    (None: all transfers are the nested factor-2 ones).  Mirrors Context::build_levels."""
+    def halve(chain):
+        while True:
+            n = chain[-1]
+            if n % 2 or nrb * (n // 2) < 2 or ncb * (n // 2) < 2 or len(chain) >= MAX_LEVELS:
+                return chain
+            chain.append(n // 2)
+    dp = lambda n: (nrb * n + 1) * ((ncb * n + 7) // 8 * 8)
+    chain = halve([N])
+    n = chain[-1]
+    if not bridge or n % 2 == 0 or n < 3 or (nrb * n - 1) * (ncb * n - 1) <= DIRECT_MAX:
+        return chain, None
+    batched = [j for j, m in enumerate(chain) if dp(m) > TAIL_MAX_DP]
+    if not batched or len(chain) >= MAX_LEVELS:
+        return chain, None
+    j = batched[-1]
+    nc = 1
+    while 3 * (2 * nc) <= 2 * chain[j]:          # largest power of two with ratio >= 1.5
+        nc *= 2
+    return halve(chain[:j + 1] + [nc]), j
+
+
+def bridge_matrix(nblocks, Nf, Nc):
+    """1-D interpolation (nblocks*Nf + 1, nblocks*Nc + 1): coarse hat functions sampled at the fine vertices,
+    weight (Nf - |i Nc - I Nf|) / Nf where positive."""
+    i = np.arange(nblocks * Nf + 1)[:, None]
+    I = np.arange(nblocks * Nc + 1)[None, :]
+    return np.maximum(Nf - np.abs(i * Nc - I * Nf), 0) / Nf
+
+
+class GMG:
+    DIRECT_MAX = DIRECT_MAX
+    TAIL_MAX_DP = TAIL_MAX_DP
+
+    def __init__(self, a, N, coarse_sweeps=8, nu=2, nu_tail=4, nu_mid=3, bridge=True):
         a = np.asarray(a, float)
         self.nu, self.nu_tail, self.nu_mid = nu, nu_tail, (nu_mid or nu)
         nrb, ncb = a.shape
-        self.levels = []
-        n = N
-        while True:
-            self.levels.append(Level(a, n))
-            if n % 2:
-                break
-            nn = n // 2
-            if nrb * nn < 2 or ncb * nn < 2:
-                break
-            n = nn
+        chain, self.bridge_level = coarsening_chain(nrb, ncb, N, bridge)
+        self.levels = [Level(a, n) for n in chain]
+        if self.bridge_level is not None:
+            nf, nc = chain[self.bridge_level], chain[self.bridge_level + 1]
+            self.Py, self.Px = bridge_matrix(nrb, nf, nc), bridge_matrix(ncb, nf, nc)
         self.coarse_sweeps = coarse_sweeps
         L = self.levels[-1]
         D = (L.R - 1) * (L.C - 1)
@@ -134,15 +170,21 @@ class GMG:
         for _ in range(nu):
             L.gs_half(z, r, L.red); L.gs_half(z, r, L.black)
         d = r - L.apply(z); d[~L.mask] = 0
-        z = z + prolong(self.vcycle(restrict(d), l + 1), r.shape)
+        if l == self.bridge_level:
+            d[L.black] = 0                      # just relaxed: the kernels take the residual there as exactly zero
+            rc = self.Py.T @ d @ self.Px
+            rc[~self.levels[l + 1].mask] = 0
+            z = z + self.Py @ self.vcycle(rc, l + 1) @ self.Px.T
+        else:
+            z = z + prolong(self.vcycle(restrict(d), l + 1), r.shape)
         z[~L.mask] = 0
         for _ in range(nu):
             L.gs_half(z, r, L.black); L.gs_half(z, r, L.red)
         return z
 
 
-def pcg(a, N, tol=1e-12, maxit=1000, coarse_sweeps=8, nu=2, nu_tail=4, nu_mid=3):
-    g = GMG(a, N, coarse_sweeps, nu, nu_tail, nu_mid)
+def pcg(a, N, tol=1e-12, maxit=1000, coarse_sweeps=8, nu=2, nu_tail=4, nu_mid=3, bridge=True):
+    g = GMG(a, N, coarse_sweeps, nu, nu_tail, nu_mid, bridge)
     L = g.levels[0]
     b = np.zeros((L.R + 1, L.C + 1)); b[1:-1, 1:-1] = 1.0 / N ** 2
     x = np.zeros_like(b); r = b.copy()
