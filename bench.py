@@ -327,7 +327,7 @@ def main():
 
     secondary = {}
     if not args.no_secondary:
-        secondary = run_secondary(eng, x, y, K, args, world, rank, barrier, ev)
+        secondary = run_secondary(eng, x, y, K, args, world, rank, barrier, ev, U_np, y_host)
 
     cpu = None
     if rank == 0 and not args.no_cpu:
@@ -359,11 +359,38 @@ def main():
         dist.destroy_process_group()
 
 
-def run_secondary(eng, x, y, K, args, world, rank, barrier, ev):
-    """POD (centred Gram on the fp64 tensor cores) and 1M online reduced Galerkin solves on the snapshots in `x`."""
+def run_greedy(U_np, y_host, n):
+    """Wall time of the reference-facing greedy builders (ReducedBasis.py:112-139) on this rank's snapshots: numpy in,
+    basis out; includes the H2D copy of the snapshot matrix and the host-side QR of every round."""
+    import torch
+    from lib.ReducedBasis import ReducedBasisGreedy, GREEDY_FOR_GALERKIN, GREEDY_FOR_H10
+    from lib.SolutionsManagers import SolutionsManagerFEM
+    sm = SolutionsManagerFEM(GEO, NPB, method="lsqsparse")
+    h1 = sm.H10norm(U_np)
+    out = {"K": int(len(U_np)), "n": n}
+    for name, crit in (("galerkin", GREEDY_FOR_GALERKIN), ("h10", GREEDY_FOR_H10)):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rb = ReducedBasisGreedy(greedy_for=crit).build(n=n, sm=sm, solutions2train=U_np, a2train=y_host,
+                                                       solutions2train_h1norm=h1)
+        torch.cuda.synchronize()
+        out[name + "_s"] = time.perf_counter() - t0
+        out[name + "_selected_head"] = [int(i) for i in rb.selected_indices[:6]]
+        out[name + "_max_rel_error_last"] = float(rb.max_errors[-1])
+    return out
+
+
+def run_secondary(eng, x, y, K, args, world, rank, barrier, ev, U_np=None, y_host=None):
+    """POD (centred Gram on the fp64 tensor cores), the greedy builders and 1M online reduced Galerkin solves on the
+    snapshots in `x`."""
     import torch
     out = {}
     n = args.n_rb
+    if U_np is not None:
+        try:
+            out["greedy"] = run_greedy(U_np, y_host, n)
+        except MemoryError:
+            pass
     # measured fp64 GEMM peak of this GPU (cuBLAS DGEMM 8192^3) as the tensor-pipe denominator
     a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
     b = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
