@@ -69,6 +69,8 @@ struct TileArgs {
     const double* tab;    // weight tables, ntab entries per system
     int ntab, ncv;
     int TY, ns, nu, has_coarse;
+    int emit_res;         // persistent going-down kernels, has_coarse == 0: also store the residual r - A z of the owned rows
+                          // on the red points ((row + col) even), packed with row pitch P / 2, for k_bridge_gather
     int NR, halo_top;     // rows of the CTA's region, rows above the owned strip
     int pf_dist;          // L2 prefetch distance in CTAs (= CTAs resident on the GPU at once); 0: off
     const int* rinfo;     // persistent kernels: per (strip, row group) row types (2 bits per row) | primary class << 8
@@ -806,6 +808,14 @@ k_mgp_down(TileArgs a, const double* __restrict__ r_in, double* __restrict__ z_o
                 }
             }
         }
+        else if (a.emit_res) {
+            tile_phase_any<0, 1, true>(z, r, w, t, a);          // residual on the red points (black: zero, just relaxed)
+            double* dout = rc_out + int64_t(k) * a.g.Dp + int64_t(rho0) * (P / 2) + 2 * tx;   // red points only, pitch P / 2
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (i >= own_lo && i < own_hi)
+                    *reinterpret_cast<double2*>(dout + i * (P / 2)) = make_double2(z[i][i & 1], z[i][(i & 1) + 2]);
+        }
         // no barrier here: the next item writes exchange slots only after its own staging barrier
         wk = nx;
         stage ^= 1;
@@ -1001,6 +1011,14 @@ k_mgp_update_down(TileArgs a, const double* __restrict__ p_in, double* __restric
                         make_double2(okI && okJ0 ? rc[q][0] : 0.0, okI && okJ1 ? rc[q][1] : 0.0);
                 }
             }
+        }
+        else if (a.emit_res) {
+            tile_phase_any<0, 1, true>(z, r, w, t, a);          // residual on the red points (black: zero, just relaxed)
+            double* dout = rc_out + int64_t(k) * a.g.Dp + int64_t(rho0) * (P / 2) + 2 * tx;   // red points only, pitch P / 2
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (i >= own_lo && i < own_hi)
+                    *reinterpret_cast<double2*>(dout + i * (P / 2)) = make_double2(z[i][i & 1], z[i][(i & 1) + 2]);
         }
         wk = nx;
         stage ^= 1;
@@ -1701,7 +1719,10 @@ int Context::tile_down(int l, const double* y, int Kc, cudaStream_t st) {
             if (!a.rinfo) { set_error("tile kernels: row-info table allocation failed"); return ROMHC_ERR_CUDA; }
             const int grid = tile_persistent_grid((const void*)fn, CG * (a.NR / 4), sm, int64_t(Kc) * a.ns);
             ++g_launches;
-            fn<<<grid, dim3(CG, a.NR / 4), sm, st>>>(a, ws.r[l], ws.za[l], a.has_coarse ? ws.r[l + 1] : nullptr, ws.active, Kc);
+            a.emit_res = (l == bridge_level) ? 1 : 0;             // residual into zb[l] (free until the way up)
+            fn<<<grid, dim3(CG, a.NR / 4), sm, st>>>(a, ws.r[l], ws.za[l], a.has_coarse ? ws.r[l + 1] : (a.emit_res ? ws.zb[l] : nullptr),
+                                                     ws.active, Kc);
+            bridge_res_emitted = a.emit_res != 0;
             return ROMHC_OK;
         }
     }
@@ -1749,8 +1770,10 @@ int Context::tile_update_down(int l, int Kc, const double* p, double* x, const d
     ++g_launches;
     if (l != 0) return ROMHC_ERR_ARG;
     // systems that are no longer active keep their (converged) residual in the old buffer: nobody reads it again
-    fn<<<grid, dim3(CG, a.NR / 4), sm, st>>>(a, p, x, ws.r[0], ws.r_alt, alpha, ws.za[0], a.has_coarse ? ws.r[1] : nullptr,
-                                             ws.active, Kc);
+    a.emit_res = (l == bridge_level) ? 1 : 0;
+    fn<<<grid, dim3(CG, a.NR / 4), sm, st>>>(a, p, x, ws.r[0], ws.r_alt, alpha, ws.za[0],
+                                             a.has_coarse ? ws.r[1] : (a.emit_res ? ws.zb[0] : nullptr), ws.active, Kc);
+    bridge_res_emitted = a.emit_res != 0;
     std::swap(ws.r[0], ws.r_alt);
     return ROMHC_OK;
 }

@@ -92,6 +92,7 @@ struct Context {
     // interpolation inside each subdomain (k_bridge_restrict / k_bridge_prolong); -1: every transfer is nested
     int bridge_level = -1;
     bool use_bridge = true;
+    bool bridge_res_emitted = false;   // the last going-down kernel of the bridging level left r - A z in zb[l]
     bool fused_coarse(int l) const { return l + 1 < int(levels.size()) && l != bridge_level; }
     int coarse_D = 0, coarse_LD = 1;
     bool coarse_direct = false;

@@ -615,6 +615,35 @@ k_bridge_restrict(LevelGeo g, LevelGeo gc, const double* __restrict__ y, const d
     }
 }
 
+// The same restriction when the going-down kernel has already stored d = r - A z on the red points (packed: entry
+// j >> 1 of a row of pitch P / 2): a pure weighted gather, one thread per coarse vertex, fine values through L1 / L2
+// (every value is used by up to four coarse vertices).  grid = (coarse row bands, K), block = (32, 8): a warp walks 32 consecutive coarse columns.
+__global__ void __launch_bounds__(256)
+k_bridge_gather(LevelGeo g, LevelGeo gc, const double* __restrict__ d_in, double* __restrict__ rc_out,
+                const int* __restrict__ active) {
+    const int64_t k = blockIdx.y;
+    if (!active[k]) return;
+    const int Nf = g.N, Nc = gc.N, P = g.P;
+    const int I = 1 + blockIdx.x * blockDim.y + threadIdx.y;
+    if (I > gc.R - 1) return;
+    const double inv = 1.0 / double(Nf);
+    const double* d = d_in + k * g.Dp;
+    double* out = rc_out + k * gc.Dp + size_t(I) * gc.P;
+    const int ia = max(((I - 1) * Nf) / Nc + 1, 1), ib = min(((I + 1) * Nf - 1) / Nc, g.R - 1);
+    for (int J = 1 + threadIdx.x; J <= gc.C - 1; J += 32) {
+        const int ja = max(((J - 1) * Nf) / Nc + 1, 1), jb = min(((J + 1) * Nf - 1) / Nc, g.C - 1);
+        double acc = 0.0;
+        for (int i = ia; i <= ib; ++i) {
+            const double* row = d + size_t(i) * (P / 2);
+            double racc = 0.0;
+            for (int j = ja + ((i + ja) & 1); j <= jb; j += 2)
+                racc = fma(double(Nf - abs(j * Nc - J * Nf)), __ldg(row + (j >> 1)), racc);
+            acc = fma(double(Nf - abs(i * Nc - I * Nf)) * inv, racc, acc);
+        }
+        out[J] = acc * inv;
+    }
+}
+
 // z += P e on the red fine points: grid (row bands, K); per-column coarse index / weight tables in shared memory.
 __global__ void __launch_bounds__(256)
 k_bridge_prolong(LevelGeo g, LevelGeo gc, const double* __restrict__ e_c, double* __restrict__ z,
@@ -1220,6 +1249,14 @@ int Context::pcg_update(const double* y, int Kc, const double* p, double* x, con
 int Context::bridge_restrict(int l, const double* y, int Kc, cudaStream_t st) {
     const LevelGeo& g = levels[l];
     const LevelGeo& gc = levels[l + 1];
+    if (bridge_res_emitted) {                     // the tile kernel left d = r - A z in zb[l]: gather only
+        bridge_res_emitted = false;
+        prof_begin(PROF_BRIDGE, st);
+        ++g_launches;
+        k_bridge_gather<<<dim3((gc.R - 1 + 7) / 8, Kc), dim3(32, 8), 0, st>>>(g, gc, ws.zb[l], ws.r[l + 1], ws.active);
+        prof_end(st);
+        return ROMHC_OK;
+    }
     const size_t hdr = smem_hdr_bytes(nrb * ncb);
     auto bytes = [&](int TB) { return hdr + size_t(2) * (((TB + 1) * g.N) / gc.N + 3) * g.P * 8; };
     int TB = 16;
@@ -1269,6 +1306,7 @@ int Context::vcycle(const double* y, int Kc, cudaStream_t st, const double** z_r
         const bool has_c = fused_coarse(l);
         const LevelGeo& gc = has_c ? levels[l + 1] : g;
         bool done = false;
+        bridge_res_emitted = false;
         if (l == 0 && fuse_p) {
             // pending PCG update: fused into the tile kernel if possible, else the streaming update kernel first
             prof_begin(PROF_DOWN0, st);
