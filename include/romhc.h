@@ -70,6 +70,12 @@ int romhc_stream_sync(void* stream);
 /* ---- layout ---------------------------------------------------------------------------------------------------- */
 int romhc_pack(romhc_handle h, const double* compact_dev, double* padded_dev, int64_t K, void* stream);
 int romhc_unpack(romhc_handle h, const double* padded_dev, double* compact_dev, int64_t K, void* stream);
+/* The same conversions with the compact side in HOST memory (the (K, D) numpy arrays of the reference's API,
+ * SolutionsManagers.py:56-139): chunked through pinned bounce buffers, several host threads per chunk, DMA and layout
+ * kernel overlapped.  Pinned caller memory is copied directly.  The host array is free for reuse on return; the device
+ * side is ordered on `stream` (pack) / complete on return (unpack). */
+int romhc_pack_host(romhc_handle h, const double* compact_host, double* padded_dev, int64_t K, void* stream);
+int romhc_unpack_host(romhc_handle h, const double* padded_dev, double* compact_host, int64_t K, void* stream);
 
 /* ---- K1a: matrix-free stiffness apply  out_k = A(y_k) u_k  (y_dev == NULL: the H10 operator A_1) ----------------
  * replaces np.einsum("pqij,pq->ij", A_preassembled, a) @ u   SolutionsManagers.py:19-23 */

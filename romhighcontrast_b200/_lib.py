@@ -45,6 +45,8 @@ SIGNATURES = {
     "romhc_stream_sync": (_i, [_vp]),
     "romhc_pack": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "romhc_unpack": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "romhc_pack_host": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "romhc_unpack_host": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "romhc_apply": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "romhc_energy_norm": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "romhc_l2_norm": (_i, [_vp, _vp, _i64, _vp, _vp]),

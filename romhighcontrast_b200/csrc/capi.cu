@@ -53,6 +53,14 @@ void Context::free_host_stage() {
     hstage.bounce_cap = 0;
     if (hstage.copy2) cudaStreamDestroy(hstage.copy2);
     hstage.copy2 = nullptr;
+    for (int i = 0; i < 2; ++i) {
+        if (hstage.xfer_dev[i]) cudaFree(hstage.xfer_dev[i]);
+        hstage.xfer_dev[i] = nullptr;
+        if (hstage.xfer_done[i]) cudaEventDestroy(hstage.xfer_done[i]);
+        if (hstage.xfer_ready[i]) cudaEventDestroy(hstage.xfer_ready[i]);
+        hstage.xfer_done[i] = hstage.xfer_ready[i] = nullptr;
+    }
+    hstage.xfer_cap = 0;
     if (hstage.it_pin) cudaFreeHost(hstage.it_pin);
     if (hstage.rel_pin) cudaFreeHost(hstage.rel_pin);
     hstage.it_pin = nullptr; hstage.rel_pin = nullptr; hstage.pin_cap = 0;
@@ -398,6 +406,121 @@ int romhc_generate_solutions_host(romhc_handle h, const double* y_host, int64_t 
         if (relres_host) memcpy(relres_host, s.rel_pin, size_t(K) * 8);
     }
     return rc;
+}
+
+// ---- pageable host memory <-> padded device layout, pipelined --------------------------------------------------------
+// The reference's API hands (K, D) numpy arrays in and out of every call; a plain cudaMemcpy from / to pageable memory
+// runs at the speed of one staging thread.  Here the rows move in chunks through two pinned bounce buffers: a
+// stream-ordered host callback copies with several threads while the DMA engine moves the previous chunk, and the
+// layout kernel (k_pack / k_unpack) runs per chunk on the caller's stream.  Pinned caller memory skips the bounce.
+static bool host_ptr_is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess) pinned = at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+    cudaGetLastError();
+    return pinned;
+}
+
+static int ensure_xfer_stage(Context* c, size_t chunk_bytes, bool need_bounce) {
+    HostStage& s = c->hstage;
+    if (!s.copy) {
+        CK(cudaStreamCreateWithFlags(&s.compute, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking));
+    }
+    if (!s.copy2) CK(cudaStreamCreateWithFlags(&s.copy2, cudaStreamNonBlocking));
+    if (chunk_bytes > s.xfer_cap) {
+        for (int i = 0; i < 2; ++i) { if (s.xfer_dev[i]) cudaFree(s.xfer_dev[i]); s.xfer_dev[i] = nullptr; }
+        s.xfer_cap = 0;
+        for (int i = 0; i < 2; ++i) CK(cudaMalloc(&s.xfer_dev[i], chunk_bytes));
+        s.xfer_cap = chunk_bytes;
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (!s.xfer_done[i]) CK(cudaEventCreateWithFlags(&s.xfer_done[i], cudaEventDisableTiming));
+        if (!s.xfer_ready[i]) CK(cudaEventCreateWithFlags(&s.xfer_ready[i], cudaEventDisableTiming));
+    }
+    if (need_bounce && chunk_bytes > s.bounce_cap) {
+        for (int i = 0; i < 2; ++i) { if (s.bounce[i]) cudaFreeHost(s.bounce[i]); s.bounce[i] = nullptr; }
+        s.bounce_cap = 0;
+        for (int i = 0; i < 2; ++i) CK(cudaMallocHost((void**)&s.bounce[i], chunk_bytes));
+        s.bounce_cap = chunk_bytes;
+    }
+    return ROMHC_OK;
+}
+
+static const size_t XFER_CHUNK_BYTES = size_t(128) << 20;
+
+int romhc_pack_host(romhc_handle h, const double* compact_host, double* padded_dev, int64_t K, void* stream) {
+    CHECK_H(h);
+    if (K <= 0) return ROMHC_OK;
+    if (!compact_host || !padded_dev) { set_error("null argument"); return ROMHC_ERR_ARG; }
+    Context* c = H(h);
+    const LevelGeo& g = c->levels[0];
+    const int64_t D = int64_t(g.R - 1) * (g.C - 1);
+    const int64_t rows = std::max<int64_t>(1, std::min<int64_t>(K, int64_t(XFER_CHUNK_BYTES / (size_t(D) * 8))));
+    const bool pinned = host_ptr_is_pinned(compact_host);
+    int rc = ensure_xfer_stage(c, size_t(rows) * D * 8, !pinned); if (rc) return rc;
+    HostStage& s = c->hstage;
+    cudaStream_t st = ST(stream);
+    const int copy_threads = std::max(1, std::min(8, int(std::thread::hardware_concurrency()) / 2));
+    int64_t i = 0;
+    for (int64_t k0 = 0; k0 < K; k0 += rows, ++i) {
+        const int64_t kc = std::min(rows, K - k0);
+        const int slot = int(i & 1);
+        cudaStream_t cs = slot ? s.copy2 : s.copy;
+        const size_t bytes = size_t(kc) * D * 8;
+        CK(cudaStreamWaitEvent(cs, s.xfer_done[slot], 0));        // the layout kernel that last read this slot has finished
+        const double* src = compact_host + k0 * D;
+        if (!pinned) {
+            HostCopyTask* t = new HostCopyTask{(const char*)src, (char*)s.bounce[slot], bytes, copy_threads};
+            CK(cudaLaunchHostFunc(cs, host_copy_callback, t));
+            src = s.bounce[slot];
+        }
+        CK(cudaMemcpyAsync(s.xfer_dev[slot], src, bytes, cudaMemcpyHostToDevice, cs));
+        CK(cudaEventRecord(s.xfer_ready[slot], cs));
+        CK(cudaStreamWaitEvent(st, s.xfer_ready[slot], 0));
+        rc = c->pack(s.xfer_dev[slot], padded_dev + k0 * g.Dp, kc, st); if (rc) return rc;
+        CK(cudaEventRecord(s.xfer_done[slot], st));
+    }
+    // the caller's host array may be reused as soon as this returns: every host-side read has completed
+    CK(cudaStreamSynchronize(s.copy));
+    CK(cudaStreamSynchronize(s.copy2));
+    return ROMHC_OK;
+}
+
+int romhc_unpack_host(romhc_handle h, const double* padded_dev, double* compact_host, int64_t K, void* stream) {
+    CHECK_H(h);
+    if (K <= 0) return ROMHC_OK;
+    if (!compact_host || !padded_dev) { set_error("null argument"); return ROMHC_ERR_ARG; }
+    Context* c = H(h);
+    const LevelGeo& g = c->levels[0];
+    const int64_t D = int64_t(g.R - 1) * (g.C - 1);
+    const int64_t rows = std::max<int64_t>(1, std::min<int64_t>(K, int64_t(XFER_CHUNK_BYTES / (size_t(D) * 8))));
+    const bool pinned = host_ptr_is_pinned(compact_host);
+    int rc = ensure_xfer_stage(c, size_t(rows) * D * 8, !pinned); if (rc) return rc;
+    HostStage& s = c->hstage;
+    cudaStream_t st = ST(stream);
+    const int copy_threads = std::max(1, std::min(8, int(std::thread::hardware_concurrency()) / 2));
+    int64_t i = 0;
+    for (int64_t k0 = 0; k0 < K; k0 += rows, ++i) {
+        const int64_t kc = std::min(rows, K - k0);
+        const int slot = int(i & 1);
+        cudaStream_t cs = slot ? s.copy2 : s.copy;
+        const size_t bytes = size_t(kc) * D * 8;
+        CK(cudaStreamWaitEvent(st, s.xfer_done[slot], 0));        // the D2H copy that last read this slot has finished
+        rc = c->unpack(padded_dev + k0 * g.Dp, s.xfer_dev[slot], kc, st); if (rc) return rc;
+        CK(cudaEventRecord(s.xfer_ready[slot], st));
+        CK(cudaStreamWaitEvent(cs, s.xfer_ready[slot], 0));
+        double* dst = compact_host + k0 * D;
+        CK(cudaMemcpyAsync(pinned ? dst : s.bounce[slot], s.xfer_dev[slot], bytes, cudaMemcpyDeviceToHost, cs));
+        CK(cudaEventRecord(s.xfer_done[slot], cs));
+        if (!pinned) {
+            HostCopyTask* t = new HostCopyTask{(const char*)s.bounce[slot], (char*)dst, bytes, copy_threads};
+            CK(cudaLaunchHostFunc(cs, host_copy_callback, t));
+        }
+    }
+    CK(cudaStreamSynchronize(s.copy));
+    CK(cudaStreamSynchronize(s.copy2));
+    return ROMHC_OK;
 }
 
 int romhc_reduced_galerkin_host(romhc_handle h, const double* y_host, const double* Ahat_host, const double* bhat_host,

@@ -78,6 +78,10 @@ struct HostStage {
     double* bounce[2] = {nullptr, nullptr};   // pinned bounce buffers for pageable destinations
     size_t bounce_cap = 0;
     cudaStream_t copy2 = nullptr;
+    // romhc_pack_host / romhc_unpack_host: device staging of one compact chunk per slot, reuse events
+    double* xfer_dev[2] = {nullptr, nullptr};
+    size_t xfer_cap = 0;
+    cudaEvent_t xfer_done[2] = {nullptr, nullptr}, xfer_ready[2] = {nullptr, nullptr};
 };
 
 struct Context {

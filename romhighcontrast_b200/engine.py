@@ -70,8 +70,19 @@ class Engine:
         return y.reshape(-1, self.nb).contiguous()
 
     # ---- layout -----------------------------------------------------------------------------------
+    HOST_PIPELINE_MIN_BYTES = 8 << 20       # smaller host arrays take torch's plain copy
+
     def pad(self, compact):
-        """(K, D) compact (reference layout) -> (K, Dp) padded-grid device tensor."""
+        """(K, D) compact (reference layout) -> (K, Dp) padded-grid device tensor.  Large host arrays go through the
+        pipelined host entry point (romhc_pack_host: pinned bounce buffers, several copy threads)."""
+        if not isinstance(compact, torch.Tensor):
+            a = np.ascontiguousarray(np.asarray(compact, dtype=np.float64)).reshape(-1, self.D)
+            if a.nbytes >= self.HOST_PIPELINE_MIN_BYTES:
+                out = self.empty(a.shape[0], self.Dp)
+                _lib.check(self.lib.romhc_pack_host(self.handle, C.c_void_p(a.ctypes.data), _ptr(out), a.shape[0],
+                                                    self.stream()))
+                return out
+            compact = a
         c = self.dev(compact).reshape(-1, self.D)
         out = self.empty(c.shape[0], self.Dp)
         _lib.check(self.lib.romhc_pack(self.handle, _ptr(c), _ptr(out), c.shape[0], self.stream()))
@@ -82,6 +93,18 @@ class Engine:
         out = self.empty(K, self.D)
         _lib.check(self.lib.romhc_unpack(self.handle, _ptr(padded), _ptr(out), K, self.stream()))
         return out
+
+    def unpad_host(self, padded, out=None):
+        """(K, Dp) padded device tensor -> (K, D) numpy array (fresh unless `out` is given); the pipelined counterpart
+        of unpad(...).cpu().numpy() for results that leave through the reference's API."""
+        K = padded.shape[0]
+        U = np.empty((K, self.D)) if out is None else out
+        if U.nbytes < self.HOST_PIPELINE_MIN_BYTES:
+            U[...] = self.unpad(padded).cpu().numpy()
+            return U
+        _lib.check(self.lib.romhc_unpack_host(self.handle, _ptr(padded.contiguous()), C.c_void_p(U.ctypes.data), K,
+                                              self.stream()))
+        return U
 
     # ---- K1a / K2 -----------------------------------------------------------------------------------
     def apply(self, y, u_pad):

@@ -42,7 +42,7 @@ def state_estimation_fitting_method_least_squares(sm, measurement_points, measur
     eng = sm._engine_()
     basis = _basis_array(reduced_basis)
     c = _ls_coefficients(sm, measurement_points, measurements, basis)
-    return eng.unpad(eng.gemm_nn(c.T.contiguous(), sm._pad_rows(basis))).cpu().numpy()
+    return eng.unpad_host(eng.gemm_nn(c.T.contiguous(), sm._pad_rows(basis)))
 
 
 def pbdw_correction(sm, measurement_points, measurements, approximate_solutions, **kwargs):
@@ -55,7 +55,7 @@ def pbdw_correction(sm, measurement_points, measurements, approximate_solutions,
     Z = eng.dev(np.asarray(measurements, dtype=np.float64).reshape(V.shape[0], -1))
     Rt = sm._pad_rows(sm.generate_riesz(measurement_points, norm="l2"))     # (m, Dp)
     diff = (Z - eng.evaluate(measurement_points, V)).contiguous()            # (K, m)
-    return eng.unpad(V + eng.gemm_nn(diff, Rt)).cpu().numpy()
+    return eng.unpad_host(V + eng.gemm_nn(diff, Rt))
 
 
 def state_estimation_fitting_method_pbdw(sm, measurement_points, measurements, reduced_basis, **kwargs):
@@ -76,7 +76,7 @@ def state_estimation_fitting_method_weighted_least_squares(sm, measurement_point
     basis = _basis_array(reduced_basis)
     weights = 1.0 / inverse_christoffel_function(basis, sm, measurement_points)
     c = _ls_coefficients(sm, measurement_points, measurements, basis, weights=weights)
-    return eng.unpad(eng.gemm_nn(c.T.contiguous(), sm._pad_rows(basis))).cpu().numpy()
+    return eng.unpad_host(eng.gemm_nn(c.T.contiguous(), sm._pad_rows(basis)))
 
 
 def measurements_sampling_method_optimal(number_of_measures, xlim, ylim, basis, sm, seed=42, discretization=5, **kwargs):

@@ -90,8 +90,7 @@ class BaseReducedBasis:
         if not reconstruct:            # large observation batches: (K, D) fields would not fit; coefficients only
             return c_dev.cpu().numpy()
         basis_pad = sm._pad_rows(self.basis)
-        est = eng.unpad(eng.gemm_nn(c_dev.T.contiguous(), basis_pad))                              # c^T basis
-        solution_estimations = est.cpu().numpy()
+        solution_estimations = eng.unpad_host(eng.gemm_nn(c_dev.T.contiguous(), basis_pad))       # c^T basis
         c = c_dev.cpu().numpy()
         return (c, solution_estimations) if return_coefs else solution_estimations
 

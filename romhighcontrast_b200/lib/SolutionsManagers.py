@@ -153,7 +153,7 @@ class SolutionsManager:
             y = eng.params(np.broadcast_to(np.asarray(a, dtype=np.float64), (L.shape[0],) + tuple(self.blocks_geometry)))
         w, iters, relres = eng.solve(y, rhs=eng.pad(L))
         self.last_solver_report = {"iterations": iters.cpu().numpy(), "relative_residual": relres.cpu().numpy()}
-        return eng.unpad(w).cpu().numpy()
+        return eng.unpad_host(w)
 
     def generate_fm_solutions(self, a: Union[np.ndarray, List[np.ndarray]], coefficients_rom: List[np.ndarray], *,
                               return_coefs=False):
@@ -168,7 +168,7 @@ class SolutionsManager:
         Cc = eng.reduced_solve(y, Ahat, bhat)                           # :104-105
         if return_coefs:
             return Cc.cpu().numpy()
-        return eng.unpad(eng.gemm_nn(Cc, Phi)).cpu().numpy()            # :106
+        return eng.unpad_host(eng.gemm_nn(Cc, Phi))            # :106
 
     def project_solutions(self, solutions: List[np.ndarray], coefficients_rom: List[np.ndarray], *,
                           return_coefs=False):
@@ -183,7 +183,7 @@ class SolutionsManager:
         Cc = self._projection_coefficients_dev(eng, U, Phi)
         if return_coefs:
             return Cc.cpu().numpy()
-        return eng.unpad(eng.gemm_nn(Cc, Phi)).cpu().numpy()            # :139
+        return eng.unpad_host(eng.gemm_nn(Cc, Phi))            # :139
 
     @staticmethod
     def _projection_coefficients_dev(eng, U_pad, Phi_pad):

@@ -276,3 +276,31 @@ def test_notebook_inverse_methods():
     ww /= ww.sum()
     p2 = gp[np.random.choice(len(gp), size=8, p=ww, replace=False)]
     np.testing.assert_allclose(p1, p2)
+
+
+def test_host_layout_transfers_match_device_path():
+    """romhc_pack_host / romhc_unpack_host (pipelined pageable transfers behind Engine.pad / unpad_host) reproduce the
+    plain copy + layout kernels bit for bit: several chunks, a ragged last chunk, pageable and pinned host memory."""
+    import torch
+    from romhighcontrast_b200.engine import Engine
+    eng = Engine((3, 3), 43)                              # D = 16 384: 1024 rows per 128 MB chunk
+    K = 2500
+    rng = np.random.default_rng(0)
+    U = rng.standard_normal((K, eng.D))
+    ref = eng.empty(K, eng.Dp)
+    from romhighcontrast_b200 import _lib
+    Ud = torch.as_tensor(U).to(eng.device)
+    _lib.check(eng.lib.romhc_pack(eng.handle, Ud.data_ptr(), ref.data_ptr(), K, eng.stream()))
+    got = eng.pad(U)                                      # pageable numpy -> pipelined path
+    assert torch.equal(got, ref)
+    Upin = torch.as_tensor(U).pin_memory().numpy()
+    assert torch.equal(eng.pad(Upin), ref)                # pinned: direct DMA
+    back = eng.unpad_host(ref)
+    np.testing.assert_array_equal(back, U)
+    out_pin = torch.empty((K, eng.D), dtype=torch.float64, pin_memory=True).numpy()
+    np.testing.assert_array_equal(eng.unpad_host(ref, out=out_pin), U)
+    # small arrays take the plain path
+    np.testing.assert_array_equal(eng.unpad_host(ref[:3]), U[:3])
+    assert torch.equal(eng.pad(U[:3]), ref[:3])
+    # twice in a row (slot reuse across calls)
+    assert torch.equal(eng.pad(U * 2.0), ref * 2.0)
