@@ -391,6 +391,13 @@ def run_secondary(eng, x, y, K, args, world, rank, barrier, ev, U_np=None, y_hos
             out["greedy"] = run_greedy(U_np, y_host, n)
         except MemoryError:
             pass
+    # PCG iteration counts against the contrast of the coefficient field (512 systems each, 10^U(0, log10 cmax))
+    sweep = {}
+    for cmax in (1e0, 1e2, 1e4, 1e6, 1e8, 1e10):
+        yc = np.ones((512,) + GEO) if cmax == 1.0 else 10 ** np.random.default_rng(7).uniform(0, np.log10(cmax), (512,) + GEO)
+        _, itc, _ = eng.solve(eng.params(yc))
+        sweep["%g" % cmax] = {"mean": float(itc.double().mean()), "max": int(itc.max())}
+    out["pcg_iterations_vs_contrast"] = sweep
     # measured fp64 GEMM peak of this GPU (cuBLAS DGEMM 8192^3) as the tensor-pipe denominator
     a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
     b = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")

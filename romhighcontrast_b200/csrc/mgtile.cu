@@ -367,7 +367,7 @@ k_mgt_down(TileArgs a, const double* __restrict__ r_in, double* __restrict__ z_o
     // r_c(I, J) = d(2I, 2J) + (d(2I-1, 2J+1) + d(2I+1, 2J-1)) / 2: tile-local (0,0), (0,2), (2,0), (2,2)
     const LevelGeo& gc = a.gc;
     const int CG = t.CG(), CGp = t.CGp();
-    const double dN31 = lds_f64(t.eb + (1 - 4) * CG * 8), dN33 = lds_f64(t.eb + (3 - 4) * CG * 8);
+    const double dN31 = lds_f64(t.eb - 3 * CG * 8), dN33 = lds_f64(t.eb - 1 * CG * 8);
     const double dW13 = lds_f64(t.xr + (1 * CGp - 1) * 8), dW33 = lds_f64(t.xr + (3 * CGp - 1) * 8);
     double rc[2][2];
     rc[0][0] = z[0][0] + 0.5 * (dN31 + dW13);
@@ -787,7 +787,7 @@ k_mgp_down(TileArgs a, const double* __restrict__ r_in, double* __restrict__ z_o
             tile_publish<0>(z, t);
             __syncthreads();
             const LevelGeo& gc = a.gc;
-            const double dN31 = lds_f64(t.eb + (1 - 4) * CG * 8), dN33 = lds_f64(t.eb + (3 - 4) * CG * 8);
+            const double dN31 = lds_f64(t.eb - 3 * CG * 8), dN33 = lds_f64(t.eb - 1 * CG * 8);
             const double dW13 = lds_f64(t.xr + (1 * CGp - 1) * 8), dW33 = lds_f64(t.xr + (3 * CGp - 1) * 8);
             double rc[2][2];
             rc[0][0] = z[0][0] + 0.5 * (dN31 + dW13);
@@ -991,7 +991,7 @@ k_mgp_update_down(TileArgs a, const double* __restrict__ p_in, double* __restric
             tile_publish<0>(z, t);
             __syncthreads();
             const LevelGeo& gc = a.gc;
-            const double dN31 = lds_f64(t.eb + (1 - 4) * CG * 8), dN33 = lds_f64(t.eb + (3 - 4) * CG * 8);
+            const double dN31 = lds_f64(t.eb - 3 * CG * 8), dN33 = lds_f64(t.eb - 1 * CG * 8);
             const double dW13 = lds_f64(t.xr + (1 * CGp - 1) * 8), dW33 = lds_f64(t.xr + (3 * CGp - 1) * 8);
             double rc[2][2];
             rc[0][0] = z[0][0] + 0.5 * (dN31 + dW13);
@@ -1346,7 +1346,7 @@ k_mgt_tail(TailTileArgs p, const double* __restrict__ r_in, double* __restrict__
         __syncthreads();
         if (act) {
             const int CG = t.cg, CGp = CG + 2;
-            const double dN31 = lds_f64(t.eb + (1 - 4) * CG * 8), dN33 = lds_f64(t.eb + (3 - 4) * CG * 8);
+            const double dN31 = lds_f64(t.eb - 3 * CG * 8), dN33 = lds_f64(t.eb - 1 * CG * 8);
             const double dW13 = lds_f64(t.xr + (1 * CGp - 1) * 8), dW33 = lds_f64(t.xr + (3 * CGp - 1) * 8);
             double rc[2][2];
             rc[0][0] = z[0][0] + 0.5 * (dN31 + dW13);
