@@ -16,6 +16,9 @@
  *     R = nrb*N, C = ncb*N.  The reference's "compact" layout is u[(r-1)*(C-1) + (c-1)], D = (R-1)*(C-1)
  *     (src/lib/SolutionsManagers.py:153-163).  romhc_pack / romhc_unpack convert.
  *   - parameters y are (K, nrb*ncb) row-major: y[k][p*ncb + q] = a[k][p][q] (SolutionsManagers.py:190-192).
+ *   - threading: a context owns its workspaces, staging buffers and streams; calls on ONE context must not overlap
+ *     (the reference is single-threaded Python).  Different contexts (one per thread, or one per GPU) are
+ *     independent.  Context-free functions (romhc_gemm_*, romhc_reduced_solve, ...) are reentrant.
  */
 #ifndef ROMHC_H
 #define ROMHC_H
