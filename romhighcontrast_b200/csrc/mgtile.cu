@@ -520,8 +520,11 @@ __device__ __forceinline__ TileStage tile_stage_carve(uint32_t base, const TileA
 }
 static size_t tile_stage_bytes(int ntab, int NR, int CG, int ns, bool with_z, int e_rows, int Pc) {
     const int NRG = NR / 4;
+    // + 32 bytes: neighbour reads at the very end of the last strip (east neighbour of the region's last point, coarse
+    // vertex right of the last column) may touch one element past it; the values are never used, but the address has to
+    // stay inside the CTA's shared-memory window
     return (size_t(tile_stage_head(ntab, 4 * CG, 3 * ns * NRG)) + size_t(2) * NR * (CG + 2) + size_t(2) * (NRG + 2) * 4 * CG +
-            size_t(with_z ? 2 : 1) * NR * 4 * CG + size_t(e_rows) * Pc) * 8;
+            size_t(with_z ? 2 : 1) * NR * 4 * CG + size_t(e_rows) * Pc) * 8 + 32;
 }
 __device__ __forceinline__ int4 lds_s32x4(uint32_t a) {
     int4 v;
@@ -1753,9 +1756,7 @@ int Context::tile_update_down(int l, int Kc, const double* p, double* x, const d
     a.halo_top = 2 * nu + 2;
     a.pf_dist = 0; a.rinfo = nullptr;
     const int CG = a.g.P / 4;
-    // + 16: the east neighbour of the region's last point is read one element past the p strip (value unused: that
-    // row lies outside the validity cone, but the address must stay inside the CTA's shared-memory window)
-    auto bytes = [&]() { return tile_stage_bytes(a.ntab, a.NR, CG, (a.g.R + a.TY - 1) / a.TY, true, 0, 0) + 16; };
+    auto bytes = [&]() { return tile_stage_bytes(a.ntab, a.NR, CG, (a.g.R + a.TY - 1) / a.TY, true, 0, 0); };
     for (int cap = tile_ty_cap; cap >= 2; cap -= 2) {
         tile_pick_ty(a.g, 4 * nu + 3, tile_maxt_down, cap, &a.TY, &a.NR);
         if (bytes() <= 227 * 1024) break;

@@ -1,0 +1,72 @@
+"""Residual-estimator greedy (additive): the estimator is the exact dual norm of the residual, it
+brackets the true H10 error with the coercivity / continuity constants, and the snapshot-free greedy builds a basis
+whose true error decays -- all checked against the CPU oracle (sparse direct solves)."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+pytestmark = pytest.mark.gpu
+
+GEO, N = (2, 2), 16
+
+
+def test_estimator_is_the_residual_dual_norm_and_brackets_the_error():
+    from lib.SolutionsManagers import SolutionsManagerFEM
+    from romhighcontrast_b200.greedy_residual import ReducedBasisGreedyResidual
+    from oracle import FEMOracle
+    rng = np.random.default_rng(3)
+    K, n = 400, 8
+    a_train = 10 ** rng.uniform(0, 3, (K,) + GEO)
+    sm = SolutionsManagerFEM(GEO, N, method="lsqsparse")
+    rb = ReducedBasisGreedyResidual().build(n=n, sm=sm, a2train=a_train)
+    assert rb.snapshot_solves == n == len(rb.selected_indices) and rb.basis.shape == (n, sm.vspace_dim)
+    assert len(set(rb.selected_indices)) == n
+    Q = rb.basis_orth
+    np.testing.assert_allclose(Q @ Q.T, np.eye(n), atol=1e-12)
+    # span(Q) == span(selected snapshots), which are the oracle's snapshots of the selected parameters
+    o = FEMOracle(GEO, N)
+    U_sel = o.generate_solutions(a_train[rb.selected_indices])
+    assert np.abs(rb.basis - U_sel).max() <= 1e-9 * np.abs(U_sel).max()
+    assert np.linalg.norm(U_sel - (U_sel @ Q.T) @ Q) <= 1e-9 * np.linalg.norm(U_sel)
+    # fresh parameters: estimator vs the dual norm computed with sparse direct solves, and the two-sided bound
+    a_test = 10 ** rng.uniform(0, 3, (12,) + GEO)
+    lower, upper = rb.error_bounds(sm, a_test)
+    A1 = o.A1.tocsc() if hasattr(o.A1, "tocsc") else o.A1
+    lu = spla.splu(A1)
+    b = np.full(o.vspace_dim, 1.0 / N ** 2)
+    U_true = o.generate_solutions(a_test)
+    U_rb = o.generate_fm_solutions(a_test, Q)
+    for k in range(len(a_test)):
+        r = b - o.matrix(a_test[k]) @ U_rb[k]
+        dual = np.sqrt(r @ lu.solve(r))
+        est = upper[k] * a_test[k].min()
+        assert abs(est - dual) <= 1e-6 * dual + 1e-9 * np.sqrt(b @ lu.solve(b)), (k, est, dual)
+        e = U_true[k] - U_rb[k]
+        err = np.sqrt(e @ (A1 @ e))
+        assert lower[k] * (1 - 1e-6) <= err <= upper[k] * (1 + 1e-6), (k, lower[k], err, upper[k])
+    # the snapshot-free greedy drives the TRUE worst-case training error down
+    U_train = o.generate_solutions(a_train)
+    def worst(m):
+        Qm = np.linalg.qr(rb.basis[:m].T)[0].T
+        E = U_train - o.generate_fm_solutions(a_train, Qm)
+        return (o.H10norm(E) / o.H10norm(U_train)).max()
+    w2, w8 = worst(2), worst(8)
+    assert w8 < 0.5 * w2, (w2, w8)
+    assert rb.max_estimates[-1] < 0.5 * rb.max_estimates[1]                       # and so does the estimator's maximum
+
+
+def test_relative_variant_and_full_size_run():
+    """BASELINE configs[2] geometry, 20 000 training parameters, n = 10: ten snapshot solves instead of 20 000."""
+    from lib.SolutionsManagers import SolutionsManagerFEM
+    from romhighcontrast_b200.greedy_residual import ReducedBasisGreedyResidual
+    geo, Nb, K, n = (4, 4), 64, 20000, 10
+    a_train = 10 ** np.random.default_rng(42).uniform(0, 6, (K,) + geo)
+    sm = SolutionsManagerFEM(geo, Nb, method="lsqsparse")
+    rb = ReducedBasisGreedyResidual(relative=True).build(n=n, sm=sm, a2train=a_train)
+    assert rb.snapshot_solves == n and rb.basis.shape == (n, sm.vspace_dim)
+    # Galerkin optimality in the energy norm: the reduced solution of a selected parameter is its own snapshot
+    approx = sm.generate_fm_solutions(a_train[rb.selected_indices[:3]], rb.basis_orth)
+    err = sm.H10norm(approx - rb.basis[:3]) / sm.H10norm(rb.basis[:3])
+    assert err.max() < 1e-8, err
+    lower, upper = rb.error_bounds(sm, a_train[:1000])
+    assert np.all(lower <= upper) and np.all(np.isfinite(upper))
