@@ -69,6 +69,7 @@ struct TileArgs {
     const double* tab;    // weight tables, ntab entries per system
     int ntab, ncv;
     int TY, ns, nu, has_coarse;
+    int out_f32;          // k_mgp_up: store z as fp32 (row pitch P floats, system pitch Dp floats) and form r.z from the rounded values
     int emit_res;         // persistent going-down kernels, has_coarse == 0: also store the residual r - A z of the owned rows
                           // on the red points ((row + col) even), packed with row pitch P / 2, for k_bridge_gather
     int NR, halo_top;     // rows of the CTA's region, rows above the owned strip
@@ -1155,7 +1156,14 @@ k_mgp_up(TileArgs a, const double* __restrict__ e_c, const double* __restrict__ 
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (i >= own_lo && i < own_hi) {
-                tile_store_row(zo + i * P, z[i]);
+                if (a.out_f32) {
+                    const float f0 = float(z[i][0]), f1 = float(z[i][1]), f2 = float(z[i][2]), f3 = float(z[i][3]);
+                    float* zf = reinterpret_cast<float*>(z_out) + int64_t(k) * a.g.Dp + int64_t(rho0 + i) * P + 4 * tx;
+                    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(zf), "f"(f0), "f"(f1), "f"(f2), "f"(f3) : "memory");
+                    z[i][0] = double(f0); z[i][1] = double(f1); z[i][2] = double(f2); z[i][3] = double(f3);
+                } else {
+                    tile_store_row(zo + i * P, z[i]);
+                }
                 acc4[i] = fma(r[i][0], z[i][0], r[i][1] * z[i][1]) + fma(r[i][2], z[i][2], r[i][3] * z[i][3]);
             }
         }
@@ -1807,7 +1815,9 @@ int Context::tile_up(int l, const double* y, int Kc, const double* e, double* pa
             if (!a.rinfo) { set_error("tile kernels: row-info table allocation failed"); return ROMHC_ERR_CUDA; }
             const int grid = tile_persistent_grid((const void*)fn, CG * (a.NR / 4), sm, int64_t(Kc) * a.ns);
             ++g_launches;
+            a.out_f32 = (l == 0 && use_z32 && z32_want) ? 1 : 0;
             fn<<<grid, dim3(CG, a.NR / 4), sm, st>>>(a, e, ws.za[l], ws.r[l], ws.zb[l], ws.active, part_rz, Kc);
+            if (l == 0) z32_out = a.out_f32 != 0;
             *ns_out = a.ns;
             return ROMHC_OK;
         }

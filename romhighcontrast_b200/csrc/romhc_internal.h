@@ -110,6 +110,11 @@ struct Context {
     bool tile_prefetch = true;          // L2 prefetch of the next CTA's operand rows (non-persistent tile kernels)
     bool tile_persistent = true;        // persistent, TMA-pipelined tile kernels (one CTA per SM)
     bool use_fused = true;              // PCG update fused into the finest level's going-down kernel
+    // The preconditioned residual z = M r travels from the finest going-up kernel to k_pcg_p_apply as fp32 (half a stream
+    // less in each): z only steers the search direction, so rounding it perturbs the preconditioner by 6e-8 relative and
+    // leaves x, r, p and every reduction in fp64 (r.z is formed from the ROUNDED z, consistent with what p_apply reads).
+    // z32_want: requested for this V-cycle (solves: yes, the precond() test hook: no); z32_out: what the V-cycle produced
+    bool use_z32 = true, z32_want = false, z32_out = false;
     int tile_nsm = 148;
     std::map<std::array<int, 4>, int*> tile_rinfo_cache;   // (level, TY, halo, NR) -> device row-info table
     bool tile_ready = false;

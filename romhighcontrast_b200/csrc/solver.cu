@@ -314,7 +314,7 @@ __global__ void k_reduce_partials(const double* __restrict__ part, int np, doubl
 __global__ void __launch_bounds__(512)
 k_pcg_p_apply(LevelGeo g, const double* __restrict__ y, const double* __restrict__ z, const double* __restrict__ p_in,
               double* __restrict__ p_out, const double* __restrict__ beta, const int* __restrict__ active,
-              double* __restrict__ part_pAp, int TY, int nstrips) {
+              double* __restrict__ part_pAp, int TY, int nstrips, int z32) {
     const int64_t k = blockIdx.y;
     if (!active[k]) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -330,26 +330,53 @@ k_pcg_p_apply(LevelGeo g, const double* __restrict__ y, const double* __restrict
     __syncthreads();
     double* Zs = h.data;
     double* Ps = Zs + size_t(nrow) * P;
+    // z32: z arrives as fp32 (row pitch P floats, system pitch Dp floats) and is staged in the first half of Zs
+    float* Zf = reinterpret_cast<float*>(Zs);
     if (tid == 0) {
-        mbar_expect_tx(h.bar, 2u * strip_tx_bytes(g, row0, nrow));
-        strip_issue(Zs, z + k * g.Dp, g, row0, nrow, h.bar);
+        const uint32_t zb = strip_tx_bytes(g, row0, nrow);
+        mbar_expect_tx(h.bar, zb + (z32 ? zb / 2 : zb));
+        if (z32) {
+            const int lo = max(row0, 0), hi = min(row0 + nrow, g.R + 1);
+            if (hi > lo)
+                bulk_g2s(Zf + size_t(lo - row0) * P, reinterpret_cast<const float*>(z) + k * g.Dp + size_t(lo) * P,
+                         uint32_t(hi - lo) * uint32_t(P) * 4u, h.bar);
+        } else {
+            strip_issue(Zs, z + k * g.Dp, g, row0, nrow, h.bar);
+        }
         strip_issue(Ps, p_in + k * g.Dp, g, row0, nrow, h.bar);
     }
-    strip_zero_oob(Zs, g, row0, nrow, tid, nt);
+    if (z32) {
+        const int lo = min(max(row0, 0), row0 + nrow), hi = max(min(row0 + nrow, g.R + 1), lo);
+        for (int i = tid; i < (lo - row0) * P; i += nt) Zf[i] = 0.f;
+        for (int i = (hi - row0) * P + tid; i < nrow * P; i += nt) Zf[i] = 0.f;
+    } else {
+        strip_zero_oob(Zs, g, row0, nrow, tid, nt);
+    }
     strip_zero_oob(Ps, g, row0, nrow, tid, nt);
     const double b = beta[k];
     mbar_wait(h.bar, 0);
     __syncthreads();
     {
         double2* P2 = reinterpret_cast<double2*>(Ps);
-        const double2* Z2 = reinterpret_cast<const double2*>(Zs);
         const int n2 = nrow * P / 2;
-        for (int i = tid; i < n2; i += nt) {
-            double2 pv = P2[i];
-            const double2 zv = Z2[i];
-            pv.x = fma(b, pv.x, zv.x);
-            pv.y = fma(b, pv.y, zv.y);
-            P2[i] = pv;
+        if (z32) {
+            const float2* Z2 = reinterpret_cast<const float2*>(Zf);
+            for (int i = tid; i < n2; i += nt) {
+                double2 pv = P2[i];
+                const float2 zv = Z2[i];
+                pv.x = fma(b, pv.x, double(zv.x));
+                pv.y = fma(b, pv.y, double(zv.y));
+                P2[i] = pv;
+            }
+        } else {
+            const double2* Z2 = reinterpret_cast<const double2*>(Zs);
+            for (int i = tid; i < n2; i += nt) {
+                double2 pv = P2[i];
+                const double2 zv = Z2[i];
+                pv.x = fma(b, pv.x, zv.x);
+                pv.y = fma(b, pv.y, zv.y);
+                P2[i] = pv;
+            }
         }
     }
     fence_proxy_async();
@@ -1298,6 +1325,7 @@ int Context::vcycle(const double* y, int Kc, cudaStream_t st, const double** z_r
     const int nb = nrb * ncb;
     const int nstrip_levels = std::min(tail_level, L + 1);
     const size_t hdr = smem_hdr_bytes(nb);
+    z32_out = false;                          // set by the finest going-up kernel if it wrote z as fp32
     if (fuse_p && nstrip_levels == 0) {       // the whole hierarchy lives in the tail kernel: plain update first
         const int rc_u = pcg_update(y, Kc, fuse_p, fuse_x, fuse_alpha, st); if (rc_u) return rc_u;
     }
@@ -1422,6 +1450,7 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
     const double* z = nullptr;
     int np_rz = 1;
     prof_window = false;
+    z32_want = true;
     rc = vcycle(y, Kc, st, &z, &np_rz); if (rc) return rc;
     const double tol2 = rtol * rtol;
     int* n_active = ws_flags + 8;   // one counter per iteration slot (mod 32)
@@ -1433,7 +1462,7 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
         prof_window = (it <= min_check_iter);
         prof_begin(PROF_PAPPLY, st);
         ++g_launches; k_pcg_p_apply<<<dim3(nsp, Kc), block, bytes_p(TYp), st>>>(g, y, z, ws.p[cur], ws.p[cur ^ 1], ws.beta, ws.active,
-                                                        ws.part_pAp, TYp, nsp);
+                                                        ws.part_pAp, TYp, nsp, z32_out ? 1 : 0);
         prof_end(st);
         cur ^= 1;
         ++g_launches; k_scalar_alpha<<<gs, 128, 0, st>>>(Kc, nsp, ws.part_pAp, ws.rz, ws.alpha, ws.active, ws_flags + 0);
@@ -1504,6 +1533,7 @@ int Context::precond(const double* y, const double* r, double* z, int64_t K, cud
     }
     rc = tile_weight_table(y, Kc, st); if (rc) return rc;
     const double* zr = nullptr; int np = 1;
+    z32_want = false;                         // the test hook hands z back in fp64
     rc = vcycle(y, Kc, st, &zr, &np); if (rc) return rc;
     CK(cudaMemcpyAsync(z, zr, size_t(Kc) * g.Dp * 8, cudaMemcpyDeviceToDevice, st));
     CK(cudaStreamSynchronize(st));
