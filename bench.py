@@ -31,7 +31,7 @@ CMAX = 1e6
 KIND_NAMES = ["k_pcg_p_apply", "k_pcg_update", "k_mg_down(l0)", "k_mg_down(l>=1)", "k_mg_tail", "k_mg_up(l0)",
               "k_mg_up(l>=1)"]
 # algorithmic fp64 streams per fine-level DOF per launch (SURVEY 8d stream counting; DESIGN.md "kernels")
-KIND_STREAMS = [2.5, 5.0, 2.25, 2.25 / 4, 2.0 / 16, 2.75, 3.25 / 4]   # z = M r travels as fp32 (half a stream) from up(l0) to p_apply
+KIND_STREAMS = [2.5, 5.0, 1.75, 2.25 / 4, 2.0 / 16, 2.25, 3.25 / 4]   # z_A and z = M r travel as fp32 (half a stream each way) on the finest level
 
 
 def sample_params(K, seed):

@@ -69,6 +69,7 @@ struct TileArgs {
     const double* tab;    // weight tables, ntab entries per system
     int ntab, ncv;
     int TY, ns, nu, has_coarse;
+    int in_f32;           // k_mgp_up: z_in (the going-down kernel's z_A) is fp32; going-down kernels: store z_A as fp32
     int out_f32;          // k_mgp_up: store z as fp32 (row pitch P floats, system pitch Dp floats) and form r.z from the rounded values
     int emit_res;         // persistent going-down kernels, has_coarse == 0: also store the residual r - A z of the owned rows
                           // on the red points ((row + col) even), packed with row pitch P / 2, for k_bridge_gather
@@ -605,6 +606,19 @@ __device__ __forceinline__ void tile_lds_row(double (&v)[4], uint32_t addr) {
     v[0] = h ? b.x : a.x; v[1] = h ? b.y : a.y; v[2] = h ? a.x : b.x; v[3] = h ? a.y : b.y;
 }
 
+// fp32 rows (row pitch P floats): thread tx reads the 16 bytes at base + 16 tx -- consecutive, conflict free
+__device__ __forceinline__ void tile_lds_row_f32(double (&v)[4], uint32_t addr) {
+    float a, b, c, d;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr) : "memory");
+    v[0] = double(a); v[1] = double(b); v[2] = double(c); v[3] = double(d);
+}
+// store a row as fp32 and keep the ROUNDED values in the registers (what the reader of the row will see)
+__device__ __forceinline__ void tile_store_row_f32(float* row, double (&v)[4]) {
+    const float a = float(v[0]), b = float(v[1]), c = float(v[2]), d = float(v[3]);
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+    v[0] = double(a); v[1] = double(b); v[2] = double(c); v[3] = double(d);
+}
+
 // straight-line half sweep for a tile whose four rows all have the primary class (t.rt == 0x55)
 template <int X, int MODE, bool NEED_DG, int CGT, bool CS>
 __device__ __forceinline__ void tile_phase_fast(double (&z)[4][4], const double (&r)[4][4], const ColWeights<NEED_DG>& w,
@@ -785,7 +799,10 @@ k_mgp_down(TileArgs a, const double* __restrict__ r_in, double* __restrict__ z_o
         const int own_lo = y0 - rho0, own_hi = min(y0 + a.TY, R + 1) - rho0;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            if (i >= own_lo && i < own_hi) tile_store_row(zo + i * P, z[i]);
+            if (i >= own_lo && i < own_hi) {
+                if (a.in_f32) tile_store_row_f32(reinterpret_cast<float*>(z_out) + (zo - z_out) + i * P, z[i]);
+                else          tile_store_row(zo + i * P, z[i]);
+            }
         if (a.has_coarse) {
             tile_phase_any<0, 1, true>(z, r, w, t, a);
             tile_publish<0>(z, t);
@@ -989,7 +1006,10 @@ k_mgp_update_down(TileArgs a, const double* __restrict__ p_in, double* __restric
         double* zo = z_out + goff;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            if (i >= own_lo && i < own_hi) tile_store_row(zo + i * P, z[i]);
+            if (i >= own_lo && i < own_hi) {
+                if (a.in_f32) tile_store_row_f32(reinterpret_cast<float*>(z_out) + (zo - z_out) + i * P, z[i]);
+                else          tile_store_row(zo + i * P, z[i]);
+            }
         if (a.has_coarse) {
             tile_phase_any<0, 1, true>(z, r, w, t, a);
             tile_publish<0>(z, t);
@@ -1053,12 +1073,23 @@ k_mgp_up(TileArgs a, const double* __restrict__ e_c, const double* __restrict__ 
     auto issue = [&](const TileWalk& wk, int stage, int parts) {
         const int row0 = wk.strip * a.TY - a.halo_top;
         if (parts & 1) {
-            uint32_t tot = s.tb + 2u * tile_rows_bytes(row0, NR, R, P);
+            const uint32_t rb = tile_rows_bytes(row0, NR, R, P);
+            uint32_t tot = s.tb + rb + (a.in_f32 ? rb / 2 : rb);
             if (a.has_coarse) tot += tile_rows_bytes(row0 >> 1, NR / 2 + 1, Rc, Pc);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s.bar), "r"(tot) : "memory");
             tile_tma(s.T0 + stage * s.tb, a.tab + int64_t(wk.k) * a.ntab * TWD, s.tb, s.bar);
         }
-        if (parts & 8) tile_tma_rows(s.Zs, z_in + int64_t(wk.k) * a.g.Dp, P, R, row0, NR, row0, s.bar);
+        if (parts & 8) {
+            if (a.in_f32) {                                      // fp32 rows: P floats each, same element offsets
+                const int lo = max(row0, 0), hi = min(row0 + NR, R + 1);
+                if (hi > lo)
+                    tile_tma(s.Zs + uint32_t(lo - row0) * uint32_t(P) * 4u,
+                             reinterpret_cast<const float*>(z_in) + int64_t(wk.k) * a.g.Dp + size_t(lo) * P,
+                             uint32_t(hi - lo) * uint32_t(P) * 4u, s.bar);
+            } else {
+                tile_tma_rows(s.Zs, z_in + int64_t(wk.k) * a.g.Dp, P, R, row0, NR, row0, s.bar);
+            }
+        }
         if (parts & 2) tile_tma_rows(s.Rs, r_in + int64_t(wk.k) * a.g.Dp, P, R, row0, NR, row0, s.bar);
         if ((parts & 4) && a.has_coarse)
             tile_tma_rows(s.Es, e_c + int64_t(wk.k) * a.gc.Dp, Pc, Rc, row0 >> 1, NR / 2 + 1, row0 >> 1, s.bar);
@@ -1093,7 +1124,8 @@ k_mgp_up(TileArgs a, const double* __restrict__ e_c, const double* __restrict__ 
         if ((rinfo & 0xff) == 0x55) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                tile_lds_row(z[i], s.Zs + own + i * P * 8);
+                if (a.in_f32) tile_lds_row_f32(z[i], s.Zs + own / 2 + i * P * 4);
+                else          tile_lds_row(z[i], s.Zs + own + i * P * 8);
                 tile_lds_row(r[i], s.Rs + own + i * P * 8);
             }
         } else {
@@ -1102,7 +1134,8 @@ k_mgp_up(TileArgs a, const double* __restrict__ e_c, const double* __restrict__ 
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { z[i][j] = 0.0; r[i][j] = 0.0; }
                 if (unsigned(rho0 + i) <= unsigned(R)) {
-                    tile_lds_row(z[i], s.Zs + own + i * P * 8);
+                    if (a.in_f32) tile_lds_row_f32(z[i], s.Zs + own / 2 + i * P * 4);
+                    else          tile_lds_row(z[i], s.Zs + own + i * P * 8);
                     tile_lds_row(r[i], s.Rs + own + i * P * 8);
                 }
             }
@@ -1702,6 +1735,21 @@ static void tile_pick_ty(const LevelGeo& g, int extra_rows, int maxt, int cap, i
     *NR_out = ((TY + extra_rows + 3) / 4) * 4;
 }
 
+// will the going-up kernel of level l run as the persistent tile kernel (the only reader that understands an fp32 z_A)?
+bool Context::tile_up_persistent_ok(int l) const {
+    if (!use_tile || !tile_persistent || !tile_level_ok(l)) return false;
+    const LevelGeo& g = levels[l];
+    const bool has_c = fused_coarse(l);
+    const int CG = g.P / 4, nu = nu_of(l);
+    for (int cap = tile_ty_cap; cap >= 2; cap -= 2) {
+        int TY, NR;
+        tile_pick_ty(g, 4 * nu, tile_maxt_up, cap, &TY, &NR);
+        if (tile_stage_bytes(tile_ntab(), NR, CG, (g.R + TY - 1) / TY, true, has_c ? NR / 2 + 1 : 0, has_c ? levels[l + 1].P : g.P) <= 227 * 1024)
+            return true;
+    }
+    return false;
+}
+
 int Context::tile_down(int l, const double* y, int Kc, cudaStream_t st) {
     (void)y;
     TileArgs a;
@@ -1731,6 +1779,8 @@ int Context::tile_down(int l, const double* y, int Kc, cudaStream_t st) {
             const int grid = tile_persistent_grid((const void*)fn, CG * (a.NR / 4), sm, int64_t(Kc) * a.ns);
             ++g_launches;
             a.emit_res = (l == bridge_level) ? 1 : 0;             // residual into zb[l] (free until the way up)
+            a.in_f32 = (l == 0 && use_z32 >= 2 && z32_want && l != bridge_level && tile_up_persistent_ok(l)) ? 1 : 0;
+            if (l == 0) za_f32 = a.in_f32 != 0;
             fn<<<grid, dim3(CG, a.NR / 4), sm, st>>>(a, ws.r[l], ws.za[l], a.has_coarse ? ws.r[l + 1] : (a.emit_res ? ws.zb[l] : nullptr),
                                                      ws.active, Kc);
             bridge_res_emitted = a.emit_res != 0;
@@ -1780,6 +1830,8 @@ int Context::tile_update_down(int l, int Kc, const double* p, double* x, const d
     if (l != 0) return ROMHC_ERR_ARG;
     // systems that are no longer active keep their (converged) residual in the old buffer: nobody reads it again
     a.emit_res = (l == bridge_level) ? 1 : 0;
+    a.in_f32 = (use_z32 >= 2 && z32_want && l != bridge_level && tile_up_persistent_ok(l)) ? 1 : 0;
+    za_f32 = a.in_f32 != 0;
     fn<<<grid, dim3(CG, a.NR / 4), sm, st>>>(a, p, x, ws.r[0], ws.r_alt, alpha, ws.za[0],
                                              a.has_coarse ? ws.r[1] : (a.emit_res ? ws.zb[0] : nullptr), ws.active, Kc);
     bridge_res_emitted = a.emit_res != 0;
@@ -1816,12 +1868,14 @@ int Context::tile_up(int l, const double* y, int Kc, const double* e, double* pa
             const int grid = tile_persistent_grid((const void*)fn, CG * (a.NR / 4), sm, int64_t(Kc) * a.ns);
             ++g_launches;
             a.out_f32 = (l == 0 && use_z32 && z32_want) ? 1 : 0;
+            a.in_f32 = (l == 0 && za_f32) ? 1 : 0;
             fn<<<grid, dim3(CG, a.NR / 4), sm, st>>>(a, e, ws.za[l], ws.r[l], ws.zb[l], ws.active, part_rz, Kc);
             if (l == 0) z32_out = a.out_f32 != 0;
             *ns_out = a.ns;
             return ROMHC_OK;
         }
     }
+    if (l == 0 && za_f32) { set_error("tile kernels: fp32 z_A without the persistent going-up kernel"); return ROMHC_ERR_ARG; }
     tile_pick_ty(a.g, 4 * nu, tile_maxt_up, tile_ty_cap, &a.TY, &a.NR);
     a.ns = (a.g.R + a.TY - 1) / a.TY;
     const size_t sm = tile_smem_bytes(a.ntab, a.NR, CG);

@@ -1326,6 +1326,7 @@ int Context::vcycle(const double* y, int Kc, cudaStream_t st, const double** z_r
     const int nstrip_levels = std::min(tail_level, L + 1);
     const size_t hdr = smem_hdr_bytes(nb);
     z32_out = false;                          // set by the finest going-up kernel if it wrote z as fp32
+    za_f32 = false;                           // set by the finest going-down kernel if it wrote z_A as fp32
     if (fuse_p && nstrip_levels == 0) {       // the whole hierarchy lives in the tail kernel: plain update first
         const int rc_u = pcg_update(y, Kc, fuse_p, fuse_x, fuse_alpha, st); if (rc_u) return rc_u;
     }
