@@ -392,3 +392,39 @@ def test_pod_iterative_eigensolver(torch_mod, K, D, n, decay):
     Vn = V.cpu().numpy()
     for i in range(n):
         assert abs(abs(Vn[:, i] @ Uo[:, i]) - 1.0) < 1e-7, i
+
+
+def test_solve_rhs_is_scale_invariant(torch_mod):
+    """caller-supplied right-hand sides keep fp64 inside the preconditioner (the fp32 transport of z_A / z is reserved for
+    the reference's load vector): a right-hand side scaled by 1e-30 gives the solution scaled by 1e-30"""
+    geo, N = (2, 2), 32
+    eng = make_engine(geo, N)
+    K = 6
+    y = eng.params(rand_y(geo, K, seed=5))
+    rhs = eng.pad(np.random.default_rng(6).standard_normal((K, eng.D)))
+    x1, it1, _ = eng.solve(y, rhs=rhs)
+    x2, it2, _ = eng.solve(y, rhs=(1e-30 * rhs).contiguous())
+    assert eng.last_solve_stats["status"] == 0
+    assert torch_mod.equal(it1, it2)
+    d = torch_mod.linalg.vector_norm(x2 * 1e30 - x1, dim=1) / torch_mod.linalg.vector_norm(x1, dim=1)
+    assert float(d.max()) < 1e-9, d
+
+
+@pytest.mark.parametrize("z32", [0, 1, 2])
+def test_solve_fp32_transport_modes_agree(torch_mod, z32):
+    """option z32: 0 all fp64, 1 z = M r as fp32, 2 also z_A -- same solutions to 1e-10, iteration counts within one"""
+    from oracle import FEMOracle
+    geo, N = (4, 4), 16
+    eng = make_engine(geo, N)
+    eng.set_option("z32", z32)
+    K = 64
+    y = rand_y(geo, K, cmax=1e10, seed=8)
+    x, it, rel = eng.solve(eng.params(y))
+    ref = make_engine(geo, N)
+    ref.set_option("z32", 0)
+    x0, it0, _ = ref.solve(ref.params(y))
+    d = torch_mod.linalg.vector_norm(x - x0, dim=1) / torch_mod.linalg.vector_norm(x0, dim=1)
+    assert float(d.max()) < 1e-10
+    assert int((it - it0).abs().max()) <= 1
+    Uo = FEMOracle(geo, N).generate_solutions(y[:3])
+    assert relerr(eng.unpad(x[:3]).cpu().numpy(), Uo) < 1e-9
