@@ -31,7 +31,7 @@ CMAX = 1e6
 KIND_NAMES = ["k_pcg_p_apply", "k_pcg_update", "k_mg_down(l0)", "k_mg_down(l>=1)", "k_mg_tail", "k_mg_up(l0)",
               "k_mg_up(l>=1)"]
 # algorithmic fp64 streams per fine-level DOF per launch (SURVEY 8d stream counting; DESIGN.md "kernels")
-KIND_STREAMS = [2.5, 5.0, 1.75, 2.25 / 4, 2.0 / 16, 2.25, 3.25 / 4]   # z_A and z = M r travel as fp32 (half a stream each way) on the finest level
+KIND_STREAMS = [1.5, 5.0, 1.75, 2.25 / 4, 2.0 / 16, 2.25, 3.25 / 4]   # z_A, z = M r and p travel as fp32 (half a stream each way) on the finest level
 
 
 def sample_params(K, seed):
@@ -294,7 +294,7 @@ def main():
             avg_ms = pms[i] / pn[i]
             streams = KIND_STREAMS[i]
             if nm == "k_mg_down(l0)" and pn[1] == 0:
-                streams += 4.0                                    # fused with the PCG update: R p, x; W x, r on top
+                streams += 3.5                                    # fused with the PCG update: R p (fp32), x; W x, r on top
                 nm = "k_mg_update_down(l0)"
             if nm == "k_mg_tail":
                 streams = 2.0 / 4.0 ** eng.tail_level            # reads r, writes z of its first level
@@ -314,7 +314,7 @@ def main():
         traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "r1_dram_traffic_k10000.json")))
-            ncu_name = {"k_mg_update_down(l0)": "k_mgp_update_down<64>", "k_mg_down(l0)": "k_mgp_down<64>",
+            ncu_name = {"k_mg_update_down(l0)": "k_mgp_update_down<64>",   # (keys of the JSON drop the second template argument) "k_mg_down(l0)": "k_mgp_down<64>",
                         "k_mg_up(l0)": "k_mgp_up<64>"}.get(dom["kernel"], dom["kernel"])
             if tr.get("K") == K and ncu_name in tr["kernels"] and all(v is None for v in (args.strip_kb, args.nu, args.nu_mid, args.nu_tail, args.tile, args.tile_ty, args.fused)):
                 traffic = tr["kernels"][ncu_name]["dram_bytes_per_launch"] / 1e9

@@ -48,8 +48,8 @@ int romhc_destroy(romhc_handle h);
  * "workspace_gb", "check_every", "min_check_iter", "nu" / "nu_mid" / "nu_tail" (Gauss-Seidel sweeps of the V(nu,nu) cycle on the
  * finest / intermediate / small levels, defaults 2 / 3 / 4), "strip_kb" (shared memory per strip CTA, default 113 = two
  * CTAs per SM), "threads" (256 / 512 per strip CTA), "profile", "bridge" (1: non-nested transfer to a power-of-two
- * hierarchy when N has an odd factor, default; 0: stop coarsening at the odd level), "z32" (2, default: the two vectors
- * internal to the preconditioner on the finest level travel between kernels as fp32; 1: only z = M r; 0: all fp64;
+ * hierarchy when N has an odd factor, default; 0: stop coarsening at the odd level), "z32" (3, default: z = M r, the smoothed
+ * iterate z_A and the search direction p of the finest level travel between kernels as fp32; 2: z and z_A; 1: only z; 0: all fp64;
  * solves with a caller-supplied right-hand side always use fp64) */
 int romhc_set_option(romhc_handle h, const char* name, double value);
 /* info[0..15] = D, Dp, P, R, C, nlevels, tail_level, coarse_D, coarse_direct, nrb, ncb, N, workspace bytes per system,

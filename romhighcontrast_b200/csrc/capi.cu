@@ -183,7 +183,7 @@ int romhc_set_option(romhc_handle h, const char* name, double value) {
     }
     else if (!strcmp(name, "gram_variant")) romhc::g_gram_variant = (int)value;
     else if (!strcmp(name, "fused")) c->use_fused = value != 0.0;
-    else if (!strcmp(name, "z32")) c->use_z32 = std::max(0, std::min(2, (int)value));
+    else if (!strcmp(name, "z32")) c->use_z32 = std::max(0, std::min(3, (int)value));
     else if (!strcmp(name, "tile_persistent")) c->tile_persistent = value != 0.0;
     else if (!strcmp(name, "tile_prefetch")) c->tile_prefetch = value != 0.0;
     else if (!strcmp(name, "tile_ty")) c->tile_ty_cap = std::max(4, std::min(64, ((int)value) & ~3));

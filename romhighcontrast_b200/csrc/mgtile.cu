@@ -69,6 +69,7 @@ struct TileArgs {
     const double* tab;    // weight tables, ntab entries per system
     int ntab, ncv;
     int TY, ns, nu, has_coarse;
+    int p_f32;            // k_mgp_update_down: the search direction p is stored as fp32 (k_pcg_p_apply wrote it that way)
     int in_f32;           // k_mgp_up: z_in (the going-down kernel's z_A) is fp32; going-down kernels: store z_A as fp32
     int out_f32;          // k_mgp_up: store z as fp32 (row pitch P floats, system pitch Dp floats) and form r.z from the rounded values
     int emit_res;         // persistent going-down kernels, has_coarse == 0: also store the residual r - A z of the owned rows
@@ -612,6 +613,11 @@ __device__ __forceinline__ void tile_lds_row_f32(double (&v)[4], uint32_t addr) 
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr) : "memory");
     v[0] = double(a); v[1] = double(b); v[2] = double(c); v[3] = double(d);
 }
+__device__ __forceinline__ double lds_f32_as_f64(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return double(v);
+}
 // store a row as fp32 and keep the ROUNDED values in the registers (what the reader of the row will see)
 __device__ __forceinline__ void tile_store_row_f32(float* row, double (&v)[4]) {
     const float a = float(v[0]), b = float(v[1]), c = float(v[2]), d = float(v[3]);
@@ -871,7 +877,7 @@ __device__ __forceinline__ void tile_apply_row(double (&r)[4][4], const double (
     }
 }
 
-template <int CGT>
+template <int CGT, bool P32>
 __global__ void __launch_bounds__(TILE_MAXT, 1)
 k_mgp_update_down(TileArgs a, const double* __restrict__ p_in, double* __restrict__ x_io, const double* __restrict__ r_in,
                   double* __restrict__ r_out, const double* __restrict__ alpha, double* __restrict__ z_out, double* __restrict__ rc_out,
@@ -895,10 +901,19 @@ k_mgp_update_down(TileArgs a, const double* __restrict__ p_in, double* __restric
     auto issue = [&](const TileWalk& wk, int stage, int parts) {
         const int row0 = wk.strip * a.TY - a.halo_top;
         if (parts & 1) {
+            const uint32_t rb = tile_rows_bytes(row0, NR, R, P);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s.bar),
-                         "r"(s.tb + 2u * tile_rows_bytes(row0, NR, R, P)) : "memory");
+                         "r"(s.tb + rb + (P32 ? rb / 2 : rb)) : "memory");
             tile_tma(s.T0 + stage * s.tb, a.tab + int64_t(wk.k) * a.ntab * TWD, s.tb, s.bar);
-            tile_tma_rows(s.Zs, p_in + int64_t(wk.k) * a.g.Dp, P, R, row0, NR, row0, s.bar);
+            if (P32) {                                        // fp32 rows: P floats each, same element offsets
+                const int lo = max(row0, 0), hi = min(row0 + NR, R + 1);
+                if (hi > lo)
+                    tile_tma(s.Zs + uint32_t(lo - row0) * uint32_t(P) * 4u,
+                             reinterpret_cast<const float*>(p_in) + int64_t(wk.k) * a.g.Dp + size_t(lo) * P,
+                             uint32_t(hi - lo) * uint32_t(P) * 4u, s.bar);
+            } else {
+                tile_tma_rows(s.Zs, p_in + int64_t(wk.k) * a.g.Dp, P, R, row0, NR, row0, s.bar);
+            }
         }
         if (parts & 2) tile_tma_rows(s.Rs, r_in + int64_t(wk.k) * a.g.Dp, P, R, row0, NR, row0, s.bar);
         if (parts & 4) tile_prefetch_rows(x_io, a.g, wk.k, wk.strip * a.TY, a.TY);
@@ -934,8 +949,10 @@ k_mgp_update_down(TileArgs a, const double* __restrict__ p_in, double* __restric
         const bool all_rows = (rinfo & 0xff) == 0x55;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            if (all_rows || unsigned(rho0 + i) <= unsigned(R)) tile_lds_row(z[i], s.Zs + own + i * P * 8);
-            else { z[i][0] = z[i][1] = z[i][2] = z[i][3] = 0.0; }
+            if (all_rows || unsigned(rho0 + i) <= unsigned(R)) {
+                if (P32) tile_lds_row_f32(z[i], s.Zs + own / 2 + i * P * 4);
+                else         tile_lds_row(z[i], s.Zs + own + i * P * 8);
+            } else { z[i][0] = z[i][1] = z[i][2] = z[i][3] = 0.0; }
         }
         // x += alpha p on the owned rows
 #pragma unroll
@@ -955,14 +972,17 @@ k_mgp_update_down(TileArgs a, const double* __restrict__ p_in, double* __restric
         // r -= alpha A p; neighbours of the tile from the staged p strip (rows outside the region: zero, those region
         // rows are outside the validity cone anyway)
         {
-            const uint32_t pb = s.Zs + own;
+            const uint32_t pb = P32 ? s.Zs + own / 2 : s.Zs + own;   // fp32 strip: row pitch P * 4 bytes
+            const uint32_t prow = P32 ? uint32_t(P) * 4u : uint32_t(P) * 8u;
             double pN[4], pS[4];
-            if (ty > 0) tile_lds_row(pN, pb - P * 8); else { pN[0] = pN[1] = pN[2] = pN[3] = 0.0; }
+            if (ty > 0) { if (P32) tile_lds_row_f32(pN, pb - prow); else tile_lds_row(pN, pb - prow); }
+            else { pN[0] = pN[1] = pN[2] = pN[3] = 0.0; }
 #pragma unroll
             for (int I = 0; I < 4; ++I) {
                 const int rtype = (t.rt >> (2 * I)) & 3;
                 if (I == 3) {
-                    if (ty < NRG - 1) tile_lds_row(pS, pb + 4 * P * 8); else { pS[0] = pS[1] = pS[2] = pS[3] = 0.0; }
+                    if (ty < NRG - 1) { if (P32) tile_lds_row_f32(pS, pb + 4 * prow); else tile_lds_row(pS, pb + 4 * prow); }
+                    else { pS[0] = pS[1] = pS[2] = pS[3] = 0.0; }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) pS[j] = z[I + 1 < 4 ? I + 1 : 3][j];
@@ -972,7 +992,8 @@ k_mgp_update_down(TileArgs a, const double* __restrict__ p_in, double* __restric
                     for (int j = 0; j < 4; ++j) pN[j] = z[I > 0 ? I - 1 : 0][j];
                 }
                 if (rtype != 0) {
-                    const double pWh = lds_f64(pb + I * P * 8 - 8), pEh = lds_f64(pb + I * P * 8 + 32);
+                    const double pWh = P32 ? lds_f32_as_f64(pb + I * prow - 4) : lds_f64(pb + I * prow - 8);
+                    const double pEh = P32 ? lds_f32_as_f64(pb + I * prow + 16) : lds_f64(pb + I * prow + 32);
                     if (rtype == 1) tile_apply_row<false>(r, z, w, t, a, I, -al, pWh, pEh, pN, pS);
                     else            tile_apply_row<true>(r, z, w, t, a, I, -al, pWh, pEh, pN, pS);
                 }
@@ -1565,9 +1586,11 @@ int Context::tile_setup() {
         int& m = i < 3 ? tile_maxt_down : tile_maxt_up;
         m = std::min(m, fa.maxThreadsPerBlock);
     }
-    const void* ffns[] = {(const void*)k_mgp_update_down<64>, (const void*)k_mgp_update_down<32>,
-                          (const void*)k_mgp_update_down<16>, (const void*)k_mgp_update_down<0>};
-    for (int i = 0; i < 4; ++i) {
+    const void* ffns[] = {(const void*)k_mgp_update_down<64, false>, (const void*)k_mgp_update_down<32, false>,
+                          (const void*)k_mgp_update_down<16, false>, (const void*)k_mgp_update_down<0, false>,
+                          (const void*)k_mgp_update_down<64, true>,  (const void*)k_mgp_update_down<32, true>,
+                          (const void*)k_mgp_update_down<16, true>,  (const void*)k_mgp_update_down<0, true>};
+    for (int i = 0; i < 8; ++i) {
         CK(cudaFuncSetAttribute(ffns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         cudaFuncAttributes fa;
         CK(cudaFuncGetAttributes(&fa, ffns[i]));
@@ -1737,7 +1760,7 @@ static void tile_pick_ty(const LevelGeo& g, int extra_rows, int maxt, int cap, i
 
 // will the going-up kernel of level l run as the persistent tile kernel (the only reader that understands an fp32 z_A)?
 bool Context::tile_up_persistent_ok(int l) const {
-    if (!use_tile || !tile_persistent || !tile_level_ok(l)) return false;
+    if (!use_tile || !tile_persistent || l >= tail_level || !tile_level_ok(l)) return false;
     const LevelGeo& g = levels[l];
     const bool has_c = fused_coarse(l);
     const int CG = g.P / 4, nu = nu_of(l);
@@ -1800,6 +1823,21 @@ int Context::tile_down(int l, const double* y, int Kc, cudaStream_t st) {
 
 // x += alpha p, r -= alpha A p and the going-down kernel of level l in one launch (persistent tile kernels only);
 // returns ROMHC_ERR_ARG if the configuration does not fit (the caller then runs the two kernels separately)
+// can the fused update + going-down kernel run on level 0 (the only reader that understands an fp32 p)?
+bool Context::tile_fused_ok() const {
+    if (!use_tile || !tile_persistent || !use_fused || tail_level < 1 || !tile_level_ok(0)) return false;   // tail_level 0: level 0 lives in the tail kernel
+    const LevelGeo& g = levels[0];
+    const int CG = g.P / 4, nu = nu_of(0);
+    int TY = 0, NR = 0;
+    size_t sm = 0;
+    for (int cap = tile_ty_cap; cap >= 2; cap -= 2) {
+        tile_pick_ty(g, 4 * nu + 3, tile_maxt_down, cap, &TY, &NR);
+        sm = tile_stage_bytes(tile_ntab(), NR, CG, (g.R + TY - 1) / TY, true, 0, 0);
+        if (sm <= 227 * 1024) break;
+    }
+    return sm <= 227 * 1024 && NR >= 4 * nu + 6;
+}
+
 int Context::tile_update_down(int l, int Kc, const double* p, double* x, const double* alpha, cudaStream_t st) {
     if (!tile_persistent || !use_fused) return ROMHC_ERR_ARG;
     TileArgs a;
@@ -1822,7 +1860,8 @@ int Context::tile_update_down(int l, int Kc, const double* p, double* x, const d
     const size_t sm = bytes();
     if (sm > 227 * 1024 || a.NR < 4 * nu + 6) return ROMHC_ERR_ARG;
     a.ns = (a.g.R + a.TY - 1) / a.TY;
-    auto fn = CG == 64 ? k_mgp_update_down<64> : (CG == 32 ? k_mgp_update_down<32> : (CG == 16 ? k_mgp_update_down<16> : k_mgp_update_down<0>));
+    auto fn = p_f32 ? (CG == 64 ? k_mgp_update_down<64, true> : (CG == 32 ? k_mgp_update_down<32, true> : (CG == 16 ? k_mgp_update_down<16, true> : k_mgp_update_down<0, true>)))
+                    : (CG == 64 ? k_mgp_update_down<64, false> : (CG == 32 ? k_mgp_update_down<32, false> : (CG == 16 ? k_mgp_update_down<16, false> : k_mgp_update_down<0, false>)));
     a.rinfo = tile_rinfo(l, a.TY, a.halo_top, a.NR);
     if (!a.rinfo) { set_error("tile kernels: row-info table allocation failed"); return ROMHC_ERR_CUDA; }
     const int grid = tile_persistent_grid((const void*)fn, CG * (a.NR / 4), sm, int64_t(Kc) * a.ns);
@@ -1832,6 +1871,7 @@ int Context::tile_update_down(int l, int Kc, const double* p, double* x, const d
     a.emit_res = (l == bridge_level) ? 1 : 0;
     a.in_f32 = (use_z32 >= 2 && z32_want && l != bridge_level && tile_up_persistent_ok(l)) ? 1 : 0;
     za_f32 = a.in_f32 != 0;
+    a.p_f32 = p_f32 ? 1 : 0;
     fn<<<grid, dim3(CG, a.NR / 4), sm, st>>>(a, p, x, ws.r[0], ws.r_alt, alpha, ws.za[0],
                                              a.has_coarse ? ws.r[1] : (a.emit_res ? ws.zb[0] : nullptr), ws.active, Kc);
     bridge_res_emitted = a.emit_res != 0;

@@ -114,7 +114,8 @@ struct Context {
     // less in each): z only steers the search direction, so rounding it perturbs the preconditioner by 6e-8 relative and
     // leaves x, r, p and every reduction in fp64 (r.z is formed from the ROUNDED z, consistent with what p_apply reads).
     // z32_want: requested for this V-cycle (solves: yes, the precond() test hook: no); z32_out: what the V-cycle produced
-    int use_z32 = 2;                    // 0: off, 1: z_B only (up -> p_apply), 2: also z_A (finest down -> up)
+    int use_z32 = 3;                    // 0: off, 1: z_B only (up -> p_apply), 2: also z_A (finest down -> up), 3: also p
+    bool p_f32 = false;                 // this solve keeps the search direction p as fp32 (k_pcg_p_apply <-> fused update kernel)
     bool z32_want = false, z32_out = false;
     bool za_f32 = false;                // the finest going-down kernel stored z_A as fp32 (only the persistent going-up kernel reads that)
     int tile_nsm = 148;
@@ -193,6 +194,7 @@ struct Context {
     int tile_pf_dist(const void* func, int threads, size_t smem);
     bool tile_level_ok(int l) const;
     bool tile_up_persistent_ok(int l) const;
+    bool tile_fused_ok() const;
     int tile_weight_table(const double* y, int Kc, cudaStream_t st);
     int tile_tail(const double* y, int Kc, double* part_rz, cudaStream_t st);
     int tile_update_down(int l, int Kc, const double* p, double* x, const double* alpha, cudaStream_t st);

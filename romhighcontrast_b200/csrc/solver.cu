@@ -314,7 +314,7 @@ __global__ void k_reduce_partials(const double* __restrict__ part, int np, doubl
 __global__ void __launch_bounds__(512)
 k_pcg_p_apply(LevelGeo g, const double* __restrict__ y, const double* __restrict__ z, const double* __restrict__ p_in,
               double* __restrict__ p_out, const double* __restrict__ beta, const int* __restrict__ active,
-              double* __restrict__ part_pAp, int TY, int nstrips, int z32) {
+              double* __restrict__ part_pAp, int TY, int nstrips, int z32, int p32) {
     const int64_t k = blockIdx.y;
     if (!active[k]) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -330,36 +330,62 @@ k_pcg_p_apply(LevelGeo g, const double* __restrict__ y, const double* __restrict
     __syncthreads();
     double* Zs = h.data;
     double* Ps = Zs + size_t(nrow) * P;
-    // z32: z arrives as fp32 (row pitch P floats, system pitch Dp floats) and is staged in the first half of Zs
+    // z32: z arrives as fp32 (row pitch P floats, system pitch Dp floats) and is staged in the first half of Zs.
+    // p32 (needs z32): p is kept as fp32 too -- p_in is staged in the second half of Zs, the new p is ROUNDED to fp32
+    // (p.Ap below and the fused update kernel then see exactly the same direction) and leaves from the first half.
     float* Zf = reinterpret_cast<float*>(Zs);
+    float* Pf = Zf + size_t(nrow) * P;
     if (tid == 0) {
         const uint32_t zb = strip_tx_bytes(g, row0, nrow);
-        mbar_expect_tx(h.bar, zb + (z32 ? zb / 2 : zb));
+        mbar_expect_tx(h.bar, (z32 ? zb / 2 : zb) + (p32 ? zb / 2 : zb));
+        const int lo = max(row0, 0), hi = min(row0 + nrow, g.R + 1);
         if (z32) {
-            const int lo = max(row0, 0), hi = min(row0 + nrow, g.R + 1);
             if (hi > lo)
                 bulk_g2s(Zf + size_t(lo - row0) * P, reinterpret_cast<const float*>(z) + k * g.Dp + size_t(lo) * P,
                          uint32_t(hi - lo) * uint32_t(P) * 4u, h.bar);
         } else {
             strip_issue(Zs, z + k * g.Dp, g, row0, nrow, h.bar);
         }
-        strip_issue(Ps, p_in + k * g.Dp, g, row0, nrow, h.bar);
+        if (p32) {
+            if (hi > lo)
+                bulk_g2s(Pf + size_t(lo - row0) * P, reinterpret_cast<const float*>(p_in) + k * g.Dp + size_t(lo) * P,
+                         uint32_t(hi - lo) * uint32_t(P) * 4u, h.bar);
+        } else {
+            strip_issue(Ps, p_in + k * g.Dp, g, row0, nrow, h.bar);
+        }
     }
-    if (z32) {
+    {
         const int lo = min(max(row0, 0), row0 + nrow), hi = max(min(row0 + nrow, g.R + 1), lo);
-        for (int i = tid; i < (lo - row0) * P; i += nt) Zf[i] = 0.f;
-        for (int i = (hi - row0) * P + tid; i < nrow * P; i += nt) Zf[i] = 0.f;
-    } else {
-        strip_zero_oob(Zs, g, row0, nrow, tid, nt);
+        const int ntop = (lo - row0) * P, nbot0 = (hi - row0) * P, nall = nrow * P;
+        if (z32) {
+            for (int i = tid; i < ntop; i += nt) Zf[i] = 0.f;
+            for (int i = nbot0 + tid; i < nall; i += nt) Zf[i] = 0.f;
+        } else {
+            strip_zero_oob(Zs, g, row0, nrow, tid, nt);
+        }
+        if (p32) {
+            for (int i = tid; i < ntop; i += nt) Pf[i] = 0.f;
+            for (int i = nbot0 + tid; i < nall; i += nt) Pf[i] = 0.f;
+        } else {
+            strip_zero_oob(Ps, g, row0, nrow, tid, nt);
+        }
     }
-    strip_zero_oob(Ps, g, row0, nrow, tid, nt);
     const double b = beta[k];
     mbar_wait(h.bar, 0);
     __syncthreads();
     {
         double2* P2 = reinterpret_cast<double2*>(Ps);
         const int n2 = nrow * P / 2;
-        if (z32) {
+        if (p32) {
+            float2* Z2 = reinterpret_cast<float2*>(Zf);
+            const float2* Q2 = reinterpret_cast<const float2*>(Pf);
+            for (int i = tid; i < n2; i += nt) {
+                const float2 zv = Z2[i], qv = Q2[i];
+                const float2 pf = make_float2(float(fma(b, double(qv.x), double(zv.x))), float(fma(b, double(qv.y), double(zv.y))));
+                Z2[i] = pf;                                       // the fp32 image that goes back to global memory
+                P2[i] = make_double2(double(pf.x), double(pf.y));
+            }
+        } else if (z32) {
             const float2* Z2 = reinterpret_cast<const float2*>(Zf);
             for (int i = tid; i < n2; i += nt) {
                 double2 pv = P2[i];
@@ -381,7 +407,17 @@ k_pcg_p_apply(LevelGeo g, const double* __restrict__ y, const double* __restrict
     }
     fence_proxy_async();
     __syncthreads();
-    if (tid == 0) { strip_store(p_out + k * g.Dp, Ps, g, row0, y0, y0 + TY); bulk_commit(); }
+    if (tid == 0) {
+        if (p32) {
+            const int lo = max(y0, 0), hi = min(y0 + TY, g.R + 1);
+            if (hi > lo)
+                bulk_s2g(reinterpret_cast<float*>(p_out) + k * g.Dp + size_t(lo) * P, Zf + size_t(lo - row0) * P,
+                         uint32_t(hi - lo) * uint32_t(P) * 4u);
+        } else {
+            strip_store(p_out + k * g.Dp, Ps, g, row0, y0, y0 + TY);
+        }
+        bulk_commit();
+    }
     double acc = 0.0;
     for_points<true>(sc, y0, y0 + TY - 1, -1,
                      [&](int r, int c, const ColW& w) {
@@ -1344,6 +1380,7 @@ int Context::vcycle(const double* y, int Kc, cudaStream_t st, const double** z_r
             else {
                 prof_cancel();
                 if (rc_f != ROMHC_ERR_ARG) return rc_f;
+                if (p_f32) { set_error("fp32 search direction without the fused update kernel"); return ROMHC_ERR_ARG; }
                 const int rc_u = pcg_update(y, Kc, fuse_p, fuse_x, fuse_alpha, st); if (rc_u) return rc_u;
             }
         }
@@ -1455,7 +1492,11 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
     // coefficients up to ~1e20 nothing inside the preconditioner leaves the fp32 range before rtol is reached; a
     // caller-supplied right-hand side may be scaled arbitrarily and keeps fp64 throughout
     z32_want = (rhs == nullptr);
+    // p as fp32 needs its only two users to be the kernels that understand it: k_pcg_p_apply with an fp32 z (written by
+    // the persistent going-up kernel) and the fused update + going-down kernel
+    p_f32 = z32_want && use_z32 >= 3 && tile_fused_ok() && tile_up_persistent_ok(0);
     rc = vcycle(y, Kc, st, &z, &np_rz); if (rc) return rc;
+    if (p_f32 && !z32_out) { set_error("fp32 search direction without an fp32 z"); return ROMHC_ERR_ARG; }
     const double tol2 = rtol * rtol;
     int* n_active = ws_flags + 8;   // one counter per iteration slot (mod 32)
     ++g_launches; k_scalar_beta<<<gs, 128, 0, st>>>(Kc, np_rz, ws.part_rz, ws.rz, ws.rz0, ws.beta, ws.active, ws.iters, ws.relres, 0,
@@ -1466,7 +1507,7 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
         prof_window = (it <= min_check_iter);
         prof_begin(PROF_PAPPLY, st);
         ++g_launches; k_pcg_p_apply<<<dim3(nsp, Kc), block, bytes_p(TYp), st>>>(g, y, z, ws.p[cur], ws.p[cur ^ 1], ws.beta, ws.active,
-                                                        ws.part_pAp, TYp, nsp, z32_out ? 1 : 0);
+                                                        ws.part_pAp, TYp, nsp, z32_out ? 1 : 0, p_f32 ? 1 : 0);
         prof_end(st);
         cur ^= 1;
         ++g_launches; k_scalar_alpha<<<gs, 128, 0, st>>>(Kc, nsp, ws.part_pAp, ws.rz, ws.alpha, ws.active, ws_flags + 0);
@@ -1537,7 +1578,7 @@ int Context::precond(const double* y, const double* r, double* z, int64_t K, cud
     }
     rc = tile_weight_table(y, Kc, st); if (rc) return rc;
     const double* zr = nullptr; int np = 1;
-    z32_want = false;                         // the test hook hands z back in fp64
+    z32_want = false; p_f32 = false;          // the test hook hands z back in fp64
     rc = vcycle(y, Kc, st, &zr, &np); if (rc) return rc;
     CK(cudaMemcpyAsync(z, zr, size_t(Kc) * g.Dp * 8, cudaMemcpyDeviceToDevice, st));
     CK(cudaStreamSynchronize(st));

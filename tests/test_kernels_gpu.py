@@ -410,9 +410,10 @@ def test_solve_rhs_is_scale_invariant(torch_mod):
     assert float(d.max()) < 1e-9, d
 
 
-@pytest.mark.parametrize("z32", [0, 1, 2])
+@pytest.mark.parametrize("z32", [0, 1, 2, 3])
 def test_solve_fp32_transport_modes_agree(torch_mod, z32):
-    """option z32: 0 all fp64, 1 z = M r as fp32, 2 also z_A -- same solutions to 1e-10, iteration counts within one"""
+    """option z32: 0 all fp64, 1 z = M r as fp32, 2 also z_A, 3 also the search direction p (default) -- same solutions to
+    1e-10, iteration counts within one"""
     from oracle import FEMOracle
     geo, N = (4, 4), 16
     eng = make_engine(geo, N)
