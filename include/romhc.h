@@ -126,8 +126,11 @@ int romhc_reduced_solve(const double* y_dev, int nb, const double* Ahat_dev, con
                         int rhs_per_system, int n, int64_t K, double* C_dev, int* info_dev, void* stream);
 
 /* ---- K3 and the dense helpers (row-major, ld in doubles) ---------------------------------------------------------------
- * gemm_nt: C[M,N] = A[M,Kd] B[N,Kd]^T on the fp64 tensor cores; symmetric != 0 (A == B): Gram matrix, only the lower
+ * gemm_nt: C[M,N] = A[M,Kd] B[N,Kd]^T on the fp64 tensor cores; symmetric == 1 (A == B): Gram matrix, only the lower
  *          tiles are computed and mirrored.                   replaces PCA(...).fit  ReducedBasis.py:196
+ *          symmetric == 2: plain product, split-K allowed -- for a small C with a long contraction (Krylov-basis
+ *          products of the Gram-free POD) the contraction is spread over ~2 CTAs per SM and the partial sums are
+ *          reduced in a fixed order (deterministic; needs 16-byte aligned operands, otherwise the plain kernel runs).
  * gemm_nn: C[M,N] = A[M,Kd] B[Kd,N], small Kd (c Phi)         SolutionsManagers.py:106,139
  * gemm_tn: C[M,N] = A[Kd,M]^T B[Kd,N], M <= 32 (V^T Xc)       POD back-projection */
 int romhc_gemm_nt(const double* A_dev, int64_t lda, const double* B_dev, int64_t ldb, double* C_dev, int64_t ldc,

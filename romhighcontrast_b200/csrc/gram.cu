@@ -33,12 +33,23 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // smem row pitch 20 doubles: the 16 lanes of a half-warp (g = 0..3, t = 0..3) read (g*20 + t) mod 16 = distinct banks.
 #define GK_BK 16
 #define GK_PITCH 20
-template <int BM, int BN, int WM, int WN, int STAGES, int VEC, int MINB = 1>
+// SPLITK (small C, long contraction: the Krylov-basis products of pod.krylov_pca): blockIdx.y selects a range of
+// `symmetric` (re-used as the chunk length, a multiple of GK_BK) contraction indices and writes its own M x Nn partial
+// (C = scratch, ldc = Nn); k_gemm_tn_reduce sums the partials in a fixed order.  The default instantiations compile
+// exactly as before.
+template <int BM, int BN, int WM, int WN, int STAGES, int VEC, int MINB = 1, bool SPLITK = false>
 __global__ void __launch_bounds__(256, MINB)
 k_gemm_nt(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb, double* __restrict__ C,
           int64_t ldc, int64_t M, int64_t Nn, int64_t Kd, int symmetric, int ntile_n) {
     constexpr int WTM = BM / WM, WTN = BN / WN;       // warp tile
     constexpr int MT = WTM / 8, NT = WTN / 8;         // 8x8 mma tiles per warp
+    if constexpr (SPLITK) {
+        const int64_t kc = symmetric, k0 = int64_t(blockIdx.y) * kc;
+        A += k0; B += k0;
+        Kd = (Kd - k0 < kc) ? Kd - k0 : kc;
+        C += int64_t(blockIdx.y) * M * ldc;
+        symmetric = 0;
+    }
     extern __shared__ __align__(16) double smg[];
     double* sA = smg;
     double* sB = smg + size_t(STAGES) * BM * GK_PITCH;
@@ -152,11 +163,60 @@ static int launch_gemm_nt(const double* A, int64_t lda, const double* B, int64_t
     return ROMHC_OK;
 }
 
+__global__ void k_gemm_tn_reduce(const double* __restrict__ part, int nchunks, int Mm, int64_t Nn, double* __restrict__ C,
+                                 int64_t ldc);
+static void* g_tn_scratch = nullptr;
+static size_t g_tn_bytes = 0;
+static int scratch_reserve(size_t need) {
+    if (need > g_tn_bytes) {
+        if (g_tn_scratch) cudaFree(g_tn_scratch);
+        g_tn_scratch = nullptr; g_tn_bytes = 0;
+        CK(cudaMalloc(&g_tn_scratch, need));
+        g_tn_bytes = need;
+    }
+    return ROMHC_OK;
+}
+
+// Split-K form for few output tiles and a long contraction (M, Nn <= a few thousand, Kd ~ 10^5): enough K ranges to
+// put ~2 CTAs on every SM, partials in scratch, deterministic reduction.
+template <int BM, int BN, int WM, int WN, int STAGES, int MINB>
+static int launch_gemm_nt_splitk(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                                 int64_t M, int64_t Nn, int64_t Kd, int nsplit, cudaStream_t st) {
+    auto kern = k_gemm_nt<BM, BN, WM, WN, STAGES, 16, MINB, true>;
+    const size_t sm = size_t(STAGES) * (BM + BN) * GK_PITCH * 8;
+    static bool configured = false;
+    if (!configured) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
+        configured = true;
+    }
+    const int64_t kc = ((Kd + nsplit - 1) / nsplit + GK_BK - 1) / GK_BK * GK_BK;
+    nsplit = int((Kd + kc - 1) / kc);
+    if (int rc = scratch_reserve(size_t(nsplit) * M * Nn * 8)) return rc;
+    const int64_t tmn = (M + BM - 1) / BM, tnn = (Nn + BN - 1) / BN;
+    ++g_launches; kern<<<dim3((unsigned)(tmn * tnn), (unsigned)nsplit), 256, sm, st>>>(A, lda, B, ldb, (double*)g_tn_scratch, Nn, M, Nn,
+                                                                                   Kd, int(kc), int(tnn));
+    CK(cudaGetLastError());
+    ++g_launches; k_gemm_tn_reduce<<<dim3((unsigned)((Nn + 255) / 256), (unsigned)M), 256, 0, st>>>((double*)g_tn_scratch, nsplit, int(M),
+                                                                                       Nn, C, ldc);
+    CK(cudaGetLastError());
+    return ROMHC_OK;
+}
+
 int gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M, int64_t Nn,
             int64_t Kd, int symmetric, cudaStream_t st) {
     if (M <= 0 || Nn <= 0) return ROMHC_OK;
-    if (symmetric && (M != Nn)) { set_error("gemm_nt: symmetric needs M == N"); return ROMHC_ERR_ARG; }
     const bool al16 = (lda % 2 == 0) && (ldb % 2 == 0) && ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0);
+    if (symmetric == 2) {          // caller allows split-K (never symmetric); fall through when it would not help
+        symmetric = 0;
+        const bool skinny = Nn <= 32;
+        const int64_t tiles = ((M + 127) / 128) * (skinny ? 1 : (Nn + 63) / 64);
+        const int64_t want = (2 * 148 + tiles - 1) / tiles, cap = Kd / 2048;
+        const int nsplit = int(std::min<int64_t>(std::min<int64_t>(want, cap), 4096));
+        if (al16 && nsplit >= 2 && M <= 65535)
+            return skinny ? launch_gemm_nt_splitk<128, 32, 8, 1, 4, 1>(A, lda, B, ldb, C, ldc, M, Nn, Kd, nsplit, st)
+                          : launch_gemm_nt_splitk<128, 64, 4, 2, 3, 2>(A, lda, B, ldb, C, ldc, M, Nn, Kd, nsplit, st);
+    }
+    if (symmetric && (M != Nn)) { set_error("gemm_nt: symmetric needs M == N"); return ROMHC_ERR_ARG; }
     int rc;
     if (Nn <= 32 && !symmetric) {
         rc = al16 ? launch_gemm_nt<128, 32, 8, 1, 4, 16>(A, lda, B, ldb, C, ldc, M, Nn, Kd, 0, st)
@@ -209,6 +269,11 @@ int gemm_nn(const double* A, int64_t lda, const double* B, int64_t ldb, double* 
     if (M <= 0 || Nn <= 0) return ROMHC_OK;
     if (Kd > 2048) { set_error("gemm_nn: contraction dim %lld too large for this kernel", (long long)Kd); return ROMHC_ERR_ARG; }
     const int64_t rows_blocks = (M + NN_ROWS - 1) / NN_ROWS;
+    static size_t smem_configured = 48 * 1024;      // Kd > 768 (Krylov bases of krylov_pca) needs the opt-in window
+    if (size_t(NN_ROWS) * Kd * 8 > smem_configured) {
+        CK(cudaFuncSetAttribute(k_gemm_nn, cudaFuncAttributeMaxDynamicSharedMemorySize, NN_ROWS * 2048 * 8));
+        smem_configured = size_t(NN_ROWS) * 2048 * 8;
+    }
     for (int64_t b0 = 0; b0 < rows_blocks; b0 += 65535) {
         const int nb = int(std::min<int64_t>(65535, rows_blocks - b0));
         ++g_launches; k_gemm_nn<<<dim3((unsigned)((Nn + 255) / 256), nb), 256, size_t(NN_ROWS) * Kd * 8, st>>>(
@@ -254,20 +319,12 @@ __global__ void k_gemm_tn_reduce(const double* __restrict__ part, int nchunks, i
     for (int c = 0; c < nchunks; ++c) s += part[(int64_t(c) * Mm + m) * Nn + col];
     C[int64_t(m) * ldc + col] = s;
 }
-static void* g_tn_scratch = nullptr;
-static size_t g_tn_bytes = 0;
 int gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M, int64_t Nn,
             int64_t Kd, cudaStream_t st) {
     if (M <= 0 || Nn <= 0) return ROMHC_OK;
     if (M > TN_MAXM) { set_error("gemm_tn: M = %lld > %d", (long long)M, TN_MAXM); return ROMHC_ERR_ARG; }
     const int nch = int((Kd + TN_CHUNK - 1) / TN_CHUNK);
-    const size_t need = size_t(nch) * M * Nn * 8;
-    if (need > g_tn_bytes) {
-        if (g_tn_scratch) cudaFree(g_tn_scratch);
-        g_tn_scratch = nullptr; g_tn_bytes = 0;
-        CK(cudaMalloc(&g_tn_scratch, need));
-        g_tn_bytes = need;
-    }
+    if (int rc = scratch_reserve(size_t(nch) * M * Nn * 8)) return rc;
     ++g_launches; k_gemm_tn_partial<<<dim3((unsigned)((Nn + 255) / 256), nch), 256, 0, st>>>(A, lda, B, ldb, (double*)g_tn_scratch,
                                                                                  int(M), Nn, Kd);
     ++g_launches; k_gemm_tn_reduce<<<dim3((unsigned)((Nn + 255) / 256), (unsigned)M), 256, 0, st>>>((double*)g_tn_scratch, nch, int(M),
@@ -301,13 +358,7 @@ __global__ void k_center(double* __restrict__ X, int64_t ld, int64_t K, int64_t 
 int column_mean(const double* X, int64_t ld, int64_t K, int64_t D, double* mean, cudaStream_t st) {
     const int rows_per = 128;
     const int np = int((K + rows_per - 1) / rows_per);
-    const size_t need = size_t(np) * D * 8;
-    if (need > g_tn_bytes) {
-        if (g_tn_scratch) cudaFree(g_tn_scratch);
-        g_tn_scratch = nullptr; g_tn_bytes = 0;
-        CK(cudaMalloc(&g_tn_scratch, need));
-        g_tn_bytes = need;
-    }
+    if (int rc = scratch_reserve(size_t(np) * D * 8)) return rc;
     ++g_launches; k_colsum_partial<<<dim3((unsigned)((D + 255) / 256), np), 256, 0, st>>>(X, ld, K, D, (double*)g_tn_scratch, rows_per);
     ++g_launches; k_colsum_final<<<(unsigned)((D + 255) / 256), 256, 0, st>>>((double*)g_tn_scratch, np, D, 1.0 / double(K), mean);
     CK(cudaGetLastError());

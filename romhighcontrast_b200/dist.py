@@ -10,7 +10,8 @@ no data-path collective is needed.  Only two stages exchange data:
   * POD:     one all_to_all that turns the K-sharded snapshot matrix into a D-sharded one (full columns local, so
              the column mean needs no further exchange), a local centred SYRK (fp64 DMMA) over the D slice, one
              all_reduce of the K x K partial Gram matrices, a replicated small eigensolve and an all_gather of the
-             (n, D / G) back-projected component slices.
+             (n, D / G) back-projected component slices.  For K ~ 10^5 (configs[4]) the Gram-free route
+             (method="krylov") replaces all of that by one (b, Dp) all_reduce per block-Lanczos step.
 
 All collective helpers work on CPU tensors with the gloo backend as well; tests/test_dist_cpu.py runs them with
 world_size 2 on the host.
@@ -148,8 +149,20 @@ def _all_gather_uneven(parts, t_local):
 # --------------------------------------------------------------------------------------------------------------
 # sharded POD and greedy on top of the device engine
 # --------------------------------------------------------------------------------------------------------------
-def distributed_pca(eng, X_local_pad: torch.Tensor, n: int, counts=None, timings=None):
-    """PCA(n) of the K-sharded padded snapshots; returns (components (n, Dp), singular values (n,)) on every rank."""
+def distributed_pca(eng, X_local_pad: torch.Tensor, n: int, counts=None, timings=None, method="gram"):
+    """PCA(n) of the K-sharded padded snapshots; returns (components (n, Dp), singular values (n,)) on every rank.
+
+    method="gram": all_to_all + partial SYRK + all_reduce of the K x K Gram (the north-star's fp64 Gram GEMM; right for
+    K ~ 10^4).  method="krylov": Gram-free block Lanczos on the K-sharded rows as they are (pod.krylov_pca): one
+    all_reduce of (b, Dp) doubles per step, no all_to_all, no K x K matrix -- the route for K ~ 10^5 (configs[4]: the
+    Gram alone would be 80 GB and 2.6e15 flop)."""
+    if method == "krylov":
+        from .pod import krylov_pca
+        K_total = None if counts is None else int(sum(counts))
+        comps, sig, _ = krylov_pca(eng, X_local_pad, n, K_total=K_total, stats=timings)
+        return comps, sig
+    if method != "gram":
+        raise ValueError(f"distributed_pca: unknown method {method!r}")
     from .pod import top_eigenpairs
     Dp = X_local_pad.shape[1]
     ev = (lambda: torch.cuda.Event(enable_timing=True)) if X_local_pad.is_cuda else None

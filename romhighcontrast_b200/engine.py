@@ -184,12 +184,14 @@ class Engine:
         return Cc
 
     # ---- dense helpers -------------------------------------------------------------------------------------
-    def gemm_nt(self, A, B, symmetric=False):
+    def gemm_nt(self, A, B, symmetric=False, splitk=False):
+        """A B^T on the fp64 tensor cores.  splitk: small output with a long contraction (Krylov-basis products):
+        the contraction is split over enough CTAs to fill the GPU, partial sums reduced in a fixed order."""
         M, Kd = A.shape
         Nn = B.shape[0]
         out = self.empty(M, Nn)
         _lib.check(self.lib.romhc_gemm_nt(_ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(out), Nn, M, Nn, Kd,
-                                          1 if symmetric else 0, self.stream()))
+                                          1 if symmetric else (2 if splitk else 0), self.stream()))
         return out
 
     def gemm_nn(self, A, B):

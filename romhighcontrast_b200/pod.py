@@ -79,3 +79,131 @@ def pca_components(eng, X_pad, n, center_in_place=False):
     sign = torch.sign(comps[torch.arange(comps.shape[0], device=comps.device), idx])
     sign = torch.where(sign == 0, torch.ones_like(sign), sign)
     return comps * sign[:, None], sig, mean
+
+
+def _orthonormal_rows(eng, W, thr):
+    """Orthonormal rows spanning the directions of W (b, Dp) whose singular value exceeds thr (None if there are none).
+
+    Symmetric orthonormalisation through the b x b Gram matrix (split-K DMMA product + host eigh): unlike an unpivoted
+    QR it is rank revealing, so exhausted Krylov directions (rounding noise) are dropped instead of being normalised
+    into vectors that are no longer orthogonal to the basis."""
+    Gs = eng.gemm_nt(W, W, splitk=True).cpu().numpy()
+    ev, E = np.linalg.eigh(0.5 * (Gs + Gs.T))
+    keep = ev > thr * thr
+    if not keep.any():
+        return None
+    Tm = np.ascontiguousarray((E[:, keep] / np.sqrt(ev[keep])).T[::-1])        # strongest direction first
+    return eng.gemm_nn(torch.as_tensor(Tm, device=W.device), W)
+
+
+def krylov_pca(eng, X_local_pad, n, K_total=None, center_in_place=False, extra=12, tol=1e-13, max_dim=960, seed=0,
+               stats=None):
+    """PCA(n) without the K x K Gram matrix: block Lanczos on S = Xc^T Xc (D x D), applied as two tall-skinny products.
+
+    For K >> 10^4 (BASELINE configs[4]: K = 100 000, D = 261 121) the Gram route costs K^2 D = 2.6e15 flop, an
+    all_to_all of the whole snapshot set (209 GB) and an 80 GB matrix; the n = 20 leading pairs need none of it.
+    Every Lanczos step applies S to a block W (b, Dp), b = n + extra <= 32, as
+
+        Y_r = X_r W^T          (K_r, b)   gemm_nt, fp64 DMMA, X_r streamed once
+        Z   = sum_r Y_r^T X_r  (b, Dp)    gemm_tn, X_r streamed once more; ONE all_reduce of b * Dp doubles (67 MB)
+
+    on the K-sharded snapshots exactly as the solver left them (no transpose, no Gram): 4 K D b flop and two passes
+    over X per step, a few dozen steps.  The Krylov basis (rows of length Dp) and all orthogonalisation work are
+    replicated -- every rank performs the same arithmetic on the same all-reduced data, and rank 0's stop decision is
+    broadcast -- so the Ritz vectors are the principal components themselves on every rank: no back-projection, no
+    division by sigma.  The products against the basis have a tiny output and a contraction of length Dp: they run
+    on the split-K form of the DMMA kernel.  Same conventions as pca_components (sklearn PCA, ReducedBasis.py:196):
+    Euclidean, mean-centred with the GLOBAL column mean, singular values sqrt(lambda),
+    svd_flip(u_based_decision=False) signs.
+
+    X_local_pad (K_r, Dp): this rank's rows (K_r may be 0 on some ranks as long as K_total > 0).
+    Returns (components (n, Dp), singular_values (n,), mean (Dp,)) on every rank."""
+    from . import dist as rd
+    w = rd.world()
+    Kr, Dp = X_local_pad.shape
+    dev = X_local_pad.device
+    if K_total is None:
+        kt = torch.tensor([Kr], dtype=torch.int64, device=dev)
+        if w > 1:
+            torch.distributed.all_reduce(kt)
+        K_total = int(kt.item())
+    if K_total <= 0:
+        raise ValueError("krylov_pca: empty snapshot set")
+    X = X_local_pad if center_in_place else X_local_pad.clone()
+    colsum = eng.column_mean(X) * float(Kr) if Kr else torch.zeros(Dp, dtype=torch.float64, device=dev)
+    if w > 1:
+        torch.distributed.all_reduce(colsum)
+    mean = colsum / float(K_total)
+    if Kr:
+        eng.center_rows_(X, mean)
+    n = int(min(n, K_total, Dp))
+    if n <= 0:
+        return (torch.empty(0, Dp, dtype=torch.float64, device=dev), torch.empty(0, dtype=torch.float64, device=dev), mean)
+    b = int(min(32, Dp, n + extra))
+    max_dim = int(min(max_dim, Dp))
+
+    def apply_S(W):                                           # (b', Dp) -> (b', Dp), identical on every rank
+        if Kr:
+            Zw = eng.gemm_tn(eng.gemm_nt(X, W), X)
+        else:
+            Zw = torch.zeros_like(W)
+        if w > 1:
+            torch.distributed.all_reduce(Zw)
+        return Zw
+
+    def ritz(Vd, Zd):
+        T = eng.gemm_nt(Vd, Zd, splitk=True).cpu().numpy()    # (dim, dim) projected operator
+        wv, S = np.linalg.eigh(0.5 * (T + T.T))
+        order = np.argsort(wv)[::-1][:n]
+        lam = torch.as_tensor(np.ascontiguousarray(wv[order]), device=dev)
+        St = torch.as_tensor(np.ascontiguousarray(S[:, order].T), device=dev)      # (n, dim)
+        comps = eng.gemm_nn(St, Vd)
+        res = torch.linalg.vector_norm(eng.gemm_nn(St, Zd) - comps * lam[:, None], dim=1)
+        return lam, comps, float(res.max())
+
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    Q = _orthonormal_rows(eng, torch.randn(b, Dp, dtype=torch.float64, device=dev, generator=gen), 0.0)
+    V = torch.empty(max_dim, Dp, dtype=torch.float64, device=dev)      # Krylov basis, rows
+    Z = torch.empty(max_dim, Dp, dtype=torch.float64, device=dev)      # S applied to the basis rows
+    dim = steps = 0
+    lam = comps = None
+    scale = 0.0                                               # running estimate of lambda_1
+    flag = torch.zeros(1, dtype=torch.int64, device=dev)
+    while True:
+        bq = Q.shape[0]
+        V[dim:dim + bq] = Q
+        Zj = apply_S(Q)
+        Z[dim:dim + bq] = Zj
+        dim += bq
+        steps += 1
+        Vd, Zd = V[:dim], Z[:dim]
+        scale = max(scale, float(torch.linalg.vector_norm(Zj, dim=1).max()))
+        # next block: S Q orthogonalised against the whole basis (block Gram-Schmidt, repeated), directions below the
+        # requested accuracy dropped
+        Qn = None
+        if dim + 1 <= max_dim and scale > 0.0:
+            Wn = Zj
+            for sweep in range(3):
+                for _ in range(2):
+                    Wn = Wn - eng.gemm_nn(eng.gemm_nt(Vd, Wn, splitk=True).T.contiguous(), Vd)
+                Wn = _orthonormal_rows(eng, Wn, 0.01 * tol * scale if sweep == 0 else 0.5)
+                if Wn is None:
+                    break
+            if Wn is not None:
+                Qn = Wn[:max_dim - dim].contiguous()
+        last = Qn is None
+        if (steps >= 2 and steps % 2 == 0) or last:
+            lam, comps, res = ritz(Vd, Zd)
+            flag[0] = int(last or res <= tol * max(float(lam[0]), 1e-300))
+            if w > 1:
+                torch.distributed.broadcast(flag, src=0)
+            if int(flag.item()):
+                break
+        Q = Qn
+    if stats is not None:
+        stats.update(steps=steps, krylov_dim=dim, block=b, residual=res)
+    sig = torch.sqrt(torch.clamp(lam, min=0.0))
+    idx = comps.abs().argmax(dim=1)
+    sign = torch.sign(comps[torch.arange(comps.shape[0], device=dev), idx])
+    sign = torch.where(sign == 0, torch.ones_like(sign), sign)
+    return (comps * sign[:, None]).contiguous(), sig, mean

@@ -72,6 +72,28 @@ def _worker(rank, world, port, tmp):
         assert torch.allclose(G, full @ full.T)
         back = rd.all_gather_cols(Xs[:3].contiguous(), Dp)
         assert torch.equal(back, full[:3])
+        # Gram-free POD on K-sharded rows (uneven shards): both ranks get the SVD of the full centred matrix
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from host_engine import HostEngine
+        rng = np.random.default_rng(5)
+        Kt, Dp, n = 130, 96, 6
+        Xf = (rng.standard_normal((Kt, 40)) * 0.7 ** np.arange(40)) @ rng.standard_normal((40, Dp)) + rng.standard_normal(Dp)
+        cut = 37
+        mine = torch.as_tensor(Xf[:cut].copy() if rank == 0 else Xf[cut:].copy())
+        comps, sig = rd.distributed_pca(HostEngine(), mine, n, counts=[cut, Kt - cut], method="krylov")
+        Xc = Xf - Xf.mean(axis=0)
+        _, s_ref, vt = np.linalg.svd(Xc, full_matrices=False)
+        np.testing.assert_allclose(sig.numpy(), s_ref[:n], rtol=1e-9)
+        vt = vt[:n] * np.sign(vt[np.arange(n), np.abs(vt[:n]).argmax(axis=1)])[:, None]
+        assert np.abs(comps.numpy() - vt).max() < 1e-7
+        both = [torch.empty_like(comps) for _ in range(world)]
+        dist.all_gather(both, comps)
+        assert torch.equal(both[0], both[1])                      # replicated Lanczos: bit-identical on all ranks
+        # a rank with no rows takes part in the collectives only
+        empty = torch.as_tensor(Xf if rank == 0 else np.empty((0, Dp)))
+        comps2, sig2 = rd.distributed_pca(HostEngine(), empty, n, counts=[Kt, 0], method="krylov")
+        np.testing.assert_allclose(sig2.numpy(), s_ref[:n], rtol=1e-9)
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
