@@ -84,20 +84,22 @@ def pca_components(eng, X_pad, n, center_in_place=False):
 def _orthonormal_rows(eng, W, thr):
     """Orthonormal rows spanning the directions of W (b, Dp) whose singular value exceeds thr (None if there are none).
 
-    Symmetric orthonormalisation through the b x b Gram matrix (split-K DMMA product + host eigh): unlike an unpivoted
-    QR it is rank revealing, so exhausted Krylov directions (rounding noise) are dropped instead of being normalised
-    into vectors that are no longer orthogonal to the basis."""
-    Gs = eng.gemm_nt(W, W, splitk=True).cpu().numpy()
-    ev, E = np.linalg.eigh(0.5 * (Gs + Gs.T))
-    keep = ev > thr * thr
+    Householder QR of W^T (stable whatever the conditioning) followed by the SVD of the small R factor on the host, so
+    the step is rank revealing: exhausted Krylov directions (rounding noise) are dropped instead of being normalised
+    into vectors that are no longer orthogonal to the basis, while directions that are merely small -- the block's
+    singular values span many decades once the leading modes have converged -- are kept at full relative accuracy
+    (a b x b Gram matrix would lose everything below sqrt(eps) of the largest one)."""
+    Qf, R = torch.linalg.qr(W.T)                              # (Dp, b), (b, b)
+    Ur, sv, _ = np.linalg.svd(R.cpu().numpy())
+    keep = sv > thr
     if not keep.any():
         return None
-    Tm = np.ascontiguousarray((E[:, keep] / np.sqrt(ev[keep])).T[::-1])        # strongest direction first
-    return eng.gemm_nn(torch.as_tensor(Tm, device=W.device), W)
+    Tm = torch.as_tensor(np.array(Ur[:, keep].T, order="C", copy=True), device=W.device)       # strongest first
+    return eng.gemm_nn(Tm, Qf.T.contiguous())
 
 
-def krylov_pca(eng, X_local_pad, n, K_total=None, center_in_place=False, extra=12, tol=1e-13, max_dim=960, seed=0,
-               stats=None):
+def krylov_pca(eng, X_local_pad, n, K_total=None, center_in_place=False, extra=12, rtol=1e-10, floor=2e-14, max_dim=960,
+               seed=0, stats=None):
     """PCA(n) without the K x K Gram matrix: block Lanczos on S = Xc^T Xc (D x D), applied as two tall-skinny products.
 
     For K >> 10^4 (BASELINE configs[4]: K = 100 000, D = 261 121) the Gram route costs K^2 D = 2.6e15 flop, an
@@ -115,6 +117,11 @@ def krylov_pca(eng, X_local_pad, n, K_total=None, center_in_place=False, extra=1
     on the split-K form of the DMMA kernel.  Same conventions as pca_components (sklearn PCA, ReducedBasis.py:196):
     Euclidean, mean-centred with the GLOBAL column mean, singular values sqrt(lambda),
     svd_flip(u_based_decision=False) signs.
+
+    Stops when every wanted Ritz pair has ||S v_i - lam_i v_i|| <= max(rtol * lam_i, floor * lam_1): the residual bounds
+    the eigenvalue error, so sigma_i is accurate to rtol / 2 relative (1e-9 is the parity bar) down to the modes whose
+    lam_i / lam_1 reaches the rounding level of S itself (floor); also when the residuals stop improving below
+    1e-11 lam_1, or the basis reaches max_dim rows.
 
     X_local_pad (K_r, Dp): this rank's rows (K_r may be 0 on some ranks as long as K_total > 0).
     Returns (components (n, Dp), singular_values (n,), mean (Dp,)) on every rank."""
@@ -159,15 +166,24 @@ def krylov_pca(eng, X_local_pad, n, K_total=None, center_in_place=False, extra=1
         St = torch.as_tensor(np.ascontiguousarray(S[:, order].T), device=dev)      # (n, dim)
         comps = eng.gemm_nn(St, Vd)
         res = torch.linalg.vector_norm(eng.gemm_nn(St, Zd) - comps * lam[:, None], dim=1)
-        return lam, comps, float(res.max())
+        lam1 = max(float(lam[0]), 1e-300)
+        excess = float((res / torch.clamp(torch.maximum(rtol * lam, torch.full_like(lam, floor * lam1)), min=1e-300)).max())
+        return lam, comps, float(res.max()), excess, lam1
 
+    # start block: S applied to a random block.  It lies in the row space of Xc, so slots that are zero in every
+    # snapshot (the padded grid's Dirichlet / alignment slots) are exactly zero in every basis row and component.
     gen = torch.Generator(device=dev).manual_seed(seed)
-    Q = _orthonormal_rows(eng, torch.randn(b, Dp, dtype=torch.float64, device=dev, generator=gen), 0.0)
+    R0 = torch.randn(b, Dp, dtype=torch.float64, device=dev, generator=gen)
+    S0 = apply_S(R0)
+    Q = _orthonormal_rows(eng, S0, 1e-12 * float(torch.linalg.vector_norm(S0, dim=1).max()))
+    if Q is None:                                             # Xc == 0: every singular value is zero
+        Q = _orthonormal_rows(eng, R0, 0.0)
     V = torch.empty(max_dim, Dp, dtype=torch.float64, device=dev)      # Krylov basis, rows
     Z = torch.empty(max_dim, Dp, dtype=torch.float64, device=dev)      # S applied to the basis rows
     dim = steps = 0
     lam = comps = None
     scale = 0.0                                               # running estimate of lambda_1
+    prev_res = float("inf")
     flag = torch.zeros(1, dtype=torch.int64, device=dev)
     while True:
         bq = Q.shape[0]
@@ -186,15 +202,17 @@ def krylov_pca(eng, X_local_pad, n, K_total=None, center_in_place=False, extra=1
             for sweep in range(3):
                 for _ in range(2):
                     Wn = Wn - eng.gemm_nn(eng.gemm_nt(Vd, Wn, splitk=True).T.contiguous(), Vd)
-                Wn = _orthonormal_rows(eng, Wn, 0.01 * tol * scale if sweep == 0 else 0.5)
+                Wn = _orthonormal_rows(eng, Wn, 1e-15 * scale if sweep == 0 else 0.5)
                 if Wn is None:
                     break
             if Wn is not None:
                 Qn = Wn[:max_dim - dim].contiguous()
         last = Qn is None
-        if (steps >= 2 and steps % 2 == 0) or last:
-            lam, comps, res = ritz(Vd, Zd)
-            flag[0] = int(last or res <= tol * max(float(lam[0]), 1e-300))
+        if (steps >= 2 and (dim <= 256 or steps % 2 == 0)) or last:
+            lam, comps, res, excess, lam1 = ritz(Vd, Zd)
+            stalled = res <= 1e-11 * lam1 and res > 0.5 * prev_res
+            prev_res = res
+            flag[0] = int(last or excess <= 1.0 or stalled)
             if w > 1:
                 torch.distributed.broadcast(flag, src=0)
             if int(flag.item()):
@@ -206,4 +224,9 @@ def krylov_pca(eng, X_local_pad, n, K_total=None, center_in_place=False, extra=1
     idx = comps.abs().argmax(dim=1)
     sign = torch.sign(comps[torch.arange(comps.shape[0], device=dev), idx])
     sign = torch.where(sign == 0, torch.ones_like(sign), sign)
-    return (comps * sign[:, None]).contiguous(), sig, mean
+    comps = comps * sign[:, None]
+    if comps.shape[0] < n:        # rank of Xc below n: the remaining singular values are zero; zero rows, as the Gram
+        pad = n - comps.shape[0]  # route's V^T Xc gives for sigma = 0
+        comps = torch.cat((comps, torch.zeros(pad, Dp, dtype=torch.float64, device=dev)))
+        sig = torch.cat((sig, torch.zeros(pad, dtype=torch.float64, device=dev)))
+    return comps.contiguous(), sig, mean

@@ -80,7 +80,7 @@ def test_krylov_pca_matches_gram_route_and_oracle(torch_mod):
         if so[i] / so[0] > 1e-6:
             assert np.abs(c[i] - co[i]).max() < 1e-7, i
     np.testing.assert_allclose(c @ c.T, np.eye(n), atol=1e-12)
-    assert stats["krylov_dim"] <= 960 and stats["residual"] <= 1e-13 * float(sig[0]) ** 2
+    assert stats["krylov_dim"] <= 960 and stats["residual"] <= 1e-10 * float(sig[0]) ** 2
     # the padded slots of every component stay exactly zero (the layout's Dirichlet convention)
     assert float((eng.pad(eng.unpad(comps)) - comps).abs().max()) == 0.0
     # a K-split of the same rows through the K_total argument (what each rank of a sharded run sees, minus the
