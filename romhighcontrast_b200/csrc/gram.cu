@@ -210,11 +210,19 @@ int gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* 
         symmetric = 0;
         const bool skinny = Nn <= 32;
         const int64_t tiles = ((M + 127) / 128) * (skinny ? 1 : (Nn + 63) / 64);
-        const int64_t want = (2 * 148 + tiles - 1) / tiles, cap = Kd / 2048;
-        const int nsplit = int(std::min<int64_t>(std::min<int64_t>(want, cap), 4096));
+        // number of contraction ranges: fill 1..4 waves of 2 CTAs per SM as completely as possible, >= 2048 indices each
+        const int64_t cap = std::min<int64_t>(Kd / 2048, 4096), slots = 2 * 148;
+        int64_t nsplit = 1;
+        double best = 0.0;
+        for (int64_t w = 1; w <= 4; ++w) {
+            const int64_t ns = std::max<int64_t>(1, std::min<int64_t>(slots * w / tiles, cap));
+            const int64_t waves = (tiles * ns + slots - 1) / slots;
+            const double eff = double(tiles * ns) / double(slots * waves);
+            if (eff > best + 0.02) { best = eff; nsplit = ns; }
+        }
         if (al16 && nsplit >= 2 && M <= 65535)
-            return skinny ? launch_gemm_nt_splitk<128, 32, 8, 1, 4, 1>(A, lda, B, ldb, C, ldc, M, Nn, Kd, nsplit, st)
-                          : launch_gemm_nt_splitk<128, 64, 4, 2, 3, 2>(A, lda, B, ldb, C, ldc, M, Nn, Kd, nsplit, st);
+            return skinny ? launch_gemm_nt_splitk<128, 32, 8, 1, 4, 1>(A, lda, B, ldb, C, ldc, M, Nn, Kd, int(nsplit), st)
+                          : launch_gemm_nt_splitk<128, 64, 4, 2, 3, 2>(A, lda, B, ldb, C, ldc, M, Nn, Kd, int(nsplit), st);
     }
     if (symmetric && (M != Nn)) { set_error("gemm_nt: symmetric needs M == N"); return ROMHC_ERR_ARG; }
     int rc;
@@ -319,10 +327,139 @@ __global__ void k_gemm_tn_reduce(const double* __restrict__ part, int nchunks, i
     for (int c = 0; c < nchunks; ++c) s += part[(int64_t(c) * Mm + m) * Nn + col];
     C[int64_t(m) * ldc + col] = s;
 }
+// ---- the same product on the fp64 tensor cores -------------------------------------------------------------------------
+// C[m][n] = sum_k A[k][m] B[k][n]: the contraction runs over ROWS of both operands (snapshots), so a stage is TNM_BK
+// rows of B (each a contiguous 2 KB run of 256 columns: long coalesced reads, unlike the 128-byte row pieces of the NT
+// form) plus the matching TNM_BK x 32 block of A, staged by cp.async in a 3-deep ring.  8 warps, each owns all MT m-tiles
+// of 32 columns (4 n-tiles): 4 MT DMMA per (MT + 4) shared loads per k-step of 4.  Shared row pitches = 4 mod 16 doubles:
+// the 16 lanes of a half-warp (k = t4, index = g) hit 16 distinct 8-byte banks.  blockIdx.y = range of the contraction;
+// partials in scratch, summed in a fixed order by k_gemm_tn_reduce.  Two CTAs per SM (2 x 111 KB of shared memory).
+#define TNM_BK 16
+#define TNM_BN 256
+#define TNM_PA 36
+#define TNM_PB 260
+#define TNM_STAGES 3
+template <int MT>
+__global__ void __launch_bounds__(256, 2)
+k_gemm_tn_mma(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb, double* __restrict__ C,
+              int64_t ldc, int Mm, int64_t Nn, int64_t Kd, int64_t kc) {
+    extern __shared__ __align__(16) double smt[];
+    double* sA = smt;                                              // STAGES x BK x PA
+    double* sB = smt + size_t(TNM_STAGES) * TNM_BK * TNM_PA;       // STAGES x BK x PB
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int64_t n0 = int64_t(blockIdx.x) * TNM_BN;
+    const int64_t kbeg = int64_t(blockIdx.y) * kc;
+    const int64_t kend = (kbeg + kc < Kd) ? kbeg + kc : Kd;
+    C += int64_t(blockIdx.y) * Mm * ldc;
+    double acc[MT][4][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int nk = int((kend - kbeg + TNM_BK - 1) / TNM_BK);
+    auto load_stage = [&](int stage, int kb) {
+        const int64_t k0 = kbeg + int64_t(kb) * TNM_BK;
+        double* dA = sA + size_t(stage) * TNM_BK * TNM_PA;
+        double* dB = sB + size_t(stage) * TNM_BK * TNM_PB;
+        for (int v = tid; v < TNM_BK * (TNM_BN / 2); v += 256) {   // 16-byte vectors of the B rows
+            const int r = v / (TNM_BN / 2), c = (v % (TNM_BN / 2)) * 2;
+            const int64_t gr = k0 + r, gc = n0 + c;
+            int bytes = 0;
+            if (gr < kend && gc < Nn) bytes = (Nn - gc < 2) ? 8 : 16;
+            const double* src = B + (gr < kend ? gr : kbeg) * ldb + (gc < Nn ? gc : 0);
+            cp_async16(dB + r * TNM_PB + c, src, bytes);
+        }
+        for (int v = tid; v < TNM_BK * MT * 8; v += 256) {          // A block, 8 bytes at a time (any lda)
+            const int r = v / (MT * 8), c = v % (MT * 8);
+            const int64_t gr = k0 + r;
+            const bool ok = gr < kend && c < Mm;
+            const double* src = A + (ok ? gr * lda + c : kbeg * lda);
+            cp_async8(dA + r * TNM_PA + c, src, ok ? 8 : 0);
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < TNM_STAGES - 1; ++s) {
+        if (s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int kb = 0; kb < nk; ++kb) {
+        cp_async_wait<TNM_STAGES - 2>();
+        __syncthreads();
+        const int nxt = kb + TNM_STAGES - 1;
+        if (nxt < nk) load_stage(nxt % TNM_STAGES, nxt);
+        cp_async_commit();
+        const double* cA = sA + size_t(kb % TNM_STAGES) * TNM_BK * TNM_PA + t4 * TNM_PA + g;
+        const double* cB = sB + size_t(kb % TNM_STAGES) * TNM_BK * TNM_PB + t4 * TNM_PB + warp * 32 + g;
+#pragma unroll
+        for (int kk = 0; kk < TNM_BK; kk += 4) {
+            double a[MT], b[4];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) a[i] = cA[kk * TNM_PA + i * 8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = cB[kk * TNM_PB + j * 8];
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        const int row = i * 8 + g;
+        if (row >= Mm) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t col = n0 + warp * 32 + j * 8 + 2 * t4;
+            if (col < Nn) C[int64_t(row) * ldc + col] = acc[i][j][0];
+            if (col + 1 < Nn) C[int64_t(row) * ldc + col + 1] = acc[i][j][1];
+        }
+    }
+}
+
+template <int MT>
+static int launch_gemm_tn_mma(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M,
+                              int64_t Nn, int64_t Kd, cudaStream_t st) {
+    auto kern = k_gemm_tn_mma<MT>;
+    const size_t sm = size_t(TNM_STAGES) * TNM_BK * (TNM_PA + TNM_PB) * 8;
+    static bool configured = false;
+    if (!configured) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
+        configured = true;
+    }
+    const int64_t ntiles = (Nn + TNM_BN - 1) / TNM_BN;
+    int64_t nsplit = std::max<int64_t>(1, std::min<int64_t>((8 * 2 * 148 + ntiles - 1) / ntiles, Kd / 512));
+    nsplit = std::min<int64_t>(nsplit, 65535);
+    const int64_t kc = ((Kd + nsplit - 1) / nsplit + TNM_BK - 1) / TNM_BK * TNM_BK;
+    nsplit = (Kd + kc - 1) / kc;
+    if (nsplit == 1) {
+        ++g_launches; kern<<<dim3((unsigned)ntiles, 1), 256, sm, st>>>(A, lda, B, ldb, C, ldc, int(M), Nn, Kd, kc);
+        CK(cudaGetLastError());
+        return ROMHC_OK;
+    }
+    if (int rc = scratch_reserve(size_t(nsplit) * M * Nn * 8)) return rc;
+    ++g_launches; kern<<<dim3((unsigned)ntiles, (unsigned)nsplit), 256, sm, st>>>(A, lda, B, ldb, (double*)g_tn_scratch, Nn, int(M), Nn,
+                                                                               Kd, kc);
+    CK(cudaGetLastError());
+    ++g_launches; k_gemm_tn_reduce<<<dim3((unsigned)((Nn + 255) / 256), (unsigned)M), 256, 0, st>>>((double*)g_tn_scratch, int(nsplit),
+                                                                                       int(M), Nn, C, ldc);
+    CK(cudaGetLastError());
+    return ROMHC_OK;
+}
+
+int g_tn_variant = 1;       // 1: DMMA kernel (default, needs 16-byte aligned B rows); 0: the plain-FMA kernel above
 int gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M, int64_t Nn,
             int64_t Kd, cudaStream_t st) {
     if (M <= 0 || Nn <= 0) return ROMHC_OK;
     if (M > TN_MAXM) { set_error("gemm_tn: M = %lld > %d", (long long)M, TN_MAXM); return ROMHC_ERR_ARG; }
+    if (g_tn_variant == 1 && Kd > 0 && (ldb % 2 == 0) && ((uintptr_t)B % 16 == 0)) {
+        switch ((M + 7) / 8) {
+            case 1: return launch_gemm_tn_mma<1>(A, lda, B, ldb, C, ldc, M, Nn, Kd, st);
+            case 2: return launch_gemm_tn_mma<2>(A, lda, B, ldb, C, ldc, M, Nn, Kd, st);
+            case 3: return launch_gemm_tn_mma<3>(A, lda, B, ldb, C, ldc, M, Nn, Kd, st);
+            default: return launch_gemm_tn_mma<4>(A, lda, B, ldb, C, ldc, M, Nn, Kd, st);
+        }
+    }
     const int nch = int((Kd + TN_CHUNK - 1) / TN_CHUNK);
     if (int rc = scratch_reserve(size_t(nch) * M * Nn * 8)) return rc;
     ++g_launches; k_gemm_tn_partial<<<dim3((unsigned)((Nn + 255) / 256), nch), 256, 0, st>>>(A, lda, B, ldb, (double*)g_tn_scratch,

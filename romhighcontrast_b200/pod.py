@@ -81,21 +81,24 @@ def pca_components(eng, X_pad, n, center_in_place=False):
     return comps * sign[:, None], sig, mean
 
 
-def _orthonormal_rows(eng, W, thr):
+def _orthonormal_rows(eng, W, thr, passes=2):
     """Orthonormal rows spanning the directions of W (b, Dp) whose singular value exceeds thr (None if there are none).
 
-    Householder QR of W^T (stable whatever the conditioning) followed by the SVD of the small R factor on the host, so
-    the step is rank revealing: exhausted Krylov directions (rounding noise) are dropped instead of being normalised
-    into vectors that are no longer orthogonal to the basis, while directions that are merely small -- the block's
-    singular values span many decades once the leading modes have converged -- are kept at full relative accuracy
-    (a b x b Gram matrix would lose everything below sqrt(eps) of the largest one)."""
-    Qf, R = torch.linalg.qr(W.T)                              # (Dp, b), (b, b)
-    Ur, sv, _ = np.linalg.svd(R.cpu().numpy())
-    keep = sv > thr
-    if not keep.any():
-        return None
-    Tm = torch.as_tensor(np.array(Ur[:, keep].T, order="C", copy=True), device=W.device)       # strongest first
-    return eng.gemm_nn(Tm, Qf.T.contiguous())
+    Rank revealing and built from row combinations of W only, so slots that are zero in every row stay exactly zero:
+    R of a Householder QR of W^T (backward stable: singular values resolved down to eps * sigma_max, where a b x b Gram
+    matrix would lose everything below sqrt(eps)), SVD R = U S V^T on the host, rows (1 / s_i) v_i^T W for s_i > thr.
+    The division amplifies rounding by sigma_max / s_i, so a second pass on the now well-conditioned rows restores
+    orthonormality to machine precision; exhausted Krylov directions (rounding noise) are dropped instead of being
+    normalised into vectors that are no longer orthogonal to the basis."""
+    for p in range(passes):
+        R = torch.linalg.qr(W.T, mode="r")[1]                 # (b, b)
+        _, sv, Vt = np.linalg.svd(R.cpu().numpy())
+        keep = sv > (thr if p == 0 else 0.5)
+        if not keep.any():
+            return None
+        Tm = torch.as_tensor(np.array(Vt[keep] / sv[keep, None], order="C", copy=True), device=W.device)
+        W = eng.gemm_nn(Tm, W)
+    return W
 
 
 def krylov_pca(eng, X_local_pad, n, K_total=None, center_in_place=False, extra=12, rtol=1e-10, floor=2e-14, max_dim=960,
@@ -151,7 +154,7 @@ def krylov_pca(eng, X_local_pad, n, K_total=None, center_in_place=False, extra=1
 
     def apply_S(W):                                           # (b', Dp) -> (b', Dp), identical on every rank
         if Kr:
-            Zw = eng.gemm_tn(eng.gemm_nt(X, W), X)
+            Zw = eng.gemm_tn(eng.gemm_nt(X, W, splitk=True), X)
         else:
             Zw = torch.zeros_like(W)
         if w > 1:
@@ -199,10 +202,10 @@ def krylov_pca(eng, X_local_pad, n, K_total=None, center_in_place=False, extra=1
         Qn = None
         if dim + 1 <= max_dim and scale > 0.0:
             Wn = Zj
-            for sweep in range(3):
+            for sweep in range(2):
                 for _ in range(2):
                     Wn = Wn - eng.gemm_nn(eng.gemm_nt(Vd, Wn, splitk=True).T.contiguous(), Vd)
-                Wn = _orthonormal_rows(eng, Wn, 1e-15 * scale if sweep == 0 else 0.5)
+                Wn = _orthonormal_rows(eng, Wn, 1e-15 * scale if sweep == 0 else 0.5, passes=2 if sweep == 0 else 1)
                 if Wn is None:
                     break
             if Wn is not None:

@@ -40,9 +40,14 @@ def main():
     (ck, sk, _), ms_k = timed(lambda: krylov_pca(eng, X, n, stats=stats))
     (cg, sg, _), ms_g = timed(lambda: pca_components(eng, X, n))
     W = torch.randn(32, eng.Dp, dtype=torch.float64, device=eng.device)
-    _, ms_nt = timed(lambda: eng.gemm_nt(X, W), 3)
+    _, ms_nt_plain = timed(lambda: eng.gemm_nt(X, W), 3)
+    _, ms_nt = timed(lambda: eng.gemm_nt(X, W, splitk=True), 3)
+    _, ms_qr = timed(lambda: torch.linalg.qr(W.T, mode="r"), 3)
     Y = eng.gemm_nt(X, W)
     _, ms_tn = timed(lambda: eng.gemm_tn(Y, X), 3)
+    eng.set_option("tn_variant", 0)
+    _, ms_tn_fma = timed(lambda: eng.gemm_tn(Y, X), 3)
+    eng.set_option("tn_variant", 1)
     V = torch.randn(480, eng.Dp, dtype=torch.float64, device=eng.device)
     _, ms_gs = timed(lambda: eng.gemm_nt(V, W, splitk=True), 3)
     _, ms_gs_plain = timed(lambda: eng.gemm_nt(V, W), 3)
@@ -54,7 +59,10 @@ def main():
     line = {"K": K, "n": n, "D": eng.D, "krylov_ms": ms_k, "gram_route_ms": ms_g, "krylov": stats,
             "sv_rel_diff": float(((sk - sg).abs() / sg).max()), "comp_abs_diff": float((ck - cg).abs().max()),
             "pad_slots_exact_zero": float((eng.pad(eng.unpad(ck)) - ck).abs().max()) == 0.0,
-            "apply": {"X_Wt_ms": ms_nt, "Yt_X_ms": ms_tn, "X_GBps_nt": bytes_X / ms_nt / 1e6, "X_GBps_tn": bytes_X / ms_tn / 1e6},
+            "qr_r_only_ms": ms_qr,
+            "apply": {"X_Wt_ms": ms_nt, "X_Wt_plain_ms": ms_nt_plain, "Yt_X_ms": ms_tn, "Yt_X_fma_kernel_ms": ms_tn_fma, "X_GBps_nt": bytes_X / ms_nt / 1e6,
+                      "X_GBps_tn": bytes_X / ms_tn / 1e6, "TFLOPs_nt": 2e-9 * K * eng.Dp * 32 / ms_nt,
+                      "TFLOPs_tn": 2e-9 * K * eng.Dp * 32 / ms_tn},
             "basis_products_dim480": {"V_Wt_splitk_ms": ms_gs, "V_Wt_plain_ms": ms_gs_plain, "C_V_ms": ms_nn,
                                       "V_Vt_splitk_ms": ms_T, "V_Vt_plain_ms": ms_T_plain}}
     print(json.dumps(line))

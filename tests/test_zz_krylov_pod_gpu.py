@@ -56,6 +56,31 @@ def test_gemm_nn_long_contraction(torch_mod, M, Kd, N):
     assert float((eng.gemm_nn(A, B) - ref).abs().max() / ref.abs().max()) < 1e-13
 
 
+@pytest.mark.parametrize("Kd,M,N", [(700, 12, 1032), (10000, 32, 4104), (513, 20, 250), (1500, 7, 1088), (16, 1, 2),
+                                    (3000, 25, 66048), (5, 32, 512), (2049, 9, 258)])
+def test_gemm_tn_tensor_core_kernel(torch_mod, Kd, M, N):
+    """A^T B with the contraction over rows: DMMA kernel (default) against fp64 matmul and against the plain-FMA kernel."""
+    torch = torch_mod
+    eng = make_engine((2, 2), 4)
+    gen = torch.Generator(device="cpu").manual_seed(Kd + M)
+    A = torch.randn(Kd, M, dtype=torch.float64, generator=gen).cuda()
+    B = torch.randn(Kd, N, dtype=torch.float64, generator=gen).cuda()
+    ref = A.T @ B
+    scale = float(ref.abs().max())
+    out = eng.gemm_tn(A, B)
+    assert float((out - ref).abs().max()) / scale < 1e-13
+    assert torch.equal(out, eng.gemm_tn(A, B))
+    eng.set_option("tn_variant", 0)
+    try:
+        old = eng.gemm_tn(A, B)
+    finally:
+        eng.set_option("tn_variant", 1)
+    assert float((out - old).abs().max()) / scale < 1e-13
+    # rows of B that are not 16-byte aligned fall back to the plain kernel
+    B1 = torch.randn(Kd * N + 1, dtype=torch.float64, generator=gen).cuda()[1:].view(Kd, N)
+    assert float((eng.gemm_tn(A, B1) - A.T @ B1).abs().max()) / scale < 1e-13
+
+
 def test_krylov_pca_matches_gram_route_and_oracle(torch_mod):
     """(4,4) blocks, N = 8 (D = 961), K = 1500 snapshots at contrast up to 1e6, n = 20.
     Bars: singular values <= 1e-9 relative, sign-fixed components <= 1e-7 for sigma_i / sigma_1 > 1e-6."""
