@@ -102,7 +102,7 @@ def _orthonormal_rows(eng, W, thr, passes=2):
 
 
 def krylov_pca(eng, X_local_pad, n, K_total=None, center_in_place=False, extra=12, rtol=1e-10, floor=2e-14, max_dim=960,
-               seed=0, stats=None):
+               seed=0, stats=None, distributed=True):
     """PCA(n) without the K x K Gram matrix: block Lanczos on S = Xc^T Xc (D x D), applied as two tall-skinny products.
 
     For K >> 10^4 (BASELINE configs[4]: K = 100 000, D = 261 121) the Gram route costs K^2 D = 2.6e15 flop, an
@@ -126,10 +126,11 @@ def krylov_pca(eng, X_local_pad, n, K_total=None, center_in_place=False, extra=1
     lam_i / lam_1 reaches the rounding level of S itself (floor); also when the residuals stop improving below
     1e-11 lam_1, or the basis reaches max_dim rows.
 
-    X_local_pad (K_r, Dp): this rank's rows (K_r may be 0 on some ranks as long as K_total > 0).
+    X_local_pad (K_r, Dp): this rank's rows (K_r may be 0 on some ranks as long as K_total > 0); distributed=False
+    treats them as the whole set even inside an initialised process group (rank-local POD, no collective).
     Returns (components (n, Dp), singular_values (n,), mean (Dp,)) on every rank."""
     from . import dist as rd
-    w = rd.world()
+    w = rd.world() if distributed else 1
     Kr, Dp = X_local_pad.shape
     dev = X_local_pad.device
     if K_total is None:
