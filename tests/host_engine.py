@@ -27,3 +27,58 @@ class HostEngine:
     def center_rows_(self, X, mean):
         X -= mean
         return X
+
+
+class HostFEMEngine(HostEngine):
+    """The FEM operations dist.greedy_build_sharded asks of an Engine, restated on the CPU oracle's sparse matrices
+    (compact layout: Dp == D, pad / unpad are the identity).  Test infrastructure for the gloo world-size-2 run."""
+
+    def __init__(self, oracle):
+        import numpy as np
+        self.o = oracle
+        self.np = np
+        self.nb = oracle.blocks_geometry[0] * oracle.blocks_geometry[1]
+        self.D = self.Dp = oracle.vspace_dim
+
+    def dev(self, a):
+        return torch.as_tensor(self.np.ascontiguousarray(self.np.asarray(a, dtype=self.np.float64)))
+
+    def pad(self, compact):
+        return self.dev(compact).reshape(-1, self.D)
+
+    def params(self, a):
+        return self.dev(a).reshape(-1, self.nb)
+
+    def error_norm(self, U, coef, basis):
+        diff = U.numpy() if basis is None else coef.numpy() @ basis.numpy() - U.numpy()
+        return torch.as_tensor(self.o.H10norm(diff))
+
+    def project_operators(self, Phi):
+        Ahat, bhat = self.o.reduced_operators(Phi.numpy())
+        return torch.as_tensor(Ahat.reshape(self.nb, len(Phi), len(Phi))), torch.as_tensor(bhat)
+
+    def reduced_solve(self, y, Ahat, rhs):
+        Ak = self.np.einsum("qij,kq->kij", Ahat.numpy(), y.numpy())
+        r = rhs.numpy()
+        r = self.np.broadcast_to(r, (len(Ak), r.shape[-1])) if r.ndim == 1 else r
+        return torch.as_tensor(self.np.linalg.solve(Ak, r[..., None])[..., 0])
+
+    def argmax(self, v):
+        i = int(self.np.argmax(v.numpy()))
+        return i, float(v[i])
+
+
+class HostSolutionsManager:
+    """What greedy_build_sharded reads from a SolutionsManagerFEM, on top of HostFEMEngine."""
+
+    def __init__(self, oracle):
+        self.o = oracle
+        self.vspace_dim = oracle.vspace_dim
+        self.blocks_geometry = oracle.blocks_geometry
+        self._eng = HostFEMEngine(oracle)
+
+    def _engine_(self):
+        return self._eng
+
+    def _projection_coefficients_dev(self, eng, U, Phi):
+        return torch.as_tensor(self.o.projection_coefficients(U.numpy(), Phi.numpy()))

@@ -99,6 +99,46 @@ def _worker(rank, world, port, tmp):
         dist.destroy_process_group()
 
 
+def _greedy_worker(rank, world, port, tmp):
+    """dist.greedy_build_sharded over 2 ranks (argmax all_gather + owner broadcast per step) == the oracle's greedy on
+    the whole training set: same index sequence, same raw basis rows, same parameters, for both criteria."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from host_engine import HostSolutionsManager
+        from oracle import FEMOracle
+        from oracle.rb import greedy_build
+        o = FEMOracle((2, 2), 6)
+        K, n = 23, 5                                              # odd K: shards of 11 and 12
+        y = 10 ** np.random.default_rng(42).uniform(0, 6, (K, 2, 2))
+        U = o.generate_solutions(y)
+        h1 = o.H10norm(U)
+        sl = rd.local_slice(K)
+        sm = HostSolutionsManager(o)
+        for crit in ("galerkin", "$H^1_0$"):
+            basis, a, picked = rd.greedy_build_sharded(sm, n, U[sl], y[sl], h1[sl], K, greedy_for=crit)
+            b_ref, a_ref, p_ref = greedy_build(o, n, U, y, h1, greedy_for=crit)
+            assert picked == p_ref, (crit, picked, p_ref)
+            assert picked[0] == 0                                   # the exact 1.0-vs-1.0 tie of round 1 goes to index 0
+            np.testing.assert_array_equal(basis, b_ref)
+            np.testing.assert_array_equal(np.asarray(a), np.asarray(a_ref))
+        # a rank that owns nothing (K < world) still takes part in every exchange
+        basis, a, picked = rd.greedy_build_sharded(sm, 1, U[:1] if rank == 1 else U[:0], y[:1] if rank == 1 else y[:0],
+                                                   h1[:1] if rank == 1 else h1[:0], 1)
+        assert picked == [0] and np.array_equal(basis[0], U[0])
+        open(os.path.join(tmp, f"greedy_ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharded_greedy_gloo(tmp_path):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_greedy_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "greedy_ok0").exists() and (tmp_path / "greedy_ok1").exists()
+
+
 def test_two_rank_collectives_gloo(tmp_path):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
