@@ -50,7 +50,9 @@ int romhc_destroy(romhc_handle h);
  * CTAs per SM), "threads" (256 / 512 per strip CTA), "profile", "bridge" (1: non-nested transfer to a power-of-two
  * hierarchy when N has an odd factor, default; 0: stop coarsening at the odd level), "z32" (3, default: z = M r, the smoothed
  * iterate z_A and the search direction p of the finest level travel between kernels as fp32; 2: z and z_A; 1: only z; 0: all fp64;
- * solves with a caller-supplied right-hand side always use fp64) */
+ * solves with a caller-supplied right-hand side always use fp64); process-wide A/B switches of the dense helpers:
+ * "gram_variant" (1, default: 128 x 64 DMMA tiles, two CTAs per SM; 0: 128 x 128), "tn_variant" (1, default: gemm_tn on the
+ * fp64 tensor cores; 0: the plain-FMA kernel, which also serves operands whose rows are not 16-byte aligned) */
 int romhc_set_option(romhc_handle h, const char* name, double value);
 /* info[0..15] = D, Dp, P, R, C, nlevels, tail_level, coarse_D, coarse_direct, nrb, ncb, N, workspace bytes per system,
  * tail kernel shared memory, bridge_level (-1: none), cells per subdomain below the bridge */
