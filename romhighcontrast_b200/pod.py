@@ -162,6 +162,23 @@ def krylov_pca(eng, X_local_pad, n, K_total=None, center_in_place=False, extra=1
             torch.distributed.all_reduce(Zw)
         return Zw
 
+    def agree(Qb):
+        """Sharded runs: every rank continues with rank 0's block.  The replicated arithmetic is deterministic, so this
+        changes nothing in practice; it turns 'all ranks hold the same basis' from an expectation into a guarantee -- a
+        rank that kept a different number of rows would otherwise hang the next all_reduce."""
+        if w == 1:
+            return Qb
+        cnt = torch.tensor([0 if Qb is None else Qb.shape[0]], dtype=torch.int64, device=dev)
+        torch.distributed.broadcast(cnt, src=0)
+        c = int(cnt.item())
+        if c == 0:
+            return None
+        if Qb is None or Qb.shape[0] != c:
+            Qb = torch.empty(c, Dp, dtype=torch.float64, device=dev)
+        Qb = Qb.contiguous()
+        torch.distributed.broadcast(Qb, src=0)
+        return Qb
+
     def ritz(Vd, Zd):
         T = eng.gemm_nt(Vd, Zd, splitk=True).cpu().numpy()    # (dim, dim) projected operator
         wv, S = np.linalg.eigh(0.5 * (T + T.T))
@@ -182,6 +199,7 @@ def krylov_pca(eng, X_local_pad, n, K_total=None, center_in_place=False, extra=1
     Q = _orthonormal_rows(eng, S0, 1e-12 * float(torch.linalg.vector_norm(S0, dim=1).max()))
     if Q is None:                                             # Xc == 0: every singular value is zero
         Q = _orthonormal_rows(eng, R0, 0.0)
+    Q = agree(Q)
     V = torch.empty(max_dim, Dp, dtype=torch.float64, device=dev)      # Krylov basis, rows
     Z = torch.empty(max_dim, Dp, dtype=torch.float64, device=dev)      # S applied to the basis rows
     dim = steps = 0
@@ -211,6 +229,7 @@ def krylov_pca(eng, X_local_pad, n, K_total=None, center_in_place=False, extra=1
                     break
             if Wn is not None:
                 Qn = Wn[:max_dim - dim].contiguous()
+        Qn = agree(Qn)
         last = Qn is None
         if (steps >= 2 and (dim <= 256 or steps % 2 == 0)) or last:
             lam, comps, res, excess, lam1 = ritz(Vd, Zd)
