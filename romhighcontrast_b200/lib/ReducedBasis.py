@@ -211,23 +211,27 @@ class ReducedBasisRandom(BaseReducedBasis):
 
 
 class ReducedBasisPCA(BaseReducedBasis):
+    GRAM_MAX_SNAPSHOTS = 32768      # pod_method="auto": Gram route up to here (G = 8.6 GB), Gram-free block Lanczos above
+
     def __init__(self, add_inf_solutions=True):
         self.add_inf_solutions = add_inf_solutions
         self.name = "PCA" + (r" $\infty$" if add_inf_solutions else "")
         super().__init__()
 
     def build(self, n: int, sm: SolutionsManager, solutions2train, a2train: List[np.ndarray] = (()),
-              solutions2train_h1norm=1, add_inf_solutions=True, seed=42, pod_method="gram", **kwargs):
+              solutions2train_h1norm=1, add_inf_solutions=True, seed=42, pod_method="auto", **kwargs):
         """POD of the (inf-stripped) snapshots (reference :189-200).
 
         sklearn's PCA(n_components=n) is replaced by the method of snapshots on the device (column mean, centred
         Gram matrix on the fp64 tensor cores, top-n eigenpairs, back-projection) with sklearn's sign convention; it
         is deterministic, whereas the reference's randomized solver (random_state=None) moves by ~1e-8 run to run.
-        pod_method="krylov" (additive keyword; the reference's build swallows unknown keywords, :189) selects the
-        Gram-free block-Lanczos route of pod.krylov_pca, meant for training sets of ~10^5 snapshots."""
+        pod_method (additive keyword; the reference's build swallows unknown keywords, :189): "gram" is the route above,
+        "krylov" the Gram-free block-Lanczos route of pod.krylov_pca (same components and singular values to ~1e-15),
+        "auto" (default) takes the Gram route up to GRAM_MAX_SNAPSHOTS snapshots and the Gram-free one beyond, where
+        the K x K matrix (80 GB at K = 100 000) and its K^2 D flop stop being practical."""
         from ..pod import krylov_pca, pca_components
-        if pod_method not in ("gram", "krylov"):
-            raise ValueError(f"pod_method={pod_method!r} (expected 'gram' or 'krylov')")
+        if pod_method not in ("auto", "gram", "krylov"):
+            raise ValueError(f"pod_method={pod_method!r} (expected 'auto', 'gram' or 'krylov')")
         solutions2train, a2train = np.asarray(solutions2train, dtype=np.float64), np.asarray(a2train)
         basis, a, solutions2train, a2train = get_starting_basis(solutions2train, a2train, self.add_inf_solutions)
         K, D = solutions2train.shape
@@ -235,6 +239,8 @@ class ReducedBasisPCA(BaseReducedBasis):
             raise ValueError(f"n_components={n!r} must be between 0 and min(n_samples, n_features)={min(K, D)!r} "
                              "with svd_solver='full'")
         eng = sm._engine_()
+        if pod_method == "auto":
+            pod_method = "gram" if K <= self.GRAM_MAX_SNAPSHOTS else "krylov"
         comps_pad, sing, mean = (pca_components if pod_method == "gram" else krylov_pca)(
             eng, eng.pad(solutions2train), n, center_in_place=True)
         self.singular_values_ = sing.cpu().numpy()

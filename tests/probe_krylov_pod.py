@@ -1,8 +1,10 @@
 """Measurement script (not a test): POD of K snapshots on one GPU, Gram route against the Gram-free Krylov route.
 
-    python tests/probe_krylov_pod.py [K] [n]      -> one JSON line (also written to gpurun_out/krylov_pod_probe.json)
+    python tests/probe_krylov_pod.py [K] [n] [blocks]     -> one JSON line (also written to gpurun_out/krylov_pod_probe.json)
 
-Geometry of BASELINE configs[2]: (4,4) blocks, N = 64 (D = 65 025); snapshots are real solves (contrast 10^U(0,6))."""
+Default geometry: BASELINE configs[2], (4,4) blocks, N = 64 (D = 65 025); blocks = 8 gives configs[4]'s (8,8) blocks
+(D = 261 121; K = 12 500 is the per-GPU share of its 100 000 snapshots on 8 GPUs).  Snapshots are real solves
+(contrast 10^U(0,6))."""
 import json
 import os
 import sys
@@ -33,8 +35,9 @@ def timed(fn, reps=2):
 def main():
     K = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-    eng = Engine((4, 4), 64)
-    y = 10 ** np.random.default_rng(42).uniform(0, 6, (K, 4, 4))
+    nb = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+    eng = Engine((nb, nb), 64)
+    y = 10 ** np.random.default_rng(42).uniform(0, 6, (K, nb, nb))
     X, _, _ = eng.solve(eng.params(y))
     stats = {}
     (ck, sk, _), ms_k = timed(lambda: krylov_pca(eng, X, n, stats=stats))

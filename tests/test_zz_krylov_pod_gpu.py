@@ -128,3 +128,10 @@ def test_reduced_basis_pca_krylov_option(torch_mod):
     kry = ReducedBasisPCA().build(n=10, sm=sm, solutions2train=U, a2train=y, pod_method="krylov")
     np.testing.assert_allclose(kry.singular_values_, ref.singular_values_, rtol=1e-9)
     assert np.abs(np.asarray(kry.basis) - np.asarray(ref.basis)).max() < 1e-7
+    # "auto" switches on the number of snapshots
+    small = ReducedBasisPCA()
+    small.GRAM_MAX_SNAPSHOTS = 50
+    auto = small.build(n=10, sm=sm, solutions2train=U, a2train=y)
+    np.testing.assert_array_equal(np.asarray(auto.basis), np.asarray(kry.basis))
+    with pytest.raises(ValueError):
+        ReducedBasisPCA().build(n=10, sm=sm, solutions2train=U, a2train=y, pod_method="svd")
