@@ -81,23 +81,34 @@ def pca_components(eng, X_pad, n, center_in_place=False):
     return comps * sign[:, None], sig, mean
 
 
-def _orthonormal_rows(eng, W, thr, passes=2):
+def _orthonormal_rows(eng, W, thr, passes=2, conditioned=False):
     """Orthonormal rows spanning the directions of W (b, Dp) whose singular value exceeds thr (None if there are none).
 
-    Rank revealing and built from row combinations of W only, so slots that are zero in every row stay exactly zero:
-    R of a Householder QR of W^T (backward stable: singular values resolved down to eps * sigma_max, where a b x b Gram
-    matrix would lose everything below sqrt(eps)), SVD R = U S V^T on the host, rows (1 / s_i) v_i^T W for s_i > thr.
-    The division amplifies rounding by sigma_max / s_i, so a second pass on the now well-conditioned rows restores
-    orthonormality to machine precision; exhausted Krylov directions (rounding noise) are dropped instead of being
-    normalised into vectors that are no longer orthogonal to the basis."""
+    Rank revealing and built from row combinations of W only, so slots that are zero in every row stay exactly zero.
+    First pass: R of a Householder QR of W^T (backward stable: singular values resolved down to eps * sigma_max, where a
+    b x b Gram matrix would lose everything below sqrt(eps)), SVD R = U S V^T on the host, rows (1 / s_i) v_i^T W for
+    s_i > thr; exhausted Krylov directions (rounding noise) are dropped instead of being normalised into vectors that
+    are no longer orthogonal to the basis.  The division amplifies rounding by sigma_max / s_i, so a second pass restores
+    orthonormality to machine precision; its input is nearly orthonormal already (condition number O(1)), which is
+    exactly where the b x b Gram matrix W W^T -- one split-K DMMA product instead of a library QR -- is accurate:
+    rows lam_i^-1/2 e_i^T W.  conditioned=True: the caller knows W is nearly orthonormal (re-normalisation after a
+    Gram-Schmidt pass), every pass takes the Gram form."""
     for p in range(passes):
-        R = torch.linalg.qr(W.T, mode="r")[1]                 # (b, b)
-        _, sv, Vt = np.linalg.svd(R.cpu().numpy())
-        keep = sv > (thr if p == 0 else 0.5)
-        if not keep.any():
-            return None
-        Tm = torch.as_tensor(np.array(Vt[keep] / sv[keep, None], order="C", copy=True), device=W.device)
-        W = eng.gemm_nn(Tm, W)
+        if p == 0 and not conditioned:
+            R = torch.linalg.qr(W.T, mode="r")[1]             # (b, b)
+            _, sv, Vt = np.linalg.svd(R.cpu().numpy())
+            keep = sv > thr
+            if not keep.any():
+                return None
+            Tm = Vt[keep] / sv[keep, None]
+        else:
+            Gs = eng.gemm_nt(W, W, splitk=True).cpu().numpy()
+            ev, E = np.linalg.eigh(0.5 * (Gs + Gs.T))
+            keep = ev > (thr * thr if p == 0 else 0.25)
+            if not keep.any():
+                return None
+            Tm = (E[:, keep] / np.sqrt(ev[keep])).T[::-1]
+        W = eng.gemm_nn(torch.as_tensor(np.array(Tm, order="C", copy=True), device=W.device), W)
     return W
 
 
@@ -224,7 +235,8 @@ def krylov_pca(eng, X_local_pad, n, K_total=None, center_in_place=False, extra=1
             for sweep in range(2):
                 for _ in range(2):
                     Wn = Wn - eng.gemm_nn(eng.gemm_nt(Vd, Wn, splitk=True).T.contiguous(), Vd)
-                Wn = _orthonormal_rows(eng, Wn, 1e-15 * scale if sweep == 0 else 0.5, passes=2 if sweep == 0 else 1)
+                Wn = _orthonormal_rows(eng, Wn, 1e-15 * scale if sweep == 0 else 0.5, passes=2 if sweep == 0 else 1,
+                                       conditioned=sweep > 0)
                 if Wn is None:
                     break
             if Wn is not None:
