@@ -18,7 +18,10 @@
  *   - parameters y are (K, nrb*ncb) row-major: y[k][p*ncb + q] = a[k][p][q] (SolutionsManagers.py:190-192).
  *   - threading: a context owns its workspaces, staging buffers and streams; calls on ONE context must not overlap
  *     (the reference is single-threaded Python).  Different contexts (one per thread, or one per GPU) are
- *     independent.  Context-free functions (romhc_gemm_*, romhc_reduced_solve, ...) are reentrant.
+ *     independent.  Context-free functions (romhc_gemm_*, romhc_reduced_solve, ...) may be called from several host
+ *     threads at once: the ones that need device scratch (romhc_gemm_tn, romhc_gemm_nt with symmetric == 2,
+ *     romhc_column_mean) keep one buffer per host thread and device; ONE thread must not let such calls overlap on
+ *     different streams.
  */
 #ifndef ROMHC_H
 #define ROMHC_H

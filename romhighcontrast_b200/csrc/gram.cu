@@ -165,14 +165,21 @@ static int launch_gemm_nt(const double* A, int64_t lda, const double* B, int64_t
 
 __global__ void k_gemm_tn_reduce(const double* __restrict__ part, int nchunks, int Mm, int64_t Nn, double* __restrict__ C,
                                  int64_t ldc);
-static void* g_tn_scratch = nullptr;
-static size_t g_tn_bytes = 0;
+// Device scratch of the context-free dense helpers (split-K partials, gemm_tn partials, column sums): one buffer per
+// HOST THREAD and device, grown on demand (cudaFree synchronises, so a buffer still in use is never released early).
+// Two threads therefore never share partials; one thread must not overlap helper calls on different streams.
+struct HelperScratch { void* p = nullptr; size_t bytes = 0; int dev = -1; };
+static thread_local HelperScratch g_scr;
+#define g_tn_scratch (g_scr.p)
 static int scratch_reserve(size_t need) {
-    if (need > g_tn_bytes) {
-        if (g_tn_scratch) cudaFree(g_tn_scratch);
-        g_tn_scratch = nullptr; g_tn_bytes = 0;
-        CK(cudaMalloc(&g_tn_scratch, need));
-        g_tn_bytes = need;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev != g_scr.dev || need > g_scr.bytes) {
+        if (g_scr.p) cudaFree(g_scr.p);
+        g_scr = HelperScratch();
+        CK(cudaMalloc(&g_scr.p, need));
+        g_scr.bytes = need;
+        g_scr.dev = dev;
     }
     return ROMHC_OK;
 }
