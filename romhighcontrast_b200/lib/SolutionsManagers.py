@@ -61,7 +61,7 @@ class SolutionsManager:
     """Base class of the reference (:43-142).  Only the FEM subclass is GPU backed; the generic dense-operator
     constructor is kept for type compatibility."""
 
-    def __init__(self, A_preassembled=None, B_total=None, num_cores=1, method="lsq"):
+    def __init__(self, A_preassembled, B_total, num_cores=1, method="lsq"):      # reference :44
         if type(self) is SolutionsManager:
             raise Exception("Not implemented.")   # dense-operator managers (SolutionsManagerPolynomial) are out of scope
         self.method = method
@@ -219,7 +219,7 @@ class SolutionsManagerFEM(SolutionsManager):
         area = (1 / self.N) * (1 / self.N)
         self.B_total = np.full(self.vspace_dim, ((area / 6 + area / 3) + area / 3) + area / 6)
         self.num_cores = num_cores
-        super().__init__(num_cores=num_cores, method=method)
+        super().__init__(None, None, num_cores=num_cores, method=method)      # matrix-free: no dense operators to hand over
 
     # the dense reference tensors exist only on demand and only where they fit (nobody outside L1 reads them)
     def _dense(self):
