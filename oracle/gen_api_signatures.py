@@ -69,9 +69,25 @@ def main():
     args = ap.parse_args()
     SM, RB, ES = import_reference(args.ref)
     api = {"SolutionsManagers": describe(SM), "ReducedBasis": describe(RB), "Estimators": describe(ES)}
+    # instance attributes right after construction with the constructors' defaults / the experiment driver's arguments
+    # (plotting code reads .name / .linestyle / .greedy_for / .add_inf_solutions, HighContrast.py:45-56,236-241)
+    def attrs(obj):
+        return {k: ({"value": v} if isinstance(v, (int, float, str, bool, type(None))) else {"type": type(v).__name__})
+                for k, v in sorted(vars(obj).items())}
+    api["instances"] = {
+        "ReducedBasisGreedy()": attrs(RB.ReducedBasisGreedy()),
+        "ReducedBasisGreedy(greedy_for=GREEDY_FOR_H10)": attrs(RB.ReducedBasisGreedy(greedy_for=RB.GREEDY_FOR_H10)),
+        "ReducedBasisRandom()": attrs(RB.ReducedBasisRandom()),
+        "ReducedBasisRandom(False)": attrs(RB.ReducedBasisRandom(False)),
+        "ReducedBasisPCA()": attrs(RB.ReducedBasisPCA()),
+        "ReducedBasisPCA(False)": attrs(RB.ReducedBasisPCA(False)),
+        "BaseReducedBasis()": attrs(RB.BaseReducedBasis()),
+        "SolutionsManagerFEM((2, 2), 3)": attrs(SM.SolutionsManagerFEM((2, 2), 3)),
+    }
     with open(args.out, "w") as f:
         json.dump(api, f, indent=1, sort_keys=True)
-    n = sum(len(m["functions"]) + sum(len(c["members"]) for c in m["classes"].values()) for m in api.values())
+    n = sum(len(m["functions"]) + sum(len(c["members"]) for c in m["classes"].values())
+            for k, m in api.items() if k != "instances")
     print(f"wrote {args.out}: {n} callables")
 
 

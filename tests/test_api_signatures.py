@@ -46,7 +46,7 @@ def _check_params(where, ref_params, fn):
 
 
 @pytest.mark.parametrize("spelling", ["romhighcontrast_b200.lib", "src.lib", "lib"])
-@pytest.mark.parametrize("modname", sorted(API))
+@pytest.mark.parametrize("modname", sorted(k for k in API if k != "instances"))
 def test_mirror_keeps_the_reference_signatures(spelling, modname):
     mod = importlib.import_module(f"{spelling}.{modname}")
     ref = API[modname]
@@ -71,3 +71,36 @@ def test_mirror_keeps_the_reference_signatures(spelling, modname):
             if m["kind"] in ("staticmethod", "classmethod"):
                 assert type(attr).__name__ == m["kind"], where
             _check_params(where, m["params"], getattr(cls, mname) if m["kind"] != "method" else attr)
+
+
+def test_instances_expose_the_reference_attributes():
+    """Every attribute a freshly constructed reference object has (plotting code reads .name / .linestyle / .greedy_for /
+    .add_inf_solutions, HighContrast.py:45-56,236-241) exists on the mirror's object with the same simple value or the same
+    container type.  The dense A_preassembled tensors are lazy properties here and are only checked for presence."""
+    import lib.ReducedBasis as RB
+    import lib.SolutionsManagers as SM
+    make = {
+        "ReducedBasisGreedy()": lambda: RB.ReducedBasisGreedy(),
+        "ReducedBasisGreedy(greedy_for=GREEDY_FOR_H10)": lambda: RB.ReducedBasisGreedy(greedy_for=RB.GREEDY_FOR_H10),
+        "ReducedBasisRandom()": lambda: RB.ReducedBasisRandom(),
+        "ReducedBasisRandom(False)": lambda: RB.ReducedBasisRandom(False),
+        "ReducedBasisPCA()": lambda: RB.ReducedBasisPCA(),
+        "ReducedBasisPCA(False)": lambda: RB.ReducedBasisPCA(False),
+        "BaseReducedBasis()": lambda: RB.BaseReducedBasis(),
+        "SolutionsManagerFEM((2, 2), 3)": lambda: SM.SolutionsManagerFEM((2, 2), 3),
+    }
+    assert set(make) == set(API["instances"])
+    lazy = {"A_preassembled", "A_preassembled4h1_norm"}
+    for key, attrs in API["instances"].items():
+        obj = make[key]()
+        for name, desc in attrs.items():
+            where = f"{key}.{name}"
+            if name in lazy:
+                assert isinstance(inspect.getattr_static(type(obj), name), property), where
+                continue
+            assert hasattr(obj, name), where
+            value = getattr(obj, name)
+            if "value" in desc:
+                assert value == desc["value"] and type(value) is type(desc["value"]), f"{where}: {value!r} vs {desc['value']!r}"
+            else:
+                assert type(value).__name__ == desc["type"], f"{where}: {type(value).__name__} vs {desc['type']}"
