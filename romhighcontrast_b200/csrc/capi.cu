@@ -340,7 +340,10 @@ int romhc_generate_solutions_host(romhc_handle h, const double* y_host, int64_t 
     const size_t per = 2 * size_t(g.Dp + D) * 8 + c->solve_bytes_per_system();
     int64_t chunk = std::max<int64_t>(1, std::min<int64_t>({(int64_t)(c->ws_budget_bytes / per), (int64_t)32768, K}));
     if (K >= 4096) chunk = std::min<int64_t>(chunk, (K + c->host_chunks - 1) / c->host_chunks);
-    int rc = c->ensure_host_stage(chunk);
+    // the schedule below merges a short remainder into the last chunk: staging capacity = chunk + small / 2
+    const int64_t small = std::min<int64_t>(chunk, std::max<int64_t>(512, chunk / 4));
+    const int64_t stage_cap = chunk + small / 2;
+    int rc = c->ensure_host_stage(stage_cap);
     if (rc) return rc;
     HostStage& s = c->hstage;
     rc = c->ensure_pinned_stats(K);
@@ -354,7 +357,7 @@ int romhc_generate_solutions_host(romhc_handle h, const double* y_host, int64_t 
         cudaGetLastError();
     }
     if (!pinned_dst) {
-        const size_t need = size_t(chunk) * D * 8;
+        const size_t need = size_t(stage_cap) * D * 8;
         if (need > s.bounce_cap) {
             for (int i = 0; i < 2; ++i) { if (s.bounce[i]) cudaFreeHost(s.bounce[i]); s.bounce[i] = nullptr; }
             s.bounce_cap = 0;
@@ -366,44 +369,53 @@ int romhc_generate_solutions_host(romhc_handle h, const double* y_host, int64_t 
     const int copy_threads = std::max(1, std::min(8, int(std::thread::hardware_concurrency()) / 2));
     // Chunk schedule: full chunks first, then halved ones -- only the LAST chunk's D2H copy is exposed (nothing left
     // to overlap it with), so it should be small; chunks below ~600 systems would under-fill the persistent kernels.
-    int64_t nchunk = 0, kc_next = chunk;
-    const int64_t small = std::max<int64_t>(512, chunk / 4);
-    for (int64_t k0 = 0; k0 < K; ++nchunk) {
-        const int64_t left = K - k0;
-        int64_t kc = std::min<int64_t>(kc_next, left);
-        if (K >= 4096 && left <= chunk + small && left > small) kc = std::max<int64_t>(small, (left + 1) / 2);
-        if (left - kc < small / 2) kc = left;                  // no tiny remainder
-        const int slot = int(nchunk & 1);
-        if (nchunk >= 2) CK(cudaStreamWaitEvent(s.compute, s.copied[slot], 0));
-        CK(cudaMemcpyAsync(s.y[slot], y_host + k0 * nb, size_t(kc) * nb * 8, cudaMemcpyHostToDevice, s.compute));
-        rc = c->solve(s.y[slot], kc, s.x[slot], s.it[slot], s.rel[slot], s.compute, nullptr);
-        if (rc) break;
-        rc = c->unpack(s.x[slot], s.u[slot], kc, s.compute);
-        if (rc) break;
-        CK(cudaEventRecord(s.done[slot], s.compute));
-        // pageable destination: slot 0 and slot 1 use different copy streams so that the callback of one chunk and the
-        // D2H copy of the next run side by side
-        cudaStream_t cs = (!pinned_dst && slot) ? s.copy2 : s.copy;
-        CK(cudaStreamWaitEvent(cs, s.done[slot], 0));
-        if (pinned_dst) {
-            CK(cudaMemcpyAsync(U_host + k0 * D, s.u[slot], size_t(kc) * D * 8, cudaMemcpyDeviceToHost, cs));
-        } else {
-            CK(cudaMemcpyAsync(s.bounce[slot], s.u[slot], size_t(kc) * D * 8, cudaMemcpyDeviceToHost, cs));
+    // Every kc the schedule produces is <= stage_cap, the capacity the staging buffers were sized for.
+    auto pipeline = [&]() -> int {
+        int64_t nchunk = 0;
+        for (int64_t k0 = 0; k0 < K; ++nchunk) {
+            const int64_t left = K - k0;
+            int64_t kc = std::min<int64_t>(chunk, left);
+            if (K >= 4096 && left <= chunk + small && left > small) kc = std::max<int64_t>(small, (left + 1) / 2);
+            if (left - kc < small / 2) kc = left;                  // no tiny remainder
+            kc = std::min<int64_t>(kc, stage_cap);                 // never beyond the staged capacity
+            const int slot = int(nchunk & 1);
+            if (nchunk >= 2) CK(cudaStreamWaitEvent(s.compute, s.copied[slot], 0));
+            CK(cudaMemcpyAsync(s.y[slot], y_host + k0 * nb, size_t(kc) * nb * 8, cudaMemcpyHostToDevice, s.compute));
+            int r = c->solve(s.y[slot], kc, s.x[slot], s.it[slot], s.rel[slot], s.compute, nullptr);
+            if (r) return r;
+            r = c->unpack(s.x[slot], s.u[slot], kc, s.compute);
+            if (r) return r;
+            CK(cudaEventRecord(s.done[slot], s.compute));
+            // pageable destination: slot 0 and slot 1 use different copy streams so that the callback of one chunk and the
+            // D2H copy of the next run side by side
+            cudaStream_t cs = (!pinned_dst && slot) ? s.copy2 : s.copy;
+            CK(cudaStreamWaitEvent(cs, s.done[slot], 0));
+            if (pinned_dst) {
+                CK(cudaMemcpyAsync(U_host + k0 * D, s.u[slot], size_t(kc) * D * 8, cudaMemcpyDeviceToHost, cs));
+            } else {
+                CK(cudaMemcpyAsync(s.bounce[slot], s.u[slot], size_t(kc) * D * 8, cudaMemcpyDeviceToHost, cs));
+            }
+            // per-system statistics go to pinned staging first: a D2H copy into the caller's (usually pageable) arrays would
+            // block the host behind the big solution copy and serialise the pipeline
+            if (iters_host) CK(cudaMemcpyAsync(s.it_pin + k0, s.it[slot], size_t(kc) * 4, cudaMemcpyDeviceToHost, cs));
+            if (relres_host) CK(cudaMemcpyAsync(s.rel_pin + k0, s.rel[slot], size_t(kc) * 8, cudaMemcpyDeviceToHost, cs));
+            CK(cudaEventRecord(s.copied[slot], cs));
+            if (!pinned_dst) {
+                HostCopyTask* t = new HostCopyTask{(const char*)s.bounce[slot], (char*)(U_host + k0 * D), size_t(kc) * D * 8, copy_threads};
+                const cudaError_t el = cudaLaunchHostFunc(cs, host_copy_callback, t);
+                if (el != cudaSuccess) { delete t; CK(el); }
+            }
+            k0 += kc;
         }
-        // per-system statistics go to pinned staging first: a D2H copy into the caller's (usually pageable) arrays would
-        // block the host behind the big solution copy and serialise the pipeline
-        if (iters_host) CK(cudaMemcpyAsync(s.it_pin + k0, s.it[slot], size_t(kc) * 4, cudaMemcpyDeviceToHost, cs));
-        if (relres_host) CK(cudaMemcpyAsync(s.rel_pin + k0, s.rel[slot], size_t(kc) * 8, cudaMemcpyDeviceToHost, cs));
-        CK(cudaEventRecord(s.copied[slot], cs));
-        if (!pinned_dst) {
-            HostCopyTask* t = new HostCopyTask{(const char*)s.bounce[slot], (char*)(U_host + k0 * D), size_t(kc) * D * 8, copy_threads};
-            CK(cudaLaunchHostFunc(cs, host_copy_callback, t));
-        }
-        k0 += kc;
-    }
-    CK(cudaStreamSynchronize(s.copy));
-    if (s.copy2) CK(cudaStreamSynchronize(s.copy2));
-    CK(cudaStreamSynchronize(s.compute));
+        return ROMHC_OK;
+    };
+    rc = pipeline();
+    // Drain on EVERY path: queued D2H copies and host callbacks write into the caller's buffer, which the caller may
+    // release as soon as this function returns -- also when it returns an error.
+    const cudaError_t d0 = cudaStreamSynchronize(s.compute);
+    const cudaError_t d1 = cudaStreamSynchronize(s.copy);
+    const cudaError_t d2 = s.copy2 ? cudaStreamSynchronize(s.copy2) : cudaSuccess;
+    if (rc == ROMHC_OK) { CK(d0); CK(d1); CK(d2); }
     if (rc == ROMHC_OK) {
         if (iters_host) memcpy(iters_host, s.it_pin, size_t(K) * 4);
         if (relres_host) memcpy(relres_host, s.rel_pin, size_t(K) * 8);
@@ -465,29 +477,34 @@ int romhc_pack_host(romhc_handle h, const double* compact_host, double* padded_d
     HostStage& s = c->hstage;
     cudaStream_t st = ST(stream);
     const int copy_threads = std::max(1, std::min(8, int(std::thread::hardware_concurrency()) / 2));
-    int64_t i = 0;
-    for (int64_t k0 = 0; k0 < K; k0 += rows, ++i) {
-        const int64_t kc = std::min(rows, K - k0);
-        const int slot = int(i & 1);
-        cudaStream_t cs = slot ? s.copy2 : s.copy;
-        const size_t bytes = size_t(kc) * D * 8;
-        CK(cudaStreamWaitEvent(cs, s.xfer_done[slot], 0));        // the layout kernel that last read this slot has finished
-        const double* src = compact_host + k0 * D;
-        if (!pinned) {
-            HostCopyTask* t = new HostCopyTask{(const char*)src, (char*)s.bounce[slot], bytes, copy_threads};
-            CK(cudaLaunchHostFunc(cs, host_copy_callback, t));
-            src = s.bounce[slot];
+    auto pipeline = [&]() -> int {
+        int64_t i = 0;
+        for (int64_t k0 = 0; k0 < K; k0 += rows, ++i) {
+            const int64_t kc = std::min(rows, K - k0);
+            const int slot = int(i & 1);
+            cudaStream_t cs = slot ? s.copy2 : s.copy;
+            const size_t bytes = size_t(kc) * D * 8;
+            CK(cudaStreamWaitEvent(cs, s.xfer_done[slot], 0));        // the layout kernel that last read this slot has finished
+            const double* src = compact_host + k0 * D;
+            if (!pinned) {
+                HostCopyTask* t = new HostCopyTask{(const char*)src, (char*)s.bounce[slot], bytes, copy_threads};
+                const cudaError_t el = cudaLaunchHostFunc(cs, host_copy_callback, t);
+                if (el != cudaSuccess) { delete t; CK(el); }
+                src = s.bounce[slot];
+            }
+            CK(cudaMemcpyAsync(s.xfer_dev[slot], src, bytes, cudaMemcpyHostToDevice, cs));
+            CK(cudaEventRecord(s.xfer_ready[slot], cs));
+            CK(cudaStreamWaitEvent(st, s.xfer_ready[slot], 0));
+            const int r = c->pack(s.xfer_dev[slot], padded_dev + k0 * g.Dp, kc, st); if (r) return r;
+            CK(cudaEventRecord(s.xfer_done[slot], st));
         }
-        CK(cudaMemcpyAsync(s.xfer_dev[slot], src, bytes, cudaMemcpyHostToDevice, cs));
-        CK(cudaEventRecord(s.xfer_ready[slot], cs));
-        CK(cudaStreamWaitEvent(st, s.xfer_ready[slot], 0));
-        rc = c->pack(s.xfer_dev[slot], padded_dev + k0 * g.Dp, kc, st); if (rc) return rc;
-        CK(cudaEventRecord(s.xfer_done[slot], st));
-    }
-    // the caller's host array may be reused as soon as this returns: every host-side read has completed
-    CK(cudaStreamSynchronize(s.copy));
-    CK(cudaStreamSynchronize(s.copy2));
-    return ROMHC_OK;
+        return ROMHC_OK;
+    };
+    rc = pipeline();
+    // the caller's host array may be reused as soon as this returns (also on an error): every host-side read has completed
+    const cudaError_t d1 = cudaStreamSynchronize(s.copy), d2 = cudaStreamSynchronize(s.copy2);
+    if (rc == ROMHC_OK) { CK(d1); CK(d2); }
+    return rc;
 }
 
 int romhc_unpack_host(romhc_handle h, const double* padded_dev, double* compact_host, int64_t K, void* stream) {
@@ -503,27 +520,33 @@ int romhc_unpack_host(romhc_handle h, const double* padded_dev, double* compact_
     HostStage& s = c->hstage;
     cudaStream_t st = ST(stream);
     const int copy_threads = std::max(1, std::min(8, int(std::thread::hardware_concurrency()) / 2));
-    int64_t i = 0;
-    for (int64_t k0 = 0; k0 < K; k0 += rows, ++i) {
-        const int64_t kc = std::min(rows, K - k0);
-        const int slot = int(i & 1);
-        cudaStream_t cs = slot ? s.copy2 : s.copy;
-        const size_t bytes = size_t(kc) * D * 8;
-        CK(cudaStreamWaitEvent(st, s.xfer_done[slot], 0));        // the D2H copy that last read this slot has finished
-        rc = c->unpack(padded_dev + k0 * g.Dp, s.xfer_dev[slot], kc, st); if (rc) return rc;
-        CK(cudaEventRecord(s.xfer_ready[slot], st));
-        CK(cudaStreamWaitEvent(cs, s.xfer_ready[slot], 0));
-        double* dst = compact_host + k0 * D;
-        CK(cudaMemcpyAsync(pinned ? dst : s.bounce[slot], s.xfer_dev[slot], bytes, cudaMemcpyDeviceToHost, cs));
-        CK(cudaEventRecord(s.xfer_done[slot], cs));
-        if (!pinned) {
-            HostCopyTask* t = new HostCopyTask{(const char*)s.bounce[slot], (char*)dst, bytes, copy_threads};
-            CK(cudaLaunchHostFunc(cs, host_copy_callback, t));
+    auto pipeline = [&]() -> int {
+        int64_t i = 0;
+        for (int64_t k0 = 0; k0 < K; k0 += rows, ++i) {
+            const int64_t kc = std::min(rows, K - k0);
+            const int slot = int(i & 1);
+            cudaStream_t cs = slot ? s.copy2 : s.copy;
+            const size_t bytes = size_t(kc) * D * 8;
+            CK(cudaStreamWaitEvent(st, s.xfer_done[slot], 0));        // the D2H copy that last read this slot has finished
+            const int r = c->unpack(padded_dev + k0 * g.Dp, s.xfer_dev[slot], kc, st); if (r) return r;
+            CK(cudaEventRecord(s.xfer_ready[slot], st));
+            CK(cudaStreamWaitEvent(cs, s.xfer_ready[slot], 0));
+            double* dst = compact_host + k0 * D;
+            CK(cudaMemcpyAsync(pinned ? dst : s.bounce[slot], s.xfer_dev[slot], bytes, cudaMemcpyDeviceToHost, cs));
+            CK(cudaEventRecord(s.xfer_done[slot], cs));
+            if (!pinned) {
+                HostCopyTask* t = new HostCopyTask{(const char*)s.bounce[slot], (char*)dst, bytes, copy_threads};
+                const cudaError_t el = cudaLaunchHostFunc(cs, host_copy_callback, t);
+                if (el != cudaSuccess) { delete t; CK(el); }
+            }
         }
-    }
-    CK(cudaStreamSynchronize(s.copy));
-    CK(cudaStreamSynchronize(s.copy2));
-    return ROMHC_OK;
+        return ROMHC_OK;
+    };
+    rc = pipeline();
+    // drain on every path: queued copies / callbacks write into the caller's array
+    const cudaError_t d1 = cudaStreamSynchronize(s.copy), d2 = cudaStreamSynchronize(s.copy2);
+    if (rc == ROMHC_OK) { CK(d1); CK(d2); }
+    return rc;
 }
 
 int romhc_reduced_galerkin_host(romhc_handle h, const double* y_host, const double* Ahat_host, const double* bhat_host,
@@ -557,20 +580,23 @@ int romhc_reduced_galerkin_host(romhc_handle h, const double* y_host, const doub
     { const int rcp = c->ensure_pinned_stats(K); if (rcp) return rcp; }
     CK(cudaStreamSynchronize(st));
     std::vector<cudaEvent_t> ev;
-    int rc = ROMHC_OK;
-    for (int64_t k0 = 0; k0 < K && rc == ROMHC_OK; k0 += chunk) {
-        const int64_t kc = std::min<int64_t>(chunk, K - k0);
-        cudaEvent_t e;
-        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        ev.push_back(e);
-        CK(cudaMemcpyAsync(y_d + k0 * nb, y_host + k0 * nb, size_t(kc) * nb * 8, cudaMemcpyHostToDevice, s_in));
-        CK(cudaEventRecord(e, s_in));
-        CK(cudaStreamWaitEvent(s_run, e, 0));
-        rc = reduced_solve(y_d + k0 * nb, nb, A_d, b_d, 0, n, kc, C_d + k0 * n, info_d + k0, s_run);
-        if (rc != ROMHC_OK) break;
-        CK(cudaMemcpyAsync(C_host + k0 * n, C_d + k0 * n, size_t(kc) * n * 8, cudaMemcpyDeviceToHost, s_run));
-        if (info_host) CK(cudaMemcpyAsync(c->hstage.it_pin + k0, info_d + k0, size_t(kc) * 4, cudaMemcpyDeviceToHost, s_run));
-    }
+    auto pipeline = [&]() -> int {
+        for (int64_t k0 = 0; k0 < K; k0 += chunk) {
+            const int64_t kc = std::min<int64_t>(chunk, K - k0);
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ev.push_back(e);
+            CK(cudaMemcpyAsync(y_d + k0 * nb, y_host + k0 * nb, size_t(kc) * nb * 8, cudaMemcpyHostToDevice, s_in));
+            CK(cudaEventRecord(e, s_in));
+            CK(cudaStreamWaitEvent(s_run, e, 0));
+            const int r = reduced_solve(y_d + k0 * nb, nb, A_d, b_d, 0, n, kc, C_d + k0 * n, info_d + k0, s_run);
+            if (r != ROMHC_OK) return r;
+            CK(cudaMemcpyAsync(C_host + k0 * n, C_d + k0 * n, size_t(kc) * n * 8, cudaMemcpyDeviceToHost, s_run));
+            if (info_host) CK(cudaMemcpyAsync(c->hstage.it_pin + k0, info_d + k0, size_t(kc) * 4, cudaMemcpyDeviceToHost, s_run));
+        }
+        return ROMHC_OK;
+    };
+    const int rc = pipeline();
     cudaStreamSynchronize(s_in);
     cudaStreamSynchronize(s_run);
     for (cudaEvent_t e : ev) cudaEventDestroy(e);

@@ -108,8 +108,17 @@ def test_gram_and_online_stage_full_size(eng):
         r = A @ Ch[k] - bh
         assert np.linalg.norm(r) <= 1e-10 * np.linalg.norm(bh)
     # scaling property of the reduced problem: c(2 y) = c(y) / 2
-    C2 = eng.reduced_solve(eng.params(2.0 * yo[:1000]), Ahat, bhat)
-    assert float((2.0 * C2 - C[:1000]).abs().max()) <= 1e-12 * float(C[:1000].abs().max())
+    # (sqrt(2 d) and sqrt(2) sqrt(d) round differently, so the two Cholesky solves agree to eps * cond(A_k) per system,
+    #  not to a fixed 1e-12: cond reaches 1e6+ at contrast 10^U(0,6))
+    C2 = eng.reduced_solve(eng.params(2.0 * yo[:1000]), Ahat, bhat).cpu().numpy()
+    A1k = np.einsum("kq,qij->kij", yo[:1000].reshape(1000, -1), Ah)
+    cond = np.linalg.cond(A1k)
+    eps = np.finfo(float).eps
+    dev = np.linalg.norm(2.0 * C2 - Ch[:1000], axis=1)
+    assert np.all(dev <= 50 * eps * cond * np.linalg.norm(Ch[:1000], axis=1)), float((dev / (eps * cond * np.linalg.norm(Ch[:1000], axis=1))).max())
+    # and both agree with LAPACK on the same systems to the north-star tolerance
+    Cl = np.linalg.solve(A1k, np.broadcast_to(bh, (1000, n))[..., None])[..., 0]
+    assert (np.linalg.norm(Ch[:1000] - Cl, axis=1) / np.linalg.norm(Cl, axis=1)).max() < 1e-9
 
 
 def test_config1_greedy_and_pca_parity_at_full_size():
