@@ -10,6 +10,7 @@
 #include "romhc_internal.h"
 
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 namespace romhc {
@@ -103,7 +104,8 @@ int Context::project_operators(const double* basis, int n, double* Ahat, double*
 }
 
 // ======================================================================================================
-// K5: batched reduced solves  (sum_q y_kq Ahat_q) c_k = rhs_k, one warp per system, Cholesky in smem.
+// K5: batched reduced solves  (sum_q y_kq Ahat_q) c_k = rhs_k.  n <= 24: a quad of lanes per system, assembly on the
+// fp64 tensor cores, Cholesky in registers (k_reduced_solve_quad); larger n: one warp per system, Cholesky in smem.
 // Ahat is used through its lower triangle (packed) -- the reference symmetrises implicitly by calling
 // scipy.linalg.solve(assume_a='pos') (SolutionsManagers.py:29).
 // ======================================================================================================
@@ -193,112 +195,154 @@ k_reduced_solve(const double* __restrict__ y, int nb, const double* __restrict__
     }
 }
 
-// ---- thread-per-system variant (n <= 24): the packed lower triangle of every system lives in shared memory as
-// M[entry][thread] (consecutive threads -> consecutive banks: conflict free), so 32 systems per warp advance in
-// lock step with no synchronisation at all; the reduced operators are read as warp-uniform (broadcast) double2's.
-#define TPS_MAXN 24
-#define TPS_QCHUNK 16
-__global__ void __launch_bounds__(128)
-k_reduced_solve_tps(const double* __restrict__ y, int nb, const double* __restrict__ Ahat, const double* __restrict__ rhs,
-                    int rhs_per_system, int n, int64_t K, double* __restrict__ C, int* __restrict__ info, int npkp) {
-    extern __shared__ __align__(16) double sm[];
-    const int NT = blockDim.x, t = threadIdx.x;
-    const int npk = n * (n + 1) / 2;
-    double* Apk = sm;                                  // nb x npkp  (npkp = npk rounded up to even)
-    double* M = sm + size_t(nb) * npkp;                // npkp x NT
-    for (int idx = t; idx < nb * npkp; idx += NT) {
-        const int q = idx / npkp, e = idx % npkp;
+// ---- quad-per-system variant (n <= 24): assembly on the fp64 tensor cores, factorisation in registers ------------------
+// A warp owns 8 systems, 4 lanes each.  The assembly A_k = sum_q y_kq Ahat_q is the GEMM (8 systems x nb) . (nb x entries)
+// and runs as DMMA m8n8k4 tiles: the A fragment is y (lane L: system L/4, block 4 qg + L%4), the B fragment comes from a
+// shared-memory table built once per CTA, and the C fragment IS the register layout of the factorisation: lane l of a quad
+// holds rows 4m + l (m = 0..NR-1) of its system, row block m as 4m + 4 column slots (slots right of the diagonal mirror the
+// symmetric entry and are never read).  A tile is (row block m, column pair p): quad lane l receives (row 4m+l, cols 2p, 2p+1).
+// Right-looking Cholesky with the forward substitution interleaved: per column one quad-wide broadcast of the pivot and of
+// every L_jk (shuffles of width 4), all trailing updates are independent register FMAs; the diagonal keeps 1 / L_kk.
+// Back substitution: per row one partial dot product per lane and a quad reduction.  No shared memory after the assembly,
+// no synchronisation besides the shuffles; occupancy is set by registers (12 warps per SM at n = 20).
+__device__ __forceinline__ void dmma884_rs(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+#define RQ_THREADS 128
+#define RQ_MAXN 24
+// compile-time loop: the body sees its index as a constant expression, so every register-array subscript below is static
+// (nvcc does not fully unroll loops of this size from a pragma alone and would put the matrix into local memory)
+template <int I, int E, class F> __device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < E) { f(std::integral_constant<int, I>{}); static_for<I + 1, E>(f); }
+}
+template <int N> struct RqCfg {
+    static constexpr int NR = (N + 3) / 4;                       // row blocks
+    static constexpr int NE = (N + 1) & ~1;                      // columns, rounded up to a DMMA column pair
+    __host__ __device__ static constexpr int width(int m) { return 4 * m + 4 < NE ? 4 * m + 4 : NE; }
+    __host__ __device__ static constexpr int tile0(int m) { return m == 0 ? 0 : tile0(m - 1) + width(m - 1) / 2; }
+    static constexpr int NT = tile0(NR);                         // tiles (row block, column pair)
+    static constexpr int OCC = N <= 12 ? 4 : (N <= 16 ? 3 : 2);  // CTAs per SM without register spills (n = 20 on B200, 1M systems: 0.885 ms at 2, 0.920 at 3 with spills, 1.52 at 1)
+};
+
+template <int N, int OCC>
+__global__ void __launch_bounds__(RQ_THREADS, OCC)
+k_reduced_solve_quad(const double* __restrict__ y, int nb, const double* __restrict__ Ahat, const double* __restrict__ rhs,
+                     int rhs_per_system, int64_t K, double* __restrict__ C, int* __restrict__ info, int nqg) {
+    using Cfg = RqCfg<N>;
+    constexpr int NR = Cfg::NR, NT = Cfg::NT, NE = Cfg::NE;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) double sm[];       // Bt[nqg][NT][32]: B fragments, lane-contiguous
+    for (int idx = threadIdx.x; idx < nqg * NT * 32; idx += blockDim.x) {
+        const int L = idx & 31, tile = (idx >> 5) % NT, qg = (idx >> 5) / NT;
+        const int kq = L & 3, slot = L >> 2;           // B fragment of m8n8k4: lane L holds B[k = L % 4][n = L / 4]
+        int m = 0;
+        while (m + 1 < NR && Cfg::tile0(m + 1) <= tile) ++m;
+        const int p = tile - Cfg::tile0(m);
+        const int row = 4 * m + (slot >> 1), col = 2 * p + (slot & 1), q = 4 * qg + kq;
         double v = 0.0;
-        if (e < npk) {
-            int i = int((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-            while (i * (i + 1) / 2 > e) --i;
-            while ((i + 1) * (i + 2) / 2 <= e) ++i;
-            v = Ahat[(size_t(q) * n + i) * n + (e - i * (i + 1) / 2)];
-        }
-        Apk[idx] = v;
+        if (q < nb && row < N && col < N)
+            v = (col <= row) ? Ahat[(size_t(q) * N + row) * N + col] : Ahat[(size_t(q) * N + col) * N + row];
+        sm[idx] = v;
     }
     __syncthreads();
-    double* Mt = M + t;
-#define MM(e) Mt[(e) * NT]
-    for (int64_t k = int64_t(blockIdx.x) * NT + t; k < K; k += int64_t(gridDim.x) * NT) {
-        // ---- assemble sum_q y_q Ahat_q ----
-        for (int q0 = 0; q0 < nb; q0 += TPS_QCHUNK) {
-            double yq[TPS_QCHUNK];
-#pragma unroll
-            for (int q = 0; q < TPS_QCHUNK; ++q) yq[q] = (q0 + q < nb) ? y[k * nb + q0 + q] : 0.0;
-            const double* Ab = Apk + size_t(q0) * npkp;
-            const int nq = min(TPS_QCHUNK, nb - q0);
-            for (int e = 0; e < npkp; e += 2) {
-                double a0 = 0.0, a1 = 0.0;
-                if (q0) { a0 = MM(e); a1 = MM(e + 1); }
-                if (nq == TPS_QCHUNK) {
-#pragma unroll
-                    for (int q = 0; q < TPS_QCHUNK; ++q) {
-                        const double2 v = *reinterpret_cast<const double2*>(Ab + q * npkp + e);
-                        a0 = fma(yq[q], v.x, a0);
-                        a1 = fma(yq[q], v.y, a1);
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < TPS_QCHUNK; ++q) {
-                        if (q < nq) {
-                            const double2 v = *reinterpret_cast<const double2*>(Ab + q * npkp + e);
-                            a0 = fma(yq[q], v.x, a0);
-                            a1 = fma(yq[q], v.y, a1);
-                        }
-                    }
-                }
-                MM(e) = a0; MM(e + 1) = a1;
-            }
+    const int lane = threadIdx.x & 31, l = lane & 3, g = lane >> 2;
+    const int64_t nwarp = int64_t(gridDim.x) * (RQ_THREADS / 32);
+    for (int64_t s0 = (int64_t(blockIdx.x) * (RQ_THREADS / 32) + (threadIdx.x >> 5)) * 8; s0 < K; s0 += nwarp * 8) {
+        const int64_t k = s0 + g;
+        const bool live = k < K;
+        double R[NR][NE];                              // row block m uses the first width(m) slots
+        static_for<0, NR>([&](auto m_) {
+            constexpr int m = decltype(m_)::value;
+            static_for<0, Cfg::width(m)>([&](auto c_) { R[m][decltype(c_)::value] = 0.0; });
+        });
+        // ---- assembly: NT tiles x nqg DMMAs ----
+        for (int qg = 0; qg < nqg; ++qg) {
+            const int q = 4 * qg + l;
+            const double a = (live && q < nb) ? y[k * nb + q] : 0.0;
+            const double* bt = sm + size_t(qg) * NT * 32 + lane;
+            static_for<0, NR>([&](auto m_) {
+                constexpr int m = decltype(m_)::value;
+                static_for<0, Cfg::width(m) / 2>([&](auto p_) {
+                    constexpr int p = decltype(p_)::value;
+                    dmma884_rs(R[m][2 * p], R[m][2 * p + 1], a, bt[(Cfg::tile0(m) + p) * 32]);
+                });
+            });
         }
-        // ---- Cholesky (right looking); the diagonal keeps 1 / L_kk ----
+        // rows >= N of the last block stay zero (the table holds zeros there) and never act as pivots
+        double B[NR];
+        const double* rb = rhs + (rhs_per_system ? k * N : 0);
+#pragma unroll
+        for (int m = 0; m < NR; ++m) B[m] = (live && 4 * m + l < N) ? rb[4 * m + l] : 0.0;
+        // ---- Cholesky + forward substitution ----
         int bad = 0;
-        for (int kc = 0; kc < n; ++kc) {
-            const int ekk = kc * (kc + 1) / 2 + kc;
-            const double d = MM(ekk);
+        static_for<0, N>([&](auto kc_) {
+            constexpr int kc = decltype(kc_)::value, mk = kc >> 2, lk = kc & 3;
+            const double d = __shfl_sync(FULL, R[mk][kc], lk, 4);
             if (!(d > 0.0)) bad = 1;
-            const double ild = 1.0 / sqrt(d);
-            MM(ekk) = ild;
-            for (int i = kc + 1; i < n; ++i) MM(i * (i + 1) / 2 + kc) *= ild;
-            for (int j = kc + 1; j < n; ++j) {
-                const double ljk = MM(j * (j + 1) / 2 + kc);
-#pragma unroll 4
-                for (int i = j; i < n; ++i) {
-                    const int eij = i * (i + 1) / 2 + j;
-                    MM(eij) = fma(-MM(i * (i + 1) / 2 + kc), ljk, MM(eij));
-                }
-            }
+            const double ild = rsqrt(d);
+            static_for<mk, NR>([&](auto m_) { constexpr int m = decltype(m_)::value; R[m][kc] *= ild; });
+            if (l == lk) R[mk][kc] = ild;
+            const double ck = __shfl_sync(FULL, B[mk] * ild, lk, 4);
+            if (l == lk) B[mk] = ck;
+            static_for<mk, NR>([&](auto m_) {
+                constexpr int m = decltype(m_)::value;
+                if (m > mk || l > lk) B[m] = fma(-R[m][kc], ck, B[m]);
+            });
+            static_for<kc + 1, N>([&](auto j_) {
+                constexpr int j = decltype(j_)::value;
+                const double Lj = __shfl_sync(FULL, R[j >> 2][kc], j & 3, 4);
+                static_for<(j >> 2), NR>([&](auto m_) {
+                    constexpr int m = decltype(m_)::value;
+                    R[m][j] = fma(-R[m][kc], Lj, R[m][j]);
+                });
+            });
+        });
+        // ---- back substitution: L^T x = c ----
+        static_for<0, N>([&](auto ii_) {
+            constexpr int i = N - 1 - decltype(ii_)::value, mi = i >> 2, li = i & 3;
+            double sacc = 0.0;
+            static_for<mi, NR>([&](auto m_) {
+                constexpr int m = decltype(m_)::value;
+                if (m > mi || l > li) sacc = fma(R[m][i], B[m], sacc);
+            });
+            sacc += __shfl_xor_sync(FULL, sacc, 1, 4);
+            sacc += __shfl_xor_sync(FULL, sacc, 2, 4);
+            if (l == li) B[mi] = (B[mi] - sacc) * R[mi][i];
+        });
+        if (live) {
+#pragma unroll
+            for (int m = 0; m < NR; ++m)
+                if (4 * m + l < N) C[k * N + 4 * m + l] = B[m];
+            if (info && l == 0) info[k] = bad;
         }
-        // ---- L L^T c = rhs ----
-        double b[TPS_MAXN];
-        const double* rb = rhs + (rhs_per_system ? k * n : 0);
-#pragma unroll
-        for (int i = 0; i < TPS_MAXN; ++i) b[i] = (i < n) ? rb[i] : 0.0;
-#pragma unroll
-        for (int i = 0; i < TPS_MAXN; ++i) {
-            if (i < n) {
-                double v = b[i];
-#pragma unroll
-                for (int j = 0; j < i; ++j) v = fma(-MM(i * (i + 1) / 2 + j), b[j], v);
-                b[i] = v * MM(i * (i + 1) / 2 + i);
-            }
-        }
-#pragma unroll
-        for (int i = TPS_MAXN - 1; i >= 0; --i) {
-            if (i < n) {
-                double v = b[i];
-#pragma unroll
-                for (int j = i + 1; j < TPS_MAXN; ++j)
-                    if (j < n) v = fma(-MM(j * (j + 1) / 2 + i), b[j], v);
-                b[i] = v * MM(i * (i + 1) / 2 + i);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < TPS_MAXN; ++i)
-            if (i < n) C[k * n + i] = b[i];
-        if (info) info[k] = bad;
     }
-#undef MM
+}
+
+template <int N, int OCC>
+static int launch_reduced_quad(const double* y, int nb, const double* Ahat, const double* rhs, int rps, int64_t K,
+                               double* C, int* info, int nsm, cudaStream_t st) {
+    const int nqg = (nb + 3) / 4;
+    const size_t smb = size_t(nqg) * RqCfg<N>::NT * 32 * 8;
+    if (smb > 227 * 1024) return -1;
+    CK(cudaFuncSetAttribute(k_reduced_solve_quad<N, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+    const int per_sm = std::max<int>(1, std::min<int>(OCC, int((227 * 1024) / (smb + 1024))));
+    const int64_t want = (K + 8 * (RQ_THREADS / 32) - 1) / (8 * (RQ_THREADS / 32));
+    const int grid = int(std::min<int64_t>(want, int64_t(nsm) * per_sm));
+    ++g_launches;
+    k_reduced_solve_quad<N, OCC><<<grid, RQ_THREADS, smb, st>>>(y, nb, Ahat, rhs, rps, K, C, info, nqg);
+    CK(cudaGetLastError());
+    return ROMHC_OK;
+}
+
+template <int N>
+static int dispatch_reduced_quad(int n, const double* y, int nb, const double* Ahat, const double* rhs, int rps, int64_t K,
+                                 double* C, int* info, int nsm, cudaStream_t st) {
+    if (n == N) {
+        return launch_reduced_quad<N, RqCfg<N>::OCC>(y, nb, Ahat, rhs, rps, K, C, info, nsm, st);
+    }
+    if constexpr (N > 1) return dispatch_reduced_quad<N - 1>(n, y, nb, Ahat, rhs, rps, K, C, info, nsm, st);
+    return -1;
 }
 
 int reduced_solve(const double* y, int nb, const double* Ahat, const double* rhs, int rhs_per_system, int n,
@@ -309,26 +353,9 @@ int reduced_solve(const double* y, int nb, const double* Ahat, const double* rhs
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= TPS_MAXN) {
-        const int npkp = (npk + 1) & ~1;
-        const size_t tab = size_t(nb) * npkp * 8;
-        const size_t budget = 224 * 1024;
-        if (tab + size_t(32) * npkp * 8 <= budget) {
-            int nt = int((budget - tab) / (size_t(npkp) * 8));
-            nt = std::min(128, (nt / 32) * 32);
-            static bool conf = false;
-            if (!conf) {
-                CK(cudaFuncSetAttribute(k_reduced_solve_tps, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                conf = true;
-            }
-            const size_t smb = tab + size_t(nt) * npkp * 8;
-            const int per_sm = std::max<int>(1, int((227 * 1024) / (smb + 1024)));
-            const int64_t want = (K + nt - 1) / nt;
-            const int grid = int(std::min<int64_t>(want, int64_t(nsm) * per_sm));
-            ++g_launches; k_reduced_solve_tps<<<grid, nt, smb, st>>>(y, nb, Ahat, rhs, rhs_per_system, n, K, C, info, npkp);
-            CK(cudaGetLastError());
-            return ROMHC_OK;
-        }
+    if (n <= RQ_MAXN) {
+        const int rc = dispatch_reduced_quad<RQ_MAXN>(n, y, nb, Ahat, rhs, rhs_per_system, K, C, info, nsm, st);
+        if (rc >= 0) return rc;          // -1: the fragment table does not fit shared memory -> warp-per-system kernel
     }
     const size_t per_warp = size_t(npk + nb + 2) * 8;
     const size_t tab = size_t(nb) * npk * 8;

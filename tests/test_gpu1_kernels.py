@@ -232,9 +232,12 @@ def test_projection_and_reduced_solve(torch_mod, geo, N, n):
 
 
 @pytest.mark.parametrize("n,nb,K", [(1, 4, 100), (7, 16, 1000), (20, 16, 5000), (24, 9, 333), (25, 16, 500), (40, 4, 257),
-                                    (20, 64, 999), (12, 200, 100)])
+                                    (20, 64, 999), (12, 200, 100), (24, 64, 77), (64, 16, 65)]
+                         + [(n, 1 + (5 * n) % 17, 1000 + n) for n in range(2, 25)])
 def test_reduced_solve_random_spd(torch_mod, n, nb, K):
-    """both reduced-solve kernels (thread-per-system n <= 24, warp-per-system above) against numpy.linalg.solve"""
+    """both reduced-solve kernels (quad-per-system with DMMA assembly for n <= 24 -- one instantiation per n --, warp-per-system
+    above or when the fragment table exceeds shared memory) against numpy.linalg.solve; ragged K (not a multiple of the 8
+    systems a warp owns), nb not a multiple of the DMMA k = 4"""
     torch = torch_mod
     from romhighcontrast_b200 import _lib
     import ctypes as C
