@@ -34,6 +34,12 @@ KIND_NAMES = ["k_pcg_p_apply", "k_pcg_update", "k_mg_down(l0)", "k_mg_down(l>=1)
 KIND_STREAMS = [1.5, 5.0, 1.75, 2.25 / 4, 2.0 / 16, 2.25, 3.25 / 4]   # z_A, z = M r and p travel as fp32 (half a stream each way) on the finest level
 
 
+def workload_name(K):
+    """config.workload -- the same string in both arms (the driver compares them)"""
+    return (f"configs[2]: (4,4) subdomains, N=64 (256x256 cells, D=65025), {K} snapshots per GPU, contrast 10^U(0,6); "
+            "snapshot solves to rtol 1e-12")
+
+
 def sample_params(K, seed):
     return 10 ** np.random.default_rng(seed).uniform(0, np.log10(CMAX), size=(K,) + GEO)
 
@@ -83,8 +89,8 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup if args.warmup is not None else 1,
         "ms_per_step": 1e3 * t_all / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[2]: (4,4) subdomains, N=64 (256x256 cells, D=65025), contrast 10^U(0,6)",
-                   "note": "each step is a bounded sample of the 10k-snapshot workload"},
+        "config": {"workload": workload_name(args.k_snap),
+                   "note": "each step is a bounded sample of that workload (sparse assembly + SuperLU per system)"},
         "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port",
                          "sample": f"{per_core * cores} snapshot solves per step (oracle: scipy CSR + SuperLU, "
                                    f"{cores} worker processes)"},
@@ -239,6 +245,21 @@ def main():
     it_np = iters.cpu().numpy()
     stats = dict(eng.last_solve_stats)
 
+    # the all-fp64 figure next to the default (fp32 TRANSPORT of z, z_A and p on the finest level; arithmetic, x, r and
+    # every reduction are fp64): one timed pass with z32 = 0
+    eng.set_option("z32", 0)
+    eng.solve(y, out=x)
+    barrier()
+    e0, e1 = ev(), ev()
+    e0.record(); eng.solve(y, out=x); e1.record(); torch.cuda.synchronize()
+    t64 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t64, op=dist.ReduceOp.MAX)
+    eng.set_option("z32", 3)
+    precision_note = ("fp64 arithmetic, iterate, residual and reductions; fp32 transport of z, z_A, p between kernels on the "
+                      "finest level (z32=3); all-fp64 transport (z32=0): %.0f solves/s" % (world * K / (float(t64.item()) * 1e-3)))
+    eng.solve(y, out=x)                                       # leave the default-mode solution in x
+
     # ---- end to end through the host-buffer C ABI (pinned host memory both ways) --------------------------------
     U_pin = torch.empty((K, eng.D), dtype=torch.float64, pin_memory=True)
     y_pin = torch.from_numpy(np.ascontiguousarray(y_host.reshape(K, -1))).pin_memory()
@@ -340,8 +361,9 @@ def main():
             "metric": "fem_snapshot_solves_per_s", "value": value, "unit": "solves/s", "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[2]: (4,4) subdomains, N=64 (256x256 cells, D=65025), "
-                                   f"{K} snapshots per GPU, contrast 10^U(0,6); batched GMG-PCG to rtol 1e-12",
+            "config": {"workload": workload_name(K),
+                       "solver": "batched GMG-preconditioned CG, V(2,2)/(3,3)/(4,4), rtol 1e-12 on sqrt(r.z / r0.z0)",
+                       "precision": precision_note,
                        "l2": "inputs larger than L2 (%.1f GB working set per step)" % (stats["workspace_bytes"] / 1e9),
                        "tuning": {"strip_kb": args.strip_kb, "nu": args.nu, "nu_tail": args.nu_tail, "threads": args.threads},
                        "pcg_iterations": {"min": int(it_np.min()), "mean": float(it_np.mean()), "max": int(it_np.max())},
@@ -380,12 +402,145 @@ def run_greedy(U_np, y_host, n):
     return out
 
 
+def run_distributed(eng, x, U_np, y_host, K, args, world, rank, barrier, ev):
+    """POD (both routes) and the greedy builders on a training set sharded over the ranks (contiguous slices, rank r owns
+    [b_r, b_{r+1}) of the union): dist.distributed_pca(method="gram"): all_to_all -> partial centred SYRK -> all_reduce
+    of the K x K Gram -> replicated eigensolve -> all_gather of component slices; method="krylov": Gram-free block
+    Lanczos with one (32, Dp) all_reduce per step; dist.greedy_build_sharded: all_gather of (error, index) pairs +
+    broadcast of the winner.  Every collective is warmed (first repetition discarded) and the best of 3 is reported;
+    times are max over ranks.  At world == 1 the same code runs without collectives (the N = 1 point of the scaling)."""
+    import torch
+    import torch.distributed as dist
+    from romhighcontrast_b200 import dist as rd
+    from lib.ReducedBasis import ReducedBasisGreedy, GREEDY_FOR_GALERKIN, GREEDY_FOR_H10
+    from lib.SolutionsManagers import SolutionsManagerFEM
+    n = args.n_rb
+    out = {}
+
+    def maxr(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- POD of a 10k-snapshot union (configs[2]'s POD, strong scaling over the ranks) ------------------------------
+    K_pod = int(min(10000, world * K))
+    b = rd.shard_bounds(K_pod, world)
+    Kl = b[rank + 1] - b[rank]
+    counts = [b[r + 1] - b[r] for r in range(world)]
+    stage_best, tot_ms = {}, []
+    for rep in range(4):
+        Xl = x[:Kl].clone()
+        tm = {}
+        barrier()
+        e0, e1 = ev(), ev()
+        e0.record()
+        comps_g, sig_g = rd.distributed_pca(eng, Xl, n, counts=counts, timings=tm, method="gram")
+        e1.record(); torch.cuda.synchronize()
+        if rep:                                                    # repetition 0 warms NCCL channels and allocations
+            tot_ms.append(maxr(e0.elapsed_time(e1)))
+            for k_, v_ in tm.items():
+                v_ = maxr(v_)
+                stage_best[k_] = min(stage_best.get(k_, v_), v_)
+        del Xl
+    gram_bytes = 8.0 * K_pod * K_pod
+    out["pod_gram"] = {"K_total": K_pod, "rows_per_rank": Kl, "n": n, "ms": min(tot_ms), "stages_ms": stage_best,
+                       "gram_allreduce_bytes": gram_bytes if world > 1 else 0,
+                       "gram_allreduce_busbw_GBps": (gram_bytes * 2 * (world - 1) / world / (stage_best["gram_allreduce"] * 1e-3) / 1e9
+                                                     if world > 1 and stage_best.get("gram_allreduce") else None),
+                       "all_to_all_bytes_per_rank": 8.0 * Kl * eng.Dp * (world - 1) / world,
+                       "singular_values_head": [float(v) for v in sig_g[:5].cpu()]}
+    kry_ms, kst = [], {}
+    for rep in range(3):
+        Xl = x[:Kl].clone()
+        kst = {}
+        barrier()
+        e0, e1 = ev(), ev()
+        e0.record()
+        comps_k, sig_k = rd.distributed_pca(eng, Xl, n, counts=counts, timings=kst, method="krylov")
+        e1.record(); torch.cuda.synchronize()
+        if rep:
+            kry_ms.append(maxr(e0.elapsed_time(e1)))
+        del Xl
+    sv_diff = float(((sig_k - sig_g).abs() / sig_g).max())
+    sub_diff = float((comps_k - comps_g).abs().max())
+    out["pod_krylov"] = {"K_total": K_pod, "n": n, "ms": min(kry_ms), **{k_: v_ for k_, v_ in kst.items()},
+                         "sv_rel_diff_vs_gram_route": sv_diff, "components_max_abs_diff_vs_gram_route": sub_diff,
+                         "agree_1e-9": bool(sv_diff <= 1e-9)}
+    del comps_g, comps_k
+    # ---- Gram-free POD of the WHOLE union (world x K rows, weak scaling: the configs[4] pattern) --------------------
+    if world > 1:
+        kw_ms, kst = [], {}
+        for rep in range(2):
+            Xl = x.clone()
+            kst = {}
+            barrier()
+            e0, e1 = ev(), ev()
+            e0.record()
+            _, sig_w = rd.distributed_pca(eng, Xl, n, counts=[K] * world, timings=kst, method="krylov")
+            e1.record(); torch.cuda.synchronize()
+            if rep:
+                kw_ms.append(maxr(e0.elapsed_time(e1)))
+            del Xl
+        out["pod_krylov_whole_union"] = {"K_total": world * K, "n": n, "ms": min(kw_ms), **kst,
+                                         "singular_values_head": [float(v) for v in sig_w[:5].cpu()]}
+    # ---- sharded greedy on the same 10k union, both criteria ---------------------------------------------------------
+    if U_np is not None:
+        sm = SolutionsManagerFEM(GEO, NPB, method="lsqsparse")
+        U_loc, a_loc = U_np[:Kl], y_host[:Kl]
+        h1_loc = sm.H10norm(U_loc)
+        g = {"K_total": K_pod, "n": n}
+        for name, crit in (("galerkin", GREEDY_FOR_GALERKIN), ("h10", GREEDY_FOR_H10)):
+            best, tm = None, {}
+            for rep in range(2):
+                tm = {}
+                barrier()
+                t0 = time.perf_counter()
+                _, _, picked = rd.greedy_build_sharded(sm, n, U_loc, a_loc, h1_loc, K_pod, greedy_for=crit, timings=tm)
+                torch.cuda.synchronize()
+                dt = maxr(time.perf_counter() - t0)
+                best = dt if best is None else min(best, dt)
+            g[name] = {"s": best, "selected_head": [int(i) for i in picked[:6]], "stages_ms_sum_over_steps": tm}
+        # index parity: the sharded build must pick exactly what one GPU picks on the gathered set (sub-sample)
+        K_chk = int(min(2048, K_pod))
+        bc = rd.shard_bounds(K_chk, world)
+        kl = bc[rank + 1] - bc[rank]
+        Uc, ac = np.ascontiguousarray(U_np[:kl]), np.ascontiguousarray(y_host[:kl])
+        hc = sm.H10norm(Uc)
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, (Uc, ac, hc))
+        else:
+            parts = [(Uc, ac, hc)]
+        same = True
+        for name, crit in (("galerkin", GREEDY_FOR_GALERKIN), ("h10", GREEDY_FOR_H10)):
+            _, _, picked = rd.greedy_build_sharded(sm, 10, Uc, ac, hc, K_chk, greedy_for=crit)
+            if rank == 0:
+                ref = ReducedBasisGreedy(greedy_for=crit).build(n=10, sm=sm, solutions2train=np.vstack([p_[0] for p_ in parts]),
+                                                                a2train=np.concatenate([p_[1] for p_ in parts]),
+                                                                solutions2train_h1norm=np.concatenate([p_[2] for p_ in parts]))
+                same &= [int(i) for i in picked] == [int(i) for i in ref.selected_indices]
+        g["indices_equal_single_gpu_on_subsample"] = {"K": K_chk, "n": 10, "equal": bool(same)}
+        out["greedy_sharded"] = g
+    barrier()
+    return out
+
+
 def run_secondary(eng, x, y, K, args, world, rank, barrier, ev, U_np=None, y_host=None):
     """POD (centred Gram on the fp64 tensor cores), the greedy builders and 1M online reduced Galerkin solves on the
     snapshots in `x`."""
     import torch
     out = {}
     n = args.n_rb
+    # the two communicating stages (SURVEY 8e) on the K-sharded union of all ranks' snapshots -- before anything below
+    # centres the resident snapshots in place
+    try:
+        out["distributed"] = run_distributed(eng, x, U_np, y_host, K, args, world, rank, barrier, ev)
+    except Exception as exc:
+        import traceback
+        out["distributed"] = {"error": repr(exc)[:300], "trace": traceback.format_exc()[-600:]}
+        if world > 1:
+            raise                                                 # a rank that left a collective early would hang the others
     if U_np is not None:
         try:
             out["greedy"] = run_greedy(U_np, y_host, n)
@@ -427,11 +582,6 @@ def run_secondary(eng, x, y, K, args, world, rank, barrier, ev, U_np=None, y_hos
     flop = float(Kg) * (Kg + 1) * eng.D            # triangle only, algorithmic D
     out["gram"] = {"K": Kg, "ms": ms, "TFLOPs": flop / (ms * 1e-3) / 1e12, "peak_TFLOPs_cublas_dgemm_8192": dgemm_peak,
                    "frac": flop / (ms * 1e-3) / 1e12 / dgemm_peak, "flop_counted": "K(K+1)D (lower triangle)", "all_ms": gram_ms}
-    if world > 1:
-        import torch.distributed as dist
-        e0, e1 = ev(), ev()
-        barrier(); e0.record(); dist.all_reduce(G); e1.record(); torch.cuda.synchronize()
-        out["gram_allreduce_ms"] = e0.elapsed_time(e1)
     from romhighcontrast_b200.pod import top_eigenpairs
     pod_ms = []
     for _ in range(3):       # the first pass pays torch's one-time cuSOLVER initialisation (QR of the Lanczos blocks)

@@ -164,13 +164,20 @@ def krylov_pca(eng, X_local_pad, n, K_total=None, center_in_place=False, extra=1
     b = int(min(32, Dp, n + extra))
     max_dim = int(min(max_dim, Dp))
 
+    ar_events = []                                            # (start, stop) CUDA events around every block all_reduce
+
     def apply_S(W):                                           # (b', Dp) -> (b', Dp), identical on every rank
         if Kr:
             Zw = eng.gemm_tn(eng.gemm_nt(X, W, splitk=True), X)
         else:
             Zw = torch.zeros_like(W)
         if w > 1:
-            torch.distributed.all_reduce(Zw)
+            if stats is not None and Zw.is_cuda:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); torch.distributed.all_reduce(Zw); e1.record()
+                ar_events.append((e0, e1, Zw.numel() * 8))
+            else:
+                torch.distributed.all_reduce(Zw)
         return Zw
 
     def agree(Qb):
@@ -255,6 +262,11 @@ def krylov_pca(eng, X_local_pad, n, K_total=None, center_in_place=False, extra=1
         Q = Qn
     if stats is not None:
         stats.update(steps=steps, krylov_dim=dim, block=b, residual=res)
+        if ar_events:
+            torch.cuda.synchronize()
+            ms = [e0.elapsed_time(e1) for e0, e1, _ in ar_events]
+            stats.update(block_allreduce_calls=len(ms), block_allreduce_ms_min=min(ms), block_allreduce_ms_median=float(np.median(ms)),
+                         block_allreduce_ms_total=float(sum(ms)), block_allreduce_bytes=int(max(nb for _, _, nb in ar_events)))
     sig = torch.sqrt(torch.clamp(lam, min=0.0))
     idx = comps.abs().argmax(dim=1)
     sign = torch.sign(comps[torch.arange(comps.shape[0], device=dev), idx])
