@@ -151,11 +151,8 @@ static int launch_gemm_nt(const double* A, int64_t lda, const double* B, int64_t
                           int64_t M, int64_t Nn, int64_t Kd, int symmetric, cudaStream_t st) {
     auto kern = k_gemm_nt<BM, BN, WM, WN, STAGES, VEC, MINB>;
     const size_t sm = size_t(STAGES) * (BM + BN) * GK_PITCH * 8;
-    static bool configured = false;
-    if (!configured) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
-        configured = true;
-    }
+    // per call: the attribute is per device and a process may drive several
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
     const int64_t tmn = (M + BM - 1) / BM, tnn = (Nn + BN - 1) / BN;
     const int64_t ntiles = symmetric ? (BM / BN) * tmn * (tmn + 1) / 2 : tmn * tnn;
     ++g_launches; kern<<<(unsigned)ntiles, 256, sm, st>>>(A, lda, B, ldb, C, ldc, M, Nn, Kd, symmetric, int(tnn));
@@ -191,11 +188,8 @@ static int launch_gemm_nt_splitk(const double* A, int64_t lda, const double* B, 
                                  int64_t M, int64_t Nn, int64_t Kd, int nsplit, cudaStream_t st) {
     auto kern = k_gemm_nt<BM, BN, WM, WN, STAGES, 16, MINB, true>;
     const size_t sm = size_t(STAGES) * (BM + BN) * GK_PITCH * 8;
-    static bool configured = false;
-    if (!configured) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
-        configured = true;
-    }
+    // per call: the attribute is per device and a process may drive several
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
     const int64_t kc = ((Kd + nsplit - 1) / nsplit + GK_BK - 1) / GK_BK * GK_BK;
     nsplit = int((Kd + kc - 1) / kc);
     if (int rc = scratch_reserve(size_t(nsplit) * M * Nn * 8)) return rc;
@@ -257,7 +251,7 @@ int gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* 
 #define NN_ROWS 8
 __global__ void __launch_bounds__(256)
 k_gemm_nn(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb, double* __restrict__ C,
-          int64_t ldc, int64_t M, int64_t Nn, int Kd) {
+          int64_t ldc, int64_t M, int64_t Nn, int Kd, int accumulate) {
     extern __shared__ __align__(16) double sAr[];   // NN_ROWS x Kd
     const int64_t m0 = int64_t(blockIdx.y) * NN_ROWS;
     for (int i = threadIdx.x; i < NN_ROWS * Kd; i += blockDim.x) {
@@ -269,7 +263,7 @@ k_gemm_nn(const double* __restrict__ A, int64_t lda, const double* __restrict__ 
     if (col >= Nn) return;
     double acc[NN_ROWS];
 #pragma unroll
-    for (int r = 0; r < NN_ROWS; ++r) acc[r] = 0.0;
+    for (int r = 0; r < NN_ROWS; ++r) acc[r] = (accumulate && m0 + r < M) ? C[(m0 + r) * ldc + col] : 0.0;
     for (int j = 0; j < Kd; ++j) {
         const double b = B[int64_t(j) * ldb + col];
 #pragma unroll
@@ -282,17 +276,21 @@ k_gemm_nn(const double* __restrict__ A, int64_t lda, const double* __restrict__ 
 int gemm_nn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M, int64_t Nn,
             int64_t Kd, cudaStream_t st) {
     if (M <= 0 || Nn <= 0) return ROMHC_OK;
-    if (Kd > 2048) { set_error("gemm_nn: contraction dim %lld too large for this kernel", (long long)Kd); return ROMHC_ERR_ARG; }
     const int64_t rows_blocks = (M + NN_ROWS - 1) / NN_ROWS;
-    static size_t smem_configured = 48 * 1024;      // Kd > 768 (Krylov bases of krylov_pca) needs the opt-in window
-    if (size_t(NN_ROWS) * Kd * 8 > smem_configured) {
-        CK(cudaFuncSetAttribute(k_gemm_nn, cudaFuncAttributeMaxDynamicSharedMemorySize, NN_ROWS * 2048 * 8));
-        smem_configured = size_t(NN_ROWS) * 2048 * 8;
+    const int KC = 2048;                            // contraction chunk held in shared memory; longer ones accumulate into C
+    CK(cudaFuncSetAttribute(k_gemm_nn, cudaFuncAttributeMaxDynamicSharedMemorySize, NN_ROWS * KC * 8));
+    if (Kd <= 0) {
+        for (int64_t r = 0; r < M; ++r) CK(cudaMemsetAsync(C + r * ldc, 0, size_t(Nn) * 8, st));
+        return ROMHC_OK;
     }
-    for (int64_t b0 = 0; b0 < rows_blocks; b0 += 65535) {
-        const int nb = int(std::min<int64_t>(65535, rows_blocks - b0));
-        ++g_launches; k_gemm_nn<<<dim3((unsigned)((Nn + 255) / 256), nb), 256, size_t(NN_ROWS) * Kd * 8, st>>>(
-            A + b0 * NN_ROWS * lda, lda, B, ldb, C + b0 * NN_ROWS * ldc, ldc, M - b0 * NN_ROWS, Nn, int(Kd));
+    for (int64_t k0 = 0; k0 < Kd; k0 += KC) {
+        const int kc = int(std::min<int64_t>(KC, Kd - k0));
+        for (int64_t b0 = 0; b0 < rows_blocks; b0 += 65535) {
+            const int nb = int(std::min<int64_t>(65535, rows_blocks - b0));
+            ++g_launches; k_gemm_nn<<<dim3((unsigned)((Nn + 255) / 256), nb), 256, size_t(NN_ROWS) * kc * 8, st>>>(
+                A + b0 * NN_ROWS * lda + k0, lda, B + k0 * ldb, ldb, C + b0 * NN_ROWS * ldc, ldc, M - b0 * NN_ROWS, Nn, kc,
+                k0 > 0 ? 1 : 0);
+        }
     }
     CK(cudaGetLastError());
     return ROMHC_OK;
@@ -429,11 +427,8 @@ static int launch_gemm_tn_mma(const double* A, int64_t lda, const double* B, int
                               int64_t Nn, int64_t Kd, cudaStream_t st) {
     auto kern = k_gemm_tn_mma<MT>;
     const size_t sm = size_t(TNM_STAGES) * TNM_BK * (TNM_PA + TNM_PB) * 8;
-    static bool configured = false;
-    if (!configured) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
-        configured = true;
-    }
+    // per call: the attribute is per device and a process may drive several
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
     const int64_t ntiles = (Nn + TNM_BN - 1) / TNM_BN;
     int64_t nsplit = std::max<int64_t>(1, std::min<int64_t>((8 * 2 * 148 + ntiles - 1) / ntiles, Kd / 512));
     nsplit = std::min<int64_t>(nsplit, 65535);
@@ -458,7 +453,13 @@ int g_tn_variant = 1;       // 1: DMMA kernel (default, needs 16-byte aligned B 
 int gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M, int64_t Nn,
             int64_t Kd, cudaStream_t st) {
     if (M <= 0 || Nn <= 0) return ROMHC_OK;
-    if (M > TN_MAXM) { set_error("gemm_tn: M = %lld > %d", (long long)M, TN_MAXM); return ROMHC_ERR_ARG; }
+    if (M > TN_MAXM) {                       // row blocks of 32: the kernels keep all their output rows in registers
+        for (int64_t m0 = 0; m0 < M; m0 += TN_MAXM) {
+            const int rc = gemm_tn(A + m0, lda, B, ldb, C + m0 * ldc, ldc, std::min<int64_t>(TN_MAXM, M - m0), Nn, Kd, st);
+            if (rc) return rc;
+        }
+        return ROMHC_OK;
+    }
     if (g_tn_variant == 1 && Kd > 0 && (ldb % 2 == 0) && ((uintptr_t)B % 16 == 0)) {
         switch ((M + 7) / 8) {
             case 1: return launch_gemm_tn_mma<1>(A, lda, B, ldb, C, ldc, M, Nn, Kd, st);

@@ -22,6 +22,7 @@ namespace romhc {
 // grid = (N cell rows of the block, nb blocks); partial n x n matrices are reduced by k_reduce_ahat.
 // ======================================================================================================
 #define PROJ_EB 64   // edges per batch (16 cells)
+#define PROJ_MAXN 64  // n * n <= 16 entries per thread
 __global__ void __launch_bounds__(256)
 k_project_partial(LevelGeo g, const double* __restrict__ basis, int n, double* __restrict__ part) {
     extern __shared__ __align__(16) double G[];   // PROJ_EB x (n | 1)
@@ -31,7 +32,10 @@ k_project_partial(LevelGeo g, const double* __restrict__ basis, int n, double* _
     const int cr = bp * g.N + crl;                 // cell row
     const int tid = threadIdx.x, nt = blockDim.x;
     const int nn = n * n;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};         // entries tid, tid+256, ... (n <= 32)
+    const int nslot = (nn + 255) >> 8;            // entries tid, tid+256, ... (warp-uniform count, <= 16)
+    double acc[PROJ_MAXN * PROJ_MAXN / 256];
+#pragma unroll
+    for (int s = 0; s < PROJ_MAXN * PROJ_MAXN / 256; ++s) acc[s] = 0.0;
     for (int c0 = 0; c0 < g.N; c0 += PROJ_EB / 4) {
         const int ncell = min(PROJ_EB / 4, g.N - c0);
         __syncthreads();
@@ -52,21 +56,23 @@ k_project_partial(LevelGeo g, const double* __restrict__ basis, int n, double* _
         __syncthreads();
         const int ne = ncell * 4;
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const int ent = tid + s * 256;
-            if (ent < nn) {
-                const int i = ent / n, j = ent % n;
-                double a = acc[s];
-                for (int e = 0; e < ne; ++e) a = fma(G[e * ldg + i], G[e * ldg + j], a);
-                acc[s] = a;
+        for (int s = 0; s < PROJ_MAXN * PROJ_MAXN / 256; ++s) {
+            if (s < nslot) {
+                const int ent = tid + s * 256;
+                if (ent < nn) {
+                    const int i = ent / n, j = ent % n;
+                    double a = acc[s];
+                    for (int e = 0; e < ne; ++e) a = fma(G[e * ldg + i], G[e * ldg + j], a);
+                    acc[s] = a;
+                }
             }
         }
     }
     double* dst = part + (size_t(q) * g.N + crl) * nn;
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
+    for (int s = 0; s < PROJ_MAXN * PROJ_MAXN / 256; ++s) {
         const int ent = tid + s * 256;
-        if (ent < nn) dst[ent] = 0.5 * acc[s];
+        if (s < nslot && ent < nn) dst[ent] = 0.5 * acc[s];
     }
 }
 
@@ -91,7 +97,7 @@ __global__ void __launch_bounds__(256) k_project_rhs(LevelGeo g, const double* _
 }
 
 int Context::project_operators(const double* basis, int n, double* Ahat, double* bhat, cudaStream_t st) {
-    if (n < 1 || n > 32) { set_error("project_operators: n must be in [1, 32], got %d", n); return ROMHC_ERR_ARG; }
+    if (n < 1 || n > PROJ_MAXN) { set_error("project_operators: n must be in [1, %d], got %d", PROJ_MAXN, n); return ROMHC_ERR_ARG; }
     const LevelGeo& g = levels[0];
     const int nb = nrb * ncb, nn = n * n;
     int rc = ensure_scratch(size_t(nb) * g.N * nn * 8); if (rc) return rc;
@@ -361,11 +367,8 @@ int reduced_solve(const double* y, int nb, const double* Ahat, const double* rhs
     const size_t tab = size_t(nb) * npk * 8;
     const int in_smem = (tab + RS_WARPS * per_warp) <= 96 * 1024;
     const size_t smb = (in_smem ? tab : 0) + RS_WARPS * per_warp;
-    static bool configured = false;
-    if (!configured) {
-        CK(cudaFuncSetAttribute(k_reduced_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
-    }
+    // per call: the attribute is per device and a process may drive several
+    CK(cudaFuncSetAttribute(k_reduced_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     const int64_t want = (K + RS_WARPS - 1) / RS_WARPS;
     const int grid = int(std::min<int64_t>(want, int64_t(nsm) * 8));
     ++g_launches; k_reduced_solve<<<grid, RS_WARPS * 32, smb, st>>>(y, nb, Ahat, rhs, rhs_per_system, n, K, C, info, in_smem);

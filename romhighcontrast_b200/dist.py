@@ -197,11 +197,13 @@ def distributed_pca(eng, X_local_pad: torch.Tensor, n: int, counts=None, timings
         dist.all_reduce(G)
     mark("gram_allreduce")
     lam, V = top_eigenpairs(eng, G, n)
+    mark("eigensolve")
     lam = torch.clamp(lam, min=0.0)
     sig = torch.sqrt(lam)
     comps_local = eng.gemm_tn(V.contiguous(), Xs) / torch.where(sig > 0, sig, torch.ones_like(sig))[:, None]
+    mark("backproject")
     comps = all_gather_cols(comps_local, Dp)
-    mark("eig_backproject")
+    mark("components_allgather")
     idx = comps.abs().argmax(dim=1)
     sign = torch.sign(comps[torch.arange(comps.shape[0], device=comps.device), idx])
     sign = torch.where(sign == 0, torch.ones_like(sign), sign)

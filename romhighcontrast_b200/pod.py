@@ -36,6 +36,7 @@ def top_eigenpairs(eng, G, n, extra=12, tol=1e-13, max_dim=960, seed=0, host_max
     Z = torch.empty(K, max_dim, dtype=torch.float64, device=G.device)      # G @ basis
     dim = 0
     lam = vec = None
+    prev_res = float("inf")
     while True:
         V[:, dim:dim + b] = Q
         Zj = GQ(Q)
@@ -50,7 +51,13 @@ def top_eigenpairs(eng, G, n, extra=12, tol=1e-13, max_dim=960, seed=0, host_max
             Sd = torch.as_tensor(np.ascontiguousarray(S[:, order]), device=G.device)
             vec = Vd @ Sd
             res = torch.linalg.vector_norm(Zd @ Sd - vec * lam[None, :], dim=0)
-            if float(res.max()) <= tol * max(float(lam[0]), 1e-300) or dim + b > max_dim:
+            lam1 = max(float(lam[0]), 1e-300)
+            rmax = float(res.max())
+            # converged, or stalled at the rounding level of G itself (a Gram matrix summed over ranks carries a slightly
+            # higher floor than tol * lam_1; without this test the iteration ran on to max_dim: 13 ms -> 470 ms)
+            stalled = rmax <= 1e-10 * lam1 and rmax > 0.5 * prev_res
+            prev_res = rmax
+            if rmax <= tol * lam1 or stalled or dim + b > max_dim:
                 break
         W = Zj
         for _ in range(2):                                    # block Gram-Schmidt against the whole basis, twice
