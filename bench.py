@@ -154,6 +154,8 @@ def main():
     ap.add_argument("--quick", action="store_true", help="small sizes (debug)")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-config4", action="store_true", help="skip the secondary configs[4] block (512^2 mesh, (8,8) subdomains)")
+    ap.add_argument("--k-config4", type=int, default=12500, help="configs[4] snapshots per GPU (100k / 8)")
     ap.add_argument("--strip-kb", type=float, default=None, help="shared memory per strip CTA (tuning)")
     ap.add_argument("--nu", type=int, default=None, help="Gauss-Seidel sweeps of the V(nu,nu) cycle (tuning)")
     ap.add_argument("--nu-tail", type=int, default=None)
@@ -170,7 +172,7 @@ def main():
     steps = args.steps or 3
     warmup = args.warmup if args.warmup is not None else 3
     if args.quick:
-        args.k_snap, args.k_online = 512, 100000
+        args.k_snap, args.k_online, args.k_config4 = 512, 100000, 256
 
     import torch
     import torch.distributed as dist
@@ -350,6 +352,19 @@ def main():
     if not args.no_secondary:
         secondary = run_secondary(eng, x, y, K, args, world, rank, barrier, ev, U_np, y_host)
 
+    if not args.no_secondary and not args.no_config4:
+        del x, y
+        eng = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        try:
+            secondary["config4"] = run_config4(args, world, rank, local, barrier, ev)
+        except Exception as exc:
+            if world > 1:
+                raise
+            secondary["config4"] = {"error": repr(exc)[:300]}
+
     cpu = None
     if rank == 0 and not args.no_cpu:
         r, cores, n, wall = cpu_snapshot_rate(32, None)          # ~10 s of wall time on all host cores
@@ -383,7 +398,8 @@ def main():
 
 def run_greedy(U_np, y_host, n):
     """Wall time of the reference-facing greedy builders (ReducedBasis.py:112-139) on this rank's snapshots: numpy in,
-    basis out; includes the H2D copy of the snapshot matrix and the host-side QR of every round."""
+    basis out; includes the H2D copy of the (K, D) snapshot matrix (the device-resident figure is in
+    secondary.distributed.greedy_sharded)."""
     import torch
     from lib.ReducedBasis import ReducedBasisGreedy, GREEDY_FOR_GALERKIN, GREEDY_FOR_H10
     from lib.SolutionsManagers import SolutionsManagerFEM
@@ -402,7 +418,7 @@ def run_greedy(U_np, y_host, n):
     return out
 
 
-def run_distributed(eng, x, U_np, y_host, K, args, world, rank, barrier, ev):
+def run_distributed(eng, x, y_dev, y_host, K, args, world, rank, barrier, ev):
     """POD (both routes) and the greedy builders on a training set sharded over the ranks (contiguous slices, rank r owns
     [b_r, b_{r+1}) of the union): dist.distributed_pca(method="gram"): all_to_all -> partial centred SYRK -> all_reduce
     of the K x K Gram -> replicated eigensolve -> all_gather of component slices; method="krylov": Gram-free block
@@ -484,45 +500,143 @@ def run_distributed(eng, x, U_np, y_host, K, args, world, rank, barrier, ev):
             del Xl
         out["pod_krylov_whole_union"] = {"K_total": world * K, "n": n, "ms": min(kw_ms), **kst,
                                          "singular_values_head": [float(v) for v in sig_w[:5].cpu()]}
-    # ---- sharded greedy on the same 10k union, both criteria ---------------------------------------------------------
-    if U_np is not None:
-        sm = SolutionsManagerFEM(GEO, NPB, method="lsqsparse")
-        U_loc, a_loc = U_np[:Kl], y_host[:Kl]
-        h1_loc = sm.H10norm(U_loc)
-        g = {"K_total": K_pod, "n": n}
-        for name, crit in (("galerkin", GREEDY_FOR_GALERKIN), ("h10", GREEDY_FOR_H10)):
-            best, tm = None, {}
-            for rep in range(2):
-                tm = {}
-                barrier()
-                t0 = time.perf_counter()
-                _, _, picked = rd.greedy_build_sharded(sm, n, U_loc, a_loc, h1_loc, K_pod, greedy_for=crit, timings=tm)
-                torch.cuda.synchronize()
-                dt = maxr(time.perf_counter() - t0)
+    # ---- sharded greedy on the same 10k union, both criteria; snapshots stay where the solver left them ------------------
+    sm = SolutionsManagerFEM(GEO, NPB, method="lsqsparse")
+    sm.__dict__["_engine"] = eng
+    U_loc, a_loc = x[:Kl].contiguous(), y_dev[:Kl].contiguous()
+    h1_loc = eng.h10_norm(U_loc)
+    g = {"K_total": K_pod, "n": n, "input": "device-resident padded snapshots (no PCIe)"}
+    for name, crit in (("galerkin", GREEDY_FOR_GALERKIN), ("h10", GREEDY_FOR_H10)):
+        best = None
+        for rep in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            _, _, picked = rd.greedy_build_sharded(sm, n, U_loc, a_loc, h1_loc, K_pod, greedy_for=crit)
+            torch.cuda.synchronize()
+            dt = maxr(time.perf_counter() - t0)
+            if rep:
                 best = dt if best is None else min(best, dt)
-            g[name] = {"s": best, "selected_head": [int(i) for i in picked[:6]], "stages_ms_sum_over_steps": tm}
-        # index parity: the sharded build must pick exactly what one GPU picks on the gathered set (sub-sample)
-        K_chk = int(min(2048, K_pod))
-        bc = rd.shard_bounds(K_chk, world)
-        kl = bc[rank + 1] - bc[rank]
-        Uc, ac = np.ascontiguousarray(U_np[:kl]), np.ascontiguousarray(y_host[:kl])
-        hc = sm.H10norm(Uc)
-        if world > 1:
-            parts = [None] * world
-            dist.all_gather_object(parts, (Uc, ac, hc))
-        else:
-            parts = [(Uc, ac, hc)]
-        same = True
-        for name, crit in (("galerkin", GREEDY_FOR_GALERKIN), ("h10", GREEDY_FOR_H10)):
-            _, _, picked = rd.greedy_build_sharded(sm, 10, Uc, ac, hc, K_chk, greedy_for=crit)
-            if rank == 0:
-                ref = ReducedBasisGreedy(greedy_for=crit).build(n=10, sm=sm, solutions2train=np.vstack([p_[0] for p_ in parts]),
-                                                                a2train=np.concatenate([p_[1] for p_ in parts]),
-                                                                solutions2train_h1norm=np.concatenate([p_[2] for p_ in parts]))
-                same &= [int(i) for i in picked] == [int(i) for i in ref.selected_indices]
-        g["indices_equal_single_gpu_on_subsample"] = {"K": K_chk, "n": 10, "equal": bool(same)}
-        out["greedy_sharded"] = g
+        tm = {}
+        rd.greedy_build_sharded(sm, n, U_loc, a_loc, h1_loc, K_pod, greedy_for=crit, timings=tm)   # stage-synchronised pass
+        g[name] = {"s": best, "selected_head": [int(i) for i in picked[:6]], "stages_ms_sum_over_steps_synchronised": tm}
+    # index parity: the sharded build must pick exactly what one GPU picks on the gathered set (sub-sample)
+    K_chk = int(min(2048, K_pod))
+    bc = rd.shard_bounds(K_chk, world)
+    kl = bc[rank + 1] - bc[rank]
+    Uc, ac = eng.unpad(x[:kl].contiguous()).cpu().numpy(), np.ascontiguousarray(y_host[:kl])
+    hc = sm.H10norm(Uc)
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, (Uc, ac, hc))
+    else:
+        parts = [(Uc, ac, hc)]
+    same = True
+    for name, crit in (("galerkin", GREEDY_FOR_GALERKIN), ("h10", GREEDY_FOR_H10)):
+        _, _, picked = rd.greedy_build_sharded(sm, 10, Uc, ac, hc, K_chk, greedy_for=crit)
+        if rank == 0:
+            ref = ReducedBasisGreedy(greedy_for=crit).build(n=10, sm=sm, solutions2train=np.vstack([p_[0] for p_ in parts]),
+                                                            a2train=np.concatenate([p_[1] for p_ in parts]),
+                                                            solutions2train_h1norm=np.concatenate([p_[2] for p_ in parts]))
+            same &= [int(i) for i in picked] == [int(i) for i in ref.selected_indices]
+    g["indices_equal_single_gpu_on_subsample"] = {"K": K_chk, "n": 10, "equal": bool(same)}
+    out["greedy_sharded"] = g
     barrier()
+    return out
+
+
+def run_config4(args, world, rank, local, barrier, ev):
+    """BASELINE configs[4]: (8,8) subdomains, N = 64 (512 x 512 cells, D = 261 121), a 100k-snapshot training set sharded
+    over the GPUs of the box: snapshots (no collective) -> Gram-free block-Lanczos POD (one (32, Dp) all_reduce per
+    step) -> sharded greedy, both criteria (argmax all_gather + winner all_reduce per step) -> 1M online reduced
+    Galerkin solves.  K per GPU is bounded at 12 500 = 100 000 / 8: at 8 GPUs this IS the 100k set, on fewer GPUs a
+    12 500-per-GPU subset of it (one GPU cannot hold 100k x 261k doubles = 209 GB).  Snapshots never leave the device."""
+    import torch
+    import torch.distributed as dist
+    from romhighcontrast_b200 import dist as rd
+    from romhighcontrast_b200.engine import Engine
+    from lib.ReducedBasis import GREEDY_FOR_GALERKIN, GREEDY_FOR_H10
+    from lib.SolutionsManagers import SolutionsManagerFEM
+    geo, N, n = (8, 8), 64, args.n_rb
+    K = int(args.k_config4)
+    out = {"workload": f"configs[4]: (8,8) subdomains, N=64 (512x512 cells, D=261121), {K} snapshots per GPU "
+                       f"({world * K} in total), contrast 10^U(0,6)"}
+
+    def maxr(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    eng = Engine(geo, N)
+    y_host = 10 ** np.random.default_rng(4000 + rank).uniform(0, np.log10(CMAX), size=(K,) + geo)
+    y = eng.params(y_host)
+    x = eng.empty(K, eng.Dp)
+    eng.solve(y[:1024], out=x[:1024])                              # warm-up: workspace allocation, kernel attributes
+    barrier()
+    e0, e1 = ev(), ev()
+    e0.record()
+    _, iters, relres = eng.solve(y, out=x)
+    e1.record(); barrier()
+    ms = maxr(e0.elapsed_time(e1))
+    it = iters.double()
+    out["snapshots"] = {"solves_per_s": world * K / (ms * 1e-3), "ms": ms, "K_per_gpu": K,
+                        "dof_solves_per_s": world * K * eng.D / (ms * 1e-3),
+                        "pcg_iterations": {"min": int(it.min()), "mean": float(it.mean()), "max": int(it.max())},
+                        "max_relres": float(relres.max()), "chunks": eng.last_solve_stats["chunks"]}
+    if rank == 0 and not args.no_cpu:                              # parity of what was timed: 3 systems against the CPU oracle
+        from oracle import FEMOracle
+        sel = [0, K // 2, K - 1]
+        t0 = time.perf_counter()
+        Uo = FEMOracle(geo, N).generate_solutions(y_host[sel])
+        cpu_s = (time.perf_counter() - t0) / len(sel)
+        U = eng.unpad(x[sel].contiguous()).cpu().numpy()
+        out["snapshots"]["parity_rel_l2_vs_oracle"] = float(np.max(np.linalg.norm(U - Uo, axis=1) / np.linalg.norm(Uo, axis=1)))
+        out["snapshots"]["oracle_seconds_per_system_1core"] = cpu_s
+    # Gram-free POD of the sharded set
+    kst, kms = {}, []
+    for rep in range(2):
+        Xc = x.clone()
+        kst = {}
+        barrier()
+        e0, e1 = ev(), ev()
+        e0.record()
+        comps, sig = rd.distributed_pca(eng, Xc, n, counts=[K] * world, timings=kst, method="krylov")
+        e1.record(); torch.cuda.synchronize()
+        kms.append(maxr(e0.elapsed_time(e1)))
+        del Xc
+    out["pod_krylov"] = {"K_total": world * K, "n": n, "ms": min(kms), "first_call_ms": kms[0], **kst,
+                         "singular_values_head": [float(v) for v in sig[:5].cpu()]}
+    # sharded greedy on the resident snapshots
+    sm = SolutionsManagerFEM(geo, N, method="lsqsparse")
+    sm.__dict__["_engine"] = eng
+    h1 = eng.h10_norm(x)
+    g = {"K_total": world * K, "n": n}
+    for name, crit in (("galerkin", GREEDY_FOR_GALERKIN), ("h10", GREEDY_FOR_H10)):
+        best, picked = None, None
+        for rep in range(2):
+            barrier()
+            t0 = time.perf_counter()
+            _, _, picked = rd.greedy_build_sharded(sm, n, x, y, h1, world * K, greedy_for=crit)
+            torch.cuda.synchronize()
+            dt = maxr(time.perf_counter() - t0)
+            best = dt if best is None else min(best, dt)
+        g[name] = {"s": best, "selected_head": [int(i) for i in picked[:6]]}
+    out["greedy_sharded"] = g
+    # online stage on the POD basis: 1M reduced Galerkin solves over all ranks
+    Ahat, bhat = eng.project_operators(comps.contiguous())
+    Ko = args.k_online // world
+    yo = eng.params(10 ** np.random.default_rng(4100 + rank).uniform(0, np.log10(CMAX), size=(Ko,) + geo))
+    eng.reduced_solve(yo, Ahat, bhat, check=False)
+    barrier()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(5):
+        Cc = eng.reduced_solve(yo, Ahat, bhat, check=False)
+    e1.record(); torch.cuda.synchronize()
+    oms = maxr(e0.elapsed_time(e1) / 5)
+    out["reduced_galerkin"] = {"K": world * Ko, "n": n, "nb": 64, "ms": oms, "solves_per_s": world * Ko / (oms * 1e-3)}
+    del eng, x
+    torch.cuda.empty_cache()
     return out
 
 
@@ -535,7 +649,7 @@ def run_secondary(eng, x, y, K, args, world, rank, barrier, ev, U_np=None, y_hos
     # the two communicating stages on the K-sharded union of all ranks' snapshots -- before anything below
     # centres the resident snapshots in place
     try:
-        out["distributed"] = run_distributed(eng, x, U_np, y_host, K, args, world, rank, barrier, ev)
+        out["distributed"] = run_distributed(eng, x, y, y_host, K, args, world, rank, barrier, ev)
     except Exception as exc:
         import traceback
         out["distributed"] = {"error": repr(exc)[:300], "trace": traceback.format_exc()[-600:]}

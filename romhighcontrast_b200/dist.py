@@ -217,71 +217,27 @@ def distributed_pca(eng, X_local_pad: torch.Tensor, n: int, counts=None, timings
 def greedy_build_sharded(sm, n, U_local, a_local, h1_local, K_total, greedy_for="galerkin", timings=None):
     """Weak greedy (reference ReducedBasis.py:112-139) on a K-sharded training set.
 
-    Every rank passes its contiguous slice (local_slice(K_total)); all ranks return the same
-    (basis (n, D), a list, global indices).  Errors never leave the device; per step one 16-byte pair per rank is
-    exchanged and the winning snapshot is broadcast by its owner.  timings (dict, optional): wall milliseconds of the
-    device sweep, the argmax all_gather and the broadcast, summed over the n steps (host-synchronised stages)."""
-    import time as _time
-    tacc = {"sweep_ms": 0.0, "argmax_allgather_ms": 0.0, "broadcast_ms": 0.0, "host_qr_ms": 0.0}
-
-    def _tick():
-        if timings is not None and eng.device.type == "cuda":
-            torch.cuda.synchronize()
-        return _time.perf_counter()
-
-    from .lib.ReducedBasis import (GREEDY_FOR_GALERKIN, GREEDY_FOR_H10, get_high_contrast_coefficient,
-                                   sort_orthogonalize_base)
+    Every rank passes its contiguous slice (local_slice(K_total)) -- numpy arrays, or the padded device tensors the
+    solver left behind ((K_r, Dp) snapshots, (K_r, nb) parameters, (K_r,) norms) -- and all ranks return the same
+    (basis (n, D), a list, global indices).  The loop is greedy_core.greedy_select: errors never leave the device; per
+    step one all_gather of a (value, global index) pair per rank, merged on the device, and one all_reduce that
+    delivers the winning snapshot and its parameter.  timings (dict, optional): wall milliseconds of the device sweep,
+    the exchange and the Gram-Schmidt step, summed over the n steps (synchronised stage by stage when given)."""
+    from .greedy_core import greedy_select
     eng = sm._engine_()
     off = shard_bounds(K_total, world())[rank()]
-    U_local = np.asarray(U_local, dtype=np.float64)
-    a_local = np.asarray(a_local, dtype=np.float64)
-    U = eng.pad(U_local) if len(U_local) else None
-    y = eng.params(a_local) if len(a_local) else None
-    norm = eng.dev(np.broadcast_to(np.asarray(h1_local, dtype=np.float64), (len(U_local),)).copy()) if len(U_local) else None
-    basis = np.empty((0, 0))
-    basis_orth = basis.copy()
-    a_selected, a, picked = [], [], []
     D, geo = sm.vspace_dim, tuple(sm.blocks_geometry)
-    for _ in range(n):
-        t0 = _tick()
-        if U is None:
-            lv, li = 0.0, -1
-        else:
-            if len(basis_orth) == 0:
-                err = eng.error_norm(U, None, None)
-            else:
-                Phi = eng.pad(basis_orth)
-                if greedy_for == GREEDY_FOR_H10:
-                    Cc = sm._projection_coefficients_dev(eng, U, Phi)
-                elif greedy_for == GREEDY_FOR_GALERKIN:
-                    Ahat, bhat = eng.project_operators(Phi)
-                    Cc = eng.reduced_solve(y, Ahat, bhat)
-                else:
-                    raise Exception(f"Not implemented greedy for {greedy_for}")
-                err = eng.error_norm(U, Cc, Phi)
-            li, lv = eng.argmax(err / norm)
-            li += off
-        t1 = _tick()
-        _, gi, owner = global_argmax(lv, li, device=eng.device)
-        t2 = _tick()
-        row = torch.empty(D, dtype=torch.float64, device=eng.device)
-        par = torch.empty(geo, dtype=torch.float64, device=eng.device)
-        if rank() == owner:
-            row.copy_(torch.as_tensor(U_local[gi - off]))
-            par.copy_(torch.as_tensor(a_local[gi - off]))
-        broadcast_from(row, owner)
-        broadcast_from(par, owner)
-        t3 = _tick()
-        picked.append(gi)
-        max_element = row.cpu().numpy().reshape(1, -1)
-        a_new = par.cpu().numpy()
-        basis = max_element if len(basis) == 0 else np.concatenate((basis, max_element), axis=0)
-        a.append(a_new)
-        a_selected = np.append(a_selected, np.ravel(get_high_contrast_coefficient([a_new])[0]))
-        a_selected, basis_orth = sort_orthogonalize_base(a_selected, np.reshape(basis, (len(basis), -1)))
-        t4 = _time.perf_counter()
-        tacc["sweep_ms"] += 1e3 * (t1 - t0); tacc["argmax_allgather_ms"] += 1e3 * (t2 - t1)
-        tacc["broadcast_ms"] += 1e3 * (t3 - t2); tacc["host_qr_ms"] += 1e3 * (t4 - t3)
-    if timings is not None:
-        timings.update(tacc)
-    return basis, a, picked
+    if isinstance(U_local, torch.Tensor):
+        U = U_local if U_local.shape[0] else None
+        y = a_local.reshape(U_local.shape[0], -1).contiguous() if U is not None else None
+        norm = h1_local.expand(U_local.shape[0]).contiguous() if U is not None else None
+    else:
+        U_local = np.asarray(U_local, dtype=np.float64)
+        a_local = np.asarray(a_local, dtype=np.float64)
+        U = eng.pad(U_local) if len(U_local) else None
+        y = eng.params(a_local) if len(a_local) else None
+        norm = eng.dev(np.broadcast_to(np.asarray(h1_local, dtype=np.float64), (len(U_local),)).copy()) if len(U_local) else None
+    picked, _, rows, params, _ = greedy_select(sm, eng, n, U, y, norm, greedy_for, offset=off, distributed=True, timings=timings)
+    basis = eng.unpad(rows).cpu().numpy().reshape(n, D)
+    pa = params.cpu().numpy().reshape((n,) + geo)
+    return basis, [pa[i] for i in range(n)], picked

@@ -171,8 +171,9 @@ class Engine:
                                                     self.stream()))
         return Ahat, bhat
 
-    def reduced_solve(self, y, Ahat, rhs, check=True):
-        """(sum_q y[k,q] Ahat[q]) c_k = rhs ; rhs (n,) shared or (K, n)."""
+    def reduced_solve(self, y, Ahat, rhs, check=True, return_info=False):
+        """(sum_q y[k,q] Ahat[q]) c_k = rhs ; rhs (n,) shared or (K, n).  return_info: also the per-system flag tensor
+        (1: not positive definite) so that a device-resident loop can defer the check."""
         K, n = y.shape[0], Ahat.shape[-1]
         per = 1 if rhs.dim() == 2 else 0
         Cc = self.empty(K, n)
@@ -181,7 +182,7 @@ class Engine:
                                                 _ptr(info), self.stream()))
         if check and bool(info.any().item()):
             raise np.linalg.LinAlgError("reduced Galerkin matrix is not positive definite")
-        return Cc
+        return (Cc, info) if return_info else Cc
 
     # ---- dense helpers -------------------------------------------------------------------------------------
     def gemm_nt(self, A, B, symmetric=False, splitk=False):
@@ -237,10 +238,15 @@ class Engine:
                                             _ptr(out), self.stream()))
         return out
 
-    def argmax(self, v):
+    def argmax_dev(self, v):
+        """np.argmax of a device vector without leaving the device: (index (1,) int64, value (1,)) tensors."""
         idx = self.empty(1, dtype=torch.int64)
         val = self.empty(1)
-        _lib.check(self.lib.romhc_argmax(_ptr(v), v.shape[0], _ptr(idx), _ptr(val), self.stream()))
+        _lib.check(self.lib.romhc_argmax(_ptr(v.contiguous()), v.shape[0], _ptr(idx), _ptr(val), self.stream()))
+        return idx, val
+
+    def argmax(self, v):
+        idx, val = self.argmax_dev(v)
         return int(idx.item()), float(val.item())
 
     # ---- host-buffer entry points -----------------------------------------------------------------------------------

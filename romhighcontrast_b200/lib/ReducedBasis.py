@@ -127,50 +127,44 @@ class ReducedBasisGreedy(BaseReducedBasis):
               solutions2train_h1norm=1, **kwargs):
         """Weak greedy with the true H10 error (reference :112-139).
 
-        Per step, on the device: reduced operators of the current orthonormal basis, K reduced solves (Galerkin) or K
-        projections (H10), the fused error sweep || c Phi - u ||_{A_1} over the resident snapshots and an argmax with
-        np.argmax semantics.  Host: the O(n) bookkeeping and the (D, n) QR, exactly as the reference does them."""
+        The whole loop is device resident (romhighcontrast_b200/greedy_core.py): per round the reduced operators of the
+        current orthonormal basis, K reduced solves (Galerkin) or K projections (H10), the fused error sweep
+        || c Phi - u ||_{A_1} over the resident snapshots, an argmax with np.argmax semantics, a row gather and one
+        Gram-Schmidt step; the host sees the selected indices once, at the end.  `solutions2train` may also be the padded
+        device tensor (K, Dp) that `Engine.solve` returns (additive: snapshots -> build without crossing PCIe); `a2train`
+        then may be a (K, nb) device tensor as well."""
         if self.greedy_for not in (GREEDY_FOR_H10, GREEDY_FOR_GALERKIN):
             raise Exception(f"Not implemented greedy for {self.greedy_for}, "
                             f"should be one of [{GREEDY_FOR_H10}, {GREEDY_FOR_GALERKIN}]")
         import torch
+        from ..greedy_core import greedy_select
         eng = sm._engine_()
-        high_contrast_a = get_high_contrast_coefficient(a2train)
-        solutions2train = np.asarray(solutions2train, dtype=np.float64)
-        U = eng.pad(solutions2train)                                     # resident for the whole build
-        y = eng.params(np.asarray(a2train, dtype=np.float64))
-        norm = eng.dev(np.broadcast_to(np.asarray(solutions2train_h1norm, dtype=np.float64),
-                                       (len(solutions2train),)).copy())
-        ones = torch.ones(len(solutions2train), eng.nb, dtype=torch.float64, device=eng.device)
-
-        basis = np.empty((0, 0))
-        basis_orth = basis.copy()
-        a_selected = []
-        a = []
-        self.selected_indices = []
-        self.max_errors = []
-        for _ in tqdm(range(n), desc="Obtaining greedy basis."):
-            if len(basis_orth) == 0:
-                err = eng.error_norm(U, None, None)                      # approximation == 0  (:89-91, :109-111)
-            else:
-                Phi = eng.pad(basis_orth)
-                if self.greedy_for == GREEDY_FOR_H10:
-                    Cc = sm._projection_coefficients_dev(eng, U, Phi)    # :122
-                else:
-                    Ahat, bhat = eng.project_operators(Phi)              # :124
-                    Cc = eng.reduced_solve(y, Ahat, bhat)
-                err = eng.error_norm(U, Cc, Phi)
-            max_error_index, max_err = eng.argmax(err / norm)            # :129 (true division: the round-1 tie is exactly 1.0)
-            self.selected_indices.append(max_error_index)
-            self.max_errors.append(max_err)
-            max_element = np.reshape(solutions2train[max_error_index], (1, -1))
-            basis = max_element if len(basis) == 0 else np.concatenate((basis, max_element), axis=0)
-            a.append(a2train[max_error_index])
-
-            # orthonormalize for stability and choose the ordering by the contrast of the higher coefficient (:134-136)
-            a_selected = np.append(a_selected, np.ravel(high_contrast_a[max_error_index]))
-            a_selected, basis_orth = sort_orthogonalize_base(a_selected, np.reshape(basis, (len(basis), -1)))
-
+        dev_in = isinstance(solutions2train, torch.Tensor)
+        if dev_in:
+            U = solutions2train
+            K = U.shape[0]
+        else:
+            solutions2train = np.asarray(solutions2train, dtype=np.float64)
+            K = len(solutions2train)
+            U = eng.pad(solutions2train)                                 # resident for the whole build
+        y = a2train.reshape(K, -1).contiguous() if isinstance(a2train, torch.Tensor) else eng.params(np.asarray(a2train, dtype=np.float64))
+        if isinstance(solutions2train_h1norm, torch.Tensor):
+            norm = solutions2train_h1norm.to(eng.device).expand(K).contiguous()
+        else:
+            norm = eng.dev(np.broadcast_to(np.asarray(solutions2train_h1norm, dtype=np.float64), (K,)).copy())
+        picked, max_errors, rows, params, _ = greedy_select(
+            sm, eng, n, U, y, norm, self.greedy_for, progress=lambda it: tqdm(it, desc="Obtaining greedy basis."))
+        self.selected_indices = picked
+        self.max_errors = max_errors
+        if dev_in:
+            basis = eng.unpad(rows).cpu().numpy()
+        else:
+            basis = np.reshape(solutions2train[picked], (n, -1)) if n else np.empty((0, 0))
+        if isinstance(a2train, torch.Tensor):
+            pa = params.cpu().numpy().reshape((n,) + tuple(sm.blocks_geometry))
+            a = [pa[i] for i in range(n)]
+        else:
+            a = [a2train[i] for i in picked]                             # :131 (the caller's own objects)
         super().set(basis=basis, a=a)
         return self
 

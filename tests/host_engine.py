@@ -14,11 +14,11 @@ class HostEngine:
         return A @ B.T
 
     def gemm_nn(self, A, B):
-        assert A.is_contiguous() and B.is_contiguous() and A.shape[1] == B.shape[0] and A.shape[1] <= 2048
+        assert A.is_contiguous() and B.is_contiguous() and A.shape[1] == B.shape[0]
         return A @ B
 
     def gemm_tn(self, A, B):
-        assert A.is_contiguous() and B.is_contiguous() and A.shape[0] == B.shape[0] and A.shape[1] <= 32
+        assert A.is_contiguous() and B.is_contiguous() and A.shape[0] == B.shape[0]
         return A.T @ B
 
     def column_mean(self, X):
@@ -57,15 +57,26 @@ class HostFEMEngine(HostEngine):
         Ahat, bhat = self.o.reduced_operators(Phi.numpy())
         return torch.as_tensor(Ahat.reshape(self.nb, len(Phi), len(Phi))), torch.as_tensor(bhat)
 
-    def reduced_solve(self, y, Ahat, rhs):
+    def reduced_solve(self, y, Ahat, rhs, check=True, return_info=False):
         Ak = self.np.einsum("qij,kq->kij", Ahat.numpy(), y.numpy())
         r = rhs.numpy()
         r = self.np.broadcast_to(r, (len(Ak), r.shape[-1])) if r.ndim == 1 else r
-        return torch.as_tensor(self.np.linalg.solve(Ak, r[..., None])[..., 0])
+        Cc = torch.as_tensor(self.np.linalg.solve(Ak, r[..., None])[..., 0])
+        return (Cc, torch.zeros(len(Ak), dtype=torch.int32)) if return_info else Cc
+
+    def argmax_dev(self, v):
+        i = int(self.np.argmax(v.numpy()))
+        return torch.tensor([i], dtype=torch.int64), v[i].reshape(1).clone()
 
     def argmax(self, v):
         i = int(self.np.argmax(v.numpy()))
         return i, float(v[i])
+
+    def l2_norm(self, X):
+        return torch.linalg.vector_norm(X, dim=1)
+
+    def unpad(self, X):
+        return X
 
 
 class HostSolutionsManager:

@@ -149,3 +149,36 @@ def test_config1_greedy_and_pca_parity_at_full_size():
     rbp = ReducedBasisPCA().build(n=n, sm=sm, solutions2train=U, a2train=y)
     _, so, _ = pca_components(U, n)
     assert np.max(np.abs(np.asarray(rbp.singular_values_) - so) / so) < 1e-9
+
+
+def test_config4_geometry_parity():
+    """BASELINE configs[4]: (8,8) subdomains, N = 64 (512 x 512 cells, D = 261 121), contrast 10^U(0,6): three snapshots
+    against the sparse direct oracle (<= 1e-9 relative, north_star), the energy identity on all of them, the reduced
+    Galerkin stage with nb = 64 blocks against LAPACK."""
+    import torch
+    from oracle import FEMOracle
+    from romhighcontrast_b200.engine import Engine
+    geo, Nb, K, n = (8, 8), 64, 96, 12
+    eng = Engine(geo, Nb)
+    assert eng.D == 261121
+    y = 10 ** np.random.default_rng(11).uniform(0, 6, (K,) + geo)
+    yd = eng.params(y)
+    x, iters, relres = eng.solve(yd)
+    assert eng.last_solve_stats["status"] == 0 and float(relres.max()) <= 1e-12 * 1.0000001
+    assert int(iters.max()) <= 40
+    b = eng.pad(np.full((1, eng.D), 1.0 / Nb ** 2))
+    en2 = eng.energy_norm(yd, x) ** 2
+    bu = (x * b).sum(dim=1)
+    assert float(((en2 - bu).abs() / bu).max()) < 1e-10
+    pick = [0, K // 2, K - 1]
+    Uo = FEMOracle(geo, Nb).generate_solutions(y[pick])
+    U = eng.unpad(x[pick].contiguous()).cpu().numpy()
+    err = np.linalg.norm(U - Uo, axis=1) / np.linalg.norm(Uo, axis=1)
+    assert err.max() < 1e-9, err
+    # online stage with 64 blocks: orthonormal basis from the snapshots, reduced operators, reduced solves vs LAPACK
+    Phi = torch.linalg.qr(x[:n].T)[0].T.contiguous()
+    Ahat, bhat = eng.project_operators(Phi)
+    C = eng.reduced_solve(yd, Ahat, bhat).cpu().numpy()
+    A = np.einsum("kq,qij->kij", y.reshape(K, -1), Ahat.cpu().numpy())
+    Cl = np.linalg.solve(A, np.broadcast_to(bhat.cpu().numpy(), (K, n))[..., None])[..., 0]
+    assert (np.linalg.norm(C - Cl, axis=1) / np.linalg.norm(Cl, axis=1)).max() < 1e-9
