@@ -352,6 +352,11 @@ def main():
     if not args.no_secondary:
         secondary = run_secondary(eng, x, y, K, args, world, rank, barrier, ev, U_np, y_host)
 
+    if not args.no_secondary and rank == 0:
+        try:
+            secondary["config0"] = run_config0()
+        except Exception as exc:
+            secondary["config0"] = {"error": repr(exc)[:300]}
     if not args.no_secondary and not args.no_config4:
         del x, y
         eng = None
@@ -370,6 +375,10 @@ def main():
         r, cores, n, wall = cpu_snapshot_rate(32, None)          # ~10 s of wall time on all host cores
         cpu = {"value": r, "unit": "solves/s", "cores": cores, "kind": "port",
                "sample": f"{n} snapshot solves of the same workload (oracle: scipy CSR + SuperLU, {cores} processes, {wall:.1f} s)"}
+        try:      # the UNMODIFIED reference on configs[0], timed where /root/reference exists (oracle/time_reference.py)
+            cpu["true_reference_config0"] = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_timing_config0.json")))
+        except Exception:
+            cpu["true_reference_config0"] = None
 
     if rank == 0:
         line = {
@@ -637,6 +646,48 @@ def run_config4(args, world, rank, local, barrier, ev):
     out["reduced_galerkin"] = {"K": world * Ko, "n": n, "nb": 64, "ms": oms, "solves_per_s": world * Ko / (oms * 1e-3)}
     del eng, x
     torch.cuda.empty_cache()
+    return out
+
+
+def run_config0():
+    """BASELINE configs[0] through the reference-shaped class API (numpy in, numpy out), the same calls and inputs that
+    oracle/time_reference.py times on the unmodified reference (tests/golden/reference_timing_config0.json)."""
+    import torch
+    from lib.ReducedBasis import ReducedBasisGreedy, ReducedBasisPCA, GREEDY_FOR_GALERKIN, GREEDY_FOR_H10
+    from lib.SolutionsManagers import SolutionsManagerFEM
+    geo, N, K, n = (2, 2), 32, 100, 10
+    y = 10 ** np.random.default_rng(42).uniform(0, 6, (K,) + geo)
+    T = {}
+
+    def tm(name, f, *a, **kw):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = f(*a, **kw)
+        torch.cuda.synchronize()
+        T[name] = time.perf_counter() - t0
+        return r
+
+    for rep in range(2):                                           # repetition 0 pays one-time allocations
+        sm = tm("assembly_s", SolutionsManagerFEM, geo, N, num_cores=1, method="lsqsparse")
+        U = tm("snapshots_s", sm.generate_solutions, y)
+        h1 = tm("h10norm_s", sm.H10norm, U)
+        rbg = tm("greedy_galerkin_s", ReducedBasisGreedy(greedy_for=GREEDY_FOR_GALERKIN).build, n=n, sm=sm, solutions2train=U,
+                 a2train=y, solutions2train_h1norm=h1)
+        tm("greedy_h10_s", ReducedBasisGreedy(greedy_for=GREEDY_FOR_H10).build, n=n, sm=sm, solutions2train=U, a2train=y,
+           solutions2train_h1norm=h1)
+        tm("pca_s", ReducedBasisPCA().build, n=n, sm=sm, solutions2train=U, a2train=y)
+        rbg.orthonormalize()
+        tm("forward_modeling_s", rbg.forward_modeling, sm, y)
+        tm("projection_s", rbg.projection, sm, U)
+    out = {"workload": "configs[0]: (2,2) subdomains, N=32 (64x64 cells, D=3969), 100 snapshots, n=10; class API, numpy in/out",
+           "seconds": T, "snapshot_solves_per_s": K / T["snapshots_s"], "greedy_galerkin_selected": [int(i) for i in rbg.selected_indices]}
+    try:
+        ref = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_timing_config0.json")))
+        out["true_reference_seconds"] = ref["seconds"]
+        out["speedup_vs_true_reference"] = {k_: ref["seconds"][k_] / T[k_] for k_ in T if k_ in ref["seconds"] and T[k_] > 0}
+        out["true_reference_host"] = ref["host"]
+    except Exception:
+        pass
     return out
 
 

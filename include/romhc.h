@@ -160,6 +160,11 @@ int romhc_row_norms(const double* X_dev, int64_t ld, int64_t K, int64_t D, doubl
 int romhc_estimator(const double* c_dev, int64_t K, int n, const double* abasis_dev, int nb, int invert,
                     double* out_dev, void* stream);
 int romhc_argmax(const double* v_dev, int64_t K, int64_t* idx_dev, double* val_dev, void* stream);
+/* out[f][i] = prod_j basis[terms[f][j]][i] (terms (nterms, degree) int32, -1 = unused factor): the monomial features of
+ * the basis values at every DOF, i.e. PolynomialFeatures(degree, include_bias=False) on np.array(reduced_basis).T --
+ * the predict step of polynomial_state_estimation_fitting_method_least_squares, src/notebooks/InverseProblemPipeline.ipynb cell 52 */
+int romhc_poly_features(const double* basis_dev, int64_t ld, int n, int64_t D, const int* terms_dev, int nterms, int degree,
+                        double* out_dev, int64_t ldo, void* stream);
 
 /* ---- host-buffer entry points (what a reference-side ctypes binding calls; copies are inside the call) -------------------
  * romhc_generate_solutions_host == SolutionsManager.generate_solutions(a2try): y_host (K, nb) -> U_host (K, D) compact.

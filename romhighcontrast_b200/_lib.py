@@ -66,6 +66,7 @@ SIGNATURES = {
     "romhc_row_norms": (_i, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "romhc_estimator": (_i, [_vp, _i64, _i, _vp, _i, _i, _vp, _vp]),
     "romhc_argmax": (_i, [_vp, _i64, _vp, _vp, _vp]),
+    "romhc_poly_features": (_i, [_vp, _i64, _i, _i64, _vp, _i, _i, _vp, _i64, _vp]),
     "romhc_generate_solutions_host": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "romhc_reduced_galerkin_host": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp, _vp]),
 }

@@ -306,6 +306,11 @@ int romhc_estimator(const double* c, int64_t K, int n, const double* ab, int nb,
     return estimator_contract(c, K, n, ab, nb, invert, out, ST(st));
 }
 int romhc_argmax(const double* v, int64_t K, int64_t* idx, double* val, void* st) { return argmax_first(v, K, idx, val, ST(st)); }
+int romhc_poly_features(const double* basis, int64_t ld, int n, int64_t D, const int* terms, int nterms, int degree,
+                        double* out, int64_t ldo, void* st) {
+    if (!basis || !terms || !out) { set_error("null argument"); return ROMHC_ERR_ARG; }
+    return poly_features(basis, ld, n, D, terms, nterms, degree, out, ldo, ST(st));
+}
 
 // ---- host-buffer entry points --------------------------------------------------------------------------------------------
 // Pageable destinations: a device-to-host copy into pageable memory blocks the calling thread behind the whole copy and

@@ -561,4 +561,37 @@ int estimator_contract(const double* c, int64_t K, int n, const double* abasis, 
     return ROMHC_OK;
 }
 
+// ======================================================================================================
+// Monomial features of the basis functions at every DOF: out[f][i] = prod_{j < degree, terms[f][j] >= 0} basis[terms[f][j]][i]
+// (sklearn PolynomialFeatures(include_bias=False) evaluated on the rows of the basis; the predict step of the notebook's
+// polynomial least squares, InverseProblemPipeline.ipynb cell 52).  terms: (nterms, degree) int32, -1 = unused factor.
+// ======================================================================================================
+__global__ void __launch_bounds__(256)
+k_poly_features(const double* __restrict__ basis, int64_t ld, int64_t D, const int* __restrict__ terms, int degree,
+                double* __restrict__ out, int64_t ldo) {
+    const int f = blockIdx.y;
+    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i >= D) return;
+    double v = 1.0;
+    for (int j = 0; j < degree; ++j) {
+        const int t = terms[f * degree + j];
+        if (t >= 0) v *= basis[int64_t(t) * ld + i];
+    }
+    out[int64_t(f) * ldo + i] = v;
+}
+int poly_features(const double* basis, int64_t ld, int n, int64_t D, const int* terms, int nterms, int degree, double* out,
+                  int64_t ldo, cudaStream_t st) {
+    (void)n;
+    if (nterms <= 0 || D <= 0) return ROMHC_OK;
+    if (degree < 1 || degree > 8) { set_error("poly_features: degree must be in [1, 8]"); return ROMHC_ERR_ARG; }
+    for (int f0 = 0; f0 < nterms; f0 += 65535) {
+        const int nf = std::min(65535, nterms - f0);
+        ++g_launches;
+        k_poly_features<<<dim3((unsigned)((D + 255) / 256), nf), 256, 0, st>>>(basis, ld, D, terms + size_t(f0) * degree, degree,
+                                                                          out + int64_t(f0) * ldo, ldo);
+    }
+    CK(cudaGetLastError());
+    return ROMHC_OK;
+}
+
 }  // namespace romhc

@@ -238,6 +238,15 @@ class Engine:
                                             _ptr(out), self.stream()))
         return out
 
+    def poly_features(self, basis_pad, terms):
+        """terms (F, degree) int array (-1 = unused factor) -> (F, Dp) products of basis rows at every slot."""
+        t = torch.as_tensor(np.ascontiguousarray(np.asarray(terms, dtype=np.int32)), device=self.device)
+        F, deg = t.shape
+        out = self.empty(F, basis_pad.shape[1])
+        _lib.check(self.lib.romhc_poly_features(_ptr(basis_pad), basis_pad.stride(0), basis_pad.shape[0], basis_pad.shape[1],
+                                                _ptr(t), F, deg, _ptr(out), out.stride(0), self.stream()))
+        return out
+
     def argmax_dev(self, v):
         """np.argmax of a device vector without leaving the device: (index (1,) int64, value (1,)) tensors."""
         idx = self.empty(1, dtype=torch.int64)

@@ -4,7 +4,7 @@ The reference defines these only inside `src/notebooks/InverseProblemPipeline.ip
 a global `sm`.  Here they take `sm` explicitly; names and argument meaning follow the notebook:
 
 * cell 52  `state_estimation_fitting_method_least_squares`, `pbdw_correction`, `state_estimation_fitting_method_pbdw`,
-           `state_estimation_fitting_method_weighted_least_squares`
+           `state_estimation_fitting_method_weighted_least_squares`, `polynomial_state_estimation_fitting_method_least_squares`
 * cell 44  `inverse_christoffel_function`, `measurements_sampling_method_optimal`
 * cell 35  `reduced_basis_generator_greedy` (the notebook's l2 / H10 greedy: least-squares residual, argmax)
 
@@ -77,6 +77,43 @@ def state_estimation_fitting_method_weighted_least_squares(sm, measurement_point
     weights = 1.0 / inverse_christoffel_function(basis, sm, measurement_points)
     c = _ls_coefficients(sm, measurement_points, measurements, basis, weights=weights)
     return eng.unpad_host(eng.gemm_nn(c.T.contiguous(), sm._pad_rows(basis)))
+
+
+def polynomial_feature_terms(n, degree):
+    """Index tuples of sklearn's PolynomialFeatures(degree, include_bias=False) in its output order: all degree-1 terms,
+    then degree 2 in combinations_with_replacement order, ...; rows padded with -1 to `degree` factors."""
+    from itertools import combinations_with_replacement
+    terms = []
+    for d in range(1, degree + 1):
+        for comb in combinations_with_replacement(range(n), d):
+            terms.append(list(comb) + [-1] * (degree - d))
+    return np.asarray(terms, dtype=np.int32).reshape(-1, degree)
+
+
+def polynomial_state_estimation_fitting_method_least_squares(sm, measurement_points, measurements, reduced_basis, degree=2,
+                                                             **kwargs):
+    """cell 52: v*(x) = sum_j c_j phi_j(x) + sum_jk d_jk phi_j(x) phi_k(x) (+ higher degrees): a linear regression of
+    the measurements on the monomials of the basis values at the points (sklearn Pipeline(PolynomialFeatures(degree,
+    include_bias=False), LinearRegression(fit_intercept=False)) in the notebook), predicted at every DOF.
+
+    Host: the (m, F) feature matrix at the points and its least-squares solve (scipy.linalg.lstsq, as LinearRegression
+    does).  Device: the (F, Dp) monomials of the basis at every DOF (`romhc_poly_features`) and the (K, F) x (F, Dp)
+    product."""
+    from scipy import linalg as sla
+    eng = sm._engine_()
+    basis = _basis_array(reduced_basis)
+    n = basis.shape[0]
+    E = sm.evaluate_solutions(measurement_points, basis)                    # (n, m)
+    terms = polynomial_feature_terms(n, int(degree))
+    X = np.ones((E.shape[1], len(terms)))
+    for f, t in enumerate(terms):
+        for j in t:
+            if j >= 0:
+                X[:, f] *= E[j]
+    Z = np.asarray(measurements, dtype=np.float64).reshape(-1, E.shape[1])
+    coef = sla.lstsq(X, Z.T)[0].T                                            # (K, F) == LinearRegression.coef_
+    Fm = eng.poly_features(sm._pad_rows(basis), terms)                       # (F, Dp)
+    return eng.unpad_host(eng.gemm_nn(eng.dev(coef), Fm))
 
 
 def measurements_sampling_method_optimal(number_of_measures, xlim, ylim, basis, sm, seed=42, discretization=5, **kwargs):

@@ -85,13 +85,17 @@ class BaseReducedBasis:
         Z = np.asarray(measurements, dtype=np.float64)
         m = rb_evaluations_in_points.shape[1]
         pinv = np.linalg.lstsq(rb_evaluations_in_points.T, np.eye(m), rcond=-1)[0]                # (n, m)
+        single = Z.ndim == 1           # one measurement vector (m,): lstsq(E^T, z) gives c (n,), c^T basis gives (D,)
         Zd = eng.dev(Z.reshape(-1, m))
         c_dev = eng.gemm_nt(eng.dev(pinv), Zd)                                                    # (n, K)
         if not reconstruct:            # large observation batches: (K, D) fields would not fit; coefficients only
-            return c_dev.cpu().numpy()
+            c = c_dev.cpu().numpy()
+            return c[:, 0] if single else c
         basis_pad = sm._pad_rows(self.basis)
         solution_estimations = eng.unpad_host(eng.gemm_nn(c_dev.T.contiguous(), basis_pad))       # c^T basis
         c = c_dev.cpu().numpy()
+        if single:
+            c, solution_estimations = c[:, 0], solution_estimations[0]
         return (c, solution_estimations) if return_coefs else solution_estimations
 
     def parameter_estimation_inverse(self, c):

@@ -190,6 +190,11 @@ def test_pbdw_and_large_batch_online_stage():
     c, est = rb.state_estimation(sm, pts, Z, return_coefs=True)
     co, esto = state_estimation(o, rb.basis, pts, Z)
     assert relerr(est, esto) < 1e-7
+    # a single 1-D measurement vector: shapes (n,) and (D,) as np.linalg.lstsq(E.T, z.T) gives them (ReducedBasis.py:65-70)
+    c1, est1 = rb.state_estimation(sm, pts, Z[3], return_coefs=True)
+    assert c1.shape == (rb.dim,) and est1.shape == (sm.vspace_dim,)
+    np.testing.assert_allclose(c1, c[:, 3], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(est1, est[3], rtol=1e-12, atol=1e-14)
     R = sm.generate_riesz(pts, norm="l2")                                  # (m, D)
     corrected = est + (Z - est @ R.T) @ R
     assert relerr(corrected, pbdw_correction(o, pts, Z, esto)) < 1e-7
@@ -266,6 +271,16 @@ def test_notebook_inverse_methods():
     wl = 1 / w
     wls = (np.linalg.lstsq(E.T * wl[:, None], Z.T * wl[:, None], rcond=-1)[0]).T @ np.array(rb)
     assert relerr(inv.state_estimation_fitting_method_weighted_least_squares(sm, pts, Z, rb), wls) < 1e-9
+    # cell 52: polynomial least squares against the notebook's own sklearn pipeline on the oracle's evaluations
+    from sklearn.linear_model import LinearRegression
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import PolynomialFeatures
+    for degree, nb_ in ((2, 5), (3, 3), (1, 5)):
+        model = Pipeline([('PF', PolynomialFeatures(degree=degree, include_bias=False)), ('LR', LinearRegression(fit_intercept=False))])
+        model.fit(o.evaluate_solutions(pts, rb[:nb_]).T, Z.T)
+        ref_poly = model.predict(np.array(rb[:nb_]).T).T
+        got_poly = inv.polynomial_state_estimation_fitting_method_least_squares(sm, pts, Z, rb[:nb_], degree=degree)
+        assert relerr(got_poly, ref_poly) < 1e-8, (degree, relerr(got_poly, ref_poly))
     # cell 44: optimal sampling draws the same points (same seed, same density up to rounding)
     p1 = inv.measurements_sampling_method_optimal(8, sm.x_domain, sm.y_domain, rb, sm, seed=3)
     np.random.seed(3)
