@@ -185,6 +185,7 @@ int romhc_set_option(romhc_handle h, const char* name, double value) {
     else if (!strcmp(name, "gram_variant")) romhc::g_gram_variant = (int)value;
     else if (!strcmp(name, "tn_variant")) romhc::g_tn_variant = (int)value;
     else if (!strcmp(name, "fused")) c->use_fused = value != 0.0;
+    else if (!strcmp(name, "sweep")) c->use_sweep = value != 0.0;
     else if (!strcmp(name, "z32")) c->use_z32 = std::max(0, std::min(3, (int)value));
     else if (!strcmp(name, "tile_persistent")) c->tile_persistent = value != 0.0;
     else if (!strcmp(name, "tile_prefetch")) c->tile_prefetch = value != 0.0;
@@ -248,6 +249,10 @@ int romhc_error_norm(romhc_handle h, const double* U, const double* coef, const 
                      double* out, void* st) {
     CHECK_H(h);
     if (n < 0 || n > 256) { set_error("error_norm: bad n"); return ROMHC_ERR_ARG; }
+    if (n > 0 && K > 0 && H(h)->use_sweep) {
+        const int rc = H(h)->error_sweep(U, coef, basis, n, out, K, ST(st));
+        if (rc >= 0) return rc;                     // -1: wide mesh / large n -> the strip kernel below
+    }
     return H(h)->energy(nullptr, U, n > 0 ? coef : nullptr, basis, n, out, K, 0, 1, ST(st));
 }
 

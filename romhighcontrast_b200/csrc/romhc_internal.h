@@ -110,6 +110,7 @@ struct Context {
     bool tile_prefetch = true;          // L2 prefetch of the next CTA's operand rows (non-persistent tile kernels)
     bool tile_persistent = true;        // persistent, TMA-pipelined tile kernels (one CTA per SM)
     bool use_fused = true;              // PCG update fused into the finest level's going-down kernel
+    bool use_sweep = true;              // greedy error sweep: DMMA kernel (sweep.cu); false: the strip kernel k_energy
     // The preconditioned residual z = M r travels from the finest going-up kernel to k_pcg_p_apply as fp32 (half a stream
     // less in each): z only steers the search direction, so rounding it perturbs the preconditioner by 6e-8 relative and
     // leaves x, r, p and every reduction in fp64 (r.z is formed from the ROUNDED z, consistent with what p_apply reads).
@@ -171,6 +172,8 @@ struct Context {
     int apply(const double* y, const double* u, double* out, int64_t K, cudaStream_t st);
     int energy(const double* y, const double* u, const double* coef, const double* basis, int nbasis, double* out,
                int64_t K, int mode, int take_sqrt, cudaStream_t st);
+    // greedy error sweep on the fp64 tensor cores (sweep.cu); -1: configuration does not fit, use energy()
+    int error_sweep(const double* U, const double* coef, const double* basis, int n, double* out, int64_t K, cudaStream_t st);
     int pack(const double* compact, double* padded, int64_t K, cudaStream_t st);
     int unpack(const double* padded, double* compact, int64_t K, cudaStream_t st);
     // fuse_p != nullptr: the PCG update x += alpha p, r -= alpha A p is still pending and may be fused into level 0

@@ -432,3 +432,31 @@ def test_solve_fp32_transport_modes_agree(torch_mod, z32):
     assert int((it - it0).abs().max()) <= 1
     Uo = FEMOracle(geo, N).generate_solutions(y[:3])
     assert relerr(eng.unpad(x[:3]).cpu().numpy(), Uo) < 1e-9
+
+
+@pytest.mark.parametrize("geo,N,K,n", [((2, 2), 8, 37, 3), ((3, 2), 4, 100, 7), ((2, 2), 32, 129, 1), ((3, 3), 43, 70, 20),
+                                       ((4, 4), 16, 200, 12), ((4, 4), 64, 333, 20), ((4, 4), 64, 64, 32), ((2, 4), 64, 45, 5),
+                                       ((8, 8), 64, 23, 20), ((1, 3), 8, 9, 24), ((2, 3), 27, 50, 33)])
+def test_error_sweep_dmma_matches_strip_kernel_and_numpy(torch_mod, geo, N, K, n):
+    """greedy error sweep || C Phi - U ||_{A_1}: the DMMA kernel (sweep.cu: all four (systems, columns) shapes, ragged K,
+    n not a multiple of 4, pitch P != C, meshes of 64 .. 512 columns) against the strip kernel k_energy and against
+    sqrt(v^T A_1 v) evaluated with the device stencil on the explicitly formed difference."""
+    torch = torch_mod
+    eng = make_engine(geo, N)
+    rng = np.random.default_rng(K + n)
+    U = eng.pad(rng.standard_normal((K, eng.D)))
+    Phi = eng.pad(rng.standard_normal((n, eng.D)))
+    C = eng.dev(rng.standard_normal((K, n)))
+    e_new = eng.error_norm(U, C, Phi)
+    eng.set_option("sweep", 0)
+    e_old = eng.error_norm(U, C, Phi)
+    eng.set_option("sweep", 1)
+    V = eng.gemm_nn(C, Phi) - U
+    e_ref = eng.h10_norm(V.contiguous())
+    assert float(((e_new - e_ref).abs() / e_ref).max()) < 1e-12
+    assert float(((e_old - e_ref).abs() / e_ref).max()) < 1e-12
+    # small differences (the regime of the greedy loop): C Phi close to U
+    U2 = (eng.gemm_nn(C, Phi) + 1e-7 * U).contiguous()
+    d_new = eng.error_norm(U2, C, Phi)
+    d_ref = 1e-7 * eng.h10_norm(U)
+    assert float(((d_new - d_ref).abs() / d_ref).max()) < 1e-6
