@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--k-snap", type=int, default=10000, help="snapshot solves per GPU per step")
     ap.add_argument("--k-online", type=int, default=1000000)
+    ap.add_argument("--k-obs", type=int, default=100000, help="configs[3]: observations in the estimation batch (whole job)")
     ap.add_argument("--n-rb", type=int, default=20)
     ap.add_argument("--quick", action="store_true", help="small sizes (debug)")
     ap.add_argument("--no-secondary", action="store_true")
@@ -172,7 +173,7 @@ def main():
     steps = args.steps or 3
     warmup = args.warmup if args.warmup is not None else 3
     if args.quick:
-        args.k_snap, args.k_online, args.k_config4 = 512, 100000, 256
+        args.k_snap, args.k_online, args.k_config4, args.k_obs = 512, 100000, 256, 4000
 
     import torch
     import torch.distributed as dist
@@ -691,6 +692,42 @@ def run_config0():
     return out
 
 
+def run_config3(eng, x, y_dev, y_host, args, world, rank, barrier):
+    """BASELINE configs[3]: state + parameter estimation (least squares in the reduced space and the PBDW correction,
+    m = 50 point measurements) over a 100 000-observation batch on the (4,4), N = 64 model, the batch sharded over the
+    ranks (no collective).  Every observation is solved, measured, estimated and scored on the device."""
+    import torch
+    import torch.distributed as dist
+    from lib.ReducedBasis import ReducedBasisGreedy
+    from lib.SolutionsManagers import SolutionsManagerFEM
+    from romhighcontrast_b200.inverse import observation_batch_estimation
+    n, m = args.n_rb, 50
+    Kobs = int(args.k_obs) // world
+    sm = SolutionsManagerFEM(GEO, NPB, method="lsqsparse")
+    sm.__dict__["_engine"] = eng
+    Ktr = min(1000, x.shape[0])
+    Utr, ytr = x[:Ktr].contiguous(), y_dev[:Ktr].contiguous()
+    rb = ReducedBasisGreedy().build(n=n, sm=sm, solutions2train=Utr, a2train=ytr, solutions2train_h1norm=eng.h10_norm(Utr))
+    pts = np.random.default_rng(1).uniform(low=[sm.x_domain[0], sm.y_domain[0]], high=[sm.x_domain[1], sm.y_domain[1]], size=(m, 2))
+    yobs = sample_params(Kobs, seed=4400 + rank)
+    observation_batch_estimation(sm, rb, pts, yobs[:2000])             # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    res = observation_batch_estimation(sm, rb, pts, yobs)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    tm = {}
+    observation_batch_estimation(sm, rb, pts, yobs[:20000], timings=tm)   # stage-synchronised pass on a fifth of the batch
+    return {"workload": f"configs[3]: {world * Kobs} observations, m={m} point measurements, n={n} greedy basis (trained on {Ktr} snapshots), "
+                        "(4,4) subdomains, N=64; solve + measure + LS state estimate + PBDW correction + parameter estimators",
+            "observations_per_s": world * Kobs / float(dt.item()), "s": float(dt.item()),
+            "stage_seconds_on_20000": tm,
+            "median_rel_H10_error_ls": float(np.median(res["err_ls"])), "median_rel_H10_error_pbdw": float(np.median(res["err_pbdw"])),
+            "median_abs_rel_param_error_inverse": float(np.median(np.abs(1 - res["a_inverse"] / yobs)))}
+
+
 def run_secondary(eng, x, y, K, args, world, rank, barrier, ev, U_np=None, y_host=None):
     """POD (centred Gram on the fp64 tensor cores), the greedy builders and 1M online reduced Galerkin solves on the
     snapshots in `x`."""
@@ -706,6 +743,12 @@ def run_secondary(eng, x, y, K, args, world, rank, barrier, ev, U_np=None, y_hos
         out["distributed"] = {"error": repr(exc)[:300], "trace": traceback.format_exc()[-600:]}
         if world > 1:
             raise                                                 # a rank that left a collective early would hang the others
+    try:
+        out["config3"] = run_config3(eng, x, y, y_host, args, world, rank, barrier)
+    except Exception as exc:
+        out["config3"] = {"error": repr(exc)[:300]}
+        if world > 1:
+            raise
     if U_np is not None:
         try:
             out["greedy"] = run_greedy(U_np, y_host, n)

@@ -147,3 +147,58 @@ def reduced_basis_generator_greedy(sm, solutions_offline, number_of_reduced_base
         resid = S - eng.gemm_nn(X.T.contiguous(), B)
         picked.append(int(np.argmax(f_norm(resid).cpu().numpy())))
     return [S_host[i] for i in picked], picked
+
+
+def observation_batch_estimation(sm, rb, measurement_points, a_observed, chunk=10000, pbdw=True, timings=None):
+    """BASELINE configs[3] as one device pipeline: for every observed parameter (a batch of ~1e5) the snapshot is solved,
+    measured at the m points, and from the measurements alone the state (least squares in the reduced space,
+    ReducedBasis.py:65-70, optionally with the notebook's PBDW correction, cell 52) and the parameters (Estimators.py:24-37
+    through `rb.parameter_estimation_inverse / _linear`) are estimated; the (K, D) fields live only chunk-wise on the
+    device.  Returns a dict: measurements (K, m), coefficients c (n, K), a_inverse / a_linear (K, nrb, ncb), and the
+    relative H10 errors of the state estimates against the true snapshots (`err_ls`, `err_pbdw`, (K,))."""
+    import time
+    eng = sm._engine_()
+    pts = np.asarray(measurement_points, dtype=np.float64).reshape(-1, 2)
+    a_obs = np.asarray(a_observed, dtype=np.float64)
+    K, m = len(a_obs), len(pts)
+    basis = _basis_array(rb.basis)
+    n = basis.shape[0]
+    Phi = sm._pad_rows(basis)
+    E = sm.evaluate_solutions(pts, basis)                                     # (n, m)
+    pinv = eng.dev(np.linalg.lstsq(E.T, np.eye(m), rcond=-1)[0])              # (n, m)
+    Rt = sm._pad_rows(sm.generate_riesz(pts, norm="l2")) if pbdw else None    # (m, Dp)
+    Z = torch.empty((K, m), dtype=torch.float64, device=eng.device)
+    Cc = torch.empty((K, n), dtype=torch.float64, device=eng.device)
+    err_ls = torch.empty(K, dtype=torch.float64, device=eng.device)
+    err_pb = torch.empty(K, dtype=torch.float64, device=eng.device) if pbdw else None
+    x = eng.empty(min(chunk, K), eng.Dp)
+    tacc = {"solve_s": 0.0, "measure_s": 0.0, "state_ls_s": 0.0, "pbdw_s": 0.0}
+    tick = (lambda: (torch.cuda.synchronize(), time.perf_counter())[1]) if timings is not None else (lambda: 0.0)
+    for k0 in range(0, K, chunk):
+        kc = min(chunk, K - k0)
+        t0 = tick()
+        xs, _, _ = eng.solve(eng.params(a_obs[k0:k0 + kc]), out=x[:kc])
+        t1 = tick()
+        z = eng.evaluate(pts, xs)                                             # (kc, m)
+        Z[k0:k0 + kc] = z
+        t2 = tick()
+        c = eng.gemm_nt(z, pinv)                                              # (kc, n) = z pinv^T
+        Cc[k0:k0 + kc] = c
+        nrm = eng.h10_norm(xs)
+        err_ls[k0:k0 + kc] = eng.error_norm(xs, c, Phi) / nrm
+        t3 = tick()
+        if pbdw:
+            v = eng.gemm_nn(c, Phi)
+            v = v + eng.gemm_nn((z - eng.evaluate(pts, v)).contiguous(), Rt)
+            err_pb[k0:k0 + kc] = eng.h10_norm((v - xs).contiguous()) / nrm
+        t4 = tick()
+        tacc["solve_s"] += t1 - t0; tacc["measure_s"] += t2 - t1; tacc["state_ls_s"] += t3 - t2; tacc["pbdw_s"] += t4 - t3
+    c_host = Cc.T.contiguous().cpu().numpy()                                  # (n, K) as np.linalg.lstsq returns it
+    t5 = tick()
+    out = {"measurements": Z.cpu().numpy(), "coefficients": c_host,
+           "a_inverse": rb.parameter_estimation_inverse(c_host), "a_linear": rb.parameter_estimation_linear(c_host),
+           "err_ls": err_ls.cpu().numpy(), "err_pbdw": err_pb.cpu().numpy() if pbdw else None}
+    if timings is not None:
+        tacc["parameter_estimation_s"] = tick() - t5
+        timings.update(tacc)
+    return out

@@ -189,7 +189,7 @@ class SolutionsManager:
     def _projection_coefficients_dev(eng, U_pad, Phi_pad):
         import torch
         W = eng.apply(None, Phi_pad)                                    # A_1 Phi^T
-        B = eng.gemm_nt(U_pad, W)                                       # (K, n): B_km of :113-124
+        B = eng.gemm_nt(U_pad, W, splitk=True)                          # (K, n): B_km of :113-124 (79 row tiles: split over the contraction)
         Ahat, _ = eng.project_operators(Phi_pad)                        # :125-133
         ones = torch.ones(U_pad.shape[0], eng.nb, dtype=torch.float64, device=eng.device)   # a = ones, :136
         return eng.reduced_solve(ones, Ahat, B)                         # :135-138

@@ -182,3 +182,40 @@ def test_config4_geometry_parity():
     A = np.einsum("kq,qij->kij", y.reshape(K, -1), Ahat.cpu().numpy())
     Cl = np.linalg.solve(A, np.broadcast_to(bhat.cpu().numpy(), (K, n))[..., None])[..., 0]
     assert (np.linalg.norm(C - Cl, axis=1) / np.linalg.norm(Cl, axis=1)).max() < 1e-9
+
+
+def test_config3_observation_batch_100k():
+    """BASELINE configs[3]: state and parameter estimation from m = 50 point measurements over a 100 000-observation batch
+    on the (4,4), N = 64 model (romhighcontrast_b200.inverse.observation_batch_estimation); a sub-sample against the CPU
+    oracle's restatement of ReducedBasis.py:65-86 / Estimators.py:24-37 and of the notebook's PBDW correction."""
+    from lib.ReducedBasis import ReducedBasisGreedy
+    from lib.SolutionsManagers import SolutionsManagerFEM
+    from oracle import FEMOracle, pbdw_correction
+    from oracle.rb import state_estimation, estimator_inv, estimator_linear
+    from romhighcontrast_b200.inverse import observation_batch_estimation
+    geo, Nb, n, m, Kobs, Ktrain = (4, 4), 64, 20, 50, 100000, 1000
+    sm = SolutionsManagerFEM(geo, Nb)
+    ytr = 10 ** np.random.default_rng(42).uniform(0, 6, (Ktrain,) + geo)
+    Utr = sm.generate_solutions(ytr)
+    rb = ReducedBasisGreedy().build(n=n, sm=sm, solutions2train=Utr, a2train=ytr, solutions2train_h1norm=sm.H10norm(Utr))
+    pts = np.random.default_rng(1).uniform(low=[sm.x_domain[0], sm.y_domain[0]], high=[sm.x_domain[1], sm.y_domain[1]], size=(m, 2))
+    yobs = 10 ** np.random.default_rng(44).uniform(0, 6, (Kobs,) + geo)
+    res = observation_batch_estimation(sm, rb, pts, yobs)
+    Z, c = res["measurements"], res["coefficients"]
+    assert Z.shape == (Kobs, m) and c.shape == (n, Kobs) and res["a_inverse"].shape == (Kobs,) + geo
+    o = FEMOracle(geo, Nb)
+    sel = np.arange(0, Kobs, Kobs // 64)[:64]
+    Uo = o.generate_solutions(yobs[sel[:4]])
+    Zo = o.evaluate_solutions(pts, Uo)
+    assert np.abs(Z[sel[:4]] - Zo).max() <= 1e-9 * np.abs(Zo).max()
+    co, esto = state_estimation(o, np.asarray(rb.basis), pts, Z[sel])
+    assert np.linalg.norm(c[:, sel] - co) <= 1e-9 * np.linalg.norm(co)
+    np.testing.assert_allclose(res["a_inverse"][sel], estimator_inv(c[:, sel], np.asarray(rb.a)), rtol=1e-10)
+    np.testing.assert_allclose(res["a_linear"][sel], estimator_linear(c[:, sel], np.asarray(rb.a)), rtol=1e-10, atol=1e-300)
+    # state errors of the first four observations against the oracle's own estimates of the same quantities
+    h = o.H10norm(Uo)
+    e_ls = o.H10norm(esto[:4] - Uo) / h
+    np.testing.assert_allclose(res["err_ls"][sel[:4]], e_ls, rtol=1e-6)
+    e_pb = o.H10norm(pbdw_correction(o, pts, Z[sel[:4]], esto[:4]) - Uo) / h
+    np.testing.assert_allclose(res["err_pbdw"][sel[:4]], e_pb, rtol=1e-6)
+    assert np.all(np.isfinite(res["err_ls"])) and np.all(np.isfinite(res["err_pbdw"]))
