@@ -279,6 +279,24 @@ def main():
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_val = world * K / float(t_e2e.item())
     clocks = sampler.stop()
+    # the ceiling of e2e on this box: the step's D2H bytes as one plain pinned cudaMemcpyAsync per rank, all ranks at once
+    # (the host side of N GPUs shares its PCIe / memory fabric); e2e cannot beat max(resident step, that copy)
+    Ud = eng.empty(K, eng.D)
+    d2h = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        U_pin.copy_(Ud, non_blocking=True)
+        torch.cuda.synchronize()
+        td = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        d2h.append(float(td.item()))
+    del Ud
+    t_d2h = min(d2h[1:])
+    ceiling = world * K / max(t_d2h, ms_step * 1e-3)
+    e2e_ceiling = {"d2h_s_all_ranks_concurrent": t_d2h, "d2h_GBps_aggregate": world * U_pin.numel() * 8 / t_d2h / 1e9,
+                   "ceiling_solves_per_s": ceiling, "e2e_frac_of_ceiling": e2e_val / ceiling}
     # the same through the reference-facing class API (numpy in, fresh pageable numpy out): src.lib mirror -> C ABI
     api_val = None
     try:
@@ -396,8 +414,9 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": int(y_np.nbytes),
                     "d2h_bytes_per_step": int(U_np.nbytes + K * 12),
-                    "path": "romhc_generate_solutions_host (C ABI), pinned host buffers",
-                    "class_api_value": api_val, "class_api_path": "SolutionsManagerFEM.generate_solutions: numpy in, fresh numpy out"},
+                    "path": "romhc_generate_solutions_host (C ABI), pinned host buffers", "ceiling": e2e_ceiling,
+                    "class_api_value": api_val, "class_api_frac_of_e2e": (api_val / e2e_val) if api_val else None,
+                    "class_api_path": "SolutionsManagerFEM.generate_solutions: numpy in, numpy out (result in a pooled pinned block)"},
             "gpu_launches": int(launches),
             "roofline": roofline, "kernels": per_kind, "cpu_baseline": cpu, "secondary": secondary,
         }

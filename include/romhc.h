@@ -105,7 +105,7 @@ int romhc_error_norm(romhc_handle h, const double* U_pad_dev, const double* coef
 
 /* ---- K1: batched snapshot solves  A(y_k) u_k = b,  b = 1/N^2 ------------------------------------------------------
  * replaces generate_solutions / galerkin   SolutionsManagers.py:17-40, 64-68 (all three `method`s)
- * fp64 CG preconditioned by a V(1,1) geometric multigrid cycle; synchronises `stream` before returning.
+ * fp64 CG preconditioned by one geometric multigrid V-cycle (V(2,2) / (3,3) / (4,4) by level; options nu, nu_mid, nu_tail); synchronises `stream` before returning.
  * iters_dev / relres_dev (optional): per-system iteration count and final sqrt(r.z / r0.z0).
  * stats4 (optional, host): {iterations launched (sum over chunks), chunks, status bits, workspace bytes}. */
 int romhc_solve(romhc_handle h, const double* y_dev, int64_t K, double* x_pad_dev, int* iters_dev, double* relres_dev,
@@ -126,7 +126,10 @@ int romhc_project_operators(romhc_handle h, const double* basis_pad_dev, int n, 
 
 /* ---- K5: batched reduced solves  (sum_q y[k][q] Ahat[q]) c_k = rhs ---------------------------------------------------
  * replaces map(galerkin, a) on the reduced system  SolutionsManagers.py:104-105, 135-138
- * rhs_dev: (n) shared by all systems (rhs_per_system = 0) or (K, n); info_dev[k] = 1 where the matrix is not SPD. */
+ * rhs_dev: (n) shared by all systems (rhs_per_system = 0) or (K, n); info_dev[k] = 1 where the matrix is not SPD.
+ * Any n: n <= 24 quad-per-system kernel (DMMA assembly, Cholesky in registers), n <= 64 warp-per-system, larger n a
+ * blocked Cholesky a few systems at a time -- which also makes this the device form of galerkin(a, B_total, A_preassembled)
+ * on a caller's dense operators (SolutionsManagers.py:17-40) and of the generic SolutionsManager (:43-68). */
 int romhc_reduced_solve(const double* y_dev, int nb, const double* Ahat_dev, const double* rhs_dev,
                         int rhs_per_system, int n, int64_t K, double* C_dev, int* info_dev, void* stream);
 
@@ -137,7 +140,7 @@ int romhc_reduced_solve(const double* y_dev, int nb, const double* Ahat_dev, con
  *          products of the Gram-free POD) the contraction is spread over ~2 CTAs per SM and the partial sums are
  *          reduced in a fixed order (deterministic; needs 16-byte aligned operands, otherwise the plain kernel runs).
  * gemm_nn: C[M,N] = A[M,Kd] B[Kd,N], small Kd (c Phi)         SolutionsManagers.py:106,139
- * gemm_tn: C[M,N] = A[Kd,M]^T B[Kd,N], M <= 32 (V^T Xc)       POD back-projection */
+ * gemm_tn: C[M,N] = A[Kd,M]^T B[Kd,N] (V^T Xc; rows of C in blocks of 32)   POD back-projection */
 int romhc_gemm_nt(const double* A_dev, int64_t lda, const double* B_dev, int64_t ldb, double* C_dev, int64_t ldc,
                   int64_t M, int64_t N, int64_t Kd, int symmetric, void* stream);
 int romhc_gemm_nn(const double* A_dev, int64_t lda, const double* B_dev, int64_t ldb, double* C_dev, int64_t ldc,
@@ -157,6 +160,9 @@ int romhc_evaluate(romhc_handle h, const double* points_dev, int m, const double
 int romhc_interp_weights(romhc_handle h, const double* points_dev, int m, int* idx3_dev, double* w3_dev, void* stream);
 /* out[k] = ||X[k, :D]||_2 for a generic row-major matrix (SolutionsManager.l2norm is a staticmethod)  :60-62 */
 int romhc_row_norms(const double* X_dev, int64_t ld, int64_t K, int64_t D, double* out_dev, void* stream);
+/* out[k] = X[k, :D] . Y[k, :D]: with Y = X A^T this is u^T A u, H10norm of the generic dense-operator manager  :56-58 */
+int romhc_row_dots(const double* X_dev, int64_t ldx, const double* Y_dev, int64_t ldy, int64_t K, int64_t D, double* out_dev,
+                   void* stream);
 int romhc_estimator(const double* c_dev, int64_t K, int n, const double* abasis_dev, int nb, int invert,
                     double* out_dev, void* stream);
 int romhc_argmax(const double* v_dev, int64_t K, int64_t* idx_dev, double* val_dev, void* stream);

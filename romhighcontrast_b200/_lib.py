@@ -64,6 +64,7 @@ SIGNATURES = {
     "romhc_evaluate": (_i, [_vp, _vp, _i, _vp, _i64, _vp, _vp]),
     "romhc_interp_weights": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "romhc_row_norms": (_i, [_vp, _i64, _i64, _i64, _vp, _vp]),
+    "romhc_row_dots": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp]),
     "romhc_estimator": (_i, [_vp, _i64, _i, _vp, _i, _i, _vp, _vp]),
     "romhc_argmax": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "romhc_poly_features": (_i, [_vp, _i64, _i, _i64, _vp, _i, _i, _vp, _i64, _vp]),

@@ -4,6 +4,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <atomic>
@@ -307,6 +308,9 @@ int romhc_interp_weights(romhc_handle h, const double* pts, int m, int* idx3, do
 int romhc_row_norms(const double* X, int64_t ld, int64_t K, int64_t D, double* out, void* st) {
     return row_norms(X, ld, K, D, out, ST(st));
 }
+int romhc_row_dots(const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t K, int64_t D, double* out, void* st) {
+    return row_dots(X, ldx, Y, ldy, K, D, out, ST(st));
+}
 int romhc_estimator(const double* c, int64_t K, int n, const double* ab, int nb, int invert, double* out, void* st) {
     return estimator_contract(c, K, n, ab, nb, invert, out, ST(st));
 }
@@ -322,6 +326,15 @@ int romhc_poly_features(const double* basis, int64_t ld, int n, int64_t D, const
 // would serialise the pipeline, so the solutions go to pinned bounce buffers first and a stream-ordered host callback
 // moves them on with a few threads while the next chunk is being solved.
 struct HostCopyTask { const char* src; char* dst; size_t bytes; int nthreads; };
+// memcpy threads per rank for pageable destinations: the host cores are shared by the ranks of the box (torchrun exports
+// LOCAL_WORLD_SIZE), so 8 ranks x 8 threads would oversubscribe a 32-core host; ROMHC_COPY_THREADS overrides
+static int host_copy_threads() {
+    if (const char* e = getenv("ROMHC_COPY_THREADS")) { const int v = atoi(e); if (v > 0) return std::min(v, 64); }
+    int ranks = 1;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+    const int hw = std::max(1, int(std::thread::hardware_concurrency()));
+    return std::max(1, std::min(8, hw / (2 * ranks)));
+}
 static void CUDART_CB host_copy_callback(void* p) {
     HostCopyTask* t = static_cast<HostCopyTask*>(p);
     const int nt = std::max(1, t->nthreads);
@@ -376,7 +389,7 @@ int romhc_generate_solutions_host(romhc_handle h, const double* y_host, int64_t 
         }
         if (!s.copy2) CK(cudaStreamCreateWithFlags(&s.copy2, cudaStreamNonBlocking));
     }
-    const int copy_threads = std::max(1, std::min(8, int(std::thread::hardware_concurrency()) / 2));
+    const int copy_threads = host_copy_threads();
     // Chunk schedule: full chunks first, then halved ones -- only the LAST chunk's D2H copy is exposed (nothing left
     // to overlap it with), so it should be small; chunks below ~600 systems would under-fill the persistent kernels.
     // Every kc the schedule produces is <= stage_cap, the capacity the staging buffers were sized for.
@@ -486,7 +499,7 @@ int romhc_pack_host(romhc_handle h, const double* compact_host, double* padded_d
     int rc = ensure_xfer_stage(c, size_t(rows) * D * 8, !pinned); if (rc) return rc;
     HostStage& s = c->hstage;
     cudaStream_t st = ST(stream);
-    const int copy_threads = std::max(1, std::min(8, int(std::thread::hardware_concurrency()) / 2));
+    const int copy_threads = host_copy_threads();
     auto pipeline = [&]() -> int {
         int64_t i = 0;
         for (int64_t k0 = 0; k0 < K; k0 += rows, ++i) {
@@ -529,7 +542,7 @@ int romhc_unpack_host(romhc_handle h, const double* padded_dev, double* compact_
     int rc = ensure_xfer_stage(c, size_t(rows) * D * 8, !pinned); if (rc) return rc;
     HostStage& s = c->hstage;
     cudaStream_t st = ST(stream);
-    const int copy_threads = std::max(1, std::min(8, int(std::thread::hardware_concurrency()) / 2));
+    const int copy_threads = host_copy_threads();
     auto pipeline = [&]() -> int {
         int64_t i = 0;
         for (int64_t k0 = 0; k0 < K; k0 += rows, ++i) {

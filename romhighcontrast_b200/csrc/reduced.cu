@@ -353,8 +353,9 @@ static int dispatch_reduced_quad(int n, const double* y, int nb, const double* A
 
 int reduced_solve(const double* y, int nb, const double* Ahat, const double* rhs, int rhs_per_system, int n,
                   int64_t K, double* C, int* info, cudaStream_t st) {
-    if (n < 1 || n > 64) { set_error("reduced_solve: n must be in [1, 64], got %d", n); return ROMHC_ERR_ARG; }
+    if (n < 1) { set_error("reduced_solve: n must be positive, got %d", n); return ROMHC_ERR_ARG; }
     if (K <= 0) return ROMHC_OK;
+    if (n > 64) return dense_spd_solve(y, nb, Ahat, rhs, rhs_per_system, n, K, C, info, st);   // blocked Cholesky (dense.cu)
     const int npk = n * (n + 1) / 2;
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);

@@ -23,6 +23,55 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+class PinnedPool:
+    """Pinned host blocks handed out as numpy arrays (results of the reference-shaped API: numpy in, numpy out).
+
+    A fresh pageable destination costs a page fault per 4 KB on first touch plus a bounce-buffer memcpy (round 1: the
+    class API ran 27 % behind the pinned C-ABI path); a block from this pool is the D2H destination itself.  A block
+    returns to the pool when the array AND every view of it have been garbage collected (weakref finaliser on the buffer
+    owner), so arrays the caller keeps stay valid for as long as they are referenced.  Free blocks beyond `max_free_bytes`
+    are released; if pinning fails the caller falls back to a pageable array."""
+    max_free_bytes = 24 << 30
+
+    def __init__(self):
+        self.free = []                           # (capacity, address)
+        self.lib = None
+
+    def take(self, shape):
+        import weakref
+        n = int(np.prod(shape))
+        nbytes = n * 8
+        if self.lib is None:
+            self.lib = _lib.load()
+        pick = None
+        for i, (cap, addr) in enumerate(self.free):
+            if nbytes <= cap <= 2 * nbytes + (1 << 20) and (pick is None or cap < self.free[pick][0]):
+                pick = i
+        if pick is not None:
+            cap, addr = self.free.pop(pick)
+        else:
+            ptr = C.c_void_p()
+            cap = (nbytes + (1 << 21) - 1) & ~((1 << 21) - 1)
+            if self.lib.romhc_malloc_host(C.byref(ptr), cap) != 0 or not ptr.value:
+                return None
+            addr = ptr.value
+        owner = (C.c_double * n).from_address(addr)
+        weakref.finalize(owner, self._give_back, cap, addr)
+        return np.ctypeslib.as_array(owner).reshape(shape)
+
+    def _give_back(self, cap, addr):
+        try:
+            self.free.append((cap, addr))
+            while sum(c for c, _ in self.free) > self.max_free_bytes:
+                c, a = self.free.pop(0)
+                self.lib.romhc_free_host(C.c_void_p(a))
+        except Exception:                        # interpreter shutdown
+            pass
+
+
+PINNED_POOL = PinnedPool()
+
+
 class Engine:
     def __init__(self, blocks_geometry, N, device=None):
         if not torch.cuda.is_available():
@@ -94,11 +143,20 @@ class Engine:
         _lib.check(self.lib.romhc_unpack(self.handle, _ptr(padded), _ptr(out), K, self.stream()))
         return out
 
+    def host_result(self, shape):
+        """Destination of a (K, D) result that leaves through the numpy API: a pooled pinned block for large results (the
+        D2H copies land in it directly), a plain numpy array for small ones or when pinning fails."""
+        if int(np.prod(shape)) * 8 >= self.HOST_PIPELINE_MIN_BYTES:
+            arr = PINNED_POOL.take(tuple(shape))
+            if arr is not None:
+                return arr
+        return np.empty(shape)
+
     def unpad_host(self, padded, out=None):
         """(K, Dp) padded device tensor -> (K, D) numpy array (fresh unless `out` is given); the pipelined counterpart
         of unpad(...).cpu().numpy() for results that leave through the reference's API."""
         K = padded.shape[0]
-        U = np.empty((K, self.D)) if out is None else out
+        U = self.host_result((K, self.D)) if out is None else out
         if U.nbytes < self.HOST_PIPELINE_MIN_BYTES:
             U[...] = self.unpad(padded).cpu().numpy()
             return U
@@ -262,7 +320,7 @@ class Engine:
     def generate_solutions_host(self, y_host, out=None, return_stats=False):
         y = np.ascontiguousarray(np.asarray(y_host, dtype=np.float64).reshape(-1, self.nb))
         K = y.shape[0]
-        U = np.empty((K, self.D)) if out is None else out
+        U = self.host_result((K, self.D)) if out is None else out
         iters = np.empty(K, dtype=np.int32)
         relres = np.empty(K)
         _lib.check(self.lib.romhc_generate_solutions_host(

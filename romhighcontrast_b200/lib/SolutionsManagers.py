@@ -25,47 +25,112 @@ def h1_error(v: List[np.ndarray]):                                    # referenc
     return np.sqrt(np.mean(np.sum(np.power(np.gradient(v, axis=(1, 2)), 2), axis=0), axis=(1, 2)))
 
 
-def galerkin(a, B_total, A_preassembled, method="lsq"):
-    """Single reduced system, kept for API completeness (reference :17-40).
+class _DenseOps:
+    """Handle-free device primitives of libromhc (GEMMs, batched SPD solves, row norms / dots) for callers that hold
+    dense operators: galerkin() and the generic SolutionsManager(A_preassembled, B_total).  No CPU fallback."""
 
-    The batched device path is `SolutionsManager.generate_fm_solutions`; this function serves callers that hold
-    their own small (nrb, ncb, n, n) operators and runs the same batched Cholesky kernel with K = 1."""
+    def __init__(self):
+        import torch
+        from .. import _lib
+        if not torch.cuda.is_available():
+            raise _lib.RomhcError("no CUDA device: the ROMHighContrast B200 path has no CPU fallback")
+        self.torch, self._lib = torch, _lib
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def dev(self, a):
+        return self.torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.float64)), device=self.device)
+
+    def _p(self, t):
+        import ctypes as C
+        return C.c_void_p(t.data_ptr())
+
+    def _st(self):
+        import ctypes as C
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def empty(self, *shape, dtype=None):
+        return self.torch.empty(*shape, dtype=dtype or self.torch.float64, device=self.device)
+
+    def gemm_nt(self, A, B):
+        out = self.empty(A.shape[0], B.shape[0])
+        self._lib.call("romhc_gemm_nt", self._p(A), A.stride(0), self._p(B), B.stride(0), self._p(out), out.stride(0), A.shape[0],
+                       B.shape[0], A.shape[1], 0, self._st())
+        return out
+
+    def gemm_nn(self, A, B):
+        out = self.empty(A.shape[0], B.shape[1])
+        self._lib.call("romhc_gemm_nn", self._p(A), A.stride(0), self._p(B), B.stride(0), self._p(out), out.stride(0), A.shape[0],
+                       B.shape[1], A.shape[1], self._st())
+        return out
+
+    def solve_spd(self, y, Aq, rhs):
+        """(sum_q y[k][q] Aq[q]) c_k = rhs (shared (n,) or per system (K, n)) -> (K, n); LinAlgError if not SPD."""
+        K, nb, n = y.shape[0], y.shape[1], Aq.shape[-1]
+        out = self.empty(K, n)
+        info = self.empty(K, dtype=self.torch.int32)
+        self._lib.call("romhc_reduced_solve", self._p(y), nb, self._p(Aq), self._p(rhs), 1 if rhs.dim() == 2 else 0, n, K,
+                       self._p(out), self._p(info), self._st())
+        if bool(info.any().item()):
+            raise np.linalg.LinAlgError("Matrix is not positive definite.")
+        return out
+
+    def row_dots(self, X, Y):
+        out = self.empty(X.shape[0])
+        self._lib.call("romhc_row_dots", self._p(X), X.stride(0), self._p(Y), Y.stride(0), X.shape[0], X.shape[1], self._p(out),
+                       self._st())
+        return out
+
+
+def galerkin(a, B_total, A_preassembled, method="lsq"):
+    """One dense system (sum_pq a_pq A_pq) c = B_total on the caller's operators (reference :17-40), any size: the
+    batched device solver with K = 1 (n <= 64: register / shared-memory Cholesky kernels; larger: blocked Cholesky).
+    All three reference methods solve the same SPD system (they agree to 1e-12) and share this path."""
     _check_method(method)
-    from ..engine import Engine  # noqa: F401  (ensures torch/cuda are importable before touching the library)
-    from .. import _lib
-    import ctypes as C
-    import torch
-    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
-    A = np.ascontiguousarray(np.asarray(A_preassembled, dtype=np.float64))
-    b = np.ascontiguousarray(np.asarray(B_total, dtype=np.float64))
-    nb, n = a.size, b.shape[0]
-    if n > 64:
-        raise Exception("galerkin(): dense systems larger than 64 are only solved through SolutionsManagerFEM")
-    if not torch.cuda.is_available():
-        raise _lib.RomhcError("no CUDA device: the ROMHighContrast B200 path has no CPU fallback")
-    dev = torch.device("cuda", torch.cuda.current_device())
-    y = torch.as_tensor(a.reshape(1, nb), device=dev)
-    Ad = torch.as_tensor(A.reshape(nb, n, n), device=dev)
-    bd = torch.as_tensor(b, device=dev)
-    out = torch.empty(1, n, dtype=torch.float64, device=dev)
-    info = torch.empty(1, dtype=torch.int32, device=dev)
-    p = lambda t: C.c_void_p(t.data_ptr())
-    _lib.call("romhc_reduced_solve", p(y), nb, p(Ad), p(bd), 0, n, 1, p(out), p(info),
-              C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
-    if int(info.item()):
-        raise np.linalg.LinAlgError("Matrix is not positive definite.")
-    return out[0].cpu().numpy()
+    ops = _DenseOps()
+    a = np.asarray(a, dtype=np.float64)
+    A = np.asarray(A_preassembled, dtype=np.float64)
+    b = np.asarray(B_total, dtype=np.float64)
+    n = b.shape[0]
+    return ops.solve_spd(ops.dev(a.reshape(1, -1)), ops.dev(A.reshape(-1, n, n)), ops.dev(b))[0].cpu().numpy()
 
 
 class SolutionsManager:
-    """Base class of the reference (:43-142).  Only the FEM subclass is GPU backed; the generic dense-operator
-    constructor is kept for type compatibility."""
+    """Base class of the reference (:43-142).  Constructed directly it is the reference's generic manager over dense
+    preassembled operators `A_preassembled` (nrb, ncb, D, D) and a load vector `B_total` (D,): the operators are uploaded
+    once and every method runs on the device primitives of libromhc (batched SPD solves, GEMMs).  `SolutionsManagerFEM`
+    overrides the data path with the matrix-free kernels and never forms the dense tensor."""
 
-    def __init__(self, A_preassembled, B_total, num_cores=1, method="lsq"):      # reference :44
-        if type(self) is SolutionsManager:
-            raise Exception("Not implemented.")   # dense-operator managers (SolutionsManagerPolynomial) are out of scope
+    def __init__(self, A_preassembled, B_total, num_cores=1, method="lsq"):      # reference :44-51
         self.method = method
         self.mapfunction = map                    # num_cores is accepted and ignored: the batch runs on the GPU
+        if A_preassembled is None:                # matrix-free subclass (SolutionsManagerFEM) sets its own attributes
+            return
+        self.vspace_dim = len(B_total)
+        self.blocks_geometry = np.shape(A_preassembled)[:2]
+        self.A_preassembled = A_preassembled
+        self.A_preassembled4h1_norm = np.einsum("abij->ij", self.A_preassembled)
+        self.B_total = B_total
+
+    # ---- dense-operator data path (generic manager) ----------------------------------------------------------------
+    def _dense_ops_(self):
+        st = self.__dict__.get("_dense_state")
+        if st is None:
+            ops = _DenseOps()
+            D = self.vspace_dim
+            st = {"ops": ops, "A": ops.dev(np.asarray(self.A_preassembled, dtype=np.float64).reshape(-1, D, D)),
+                  "A4": ops.dev(self.A_preassembled4h1_norm), "b": ops.dev(self.B_total)}
+            self.__dict__["_dense_state"] = st
+        return st
+
+    def _dense_reduced_operators(self, Phi):
+        """Phi (n, D) device -> Ahat (nb, n, n) = Phi A_q Phi^T (reference :93-103)."""
+        st = self._dense_ops_()
+        ops, A = st["ops"], st["A"]
+        n = Phi.shape[0]
+        Ahat = ops.empty(A.shape[0], n, n)
+        for q in range(A.shape[0]):
+            Ahat[q] = ops.gemm_nt(ops.gemm_nn(Phi, A[q]), Phi)
+        return Ahat
 
     def __str__(self):
         return self.__class__.__name__
@@ -83,6 +148,7 @@ class SolutionsManager:
         d = dict(self.__dict__)
         d.pop("_engine", None)
         d.pop("_dense_cache", None)
+        d.pop("_dense_state", None)
         return d
 
     def __setstate__(self, d):
@@ -97,6 +163,10 @@ class SolutionsManager:
     # ---- norms -----------------------------------------------------------------------------------------------
     def H10norm(self, solutions: List[np.ndarray]):
         """sqrt(u^T A_1 u), A_1 = stiffness with a == 1 (reference :56-58); edge form, never NaN."""
+        if "A_preassembled" in self.__dict__:                      # generic manager: u^T A4 u through GEMM + row dots
+            st = self._dense_ops_()
+            S = st["ops"].dev(np.asarray(solutions, dtype=np.float64).reshape(-1, self.vspace_dim))
+            return np.sqrt(st["ops"].row_dots(S, st["ops"].gemm_nt(S, st["A4"])).cpu().numpy())
         eng = self._engine_()
         return eng.h10_norm(self._pad_rows(solutions)).cpu().numpy()
 
@@ -124,6 +194,10 @@ class SolutionsManager:
         if a.size == 0:
             return np.zeros((0, self.vspace_dim))
         a = a.reshape((-1,) + tuple(self.blocks_geometry))
+        if "A_preassembled" in self.__dict__:                      # generic manager: K dense SPD solves of size D
+            st = self._dense_ops_()
+            U = st["ops"].solve_spd(st["ops"].dev(a.reshape(len(a), -1)), st["A"], st["b"]).cpu().numpy()
+            return (U, None, None) if return_stats else U
         if not np.all(a > 0) or not np.all(np.isfinite(a)):
             raise np.linalg.LinAlgError("diffusion coefficients must be positive and finite")
         eng = self._engine_()
@@ -161,6 +235,14 @@ class SolutionsManager:
         if len(coefficients_rom) == 0:
             return np.zeros((len(a), self.vspace_dim))                  # reference :89-91
         _check_method(self.method)
+        if "A_preassembled" in self.__dict__:                      # generic manager
+            st = self._dense_ops_()
+            ops = st["ops"]
+            Phi = ops.dev(np.asarray(coefficients_rom, dtype=np.float64).reshape(len(coefficients_rom), -1))
+            Ahat = self._dense_reduced_operators(Phi)
+            bhat = ops.gemm_nt(Phi, st["b"].reshape(1, -1)).reshape(-1).contiguous()
+            Cc = ops.solve_spd(ops.dev(np.asarray(a, dtype=np.float64).reshape(len(a), -1)), Ahat, bhat)
+            return Cc.cpu().numpy() if return_coefs else ops.gemm_nn(Cc, Phi).cpu().numpy()
         eng = self._engine_()
         Phi = self._pad_rows(coefficients_rom)
         y = eng.params(np.asarray(a, dtype=np.float64).reshape((-1,) + tuple(self.blocks_geometry)))
@@ -176,6 +258,16 @@ class SolutionsManager:
         if len(coefficients_rom) == 0:
             return np.zeros((len(solutions), self.vspace_dim))          # reference :109-111
         _check_method(self.method)
+        if "A_preassembled" in self.__dict__:                      # generic manager
+            st = self._dense_ops_()
+            ops = st["ops"]
+            Phi = ops.dev(np.asarray(coefficients_rom, dtype=np.float64).reshape(len(coefficients_rom), -1))
+            S = ops.dev(np.asarray(solutions, dtype=np.float64).reshape(len(solutions), -1))
+            B = ops.gemm_nt(S, ops.gemm_nn(Phi, st["A4"]))         # (K, n): B_km of :113-124, summed over the blocks
+            Ahat = self._dense_reduced_operators(Phi)
+            ones = ops.torch.ones(S.shape[0], Ahat.shape[0], dtype=ops.torch.float64, device=ops.device)
+            Cc = ops.solve_spd(ones, Ahat, B)
+            return Cc.cpu().numpy() if return_coefs else ops.gemm_nn(Cc, Phi).cpu().numpy()
         eng = self._engine_()
         import torch
         Phi = self._pad_rows(coefficients_rom)

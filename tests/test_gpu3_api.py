@@ -319,3 +319,49 @@ def test_host_layout_transfers_match_device_path():
     assert torch.equal(eng.pad(U[:3]), ref[:3])
     # twice in a row (slot reuse across calls)
     assert torch.equal(eng.pad(U * 2.0), ref * 2.0)
+
+
+def test_generic_dense_manager_and_galerkin_on_reference_operators():
+    """SolutionsManager(A_preassembled, B_total) (reference :43-139) and galerkin() (:17-40) on the reference's own dense
+    operators (golden g1, D = 77: the blocked dense Cholesky path, n > 64) against the reference's outputs (golden g2 / g3);
+    a D = 961 system against the matrix-free FEM path; a small reduced system (n = 5: the quad kernel)."""
+    from src.lib.SolutionsManagers import SolutionsManager, SolutionsManagerFEM, galerkin
+    g1, g2, g3 = golden("g1_assembly_3x2_N4.npz"), golden("g2_solve_3x2_N4.npz"), golden("g3_reduced_3x2_N4.npz")
+    sm = SolutionsManager(g1["A_pre"], g1["B_total"], num_cores=1, method="lsq")
+    assert sm.vspace_dim == 77 and tuple(sm.blocks_geometry) == (3, 2) and str(sm) == "SolutionsManager"
+    np.testing.assert_array_equal(sm.A_preassembled4h1_norm, np.einsum("abij->ij", g1["A_pre"]))
+    U = sm.generate_solutions(g2["y"])
+    assert U.shape == (6, 77) and relerr(U, g2["U_lsq"]) < 1e-9
+    np.testing.assert_allclose(sm.H10norm(g2["U_lsq"]), g2["h10"], rtol=1e-9)
+    np.testing.assert_allclose(sm.l2norm(g2["U_lsq"]), g2["l2"], rtol=1e-12)
+    assert relerr(sm.generate_fm_solutions(g3["y"], g3["Phi"]), g3["fm"]) < 1e-9
+    assert relerr(sm.project_solutions(g3["U"], g3["Phi"]), g3["proj"]) < 1e-9
+    assert relerr(sm.generate_fm_solutions(g3["y"], list(g3["Phi_snap"])), g3["fm_snap"]) < 1e-9
+    np.testing.assert_array_equal(sm.generate_fm_solutions(g3["y"], []), g3["fm_empty"])
+    with pytest.raises(Exception, match="Not implemented"):
+        sm.evaluate_solutions(g3["pts"], g3["U"])
+    import pickle
+    sm_p = pickle.loads(pickle.dumps(sm))
+    assert relerr(sm_p.generate_solutions(g2["y"][:2]), g2["U_lsq"][:2]) < 1e-9
+    # galerkin(): one dense system, every reference method spelling, n = 77 (> 64: blocked Cholesky)
+    for method in ("lsq", "lsqsparse", "ridge", "LSQ"):
+        c = galerkin(g2["y"][1], g1["B_total"], g1["A_pre"], method=method)
+        assert c.shape == (77,) and relerr(c, g2["U_lsq"][1]) < 1e-9
+    with pytest.raises(Exception, match="Method cholesky Not implemented."):
+        galerkin(g2["y"][1], g1["B_total"], g1["A_pre"], method="cholesky")
+    # reduced operators of the reference's generate_fm_solutions (:93-103) through galerkin(), n = 5
+    Phi = g3["Phi"]
+    A_kl = np.einsum("...jk,dk->...jd", np.einsum("...jk,dj->...dk", g1["A_pre"], Phi), Phi)
+    c5 = galerkin(g3["y"][2], Phi @ g1["B_total"], A_kl)
+    assert relerr(c5 @ Phi, g3["fm"][2]) < 1e-9
+    # a larger dense system (D = 961, 31 block columns) against the matrix-free solver
+    fem = SolutionsManagerFEM((2, 2), 16)
+    y = 10 ** np.random.default_rng(5).uniform(0, 4, (3, 2, 2))
+    Uf = fem.generate_solutions(y)
+    gen = SolutionsManager(fem.A_preassembled, fem.B_total)
+    assert relerr(gen.generate_solutions(y), Uf) < 1e-9
+    assert relerr(galerkin(y[0], fem.B_total, fem.A_preassembled), Uf[0]) < 1e-9
+    np.testing.assert_allclose(gen.H10norm(Uf), fem.H10norm(Uf), rtol=1e-10)
+    # not positive definite -> LinAlgError, as scipy.linalg.solve(assume_a='pos') raises
+    with pytest.raises(np.linalg.LinAlgError):
+        galerkin(-np.ones((3, 2)), g1["B_total"], g1["A_pre"])
