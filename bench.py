@@ -355,7 +355,7 @@ def main():
         # DRAM bytes per launch of the same kernel from the committed ncu pass (same workload, K = 10000); null otherwise
         traffic = None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_dram_traffic_k10000.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r2_dram_traffic_k10000.json")))
             ncu_name = {"k_mg_update_down(l0)": "k_mgp_update_down<64>",   # (keys of the JSON drop the second template argument) "k_mg_down(l0)": "k_mgp_down<64>",
                         "k_mg_up(l0)": "k_mgp_up<64>"}.get(dom["kernel"], dom["kernel"])
             if tr.get("K") == K and ncu_name in tr["kernels"] and all(v is None for v in (args.strip_kb, args.nu, args.nu_mid, args.nu_tail, args.tile, args.tile_ty, args.fused)):

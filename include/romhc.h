@@ -147,6 +147,10 @@ int romhc_gemm_nn(const double* A_dev, int64_t lda, const double* B_dev, int64_t
                   int64_t M, int64_t N, int64_t Kd, void* stream);
 int romhc_gemm_tn(const double* A_dev, int64_t lda, const double* B_dev, int64_t ldb, double* C_dev, int64_t ldc,
                   int64_t M, int64_t N, int64_t Kd, void* stream);
+/* R (b, b), upper triangular, of the QR factorisation of W^T for a row block W (b <= 32 rows of length Dp): W W^T = R^T R.
+ * Householder TSQR (fixed reduction tree, backward stable): the rank-revealing orthonormalisation of the block-Lanczos
+ * POD, where sklearn's PCA (ReducedBasis.py:196) would call LAPACK on the host. */
+int romhc_tsqr_r(const double* W_dev, int64_t ld, int b, int64_t Dp, double* R_dev, void* stream);
 int romhc_column_mean(const double* X_dev, int64_t ld, int64_t K, int64_t D, double* mean_dev, void* stream);
 int romhc_center_rows(double* X_dev, int64_t ld, int64_t K, int64_t D, const double* mean_dev, void* stream);
 

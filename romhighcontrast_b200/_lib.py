@@ -59,6 +59,7 @@ SIGNATURES = {
     "romhc_gemm_nt": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i, _vp]),
     "romhc_gemm_nn": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp]),
     "romhc_gemm_tn": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp]),
+    "romhc_tsqr_r": (_i, [_vp, _i64, _i, _i64, _vp, _vp]),
     "romhc_column_mean": (_i, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "romhc_center_rows": (_i, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "romhc_evaluate": (_i, [_vp, _vp, _i, _vp, _i64, _vp, _vp]),

@@ -308,6 +308,10 @@ int romhc_interp_weights(romhc_handle h, const double* pts, int m, int* idx3, do
 int romhc_row_norms(const double* X, int64_t ld, int64_t K, int64_t D, double* out, void* st) {
     return row_norms(X, ld, K, D, out, ST(st));
 }
+int romhc_tsqr_r(const double* W, int64_t ld, int b, int64_t Dp, double* R, void* st) {
+    if (!W || !R) { set_error("null argument"); return ROMHC_ERR_ARG; }
+    return tsqr_r(W, ld, b, Dp, R, ST(st));
+}
 int romhc_row_dots(const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t K, int64_t D, double* out, void* st) {
     return row_dots(X, ldx, Y, ldy, K, D, out, ST(st));
 }

@@ -217,3 +217,128 @@ int row_dots(const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t
 }
 
 }  // namespace romhc
+
+namespace romhc {
+
+// ======================================================================================================
+// R factor of a tall-skinny matrix by Householder TSQR (b <= 32 columns): the rank-revealing orthonormalisation step of
+// the block Lanczos POD (pod._orthonormal_rows) needs R of the (Dp x b) block to full fp64 accuracy -- a b x b Gram
+// matrix would resolve only sqrt(eps) of its dynamic range.  Level 1: every CTA folds its chunk of rows, 384 at a time,
+// into a running b x b triangle ([R; tile] -> Householder QR in shared memory -> R); upper levels reduce groups of 12
+// triangles the same way until one is left.  Deterministic (fixed tree), backward stable, no library call.
+// element (i, j) of the input: in[j * ld + i] (transposed == 1: the rows of a (b, Dp) block are its columns) or in[i * ld + j].
+// ======================================================================================================
+#define TS_MAXB 32
+#define TS_TL 384
+#define TS_PITCH (TS_MAXB + 1)
+__global__ void __launch_bounds__(256)
+k_tsqr(const double* __restrict__ in, int64_t ld, int transposed, int64_t rows_total, int b, int64_t rows_per_cta,
+       double* __restrict__ Rout) {
+    extern __shared__ __align__(16) double smq[];
+    double* M = smq;                                    // (b + TS_TL) x TS_PITCH
+    double* vv = M + size_t(TS_MAXB + TS_TL) * TS_PITCH; // Householder vector
+    __shared__ double red[32];
+    __shared__ double s_tau, s_v0, s_beta;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t i0 = int64_t(blockIdx.x) * rows_per_cta;
+    const int64_t i1 = (i0 + rows_per_cta < rows_total) ? i0 + rows_per_cta : rows_total;
+    for (int i = tid; i < b * TS_PITCH; i += 256) M[i] = 0.0;
+    __syncthreads();
+    for (int64_t t0 = i0; t0 < i1 || t0 == i0; t0 += TS_TL) {
+        const int nt = int((i1 - t0 < TS_TL) ? (i1 - t0 > 0 ? i1 - t0 : 0) : TS_TL);
+        const int L = b + nt;
+        // strictly lower part of the running triangle is zero by construction; load the tile below it
+        if (transposed) {
+            for (int idx = tid; idx < nt * b; idx += 256) {
+                const int j = idx / nt, i = idx - j * nt;              // consecutive threads -> consecutive rows: coalesced
+                M[(b + i) * TS_PITCH + j] = in[int64_t(j) * ld + t0 + i];
+            }
+        } else {
+            for (int idx = tid; idx < nt * b; idx += 256) {
+                const int i = idx / b, j = idx - i * b;
+                M[(b + i) * TS_PITCH + j] = in[(t0 + i) * ld + j];
+            }
+        }
+        __syncthreads();
+        for (int j = 0; j < b; ++j) {
+            // ||M[j:, j]||^2
+            double acc = 0.0;
+            for (int i = j + tid; i < L; i += 256) { const double v = M[i * TS_PITCH + j]; acc = fma(v, v, acc); }
+            const double nrm2 = block_sum(acc, red, tid, 256);
+            if (tid == 0) {
+                const double x0 = M[j * TS_PITCH + j];
+                const double nx = sqrt(nrm2);
+                if (nx == 0.0) { s_tau = 0.0; s_v0 = 1.0; s_beta = 0.0; }
+                else {
+                    const double beta = x0 >= 0.0 ? -nx : nx;
+                    s_beta = beta; s_v0 = x0 - beta; s_tau = (beta - x0) / beta;
+                }
+            }
+            __syncthreads();
+            const double tau = s_tau, iv0 = 1.0 / s_v0;
+            for (int i = j + tid; i < L; i += 256) vv[i] = (i == j) ? 1.0 : M[i * TS_PITCH + j] * iv0;
+            __syncthreads();
+            if (tau != 0.0) {
+                for (int k = j + 1 + warp; k < b; k += 8) {            // a warp owns whole columns: dot, then update
+                    double w = 0.0;
+                    for (int i = j + lane; i < L; i += 32) w = fma(vv[i], M[i * TS_PITCH + k], w);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+                    w *= tau;
+                    for (int i = j + lane; i < L; i += 32) M[i * TS_PITCH + k] = fma(-w, vv[i], M[i * TS_PITCH + k]);
+                }
+            }
+            __syncthreads();
+            for (int i = j + tid; i < L; i += 256) M[i * TS_PITCH + j] = (i == j) ? (tau != 0.0 ? s_beta : M[i * TS_PITCH + j]) : 0.0;
+            __syncthreads();
+        }
+        if (t0 + TS_TL >= i1) break;
+    }
+    double* Ro = Rout + int64_t(blockIdx.x) * b * b;
+    for (int idx = tid; idx < b * b; idx += 256) {
+        const int i = idx / b, j = idx - i * b;
+        Ro[idx] = (j >= i) ? M[i * TS_PITCH + j] : 0.0;
+    }
+}
+
+static void* g_ts_ws = nullptr;
+static size_t g_ts_bytes = 0;
+static int g_ts_dev = -1;
+
+// W: (b, Dp) row-major block, ld = row pitch; R_out: (b, b) upper triangular with W W^T = R^T R
+int tsqr_r(const double* W, int64_t ld, int b, int64_t Dp, double* R_out, cudaStream_t st) {
+    if (b < 1 || b > TS_MAXB) { set_error("tsqr_r: block size must be in [1, %d], got %d", TS_MAXB, b); return ROMHC_ERR_ARG; }
+    if (Dp < 1) { set_error("tsqr_r: empty block"); return ROMHC_ERR_ARG; }
+    int dev = 0, nsm = 148;
+    CK(cudaGetDevice(&dev));
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const size_t smb = (size_t(TS_MAXB + TS_TL) * TS_PITCH + (TS_MAXB + TS_TL)) * 8;
+    CK(cudaFuncSetAttribute(k_tsqr, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smb)));
+    int64_t nblk = std::max<int64_t>(1, std::min<int64_t>(nsm, (Dp + 63) / 64));
+    const int64_t per = (Dp + nblk - 1) / nblk;
+    nblk = (Dp + per - 1) / per;
+    const size_t need = size_t(nblk + (nblk + 11) / 12 + 2) * b * b * 8 * 2;
+    if (dev != g_ts_dev || need > g_ts_bytes) {
+        if (g_ts_ws) cudaFree(g_ts_ws);
+        g_ts_ws = nullptr; g_ts_bytes = 0;
+        CK(cudaMalloc(&g_ts_ws, need));
+        g_ts_bytes = need; g_ts_dev = dev;
+    }
+    double* bufA = (double*)g_ts_ws;
+    double* bufB = bufA + size_t(nblk + 1) * b * b;
+    ++g_launches;
+    k_tsqr<<<(unsigned)nblk, 256, smb, st>>>(W, ld, 1, Dp, b, per, nblk == 1 ? R_out : bufA);
+    int64_t cur = nblk;
+    double* src = bufA; double* dst = bufB;
+    while (cur > 1) {
+        const int64_t groups = (cur + 11) / 12;
+        ++g_launches;
+        k_tsqr<<<(unsigned)groups, 256, smb, st>>>(src, b, 0, cur * b, b, int64_t(12) * b, groups == 1 ? R_out : dst);
+        cur = groups;
+        std::swap(src, dst);
+    }
+    CK(cudaGetLastError());
+    return ROMHC_OK;
+}
+
+}  // namespace romhc

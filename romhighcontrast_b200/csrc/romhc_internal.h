@@ -218,6 +218,7 @@ int argmax_first(const double* v, int64_t K, int64_t* idx_out, double* val_out, 
 int dense_spd_solve(const double* y, int nb, const double* A, const double* rhs, int rhs_per_system, int n, int64_t K,
                     double* C, int* info, cudaStream_t st);
 int row_dots(const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t K, int64_t D, double* out, cudaStream_t st);
+int tsqr_r(const double* W, int64_t ld, int b, int64_t Dp, double* R_out, cudaStream_t st);
 int poly_features(const double* basis, int64_t ld, int n, int64_t D, const int* terms, int nterms, int degree, double* out,
                   int64_t ldo, cudaStream_t st);
 int estimator_contract(const double* c, int64_t K, int n, const double* abasis, int nb, int invert, double* out,

@@ -269,6 +269,18 @@ class Engine:
                                           self.stream()))
         return out
 
+    def tsqr_r(self, W):
+        """R (b, b) upper triangular with W W^T = R^T R for a row block W (b <= 32, Dp): Householder TSQR on the device."""
+        b, Dp = W.shape
+        R = self.empty(b, b)
+        _lib.check(self.lib.romhc_tsqr_r(_ptr(W), W.stride(0), b, Dp, _ptr(R), self.stream()))
+        return R
+
+    def row_norms(self, X):
+        out = self.empty(X.shape[0])
+        _lib.check(self.lib.romhc_row_norms(_ptr(X), X.stride(0), X.shape[0], X.shape[1], _ptr(out), self.stream()))
+        return out
+
     def column_mean(self, X):
         K, D = X.shape
         mean = self.empty(D)

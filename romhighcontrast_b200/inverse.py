@@ -143,7 +143,8 @@ def reduced_basis_generator_greedy(sm, solutions_offline, number_of_reduced_base
         B = S[picked].contiguous()                                            # (n, Dp)
         G = eng.gemm_nt(B, B).cpu().numpy()                                  # (n, n) Gram of the basis
         rhs = eng.gemm_nt(B, S)                                               # (n, K)
-        X = torch.as_tensor(np.linalg.lstsq(G, np.eye(len(picked)), rcond=None)[0], device=S.device) @ rhs
+        Ginv = torch.as_tensor(np.ascontiguousarray(np.linalg.lstsq(G, np.eye(len(picked)), rcond=None)[0]), device=S.device)
+        X = eng.gemm_nn(Ginv, rhs)                                            # (n, K) least-squares coefficients
         resid = S - eng.gemm_nn(X.T.contiguous(), B)
         picked.append(int(np.argmax(f_norm(resid).cpu().numpy())))
     return [S_host[i] for i in picked], picked

@@ -15,12 +15,12 @@ import torch
 def top_eigenpairs(eng, G, n, extra=12, tol=1e-13, max_dim=960, seed=0, host_max=1024):
     """Largest n eigenpairs of the symmetric PSD device matrix G (K, K): (lam (n,), V (K, n)) device tensors.
 
-    K <= host_max: LAPACK on the host.  Otherwise block Lanczos with full (twice-applied) reorthogonalisation and
-    block size b = n + extra <= 32: every step costs one G @ block product -- the DMMA kernel, G is streamed once --
-    plus O(K * dim * b) orthogonalisation work; the Rayleigh-Ritz problem on the accumulated Krylov basis (dimension
-    <= max_dim) is solved on the host.  Stops when ||G v - lam v|| <= tol * lam_1 for the n wanted pairs.  (POD
-    spectra of high-dimensional parameter sets decay slowly: plain subspace iteration stalls and an aggressive
-    polynomial filter wipes out the smaller wanted directions in fp64; a Krylov basis does neither.)"""
+    K <= host_max: LAPACK on the host (the "small eigensolve").  Otherwise the same block Lanczos as the Gram-free route
+    (`_block_lanczos`: full reorthogonalisation through split-K DMMA products, rank-revealing orthonormalisation by the
+    device TSQR, Rayleigh-Ritz on the host for a basis of <= max_dim rows) with S = G: every step costs one G @ block
+    product -- the DMMA kernel, G is streamed once.  Stops when every wanted pair has ||G v - lam v|| <= max(1e-10 lam_i,
+    tol lam_1) or the residuals stall at the rounding level of G (a Gram matrix summed over ranks carries a slightly
+    higher floor than one computed in one piece).  No library GEMM / QR call anywhere on this path."""
     K = G.shape[0]
     n = min(n, K)
     if K <= host_max:
@@ -30,42 +30,14 @@ def top_eigenpairs(eng, G, n, extra=12, tol=1e-13, max_dim=960, seed=0, host_max
                 torch.as_tensor(np.ascontiguousarray(V[:, order]), device=G.device))
     b = int(min(32, K, n + extra))
     gen = torch.Generator(device=G.device).manual_seed(seed)
-    GQ = lambda X: eng.gemm_nt(G, X.T.contiguous())          # (K, b) = G X  (G symmetric)
-    Q = torch.linalg.qr(torch.randn(K, b, dtype=torch.float64, device=G.device, generator=gen))[0]
-    V = torch.empty(K, max_dim, dtype=torch.float64, device=G.device)      # Krylov basis
-    Z = torch.empty(K, max_dim, dtype=torch.float64, device=G.device)      # G @ basis
-    dim = 0
-    lam = vec = None
-    prev_res = float("inf")
-    while True:
-        V[:, dim:dim + b] = Q
-        Zj = GQ(Q)
-        Z[:, dim:dim + b] = Zj
-        dim += b
-        Vd, Zd = V[:, :dim], Z[:, :dim]
-        if dim >= 2 * b and (dim // b) % 2 == 0 or dim + b > max_dim:
-            T = (Vd.T @ Zd).cpu().numpy()                     # small (dim x dim) projected matrix
-            w, S = np.linalg.eigh(0.5 * (T + T.T))
-            order = np.argsort(w)[::-1][:n]
-            lam = torch.as_tensor(np.ascontiguousarray(w[order]), device=G.device)
-            Sd = torch.as_tensor(np.ascontiguousarray(S[:, order]), device=G.device)
-            vec = Vd @ Sd
-            res = torch.linalg.vector_norm(Zd @ Sd - vec * lam[None, :], dim=0)
-            lam1 = max(float(lam[0]), 1e-300)
-            rmax = float(res.max())
-            # converged, or stalled at the rounding level of G itself (a Gram matrix summed over ranks carries a slightly
-            # higher floor than tol * lam_1; without this test the iteration ran on to max_dim: 13 ms -> 470 ms)
-            stalled = rmax <= 1e-10 * lam1 and rmax > 0.5 * prev_res
-            prev_res = rmax
-            if rmax <= tol * lam1 or stalled or dim + b > max_dim:
-                break
-        W = Zj
-        for _ in range(2):                                    # block Gram-Schmidt against the whole basis, twice
-            W = W - Vd @ (Vd.T @ W)
-        Q, R = torch.linalg.qr(W)
-        if float(R.diagonal().abs().min()) < 1e-300:          # invariant subspace found
-            continue
-    return lam, vec.contiguous()
+    R0 = torch.randn(b, K, dtype=torch.float64, device=G.device, generator=gen)
+    apply_G = lambda Q: eng.gemm_nt(G, Q).T.contiguous()            # rows: (G Q^T)^T = Q G, G read once by the skinny DMMA kernel
+    lam, comps, _ = _block_lanczos(eng, apply_G, R0, n, rtol=1e-10, floor=tol, max_dim=int(min(max_dim, K)))
+    if comps.shape[0] < n:                                        # rank of G below n: zero eigenvalues, zero vectors
+        pad = n - comps.shape[0]
+        lam = torch.cat((lam, torch.zeros(pad, dtype=torch.float64, device=G.device)))
+        comps = torch.cat((comps, torch.zeros(pad, K, dtype=torch.float64, device=G.device)))
+    return lam, comps.T.contiguous()
 
 
 def pca_components(eng, X_pad, n, center_in_place=False):
@@ -92,7 +64,7 @@ def _orthonormal_rows(eng, W, thr, passes=2, conditioned=False):
     """Orthonormal rows spanning the directions of W (b, Dp) whose singular value exceeds thr (None if there are none).
 
     Rank revealing and built from row combinations of W only, so slots that are zero in every row stay exactly zero.
-    First pass: R of a Householder QR of W^T (backward stable: singular values resolved down to eps * sigma_max, where a
+    First pass: R of a Householder QR of W^T (device TSQR, `romhc_tsqr_r`; backward stable: singular values resolved down to eps * sigma_max, where a
     b x b Gram matrix would lose everything below sqrt(eps)), SVD R = U S V^T on the host, rows (1 / s_i) v_i^T W for
     s_i > thr; exhausted Krylov directions (rounding noise) are dropped instead of being normalised into vectors that
     are no longer orthogonal to the basis.  The division amplifies rounding by sigma_max / s_i, so a second pass restores
@@ -102,7 +74,7 @@ def _orthonormal_rows(eng, W, thr, passes=2, conditioned=False):
     Gram-Schmidt pass), every pass takes the Gram form."""
     for p in range(passes):
         if p == 0 and not conditioned:
-            R = torch.linalg.qr(W.T, mode="r")[1]             # (b, b)
+            R = eng.tsqr_r(W)                                   # (b, b): Householder TSQR on the device (csrc/dense.cu)
             _, sv, Vt = np.linalg.svd(R.cpu().numpy())
             keep = sv > thr
             if not keep.any():
@@ -117,6 +89,96 @@ def _orthonormal_rows(eng, W, thr, passes=2, conditioned=False):
             Tm = (E[:, keep] / np.sqrt(ev[keep])).T[::-1]
         W = eng.gemm_nn(torch.as_tensor(np.array(Tm, order="C", copy=True), device=W.device), W)
     return W
+
+
+def _block_lanczos(eng, apply_S, R0, n, rtol=1e-10, floor=2e-14, max_dim=960, w=1):
+    """Block Lanczos with full reorthogonalisation for the n leading eigenpairs of a symmetric PSD operator S that is
+    only APPLIED: apply_S maps a row block (b', L) to (b', L).  R0 (b, L): random start block.  Rows are the basis
+    vectors throughout (Krylov basis V, S V = Z); all large products are libromhc kernels.  w > 1: the caller's apply_S
+    all-reduces over ranks, every rank runs the same arithmetic and rank 0's block / stop decisions are broadcast.
+    Returns (lam (n',), components (n', L) rows, info dict)."""
+    dev = R0.device
+    b, Dp = R0.shape
+    def agree(Qb):
+        """Sharded runs: every rank continues with rank 0's block.  The replicated arithmetic is deterministic, so this
+        changes nothing in practice; it turns 'all ranks hold the same basis' from an expectation into a guarantee -- a
+        rank that kept a different number of rows would otherwise hang the next all_reduce."""
+        if w == 1:
+            return Qb
+        cnt = torch.tensor([0 if Qb is None else Qb.shape[0]], dtype=torch.int64, device=dev)
+        torch.distributed.broadcast(cnt, src=0)
+        c = int(cnt.item())
+        if c == 0:
+            return None
+        if Qb is None or Qb.shape[0] != c:
+            Qb = torch.empty(c, Dp, dtype=torch.float64, device=dev)
+        Qb = Qb.contiguous()
+        torch.distributed.broadcast(Qb, src=0)
+        return Qb
+
+    def ritz(Vd, Zd):
+        T = eng.gemm_nt(Vd, Zd, splitk=True).cpu().numpy()    # (dim, dim) projected operator
+        wv, S = np.linalg.eigh(0.5 * (T + T.T))
+        order = np.argsort(wv)[::-1][:n]
+        lam = torch.as_tensor(np.ascontiguousarray(wv[order]), device=dev)
+        St = torch.as_tensor(np.ascontiguousarray(S[:, order].T), device=dev)      # (n, dim)
+        comps = eng.gemm_nn(St, Vd)
+        res = eng.row_norms((eng.gemm_nn(St, Zd) - comps * lam[:, None]).contiguous())
+        lam1 = max(float(lam[0]), 1e-300)
+        excess = float((res / torch.clamp(torch.maximum(rtol * lam, torch.full_like(lam, floor * lam1)), min=1e-300)).max())
+        return lam, comps, float(res.max()), excess, lam1
+
+    # start block: S applied to a random block.  It lies in the row space of Xc, so slots that are zero in every
+    # snapshot (the padded grid's Dirichlet / alignment slots) are exactly zero in every basis row and component.
+    S0 = apply_S(R0)
+    Q = _orthonormal_rows(eng, S0, 1e-12 * float(eng.row_norms(S0).max()))
+    if Q is None:                                             # Xc == 0: every singular value is zero
+        Q = _orthonormal_rows(eng, R0, 0.0)
+    Q = agree(Q)
+    V = torch.empty(max_dim, Dp, dtype=torch.float64, device=dev)      # Krylov basis, rows
+    Z = torch.empty(max_dim, Dp, dtype=torch.float64, device=dev)      # S applied to the basis rows
+    dim = steps = 0
+    lam = comps = None
+    scale = 0.0                                               # running estimate of lambda_1
+    prev_res = float("inf")
+    flag = torch.zeros(1, dtype=torch.int64, device=dev)
+    while True:
+        bq = Q.shape[0]
+        V[dim:dim + bq] = Q
+        Zj = apply_S(Q)
+        Z[dim:dim + bq] = Zj
+        dim += bq
+        steps += 1
+        Vd, Zd = V[:dim], Z[:dim]
+        scale = max(scale, float(eng.row_norms(Zj).max()))
+        # next block: S Q orthogonalised against the whole basis (block Gram-Schmidt, repeated), directions below the
+        # requested accuracy dropped
+        Qn = None
+        if dim + 1 <= max_dim and scale > 0.0:
+            Wn = Zj
+            for sweep in range(2):
+                for _ in range(2):
+                    Wn = Wn - eng.gemm_nn(eng.gemm_nt(Vd, Wn, splitk=True).T.contiguous(), Vd)
+                Wn = _orthonormal_rows(eng, Wn, 1e-15 * scale if sweep == 0 else 0.5, passes=2 if sweep == 0 else 1,
+                                       conditioned=sweep > 0)
+                if Wn is None:
+                    break
+            if Wn is not None:
+                Qn = Wn[:max_dim - dim].contiguous()
+        Qn = agree(Qn)
+        last = Qn is None
+        if (steps >= 2 and (dim <= 256 or steps % 2 == 0)) or last:
+            lam, comps, res, excess, lam1 = ritz(Vd, Zd)
+            stalled = res <= 1e-11 * lam1 and res > 0.5 * prev_res
+            prev_res = res
+            flag[0] = int(last or excess <= 1.0 or stalled)
+            if w > 1:
+                torch.distributed.broadcast(flag, src=0)
+            if int(flag.item()):
+                break
+        Q = Qn
+    info = {"steps": steps, "krylov_dim": dim, "block": b, "residual": res}
+    return lam, comps, info
 
 
 def krylov_pca(eng, X_local_pad, n, K_total=None, center_in_place=False, extra=12, rtol=1e-10, floor=2e-14, max_dim=960,
@@ -187,86 +249,10 @@ def krylov_pca(eng, X_local_pad, n, K_total=None, center_in_place=False, extra=1
                 torch.distributed.all_reduce(Zw)
         return Zw
 
-    def agree(Qb):
-        """Sharded runs: every rank continues with rank 0's block.  The replicated arithmetic is deterministic, so this
-        changes nothing in practice; it turns 'all ranks hold the same basis' from an expectation into a guarantee -- a
-        rank that kept a different number of rows would otherwise hang the next all_reduce."""
-        if w == 1:
-            return Qb
-        cnt = torch.tensor([0 if Qb is None else Qb.shape[0]], dtype=torch.int64, device=dev)
-        torch.distributed.broadcast(cnt, src=0)
-        c = int(cnt.item())
-        if c == 0:
-            return None
-        if Qb is None or Qb.shape[0] != c:
-            Qb = torch.empty(c, Dp, dtype=torch.float64, device=dev)
-        Qb = Qb.contiguous()
-        torch.distributed.broadcast(Qb, src=0)
-        return Qb
-
-    def ritz(Vd, Zd):
-        T = eng.gemm_nt(Vd, Zd, splitk=True).cpu().numpy()    # (dim, dim) projected operator
-        wv, S = np.linalg.eigh(0.5 * (T + T.T))
-        order = np.argsort(wv)[::-1][:n]
-        lam = torch.as_tensor(np.ascontiguousarray(wv[order]), device=dev)
-        St = torch.as_tensor(np.ascontiguousarray(S[:, order].T), device=dev)      # (n, dim)
-        comps = eng.gemm_nn(St, Vd)
-        res = torch.linalg.vector_norm(eng.gemm_nn(St, Zd) - comps * lam[:, None], dim=1)
-        lam1 = max(float(lam[0]), 1e-300)
-        excess = float((res / torch.clamp(torch.maximum(rtol * lam, torch.full_like(lam, floor * lam1)), min=1e-300)).max())
-        return lam, comps, float(res.max()), excess, lam1
-
-    # start block: S applied to a random block.  It lies in the row space of Xc, so slots that are zero in every
-    # snapshot (the padded grid's Dirichlet / alignment slots) are exactly zero in every basis row and component.
-    gen = torch.Generator(device=dev).manual_seed(seed)
-    R0 = torch.randn(b, Dp, dtype=torch.float64, device=dev, generator=gen)
-    S0 = apply_S(R0)
-    Q = _orthonormal_rows(eng, S0, 1e-12 * float(torch.linalg.vector_norm(S0, dim=1).max()))
-    if Q is None:                                             # Xc == 0: every singular value is zero
-        Q = _orthonormal_rows(eng, R0, 0.0)
-    Q = agree(Q)
-    V = torch.empty(max_dim, Dp, dtype=torch.float64, device=dev)      # Krylov basis, rows
-    Z = torch.empty(max_dim, Dp, dtype=torch.float64, device=dev)      # S applied to the basis rows
-    dim = steps = 0
-    lam = comps = None
-    scale = 0.0                                               # running estimate of lambda_1
-    prev_res = float("inf")
-    flag = torch.zeros(1, dtype=torch.int64, device=dev)
-    while True:
-        bq = Q.shape[0]
-        V[dim:dim + bq] = Q
-        Zj = apply_S(Q)
-        Z[dim:dim + bq] = Zj
-        dim += bq
-        steps += 1
-        Vd, Zd = V[:dim], Z[:dim]
-        scale = max(scale, float(torch.linalg.vector_norm(Zj, dim=1).max()))
-        # next block: S Q orthogonalised against the whole basis (block Gram-Schmidt, repeated), directions below the
-        # requested accuracy dropped
-        Qn = None
-        if dim + 1 <= max_dim and scale > 0.0:
-            Wn = Zj
-            for sweep in range(2):
-                for _ in range(2):
-                    Wn = Wn - eng.gemm_nn(eng.gemm_nt(Vd, Wn, splitk=True).T.contiguous(), Vd)
-                Wn = _orthonormal_rows(eng, Wn, 1e-15 * scale if sweep == 0 else 0.5, passes=2 if sweep == 0 else 1,
-                                       conditioned=sweep > 0)
-                if Wn is None:
-                    break
-            if Wn is not None:
-                Qn = Wn[:max_dim - dim].contiguous()
-        Qn = agree(Qn)
-        last = Qn is None
-        if (steps >= 2 and (dim <= 256 or steps % 2 == 0)) or last:
-            lam, comps, res, excess, lam1 = ritz(Vd, Zd)
-            stalled = res <= 1e-11 * lam1 and res > 0.5 * prev_res
-            prev_res = res
-            flag[0] = int(last or excess <= 1.0 or stalled)
-            if w > 1:
-                torch.distributed.broadcast(flag, src=0)
-            if int(flag.item()):
-                break
-        Q = Qn
+    lam, comps, info = _block_lanczos(eng, apply_S, torch.randn(b, Dp, dtype=torch.float64, device=dev,
+                                                                generator=torch.Generator(device=dev).manual_seed(seed)),
+                                      n, rtol=rtol, floor=floor, max_dim=max_dim, w=w)
+    steps, dim, res = info["steps"], info["krylov_dim"], info["residual"]
     if stats is not None:
         stats.update(steps=steps, krylov_dim=dim, block=b, residual=res)
         if ar_events:

@@ -21,6 +21,12 @@ class HostEngine:
         assert A.is_contiguous() and B.is_contiguous() and A.shape[0] == B.shape[0]
         return A.T @ B
 
+    def tsqr_r(self, W):
+        return torch.linalg.qr(W.T.contiguous(), mode="r")[1]
+
+    def row_norms(self, X):
+        return torch.linalg.vector_norm(X, dim=1)
+
     def column_mean(self, X):
         return X.mean(dim=0)
 

@@ -135,3 +135,35 @@ def test_reduced_basis_pca_krylov_option(torch_mod):
     np.testing.assert_allclose(np.asarray(auto.basis), np.asarray(kry.basis), rtol=0, atol=1e-10)   # same route, same input
     with pytest.raises(ValueError):
         ReducedBasisPCA().build(n=10, sm=sm, solutions2train=U, a2train=y, pod_method="svd")
+
+
+@pytest.mark.parametrize("b,Dp,decades", [(32, 65792, 0), (22, 262656, 0), (32, 66048, 12), (5, 100, 0), (32, 63, 3), (1, 7, 0),
+                                          (32, 400, 8), (17, 4104, 14)])
+def test_tsqr_r_matches_lapack(b, Dp, decades):
+    """romhc_tsqr_r (Householder TSQR, csrc/dense.cu): R of the QR factorisation of W^T for a row block W (b, Dp), against
+    numpy's Householder QR up to the signs of the rows; rows spanning `decades` decades of magnitude (the regime of the
+    block Lanczos after a few steps, where a b x b Gram matrix loses everything below sqrt(eps))."""
+    import torch
+    from romhighcontrast_b200.engine import Engine
+    eng = Engine((2, 2), 4)
+    rng = np.random.default_rng(b * 1000 + Dp % 977)
+    W = rng.standard_normal((b, Dp)) * (10.0 ** -np.linspace(0, decades, b))[:, None]
+    R = eng.tsqr_r(torch.as_tensor(W, device="cuda")).cpu().numpy()
+    assert R.shape == (b, b) and np.allclose(R, np.triu(R))
+    Rn = np.linalg.qr(W.T, mode="r")
+    k = min(b, Dp)
+    # well-conditioned block (rows scaled, not dependent): entries agree with LAPACK's Householder R up to row signs,
+    # relative to the magnitude of the column (column j carries the scale of row j of W)
+    scale = np.abs(Rn).max(axis=0)
+    assert np.max(np.abs(np.abs(R[:k]) - np.abs(Rn[:k])) / scale) < 1e-11
+    # with a nearly dependent row the trailing rows of R are ill conditioned entry by entry, but the factorisation is still
+    # backward stable: W W^T = R^T R relative to the row norms, singular values to eps * sigma_max
+    if b > 3:
+        W[3] = W[1] * 0.5 + 1e-9 * W[3]
+        R = eng.tsqr_r(torch.as_tensor(W, device="cuda")).cpu().numpy()
+        Rn = np.linalg.qr(W.T, mode="r")
+    nr = np.linalg.norm(W, axis=1)
+    G = W @ W.T
+    assert np.max(np.abs(R.T @ R - G) / np.outer(nr, nr)) < 1e-13
+    sv, svn = np.linalg.svd(R, compute_uv=False), np.linalg.svd(Rn, compute_uv=False)
+    np.testing.assert_allclose(sv[:k], svn[:k], rtol=1e-9, atol=1e-14 * svn[0])
