@@ -96,14 +96,55 @@ __global__ void __launch_bounds__(256) k_project_rhs(LevelGeo g, const double* _
     if (threadIdx.x == 0) bhat[blockIdx.x] = tot * scale;
 }
 
+// ---- the same reduced operators as dense contractions on the fp64 tensor cores: W_q = A_q Phi^T by the matrix-free stencil
+// with the unit coefficient vector e_q (nb applications over the n basis rows), then ONE split-K DMMA product
+// Phi (n x Dp) . [W_0; ...; W_{nb-1}]^T (nb n x Dp) -> (n, nb n), permuted to (nb, n, n).  Any n.
+__global__ void k_unit_rows(double* __restrict__ Y, int nb, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;               // row (q, j) of the (nb n, nb) coefficient matrix
+    if (i >= nb * n * nb) return;
+    const int row = i / nb, col = i - row * nb;
+    Y[i] = (row / n == col) ? 1.0 : 0.0;
+}
+__global__ void k_permute_ahat(const double* __restrict__ Cm, int n, int nb, double* __restrict__ Ahat) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nb * n * n) return;
+    const int q = e / (n * n), i = (e / n) % n, j = e % n;
+    Ahat[e] = Cm[size_t(i) * nb * n + size_t(q) * n + j];
+}
+
+int Context::project_operators_dmma(const double* basis, int n, double* Ahat, cudaStream_t st) {
+    const LevelGeo& g = levels[0];
+    const int nb = nrb * ncb;
+    const size_t wd = size_t(nb) * n * g.Dp, yd = size_t(nb) * n * nb, cd = size_t(n) * nb * n;
+    int rc = ensure_scratch((wd + yd + cd) * 8); if (rc) return rc;
+    double* W = (double*)scratch;
+    double* Y = W + wd;
+    double* Cm = Y + yd;
+    CK(cudaMemsetAsync(W, 0, wd * 8, st));
+    ++g_launches; k_unit_rows<<<(unsigned)((yd + 255) / 256), 256, 0, st>>>(Y, nb, n);
+    for (int q = 0; q < nb; ++q) {
+        rc = apply(Y + size_t(q) * n * nb, basis, W + size_t(q) * n * g.Dp, n, st);
+        if (rc) return rc;
+    }
+    rc = gemm_nt(basis, g.Dp, W, g.Dp, Cm, int64_t(nb) * n, n, int64_t(nb) * n, g.Dp, 2, st);
+    if (rc) return rc;
+    ++g_launches; k_permute_ahat<<<(unsigned)((cd + 255) / 256), 256, 0, st>>>(Cm, n, nb, Ahat);
+    CK(cudaGetLastError());
+    return ROMHC_OK;
+}
+
 int Context::project_operators(const double* basis, int n, double* Ahat, double* bhat, cudaStream_t st) {
-    if (n < 1 || n > PROJ_MAXN) { set_error("project_operators: n must be in [1, %d], got %d", PROJ_MAXN, n); return ROMHC_ERR_ARG; }
+    if (n < 1) { set_error("project_operators: n must be positive, got %d", n); return ROMHC_ERR_ARG; }
     const LevelGeo& g = levels[0];
     const int nb = nrb * ncb, nn = n * n;
-    int rc = ensure_scratch(size_t(nb) * g.N * nn * 8); if (rc) return rc;
-    const size_t sm = size_t(PROJ_EB) * (n | 1) * 8;
-    ++g_launches; k_project_partial<<<dim3(g.N, nb), 256, sm, st>>>(g, basis, n, (double*)scratch);
-    ++g_launches; k_reduce_ahat<<<dim3((nn + 127) / 128, nb), 128, 0, st>>>((double*)scratch, g.N, nn, Ahat);
+    if (n > PROJ_MAXN || proj_variant == 1) {
+        int rc = project_operators_dmma(basis, n, Ahat, st); if (rc) return rc;
+    } else {
+        int rc = ensure_scratch(size_t(nb) * g.N * nn * 8); if (rc) return rc;
+        const size_t sm = size_t(PROJ_EB) * (n | 1) * 8;
+        ++g_launches; k_project_partial<<<dim3(g.N, nb), 256, sm, st>>>(g, basis, n, (double*)scratch);
+        ++g_launches; k_reduce_ahat<<<dim3((nn + 127) / 128, nb), 128, 0, st>>>((double*)scratch, g.N, nn, Ahat);
+    }
     if (bhat) { ++g_launches; k_project_rhs<<<n, 256, 0, st>>>(g, basis, 1.0 / (double(N) * double(N)), bhat); }
     CK(cudaGetLastError());
     return ROMHC_OK;

@@ -110,6 +110,7 @@ struct Context {
     bool tile_prefetch = true;          // L2 prefetch of the next CTA's operand rows (non-persistent tile kernels)
     bool tile_persistent = true;        // persistent, TMA-pipelined tile kernels (one CTA per SM)
     bool use_fused = true;              // PCG update fused into the finest level's going-down kernel
+    int proj_variant = 0;               // reduced operators: 0 edge-difference kernel (n <= 64), 1 stencil apply + split-K DMMA product (any n)
     bool use_sweep = true;              // greedy error sweep: DMMA kernel (sweep.cu); false: the strip kernel k_energy
     // The preconditioned residual z = M r travels from the finest going-up kernel to k_pcg_p_apply as fp32 (half a stream
     // less in each): z only steers the search direction, so rounding it perturbs the preconditioner by 6e-8 relative and
@@ -206,6 +207,7 @@ struct Context {
 
     // reduced.cu
     int project_operators(const double* basis, int n, double* Ahat, double* bhat, cudaStream_t st);
+    int project_operators_dmma(const double* basis, int n, double* Ahat, cudaStream_t st);
     int evaluate(const double* points, int m, const double* u, int64_t K, double* out, cudaStream_t st);
     int interp_weights(const double* points, int m, int* idx3, double* w3, cudaStream_t st);
 };

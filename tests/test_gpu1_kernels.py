@@ -460,3 +460,32 @@ def test_error_sweep_dmma_matches_strip_kernel_and_numpy(torch_mod, geo, N, K, n
     d_new = eng.error_norm(U2, C, Phi)
     d_ref = 1e-7 * eng.h10_norm(U)
     assert float(((d_new - d_ref).abs() / d_ref).max()) < 1e-6
+
+
+@pytest.mark.parametrize("geo,N,n", [((2, 2), 8, 5), ((3, 2), 4, 20), ((4, 4), 16, 33), ((2, 2), 8, 70), ((4, 4), 64, 20)])
+def test_project_operators_dmma_route(torch_mod, geo, N, n):
+    """reduced operators Phi A_q Phi^T as dense contractions on the fp64 tensor cores (stencil apply with unit coefficients +
+    one split-K DMMA product; the only route for n > 64) against the edge-difference kernel and against the explicit
+    Phi (A_q Phi^T) formed with the device stencil"""
+    torch = torch_mod
+    eng = make_engine(geo, N)
+    rng = np.random.default_rng(n)
+    Phi = eng.pad(rng.standard_normal((n, eng.D)))
+    eng.set_option("proj_variant", 1)
+    A1, b1 = eng.project_operators(Phi)
+    eng.set_option("proj_variant", 0)
+    if n <= 64:
+        A0, b0 = eng.project_operators(Phi)
+        assert float((A1 - A0).abs().max() / A0.abs().max()) < 1e-12
+        assert torch.equal(b0, b1)
+    for q in (0, eng.nb - 1):
+        yq = torch.zeros(n, eng.nb, dtype=torch.float64, device="cuda")
+        yq[:, q] = 1.0
+        ref = Phi @ eng.apply(yq, Phi).T
+        assert float((A1[q] - ref).abs().max() / ref.abs().max()) < 1e-12
+    # and the reduced solve on top of it (n = 70: the blocked dense Cholesky)
+    y = eng.params(rand_y(geo, 7, seed=3))
+    C = eng.reduced_solve(y, A1, b1).cpu().numpy()
+    Ak = np.einsum("kq,qij->kij", y.cpu().numpy(), A1.cpu().numpy())
+    ref = np.linalg.solve(Ak, np.broadcast_to(b1.cpu().numpy(), (7, n))[..., None])[..., 0]
+    assert relerr(C, ref) < 1e-8
