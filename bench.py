@@ -617,7 +617,9 @@ def run_config4(args, world, rank, local, barrier, ev):
     y_host = 10 ** np.random.default_rng(4000 + rank).uniform(0, np.log10(CMAX), size=(K,) + geo)
     y = eng.params(y_host)
     x = eng.empty(K, eng.Dp)
-    eng.solve(y[:1024], out=x[:1024])                              # warm-up: workspace allocation, kernel attributes
+    eng.set_option("workspace_gb", 72)                             # 180 GB of HBM: 26 GB of snapshots (+ a centred copy for the POD) + 4800-system solver chunks
+    kw = int(min(K, 32768, (72 << 30) // eng.solve_bytes_per_system))   # exactly the chunk Context::solve will use
+    eng.solve(y[:kw], out=x[:kw])                                  # warm-up at the full chunk size: workspace allocation, kernel attributes
     barrier()
     e0, e1 = ev(), ev()
     e0.record()
