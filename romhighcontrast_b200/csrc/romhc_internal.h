@@ -110,6 +110,7 @@ struct Context {
     bool tile_prefetch = true;          // L2 prefetch of the next CTA's operand rows (non-persistent tile kernels)
     bool tile_persistent = true;        // persistent, TMA-pipelined tile kernels (one CTA per SM)
     bool use_fused = true;              // PCG update fused into the finest level's going-down kernel
+    bool papply_pers = true;            // persistent, double-buffered k_pcg_p_apply (fp32 transport of z and p)
     int proj_variant = 0;               // reduced operators: 0 edge-difference kernel (n <= 64), 1 stencil apply + split-K DMMA product (any n)
     bool use_sweep = true;              // greedy error sweep: DMMA kernel (sweep.cu); false: the strip kernel k_energy
     // The preconditioned residual z = M r travels from the finest going-up kernel to k_pcg_p_apply as fp32 (half a stream
