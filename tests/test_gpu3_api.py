@@ -365,3 +365,46 @@ def test_generic_dense_manager_and_galerkin_on_reference_operators():
     # not positive definite -> LinAlgError, as scipy.linalg.solve(assume_a='pos') raises
     with pytest.raises(np.linalg.LinAlgError):
         galerkin(-np.ones((3, 2)), g1["B_total"], g1["A_pre"])
+
+
+def test_large_bases_n_above_32():
+    """the basis dimension was silently capped at 32 (projection kernel, gemm_tn), 64 (reduced solve).
+    Every builder and every online call now takes any n: greedy n = 40 against the oracle's greedy (identical indices while
+    the error gap exceeds 1e-9), PCA n = 40 (back-projection in row blocks of 32), forward modelling / projection / state
+    estimation with n = 33 and n = 70 (reduced operators through stencil apply + split-K DMMA, blocked dense Cholesky)."""
+    from src.lib.ReducedBasis import ReducedBasisGreedy, ReducedBasisPCA, BaseReducedBasis, GREEDY_FOR_GALERKIN, GREEDY_FOR_H10
+    from src.lib.SolutionsManagers import SolutionsManagerFEM
+    from oracle import FEMOracle
+    from oracle.rb import greedy_build, pca_components
+    geo, N, K = (3, 3), 8, 160
+    sm = SolutionsManagerFEM(geo, N)
+    o = FEMOracle(geo, N)
+    y = 10 ** np.random.default_rng(8).uniform(0, 4, (K,) + geo)
+    U = sm.generate_solutions(y)
+    h1 = sm.H10norm(U)
+    n = 40
+    for crit in (GREEDY_FOR_GALERKIN, GREEDY_FOR_H10):
+        rb = ReducedBasisGreedy(greedy_for=crit).build(n=n, sm=sm, solutions2train=U, a2train=y, solutions2train_h1norm=h1)
+        _, _, picked, trace = greedy_build(o, n, U, y, o.H10norm(U), greedy_for=crit, return_trace=True)
+        agree = 0
+        for step, (a_, b_) in enumerate(zip(picked, rb.selected_indices)):
+            top = np.sort(trace[step])[-2:]
+            gap = (top[1] - top[0]) / top[1]
+            if a_ != b_:
+                assert gap < 1e-9 or top[1] < 1e-7, (crit, step, a_, b_, gap, top[1])   # rounding-level ties / errors at the noise floor
+                break
+            agree += 1
+        assert agree >= 33, (crit, agree)
+        assert np.asarray(rb.basis).shape == (n, sm.vspace_dim)
+    rbp = ReducedBasisPCA().build(n=n, sm=sm, solutions2train=U, a2train=y)
+    comps, so, _ = pca_components(U, n)
+    np.testing.assert_allclose(np.asarray(rbp.singular_values_), so, rtol=1e-9, atol=1e-9 * so[0])
+    # online stage with n = 33 and n = 70 orthonormal bases
+    for nb_ in (33, 70):
+        Phi = np.linalg.qr(np.random.default_rng(nb_).standard_normal((sm.vspace_dim, nb_)))[0].T
+        rbx = BaseReducedBasis()
+        rbx.set(basis=Phi, a=y[:nb_])
+        fm = rbx.forward_modeling(sm, y[:20])
+        assert relerr(fm, o.generate_fm_solutions(y[:20], Phi)) < 1e-9
+        pj = rbx.projection(sm, U[:20])
+        assert relerr(pj, o.project_solutions(U[:20], Phi)) < 1e-9
