@@ -276,6 +276,13 @@ class Engine:
         _lib.check(self.lib.romhc_tsqr_r(_ptr(W), W.stride(0), b, Dp, _ptr(R), self.stream()))
         return R
 
+    def row_dots(self, X, Y):
+        """out[k] = X[k] . Y[k]; Y with a single row is shared by all rows of X (a GEMV that streams X once)."""
+        out = self.empty(X.shape[0])
+        ldy = 0 if Y.shape[0] == 1 else Y.stride(0)
+        _lib.check(self.lib.romhc_row_dots(_ptr(X), X.stride(0), _ptr(Y), ldy, X.shape[0], X.shape[1], _ptr(out), self.stream()))
+        return out
+
     def row_norms(self, X):
         out = self.empty(X.shape[0])
         _lib.check(self.lib.romhc_row_norms(_ptr(X), X.stride(0), X.shape[0], X.shape[1], _ptr(out), self.stream()))

@@ -57,6 +57,11 @@ def greedy_select(sm, eng, n, U, y, norm, greedy_for, offset=0, distributed=Fals
     picked = torch.zeros(n, dtype=f64, device=dev)
     maxerr = torch.zeros(n, dtype=f64, device=dev)
     bad = torch.zeros((), dtype=torch.bool, device=dev)
+    # incremental right-hand sides of the H10 criterion (device engines only; the CPU test double projects from scratch)
+    Bh = ones = None
+    if greedy_for == GREEDY_FOR_H10 and Kr and hasattr(eng, "apply"):
+        Bh = torch.zeros(Kr, n, dtype=f64, device=dev)
+        ones = torch.ones(Kr, nb, dtype=f64, device=dev)
     sync = (lambda: torch.cuda.synchronize()) if (timings is not None and dev.type == "cuda") else (lambda: None)
     tacc = {"sweep_ms": 0.0, "exchange_ms": 0.0, "orthonormalise_ms": 0.0}
     it = range(n) if progress is None else progress(range(n))
@@ -67,7 +72,15 @@ def greedy_select(sm, eng, n, U, y, norm, greedy_for, offset=0, distributed=Fals
                 err = eng.error_norm(U, None, None)                       # approximation == 0 (reference :89-91, :109-111)
             else:
                 Phi = Q[:k]
-                if greedy_for == GREEDY_FOR_H10:
+                if greedy_for == GREEDY_FOR_H10 and Bh is not None:
+                    # H10 projection (:122, SolutionsManagers.py:108-139): right-hand sides B[:, j] = U A_1 q_j.  The basis grows
+                    # by one Gram-Schmidt vector per round and the old vectors never change, so only the NEW column is a
+                    # pass over U (one GEMV) instead of a (K, Dp) x (Dp, k) product
+                    w_new = eng.apply(None, Q[k - 1:k])
+                    Bh[:, k - 1] = eng.row_dots(U, w_new)                  # GEMV: U streamed once at HBM speed
+                    Ahat, _ = eng.project_operators(Phi)
+                    Cc = eng.reduced_solve(ones, Ahat, Bh[:, :k].contiguous())
+                elif greedy_for == GREEDY_FOR_H10:
                     Cc = sm._projection_coefficients_dev(eng, U, Phi)     # :122
                 elif greedy_for == GREEDY_FOR_GALERKIN:
                     Ahat, bhat = eng.project_operators(Phi)               # :124
