@@ -212,7 +212,9 @@ int gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* 
         const bool skinny = Nn <= 32;
         const int64_t tiles = ((M + 127) / 128) * (skinny ? 1 : (Nn + 63) / 64);
         // number of contraction ranges: fill 1..4 waves of 2 CTAs per SM as completely as possible, >= 2048 indices each
-        const int64_t cap = std::min<int64_t>(Kd / 2048, 4096), slots = 2 * 148;
+        // (>= 256 for short contractions: the Krylov-basis products of the block Lanczos on a K x K Gram matrix have
+        // Kd = K ~ 10^4 and a handful of output tiles -- four ranges left them at 0.57 ms per product)
+        const int64_t cap = std::min<int64_t>(Kd / (Kd >= 32768 ? 2048 : 256), 4096), slots = 2 * 148;
         int64_t nsplit = 1;
         double best = 0.0;
         for (int64_t w = 1; w <= 4; ++w) {
