@@ -489,3 +489,25 @@ def test_project_operators_dmma_route(torch_mod, geo, N, n):
     Ak = np.einsum("kq,qij->kij", y.cpu().numpy(), A1.cpu().numpy())
     ref = np.linalg.solve(Ak, np.broadcast_to(b1.cpu().numpy(), (7, n))[..., None])[..., 0]
     assert relerr(C, ref) < 1e-8
+
+
+def test_host_entry_small_workspace_chunks(torch_mod):
+    """with a small `workspace_gb` the host-buffer pipeline runs on chunks below 512 systems; the chunk
+    schedule (remainder merged into the last chunk) must stay inside the staged capacity.  K >= 4096 so that the tapered
+    schedule is active; results equal the resident solve bit for bit, pageable and pinned destinations."""
+    torch = torch_mod
+    geo, N, K = (2, 2), 16, 4500
+    eng = make_engine(geo, N)
+    per = 2 * (eng.Dp + eng.D) * 8 + eng.solve_bytes_per_system
+    for chunk_target in (300, 286, 511):
+        eng.set_option("workspace_gb", chunk_target * per / float(1 << 30) * 1.0005)
+        y = rand_y(geo, K, seed=chunk_target)
+        U_host, iters, relres = eng.generate_solutions_host(y, return_stats=True)
+        U_pin = torch.empty((K, eng.D), dtype=torch.float64, pin_memory=True).numpy()
+        eng.generate_solutions_host(y, out=U_pin)
+        eng.set_option("workspace_gb", 48)
+        x, it_d, rel_d = eng.solve(eng.params(y))
+        ref = eng.unpad(x).cpu().numpy()
+        np.testing.assert_array_equal(U_host, ref)
+        np.testing.assert_array_equal(U_pin, ref)
+        np.testing.assert_array_equal(iters, it_d.cpu().numpy())
