@@ -408,3 +408,37 @@ def test_large_bases_n_above_32():
         assert relerr(fm, o.generate_fm_solutions(y[:20], Phi)) < 1e-9
         pj = rbx.projection(sm, U[:20])
         assert relerr(pj, o.project_solutions(U[:20], Phi)) < 1e-9
+
+
+def test_pinned_result_pool_keeps_live_arrays_intact():
+    """Large results of the numpy API live in pooled pinned blocks (engine.PinnedPool): an array the caller keeps -- or any
+    view of it -- must never be overwritten by a later call; a block returns to the pool only after the array and all its
+    views are gone, and is then reused."""
+    import gc
+    from src.lib.SolutionsManagers import SolutionsManagerFEM
+    from romhighcontrast_b200.engine import PINNED_POOL, Engine
+    sm = SolutionsManagerFEM((3, 3), 43)                    # D = 16 384: 1200 snapshots = 157 MB > the pipeline threshold
+    K = 1200
+    y1 = 10 ** np.random.default_rng(1).uniform(0, 6, (K, 3, 3))
+    y2 = 10 ** np.random.default_rng(2).uniform(0, 6, (K, 3, 3))
+    U1 = sm.generate_solutions(y1)
+    assert U1.nbytes >= Engine.HOST_PIPELINE_MIN_BYTES and U1.flags.writeable and U1.flags.c_contiguous
+    keep = U1.copy()
+    view = U1[100:200, ::7]
+    U2 = sm.generate_solutions(y2)                           # must take another block
+    np.testing.assert_array_equal(U1, keep)
+    assert not np.shares_memory(U1, U2)
+    addr1 = U1.ctypes.data
+    del U1
+    gc.collect()
+    U3 = sm.generate_solutions(y2)                           # `view` still holds the first block
+    assert U3.ctypes.data != addr1
+    np.testing.assert_array_equal(view, keep[100:200, ::7])
+    np.testing.assert_array_equal(U3, U2)
+    del view
+    gc.collect()
+    n_free = len(PINNED_POOL.free)
+    assert n_free >= 1                                       # the first block is back
+    U4 = sm.generate_solutions(y1)
+    assert U4.ctypes.data == addr1 or len(PINNED_POOL.free) < n_free   # ... and gets reused
+    np.testing.assert_array_equal(U4, keep)
