@@ -180,6 +180,168 @@ k_error_sweep(const double* __restrict__ U, const double* __restrict__ coef, con
     }
 }
 
+// ---- variant 2: independent warps -------------------------------------------------------------------------------------------
+// ncu on the kernel above: the per-row barrier phases the eight warps (all load, then all issue DMMAs): DMMA sub-pipe 39 %
+// busy, stalls `wait` / `math_pipe_throttle` / `barrier`.  Here a warp owns its column band for the whole row segment: its
+// own two-stage cp.async ring for the band's slab of the basis (band + one column), the east neighbour of the band's last
+// column from that extra column by 5 FMAs per lane and a quad reduction instead of the shared exchange.  No block barrier
+// inside the row loop; the warps drift apart and overlap each other's loads and DMMAs.
+// Measured (tests/probe_sweep.py): 1.94 ms against 1.92 ms at K = 10 000, n = 20, 256^2 (1.31 / 1.39 ms at n = 8), 16.6 against
+// 12.0 ms at 512^2 -- the barrier was not the limit: a warp has its snapshot loads in flight only while it is not computing,
+// so about half of the HBM latency stays exposed in both variants.  Kept as an option, not the default.
+template <int MT, int NTW>
+static size_t sw2_smem_bytes(int nk) {
+    const int MS = 8 * MT, PPw = 8 * NTW + 4;
+    return (size_t(MS) * sw_pitch_a(nk) + 8 * MS + size_t(8) * 2 * 4 * nk * PPw) * 8;
+}
+__device__ __forceinline__ void sw_cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+template <int MT, int NTW>
+__global__ void __launch_bounds__(SW_THREADS, (NTW <= 4) ? 2 : 1)
+k_error_sweep2(const double* __restrict__ U, const double* __restrict__ coef, const double* __restrict__ Phi, int n, int nk,
+               int64_t K, int64_t Dp, int P, int R, int nseg, double* __restrict__ part) {
+    constexpr int WB = 8 * NTW, PPw = WB + 4, MS = 8 * MT;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) double sm[];
+    const int PA = ((4 * nk + 15) & ~15) + 4;
+    double* coefA = sm;                                 // MS x PA
+    double* red = coefA + MS * PA;                      // 8 warps x MS
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int kk = 4 * nk;
+    double* ring = red + 8 * MS + size_t(warp) * 2 * kk * PPw;   // this warp's two stages of kk x PPw
+    const int seg = blockIdx.x;
+    const int64_t sys0 = int64_t(blockIdx.y) * MS;
+    const int r0 = seg * SW_RS, r1 = min(r0 + SW_RS, R);
+    for (int i = tid; i < MS * kk; i += SW_THREADS) {
+        const int s = i / kk, k = i - s * kk;
+        coefA[s * PA + k] = (sys0 + s < K && k < n) ? coef[(sys0 + s) * n + k] : 0.0;
+    }
+    const int wcol0 = warp * WB;
+    constexpr int CH = (WB + 2) / 2;                    // 16-byte chunks per basis row: the band and one more column (+ 1 unused)
+    auto load_phi = [&](int buf, int r) {
+        double* dst = ring + size_t(buf) * kk * PPw;
+        for (int v = lane; v < kk * CH; v += 32) {
+            const int k = v / CH, c = (v - k * CH) * 2;
+            const bool ok = k < n && wcol0 + c < P && r < R;
+            sw_cp_async16(dst + k * PPw + c, ok ? Phi + int64_t(k) * Dp + int64_t(r) * P + wcol0 + c : Phi, ok ? 16 : 0);
+        }
+    };
+    load_phi(0, r0);
+    sw_cp_async_commit();
+    __syncthreads();                                    // coefA complete
+    double acc[MT][NTW][2], prev[MT][NTW][2], esum[MT], vedge[MT], pedge[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+        esum[m] = 0.0; pedge[m] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NTW; ++j) prev[m][j][0] = prev[m][j][1] = 0.0;
+    }
+    const bool band_live = wcol0 < P;
+    for (int r = r0; r <= r1 && band_live; ++r) {
+        const int buf = (r - r0) & 1;
+        if (r < r1) load_phi(buf ^ 1, r + 1);
+        sw_cp_async_commit();
+        double uedge[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            const int64_t sys = sys0 + 8 * m + g;
+#pragma unroll
+            for (int j = 0; j < NTW; ++j) {
+                const int col = wcol0 + 8 * j + 2 * t;
+                double2 u = make_double2(0.0, 0.0);
+                if (r < R && sys < K && col < P) u = *reinterpret_cast<const double2*>(U + sys * Dp + int64_t(r) * P + col);
+                acc[m][j][0] = -u.x; acc[m][j][1] = -u.y;
+            }
+            uedge[m] = (r < R && sys < K && wcol0 + WB < P) ? U[sys * Dp + int64_t(r) * P + wcol0 + WB] : 0.0;
+            if (t == 0 && r + 2 <= r1 && r + 2 < R && sys < K) {
+#pragma unroll
+                for (int j = 0; j < NTW; j += 2)
+                    if (wcol0 + 8 * j < P) sw_prefetch_l2(U + sys * Dp + int64_t(r + 2) * P + wcol0 + 8 * j);
+            }
+        }
+        sw_cp_async_wait1();                            // this row's slab has landed (the next one may still be in flight)
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < MT; ++m) vedge[m] = 0.0;
+        if (r < R) {
+            const double* pa = coefA + g * PA + t;
+            const double* pb = ring + size_t(buf) * kk * PPw + t * PPw + g;
+            const double* pe = ring + size_t(buf) * kk * PPw + t * PPw + WB;
+            for (int ks = 0; ks < nk; ++ks) {
+                double a[MT], b[NTW];
+#pragma unroll
+                for (int m = 0; m < MT; ++m) a[m] = pa[8 * m * PA + 4 * ks];
+#pragma unroll
+                for (int j = 0; j < NTW; ++j) b[j] = pb[4 * ks * PPw + 8 * j];
+                const double be = pe[4 * ks * PPw];
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    vedge[m] = fma(a[m], be, vedge[m]);
+#pragma unroll
+                    for (int j = 0; j < NTW; ++j) sw_dmma884(acc[m][j][0], acc[m][j][1], a[m], b[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            double v = vedge[m];
+            v += __shfl_xor_sync(FULL, v, 1);
+            v += __shfl_xor_sync(FULL, v, 2);
+            vedge[m] = v - uedge[m];                    // v at the first column of the next band (0 beyond the grid row)
+        }
+        if (r > r0) {                                   // south edges of row r - 1
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int j = 0; j < NTW; ++j) {
+                    const double d0 = prev[m][j][0] - acc[m][j][0], d1 = prev[m][j][1] - acc[m][j][1];
+                    esum[m] = fma(d0, d0, esum[m]);
+                    esum[m] = fma(d1, d1, esum[m]);
+                }
+        }
+        if (r < r1) {                                   // east edges of row r
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+#pragma unroll
+                for (int j = 0; j < NTW; ++j) {
+                    const double d = acc[m][j][0] - acc[m][j][1];
+                    esum[m] = fma(d, d, esum[m]);
+                    const double s1 = __shfl_sync(FULL, acc[m][j][0], (lane + 1) & 31);
+                    double nxt = s1;
+                    if (j + 1 < NTW) {
+                        const double s2 = __shfl_sync(FULL, acc[m][j + 1 < NTW ? j + 1 : j][0], (lane - 3) & 31);
+                        if (t == 3) nxt = s2;
+                    } else if (t == 3) {
+                        nxt = vedge[m];
+                    }
+                    const double e = acc[m][j][1] - nxt;
+                    esum[m] = fma(e, e, esum[m]);
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int j = 0; j < NTW; ++j) { prev[m][j][0] = acc[m][j][0]; prev[m][j][1] = acc[m][j][1]; }
+        __syncwarp();                                   // every lane is done with stage buf before it is refilled
+    }
+    (void)pedge;
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+        double s = esum[m];
+        s += __shfl_xor_sync(FULL, s, 1);
+        s += __shfl_xor_sync(FULL, s, 2);
+        if (t == 0) red[warp * MS + 8 * m + g] = s;
+    }
+    __syncthreads();
+    if (tid < MS && sys0 + tid < K) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w * MS + tid];
+        part[(sys0 + tid) * nseg + seg] = s;
+    }
+}
+
 __global__ void k_sweep_reduce(const double* __restrict__ part, int np, double* __restrict__ out, int64_t K) {
     const int64_t k = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     if (k >= K) return;
@@ -188,10 +350,25 @@ __global__ void k_sweep_reduce(const double* __restrict__ part, int np, double* 
     out[k] = sqrt(s);
 }
 
+int g_sweep_variant = 1;     // 1: one barrier per row with the shared exchange (default), 2: independent warps (option "sweep" = 2)
 template <int MT, int NTW>
 static int launch_error_sweep(const LevelGeo& g, const double* U, const double* coef, const double* basis, int n, int64_t K,
                               double* part, int nseg, cudaStream_t st) {
     const int nk = (n + 3) / 4;
+    if (g_sweep_variant == 2 && sw2_smem_bytes<MT, NTW>(nk) <= 227 * 1024) {
+        const size_t smb2 = sw2_smem_bytes<MT, NTW>(nk);
+        CK(cudaFuncSetAttribute(k_error_sweep2<MT, NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smb2)));
+        const int64_t ntiles2 = (K + 8 * MT - 1) / (8 * MT);
+        for (int64_t t0 = 0; t0 < ntiles2; t0 += 65535) {
+            const int nt = int(std::min<int64_t>(65535, ntiles2 - t0));
+            const int64_t k0 = t0 * 8 * MT;
+            ++g_launches;
+            k_error_sweep2<MT, NTW><<<dim3(nseg, nt), SW_THREADS, smb2, st>>>(U + k0 * g.Dp, coef + k0 * n, basis, n, nk, K - k0, g.Dp,
+                                                                             g.P, g.R, nseg, part + k0 * nseg);
+        }
+        CK(cudaGetLastError());
+        return ROMHC_OK;
+    }
     const size_t smb = sw_smem_bytes<MT, NTW>(nk);
     CK(cudaFuncSetAttribute(k_error_sweep<MT, NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smb)));
     const int64_t ntiles = (K + 8 * MT - 1) / (8 * MT);
