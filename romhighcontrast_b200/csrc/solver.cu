@@ -190,21 +190,56 @@ __global__ void k_fill_int(int* v, int value, int n) {
 __global__ void k_post_flag(const int* __restrict__ src, volatile int* dst) { *dst = *src; __threadfence_system(); }
 
 // compact (K, D) <-> padded (K, Dp)
-__global__ void k_pack(LevelGeo g, const double* __restrict__ compact, double* __restrict__ padded, int64_t K) {
-    const int64_t row = blockIdx.x;
-    const int64_t k = row / (g.R - 1);
-    const int r = int(row - k * (g.R - 1)) + 1;
-    const double* src = compact + (k * (g.R - 1) + (r - 1)) * int64_t(g.C - 1);
-    double* dst = padded + k * g.Dp + size_t(r) * g.P;
-    for (int c = 1 + threadIdx.x; c < g.C; c += blockDim.x) dst[c] = src[c - 1];
+// compact (K, D) <-> padded (K, Dp): a CTA moves PK_ROWS grid rows of one system, one coalesced pass per row with four
+// rows in flight per thread (the first version, one 128-thread CTA per row, was launch bound: 5.0 ms for 10 000 systems at
+// 256^2 where the 10.4 GB of traffic need 1.7 ms)
+#define PK_ROWS 32
+__global__ void __launch_bounds__(256)
+k_pack(LevelGeo g, const double* __restrict__ compact, double* __restrict__ padded, int64_t K) {
+    const int64_t k = blockIdx.y;
+    const int r0 = 1 + blockIdx.x * PK_ROWS, r1 = min(r0 + PK_ROWS, g.R);
+    const int W = g.C - 1;
+    const double* src = compact + k * int64_t(g.R - 1) * W;
+    double* dst = padded + k * g.Dp;
+    for (int r = r0; r < r1; r += 4) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int rr = r + q;
+            if (rr < r1)
+                for (int c = threadIdx.x; c < W; c += blockDim.x) dst[size_t(rr) * g.P + c + 1] = src[size_t(rr - 1) * W + c];
+        }
+    }
 }
-__global__ void k_unpack(LevelGeo g, const double* __restrict__ padded, double* __restrict__ compact, int64_t K) {
-    const int64_t row = blockIdx.x;
-    const int64_t k = row / (g.R - 1);
-    const int r = int(row - k * (g.R - 1)) + 1;
-    double* dst = compact + (k * (g.R - 1) + (r - 1)) * int64_t(g.C - 1);
-    const double* src = padded + k * g.Dp + size_t(r) * g.P;
-    for (int c = 1 + threadIdx.x; c < g.C; c += blockDim.x) dst[c - 1] = src[c];
+__global__ void __launch_bounds__(256)
+k_unpack(LevelGeo g, const double* __restrict__ padded, double* __restrict__ compact, int64_t K) {
+    const int64_t k = blockIdx.y;
+    const int r0 = 1 + blockIdx.x * PK_ROWS, r1 = min(r0 + PK_ROWS, g.R);
+    const int W = g.C - 1;
+    double* dst = compact + k * int64_t(g.R - 1) * W;
+    const double* src = padded + k * g.Dp;
+    for (int r = r0; r < r1; r += 4) {
+        double v[4][2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                   // W <= 512: at most two elements per thread and row; wider rows loop below
+            const int rr = r + q;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = threadIdx.x + h * 256;
+                v[q][h] = (rr < r1 && c < W) ? src[size_t(rr) * g.P + c + 1] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int rr = r + q;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = threadIdx.x + h * 256;
+                if (rr < r1 && c < W) dst[size_t(rr - 1) * W + c] = v[q][h];
+            }
+            if (rr < r1)
+                for (int c = threadIdx.x + 512; c < W; c += 256) dst[size_t(rr - 1) * W + c] = src[size_t(rr) * g.P + c + 1];
+        }
+    }
 }
 
 // ======================================================================================================
@@ -1318,13 +1353,19 @@ int Context::energy(const double* y, const double* u, const double* coef, const 
 int Context::pack(const double* compact, double* padded, int64_t K, cudaStream_t st) {
     const LevelGeo& g = levels[0];
     CK(cudaMemsetAsync(padded, 0, size_t(K) * g.Dp * 8, st));
-    ++g_launches; k_pack<<<(unsigned)(K * (g.R - 1)), 128, 0, st>>>(g, compact, padded, K);
+    for (int64_t k0 = 0; k0 < K; k0 += 65535) {
+        const unsigned kc = unsigned(std::min<int64_t>(65535, K - k0));
+        ++g_launches; k_pack<<<dim3((g.R - 1 + PK_ROWS - 1) / PK_ROWS, kc), 256, 0, st>>>(g, compact + k0 * int64_t(g.R - 1) * (g.C - 1), padded + k0 * g.Dp, kc);
+    }
     CK(cudaGetLastError());
     return ROMHC_OK;
 }
 int Context::unpack(const double* padded, double* compact, int64_t K, cudaStream_t st) {
     const LevelGeo& g = levels[0];
-    ++g_launches; k_unpack<<<(unsigned)(K * (g.R - 1)), 128, 0, st>>>(g, padded, compact, K);
+    for (int64_t k0 = 0; k0 < K; k0 += 65535) {
+        const unsigned kc = unsigned(std::min<int64_t>(65535, K - k0));
+        ++g_launches; k_unpack<<<dim3((g.R - 1 + PK_ROWS - 1) / PK_ROWS, kc), 256, 0, st>>>(g, padded + k0 * g.Dp, compact + k0 * int64_t(g.R - 1) * (g.C - 1), kc);
+    }
     CK(cudaGetLastError());
     return ROMHC_OK;
 }
