@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libromhc.so")
+LIB_PATH = os.environ.get("ROMHC_LIB_PATH") or os.path.join(_HERE, "libromhc.so")   # (the override serves A/B probes of two builds)
 
 ROMHC_OK, ERR_ARG, ERR_CUDA, ERR_NUMERIC, ERR_NOTCONVERGED = 0, 1, 2, 3, 4
 

@@ -187,7 +187,8 @@ int romhc_set_option(romhc_handle h, const char* name, double value) {
     else if (!strcmp(name, "gram_variant")) romhc::g_gram_variant = (int)value;
     else if (!strcmp(name, "tn_variant")) romhc::g_tn_variant = (int)value;
     else if (!strcmp(name, "fused")) c->use_fused = value != 0.0;
-    else if (!strcmp(name, "papply_pers")) c->papply_pers = value != 0.0;
+    else if (!strcmp(name, "defer_x")) c->defer_x = value != 0.0;
+    else if (!strcmp(name, "papply_pers")) c->papply_pers = std::max(0, std::min(2, (int)value));
     else if (!strcmp(name, "sweep")) { c->use_sweep = value != 0.0; if (value != 0.0) romhc::g_sweep_variant = (int)value >= 2 ? 2 : 1; }
     else if (!strcmp(name, "proj_variant")) c->proj_variant = (int)value;
     else if (!strcmp(name, "z32")) c->use_z32 = std::max(0, std::min(3, (int)value));

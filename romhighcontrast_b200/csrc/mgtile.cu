@@ -77,6 +77,13 @@ struct TileArgs {
     int NR, halo_top;     // rows of the CTA's region, rows above the owned strip
     int pf_dist;          // L2 prefetch distance in CTAs (= CTAs resident on the GPU at once); 0: off
     const int* rinfo;     // persistent kernels: per (strip, row group) row types (2 bits per row) | primary class << 8
+    // k_mgp_update_down, deferred update of the iterate (fp32 search directions only): x is touched every SECOND
+    // iteration.  0: x += alpha p now; 1: leave x alone (the direction stays in its buffer, alpha in its array);
+    // 2: x += alpha_prev p_prev + alpha p -- the same two fused multiply-adds in the same order as two single updates, so x
+    // is bit-identical; the round trip of x through HBM in between is what goes away (16 of 42 bytes per point and launch)
+    int xmode;
+    const float* p_prev;
+    const double* alpha_prev;
 };
 
 // shared memory (doubles): [T: ntab * TWD][red: 32][mbarrier: 2][EL: NR * (CG + 2)][ER: same][ET: (NRG + 2) * 4 * CG][EB: same]
@@ -916,7 +923,13 @@ k_mgp_update_down(TileArgs a, const double* __restrict__ p_in, double* __restric
             }
         }
         if (parts & 2) tile_tma_rows(s.Rs, r_in + int64_t(wk.k) * a.g.Dp, P, R, row0, NR, row0, s.bar);
-        if (parts & 4) tile_prefetch_rows(x_io, a.g, wk.k, wk.strip * a.TY, a.TY);
+        if ((parts & 4) && a.xmode != 1) {
+            tile_prefetch_rows(x_io, a.g, wk.k, wk.strip * a.TY, a.TY);
+            if (a.xmode == 2) {
+                const int lo = max(wk.strip * a.TY, 0), hi = min(wk.strip * a.TY + a.TY, R + 1);
+                if (hi > lo) bulk_prefetch_l2(a.p_prev + int64_t(wk.k) * a.g.Dp + size_t(lo) * P, uint32_t(hi - lo) * uint32_t(P) * 4u);
+            }
+        }
     };
     const int tid_ = ty * int(blockDim.x) + tx, nt_ = int(blockDim.x * blockDim.y);
     const int my_parts = (tid_ == 0 ? 1 : 0) | (tid_ == (nt_ > 32 ? 32 : 0) ? 2 : 0) | (tid_ == (nt_ > 64 ? 64 : 0) ? 4 : 0);
@@ -941,9 +954,26 @@ k_mgp_update_down(TileArgs a, const double* __restrict__ p_in, double* __restric
         const int own_lo = y0 - rho0, own_hi = min(y0 + a.TY, R + 1) - rho0;   // owned tile rows: own_lo <= i < own_hi
         const int64_t goff = int64_t(k) * a.g.Dp + int64_t(rho0) * P + 4 * tx;
         double z[4][4], r[4][4];                                             // z holds p until the residual is updated
+        const int xmode = P32 ? a.xmode : 0;
+        if (xmode != 1) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)                                           // x rows: in flight during the staging wait
-            if (i >= own_lo && i < own_hi) tile_load_row(r[i], x_io + goff + i * P);
+            for (int i = 0; i < 4; ++i)                                       // x rows: in flight during the staging wait
+                if (i >= own_lo && i < own_hi) tile_load_row(r[i], x_io + goff + i * P);
+        }
+        if (xmode == 2) {
+            // the deferred direction of the previous iteration goes in first (and is gone from the registers before the
+            // staged strips are unpacked: the kernel runs at the 128-register cap)
+            const double alp = __ldg(a.alpha_prev + k);
+            const float* pq = a.p_prev + goff;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (i >= own_lo && i < own_hi) {
+                    float p0, p1, p2, p3;
+                    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(p0), "=f"(p1), "=f"(p2), "=f"(p3) : "l"(pq + i * P));
+                    r[i][0] = fma(alp, double(p0), r[i][0]); r[i][1] = fma(alp, double(p1), r[i][1]);
+                    r[i][2] = fma(alp, double(p2), r[i][2]); r[i][3] = fma(alp, double(p3), r[i][3]);
+                }
+        }
         mbar_wait(reinterpret_cast<uint64_t*>(smem_raw + (s.bar - base)), phase);
         phase ^= 1u;
         const bool all_rows = (rinfo & 0xff) == 0x55;
@@ -955,13 +985,15 @@ k_mgp_update_down(TileArgs a, const double* __restrict__ p_in, double* __restric
             } else { z[i][0] = z[i][1] = z[i][2] = z[i][3] = 0.0; }
         }
         // x += alpha p on the owned rows
+        if (xmode != 1) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (i >= own_lo && i < own_hi) {
+            for (int i = 0; i < 4; ++i)
+                if (i >= own_lo && i < own_hi) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) r[i][j] = fma(al, z[i][j], r[i][j]);
-                tile_store_row(x_io + goff + i * P, r[i]);
-            }
+                    for (int j = 0; j < 4; ++j) r[i][j] = fma(al, z[i][j], r[i][j]);
+                    tile_store_row(x_io + goff + i * P, r[i]);
+                }
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (all_rows || unsigned(rho0 + i) <= unsigned(R)) tile_lds_row(r[i], s.Rs + own + i * P * 8);
@@ -1872,6 +1904,9 @@ int Context::tile_update_down(int l, int Kc, const double* p, double* x, const d
     a.in_f32 = (use_z32 >= 2 && z32_want && l != bridge_level && tile_up_persistent_ok(l)) ? 1 : 0;
     za_f32 = a.in_f32 != 0;
     a.p_f32 = p_f32 ? 1 : 0;
+    a.xmode = p_f32 ? x_mode : 0;
+    a.p_prev = x_p_prev;
+    a.alpha_prev = x_alpha_prev;
     fn<<<grid, dim3(CG, a.NR / 4), sm, st>>>(a, p, x, ws.r[0], ws.r_alt, alpha, ws.za[0],
                                              a.has_coarse ? ws.r[1] : (a.emit_res ? ws.zb[0] : nullptr), ws.active, Kc);
     bridge_res_emitted = a.emit_res != 0;

@@ -45,7 +45,7 @@ struct SolveWorkspace {
     double* wtab;                     // per-system stencil weight tables of the tile kernels (mgtile.cu)
     double *part_pAp, *part_rz;
     int np;
-    double *alpha, *beta, *rz, *rz0, *relres;
+    double *alpha, *alpha2, *beta, *rz, *rz0, *relres;   // alpha2: the step lengths of the odd iterations (deferred x update)
     int *active, *iters;
 };
 
@@ -110,7 +110,7 @@ struct Context {
     bool tile_prefetch = true;          // L2 prefetch of the next CTA's operand rows (non-persistent tile kernels)
     bool tile_persistent = true;        // persistent, TMA-pipelined tile kernels (one CTA per SM)
     bool use_fused = true;              // PCG update fused into the finest level's going-down kernel
-    bool papply_pers = true;            // persistent, double-buffered k_pcg_p_apply (fp32 transport of z and p)
+    int papply_pers = 2;                // persistent, double-buffered k_pcg_p_apply (fp32 transport of z and p): 0 off, 1 fp64 stencil form, 2 fp32 combination + edge form (default)
     int proj_variant = 0;               // reduced operators: 0 edge-difference kernel (n <= 64), 1 stencil apply + split-K DMMA product (any n)
     bool use_sweep = true;              // greedy error sweep: DMMA kernel (sweep.cu); false: the strip kernel k_energy
     // The preconditioned residual z = M r travels from the finest going-up kernel to k_pcg_p_apply as fp32 (half a stream
@@ -120,6 +120,11 @@ struct Context {
     int use_z32 = 3;                    // 0: off, 1: z_B only (up -> p_apply), 2: also z_A (finest down -> up), 3: also p
     bool p_f32 = false;                 // this solve keeps the search direction p as fp32 (k_pcg_p_apply <-> fused update kernel)
     bool z32_want = false, z32_out = false;
+    // deferred update of the iterate (TileArgs::xmode): state of the current launch, set by solve_chunk
+    int x_mode = 0;
+    const float* x_p_prev = nullptr;
+    const double* x_alpha_prev = nullptr;
+    bool defer_x = true;                // option "defer_x": x is updated every second iteration with two directions at once
     bool za_f32 = false;                // the finest going-down kernel stored z_A as fp32 (only the persistent going-up kernel reads that)
     int tile_nsm = 148;
     std::map<std::array<int, 4>, int*> tile_rinfo_cache;   // (level, TY, halo, NR) -> device row-info table

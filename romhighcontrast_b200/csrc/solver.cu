@@ -470,6 +470,17 @@ k_pcg_p_apply(LevelGeo g, const double* __restrict__ y, const double* __restrict
 // i + 1 are already in flight into the other stage, and the bulk store of item i - 1 drains behind both.  p_new is
 // written in place over the staged z (as fp32), and p^T A p is taken straight from those rounded values (stencil form:
 // the edge form with two neighbour reads per point measured slower, 2.15 against 2.08 ms).
+//
+// EDGE32 (the default, option "papply_pers" = 2): ncu showed the XU pipe -- fp32 <-> fp64 conversions, 16 per clock and
+// SM -- as the busiest unit of this kernel (50 %, 8 conversions per point: 3 in the combination, 5 in the stencil).
+//   * the combination runs in fp32: p_new = fmaf(float(beta), p, z).  p_new is a ROUNDED direction anyway (fp32 transport);
+//     every later use (p^T A p here, A p / x / r in the fused update kernel) reads these stored values, so the recurrences
+//     of x and r stay exact fp64 identities whatever the rounding of p was;
+//   * p^T A p is summed over edges, sum w (p_i - p_j)^2, with the differences taken in fp32 -- exact whenever the two
+//     values are within a factor of two (Sterbenz), 6e-8 relative otherwise -- and squared / accumulated in fp64: two
+//     conversions per point (east and south edge).  p^T A p only enters alpha, and x, r are updated with the SAME alpha,
+//     so a 1e-7 relative perturbation of it costs (1e-7)^2 of one step's energy decrease and nothing in accuracy.
+template <bool EDGE32>
 __global__ void __launch_bounds__(512, 2)
 k_pcg_p_apply_pers(LevelGeo g, const double* __restrict__ y, const float* __restrict__ z, const float* __restrict__ p_in,
                    float* __restrict__ p_out, const double* __restrict__ beta, const int* __restrict__ active,
@@ -539,9 +550,17 @@ k_pcg_p_apply_pers(LevelGeo g, const double* __restrict__ y, const float* __rest
             float2* Z2 = reinterpret_cast<float2*>(Zf);
             const float2* Q2 = reinterpret_cast<const float2*>(Pf);
             const int i0 = (lo_r - row0) * P / 2, i1 = (hi_r - row0) * P / 2;
-            for (int i = i0 + tid; i < i1; i += nt) {
-                const float2 zv = Z2[i], qv = Q2[i];
-                Z2[i] = make_float2(float(fma(b, double(qv.x), double(zv.x))), float(fma(b, double(qv.y), double(zv.y))));
+            if (EDGE32) {
+                const float bf = float(b);
+                for (int i = i0 + tid; i < i1; i += nt) {
+                    const float2 zv = Z2[i], qv = Q2[i];
+                    Z2[i] = make_float2(fmaf(bf, qv.x, zv.x), fmaf(bf, qv.y, zv.y));
+                }
+            } else {
+                for (int i = i0 + tid; i < i1; i += nt) {
+                    const float2 zv = Z2[i], qv = Q2[i];
+                    Z2[i] = make_float2(float(fma(b, double(qv.x), double(zv.x))), float(fma(b, double(qv.y), double(zv.y))));
+                }
             }
         }
         fence_proxy_async();
@@ -553,14 +572,30 @@ k_pcg_p_apply_pers(LevelGeo g, const double* __restrict__ y, const float* __rest
             bulk_commit();
         }
         double acc = 0.0;
-        for_points<true>(sc, y0, y0 + TY - 1, -1,
-                         [&](int r, int c, const ColW& w) {
-                             const int i = (r - row0) * P + c;
-                             const double u = double(Zf[i]);
-                             const double Ap = w.wW * (u - double(Zf[i - 1])) + w.wE * (u - double(Zf[i + 1])) +
-                                               w.wN * (u - double(Zf[i - P])) + w.wS * (u - double(Zf[i + P]));
-                             acc = fma(u, Ap, acc);
-                         });
+        if (EDGE32) {
+            // every point owns its east and south edge (the boundary slots of the strip hold zeros), the first column / row
+            // also the edges to the west / north boundary
+            for_points<true>(sc, y0, y0 + TY - 1, -1,
+                             [&](int r, int c, const ColW& w) {
+                                 const int i = (r - row0) * P + c;
+                                 const float u = Zf[i];
+                                 const double dE = double(u - Zf[i + 1]), dS = double(u - Zf[i + P]);
+                                 double e = (w.wE * dE) * dE;
+                                 e = fma(w.wS * dS, dS, e);
+                                 if (c == 1) { const double uu = double(u); e = fma(w.wW * uu, uu, e); }
+                                 if (r == 1) { const double uu = double(u); e = fma(w.wN * uu, uu, e); }
+                                 acc += e;
+                             });
+        } else {
+            for_points<true>(sc, y0, y0 + TY - 1, -1,
+                             [&](int r, int c, const ColW& w) {
+                                 const int i = (r - row0) * P + c;
+                                 const double u = double(Zf[i]);
+                                 const double Ap = w.wW * (u - double(Zf[i - 1])) + w.wE * (u - double(Zf[i + 1])) +
+                                                   w.wN * (u - double(Zf[i - P])) + w.wS * (u - double(Zf[i + P]));
+                                 acc = fma(u, Ap, acc);
+                             });
+        }
         const double tot = block_sum(acc, h.red, tid, nt);
         if (tid == 0) part_pAp[int64_t(k) * nstrips + strip] = tot;
         __syncthreads();                                 // sa, rowq, red and stage st are free for the items to come
@@ -1161,6 +1196,25 @@ __global__ void k_scalar_beta(int64_t K, int np, const double* __restrict__ part
     atomicAdd(n_active, 1);
 }
 
+// Deferred update of the iterate: systems whose LAST iteration was an odd one still owe x += alpha p of that iteration
+// (odd iterations leave x alone, the following even one applies both directions; a system that converged in between is
+// skipped from then on).  Its direction is intact in the odd buffer: k_pcg_p_apply only writes active systems.
+__global__ void __launch_bounds__(256) k_x_pending(int64_t Dp, double* __restrict__ x, const float* __restrict__ p,
+                                                   const double* __restrict__ alpha, const int* __restrict__ iters) {
+    const int64_t k = blockIdx.y;
+    if (!(iters[k] & 1)) return;
+    const double al = alpha[k];
+    double2* xs = reinterpret_cast<double2*>(x + k * Dp);
+    const float2* ps = reinterpret_cast<const float2*>(p + k * Dp);
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < Dp / 2; i += int64_t(gridDim.x) * blockDim.x) {
+        double2 v = xs[i];
+        const float2 q = ps[i];
+        v.x = fma(al, double(q.x), v.x);
+        v.y = fma(al, double(q.y), v.y);
+        xs[i] = v;
+    }
+}
+
 // ======================================================================================================
 // host side
 // ======================================================================================================
@@ -1301,7 +1355,8 @@ int Context::configure_kernels() {
     CK(cudaFuncSetAttribute(k_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
     CK(cudaFuncSetAttribute(k_energy, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
     CK(cudaFuncSetAttribute(k_pcg_p_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
-    CK(cudaFuncSetAttribute(k_pcg_p_apply_pers, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    CK(cudaFuncSetAttribute(k_pcg_p_apply_pers<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    CK(cudaFuncSetAttribute(k_pcg_p_apply_pers<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
     CK(cudaFuncSetAttribute(k_pcg_update, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
     CK(cudaFuncSetAttribute(k_mg_down, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
     CK(cudaFuncSetAttribute(k_mg_up, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
@@ -1425,7 +1480,7 @@ int Context::ensure_solve_ws(int64_t Kc) {
     ws.cfac = coarse_direct ? b + o_fac : nullptr;
     ws.wtab = b + o_tab;
     ws.part_pAp = b + o_pp; ws.part_rz = b + o_pr; ws.np = np;
-    ws.alpha = b + o_sc; ws.beta = ws.alpha + Kc; ws.rz = ws.beta + Kc; ws.rz0 = ws.rz + Kc; ws.relres = ws.rz0 + Kc;
+    ws.alpha = b + o_sc; ws.beta = ws.alpha + Kc; ws.rz = ws.beta + Kc; ws.rz0 = ws.rz + Kc; ws.relres = ws.rz0 + Kc; ws.alpha2 = ws.relres + Kc;
     ws.active = (int*)(b + o_int); ws.iters = ws.active + Kc;
     if (!ws_flags) {
         CK(cudaMalloc(&ws_flags, 64 * sizeof(int)));
@@ -1635,7 +1690,7 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
     // persistent variant: two stages of (z, p) as fp32 = the same bytes as the two fp64 strips of the plain kernel
     const size_t pp_bytes = hdr + size_t(4) * (TYp + 2) * g.P * 4;
     int pp_per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pp_per_sm, k_pcg_p_apply_pers, int(block.x * block.y), pp_bytes) != cudaSuccess || pp_per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pp_per_sm, k_pcg_p_apply_pers<true>, int(block.x * block.y), pp_bytes) != cudaSuccess || pp_per_sm < 1)
         pp_per_sm = 1;
     const int pp_grid = int(std::min<int64_t>(int64_t(tile_nsm > 0 ? tile_nsm : 148) * pp_per_sm, int64_t(Kc) * nsp));
     const int gs = (Kc + 127) / 128;
@@ -1657,12 +1712,14 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
                                       tol2, n_active, ws_flags + 0);
     int it = 0, cur = 0;
     int total_launch_iters = 0, still_active = -1;
+    // (the direction of iteration `it` lives in ws.p[it & 1]: odd iterations in ws.p[1])
+    const bool dx = defer_x && p_f32 && (g.Dp % 2 == 0);
     for (it = 1; it <= maxit; ++it) {
         prof_window = (it <= min_check_iter);
         prof_begin(PROF_PAPPLY, st);
         if (papply_pers && z32_out && p_f32) {
             ++g_launches;
-            k_pcg_p_apply_pers<<<pp_grid, block, pp_bytes, st>>>(g, y, reinterpret_cast<const float*>(z),
+            (papply_pers >= 2 ? k_pcg_p_apply_pers<true> : k_pcg_p_apply_pers<false>)<<<pp_grid, block, pp_bytes, st>>>(g, y, reinterpret_cast<const float*>(z),
                                                                reinterpret_cast<const float*>(ws.p[cur]),
                                                                reinterpret_cast<float*>(ws.p[cur ^ 1]), ws.beta, ws.active,
                                                                ws.part_pAp, TYp, nsp, Kc);
@@ -1672,8 +1729,13 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
         }
         prof_end(st);
         cur ^= 1;
-        ++g_launches; k_scalar_alpha<<<gs, 128, 0, st>>>(Kc, nsp, ws.part_pAp, ws.rz, ws.alpha, ws.active, ws_flags + 0);
-        rc = vcycle(y, Kc, st, &z, &np_rz, ws.p[cur], x, ws.alpha); if (rc) return rc;
+        // deferred x update: odd iterations keep alpha in the second array and leave x alone, even ones apply both
+        double* al_it = (dx && (it & 1)) ? ws.alpha2 : ws.alpha;
+        ++g_launches; k_scalar_alpha<<<gs, 128, 0, st>>>(Kc, nsp, ws.part_pAp, ws.rz, al_it, ws.active, ws_flags + 0);
+        x_mode = dx ? ((it & 1) ? 1 : 2) : 0;
+        x_p_prev = reinterpret_cast<const float*>(ws.p[cur ^ 1]);
+        x_alpha_prev = ws.alpha2;
+        rc = vcycle(y, Kc, st, &z, &np_rz, ws.p[cur], x, al_it); if (rc) return rc;
         int* ctr = n_active + 1 + (it % 32);
         CK(cudaMemsetAsync(ctr, 0, sizeof(int), st));
         ++g_launches; k_scalar_beta<<<gs, 128, 0, st>>>(Kc, np_rz, ws.part_rz, ws.rz, ws.rz0, ws.beta, ws.active, ws.iters, ws.relres,
@@ -1685,6 +1747,12 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
             still_active = h_flags[0];
             if (still_active == 0) break;
         }
+    }
+    x_mode = 0;
+    if (dx) {
+        ++g_launches;
+        k_x_pending<<<dim3(unsigned(std::min<int64_t>((g.Dp / 2 + 255) / 256, 64)), Kc), 256, 0, st>>>(
+            g.Dp, x, reinterpret_cast<const float*>(ws.p[1]), ws.alpha2, ws.iters);
     }
     ++g_launches; k_post_flag<<<1, 1, 0, st>>>(ws_flags, d_hflags);
     if (iters_out) CK(cudaMemcpyAsync(iters_out, ws.iters, size_t(Kc) * 4, cudaMemcpyDeviceToDevice, st));

@@ -434,6 +434,58 @@ def test_solve_fp32_transport_modes_agree(torch_mod, z32):
     assert relerr(eng.unpad(x[:3]).cpu().numpy(), Uo) < 1e-9
 
 
+@pytest.mark.parametrize("geo,N,K", [((4, 4), 64, 150), ((4, 4), 32, 97), ((3, 3), 43, 40), ((8, 8), 64, 21)])
+def test_solve_deferred_x_update_is_bit_identical(torch_mod, geo, N, K):
+    """option defer_x (default 1): the iterate is touched every second PCG iteration, x += alpha_prev p_prev + alpha p, and
+    systems whose last iteration was odd get their pending direction from k_x_pending.  The same fused multiply-adds in the
+    same order as two single updates: the solutions have to be BIT-identical to defer_x = 0, whatever the iteration at which
+    a system converged (the contrast spread gives odd and even last iterations in one batch)."""
+    from romhighcontrast_b200 import _lib
+    torch = torch_mod
+    eng = make_engine(geo, N)
+    y = eng.params(rand_y(geo, K, cmax=1e6, seed=11))
+    out = {}
+    for mode in (0, 1):
+        eng.set_option("defer_x", mode)
+        eng.solve(y)                                            # (workspace and tables exist from here on)
+        n0 = _lib.launch_count()
+        x, it, rel = eng.solve(y)
+        out[mode] = (x.clone(), it.clone(), _lib.launch_count() - n0)
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    it = out[1][1]
+    if K >= 90:
+        assert int((it % 2 == 1).sum()) > 0 and int((it % 2 == 0).sum()) > 0      # both kinds of last iteration occurred
+    if out[1][2] != out[0][2]:
+        assert out[1][2] == out[0][2] + 1                       # the deferred path ran: one k_x_pending launch on top
+    else:
+        assert geo != (4, 4) or N != 64                         # configs[2] geometry must take the deferred path
+
+
+def test_solve_papply_variants_agree(torch_mod):
+    """option papply_pers: 0 one CTA per strip, 1 persistent kernel with the fp64 stencil form of p^T A p (default),
+    2 persistent kernel with the fp32 combination and the edge form on fp32 differences: solutions agree to 1e-11,
+    iteration counts within one, and all of them with the oracle to 1e-9"""
+    from oracle import FEMOracle
+    torch = torch_mod
+    geo, N, K = (4, 4), 64, 80
+    eng = make_engine(geo, N)
+    yh = rand_y(geo, K, cmax=1e6, seed=12)
+    y = eng.params(yh)
+    res = {}
+    for mode in (1, 0, 2):
+        eng.set_option("papply_pers", mode)
+        x, it, rel = eng.solve(y)
+        res[mode] = (x.clone(), it.clone())
+        assert float(rel.max()) <= 1e-12
+    for mode in (0, 2):
+        d = torch.linalg.vector_norm(res[mode][0] - res[1][0], dim=1) / torch.linalg.vector_norm(res[1][0], dim=1)
+        assert float(d.max()) < 1e-11, mode
+        assert int((res[mode][1] - res[1][1]).abs().max()) <= 1, mode
+    Uo = FEMOracle(geo, N).generate_solutions(yh[:2])
+    for mode in (0, 1, 2):
+        assert relerr(eng.unpad(res[mode][0][:2]).cpu().numpy(), Uo) < 1e-9, mode
+
+
 @pytest.mark.parametrize("geo,N,K,n", [((2, 2), 8, 37, 3), ((3, 2), 4, 100, 7), ((2, 2), 32, 129, 1), ((3, 3), 43, 70, 20),
                                        ((4, 4), 16, 200, 12), ((4, 4), 64, 333, 20), ((4, 4), 64, 64, 32), ((2, 4), 64, 45, 5),
                                        ((8, 8), 64, 23, 20), ((1, 3), 8, 9, 24), ((2, 3), 27, 50, 33)])

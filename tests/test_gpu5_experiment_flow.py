@@ -104,3 +104,97 @@ def test_experiment_flow_matches_oracle():
     back = joblib.load(buf)
     np.testing.assert_array_equal(back["Greedy galerkin"]["basis"].basis, data["Greedy galerkin"]["basis"].basis)
     assert back["Greedy galerkin"]["basis"][:3].dim == 3
+
+
+def test_experiment_driver_against_the_reference_drivers_record(tmp_path, capsys):
+    """The experiment driver (tests/experiment_driver.py: the reference's `experiment()` restated and pinned bit for bit
+    on the unmodified reference classes by tests/test_experiment_driver_cpu.py) runs on the GPU classes, and its `data`
+    dictionary is compared with what the reference's OWN driver produced on the reference's classes
+    (tests/golden/g9_experiment_4x4_N6.npz): same keys and timing entries, same training set and measurement points,
+    same selected snapshots, same error curves, same AttributeError on the cached path (HighContrast.py:172)."""
+    import types
+    import experiment_driver as drv
+    import lib.ReducedBasis as RB
+    import lib.SolutionsManagers as SM
+    from conftest import golden
+    g = golden("g9_experiment_4x4_N6.npz")
+    ns = types.SimpleNamespace(SolutionsManagerFEM=SM.SolutionsManagerFEM, ReducedBasisGreedy=RB.ReducedBasisGreedy,
+                               ReducedBasisRandom=RB.ReducedBasisRandom, INFINIT_A=RB.INFINIT_A,
+                               GREEDY_FOR_H10=RB.GREEDY_FOR_H10, GREEDY_FOR_GALERKIN=RB.GREEDY_FOR_GALERKIN)
+    kw = dict(N=6, refinement=10, vn_max_dim=8, num_measurements=30, blocks_geometry=(4, 4),
+              high_contrast_blocks=[[(0, 1)], [(1, 3)], [(2, 1), (2, 2), (2, 3)]], max_samples=120, seed=42,
+              method="lsqsparse")                                  # oracle/gen_golden_experiment.py CONFIG
+    builders = drv.default_builders(ns)
+    sm, data, a, a_hc, points = drv.experiment(ns, tmp_path / "exp", builders, recalculate=True, recalculate_basis=True, **kw)
+    # host-side bookkeeping: identical
+    assert [b.name for b in builders] == list(g["names"])
+    assert sorted(data.keys()) == list(g["data_keys"])
+    np.testing.assert_array_equal(a, g["a"])
+    np.testing.assert_array_equal(a_hc, g["a_high_contrast"])
+    np.testing.assert_array_equal(points, g["points"])
+    assert isinstance(data["time2calculate_solutions"], float) and isinstance(data["time2calculate_h1norm"], float)
+    # snapshots: rows without a 1e10 block to 1e-9 against the reference's SuperLU path, the others to the reference's own
+    # accuracy there (DESIGN section 5: cond ~ 1e12, the reference is ~1e-5 off the exact discrete solution)
+    U, Ug = data["solutions"], g["solutions"]
+    fin = a.max(axis=(1, 2)) < 1e7
+    row_err = np.linalg.norm(U - Ug, axis=1) / np.linalg.norm(Ug, axis=1)
+    assert row_err[fin].max() < 1e-9 and row_err.max() < 1e-3, (row_err[fin].max(), row_err.max())
+    np.testing.assert_allclose(data["solutions_H1norm"][fin], g["solutions_H1norm"][fin], rtol=1e-9)
+    np.testing.assert_allclose(data["solutions_H1norm"], g["solutions_H1norm"], rtol=1e-3)
+    report, bad = {}, []
+
+    def compare(tag, mine, ref, rows, rtol, atol):
+        """|mine - ref| <= rtol |ref| + atol on `rows`; the worst ratio to that bound goes into the report"""
+        if not rows.any():
+            return
+        ratio = float((np.abs(mine - ref)[rows] / (rtol * np.abs(ref)[rows] + atol)).max())
+        report[tag] = max(report.get(tag, 0.0), ratio)
+        if not ratio <= 1.0:
+            bad.append((tag, ratio))
+
+    for i, name in enumerate(g["names"]):
+        d = data[str(name)]
+        assert sorted(d.keys()) == list(g[f"b{i}_keys"]), name
+        rb = d["basis"]
+        assert isinstance(d["time2build"], float) and rb.dim == kw["vn_max_dim"]
+        idx = np.array([int(np.argmin(np.abs(U - b).sum(axis=1))) for b in np.asarray(rb.basis)])
+        np.testing.assert_array_equal(idx, g[f"b{i}_idx"], err_msg=str(name))          # same snapshots, same order
+        np.testing.assert_array_equal(np.asarray(rb.basis), U[idx])                    # raw rows, bit for bit
+        np.testing.assert_array_equal(np.asarray(rb.a), g[f"b{i}_a"])
+        assert sorted(d["errors"].keys()) == list(g[f"b{i}_ns"]) == sorted(d["times"].keys())
+        for n in g[f"b{i}_ns"]:
+            e, t = d["errors"][n], d["times"][n]
+            assert type(e).__name__ == type(t).__name__ == "TypeOfProblems" and e._fields == tuple(g["fields"])
+            assert all(isinstance(v, float) for v in t)
+            clean = bool(fin[idx][:n].all())        # no 1e10 snapshot in the basis: nothing of the reference's 1e-5 there
+            kind = "finite basis" if clean else "1e10 rows in basis"
+            for f in ("forward_modeling", "projection"):
+                mine, ref = np.asarray(getattr(e, f)), g[f"b{i}_n{n}_{f}"]
+                assert mine.shape == ref.shape == (len(a),)
+                # relative H10 errors of the approximations (values between 1e-16, a snapshot of the span, and 1)
+                if clean:
+                    compare(f"{f} | {kind} | finite rows", mine, ref, fin, 1e-7, 1e-9)
+                else:
+                    compare(f"{f} | {kind} | finite rows", mine, ref, fin, 2e-3, 1e-6)
+                compare(f"{f} | {kind} | 1e10 rows", mine, ref, ~fin, 5e-2, 1e-5)
+            # state estimation: least squares on raw snapshots; only defined up to cond(E) eps
+            E = sm.evaluate_solutions(points, np.asarray(rb.basis)[:n])
+            cond = np.linalg.cond(E)
+            if cond < 1e6:
+                mine, ref = np.asarray(e.state_estimation), g[f"b{i}_n{n}_state_estimation"]
+                compare(f"state_estimation | {kind} | finite rows, cond(E) < 1e6", mine, ref, fin,
+                        1e-7 if clean else 2e-3, 1e-10 * cond if clean else 1e-6)
+                for f in ("parameter_estimation_inverse", "parameter_estimation_linear"):
+                    mine, ref = np.asarray(getattr(e, f)), g[f"b{i}_n{n}_{f}"]
+                    assert mine.shape == ref.shape == a.shape
+                    compare(f"{f} | {kind} | finite rows, cond(E) < 1e6", mine, ref, np.broadcast_to(fin[:, None, None], a.shape),
+                            1e-7 if clean else 2e-3, 1e-10 * cond if clean else 1e-6)
+    with capsys.disabled():
+        print("\n[experiment driver vs reference record] worst |mine - ref| / (rtol |ref| + atol) per comparison:")
+        for k, v in sorted(report.items()):
+            print("   %-90s %.2e" % (k, v))
+    assert not bad, bad
+    # cached path: the second call finds everything in data.compressed and trips over `.marker`, like the reference
+    with pytest.raises(AttributeError) as ei:
+        drv.experiment(ns, tmp_path / "exp", builders, **kw)
+    assert f"{type(ei.value).__name__}: {ei.value}" == str(g["cached_call_exception"])
