@@ -110,7 +110,8 @@ struct Context {
     bool tile_prefetch = true;          // L2 prefetch of the next CTA's operand rows (non-persistent tile kernels)
     bool tile_persistent = true;        // persistent, TMA-pipelined tile kernels (one CTA per SM)
     bool use_fused = true;              // PCG update fused into the finest level's going-down kernel
-    int papply_pers = 2;                // persistent, double-buffered k_pcg_p_apply (fp32 transport of z and p): 0 off, 1 fp64 stencil form, 2 fp32 combination + edge form (default)
+    int papply_pers = 1;                // persistent, double-buffered k_pcg_p_apply (fp32 transport of z and p): 0 off, 1 fp64 stencil form (default),
+                                        // 2 fp32 combination + edge form on fp32 differences (-5 % kernel time, +0.06 iterations: no net gain)
     int proj_variant = 0;               // reduced operators: 0 edge-difference kernel (n <= 64), 1 stencil apply + split-K DMMA product (any n)
     bool use_sweep = true;              // greedy error sweep: DMMA kernel (sweep.cu); false: the strip kernel k_energy
     // The preconditioned residual z = M r travels from the finest going-up kernel to k_pcg_p_apply as fp32 (half a stream
@@ -124,7 +125,8 @@ struct Context {
     int x_mode = 0;
     const float* x_p_prev = nullptr;
     const double* x_alpha_prev = nullptr;
-    bool defer_x = true;                // option "defer_x": x is updated every second iteration with two directions at once
+    bool defer_x = false;               // option "defer_x": x is updated every second iteration with two directions at once (bit-identical; -3 % on the
+                                        // fused kernel for 36 % fewer bytes on its odd launches: the kernel is latency bound, so off by default)
     bool za_f32 = false;                // the finest going-down kernel stored z_A as fp32 (only the persistent going-up kernel reads that)
     int tile_nsm = 148;
     std::map<std::array<int, 4>, int*> tile_rinfo_cache;   // (level, TY, halo, NR) -> device row-info table

@@ -471,7 +471,7 @@ k_pcg_p_apply(LevelGeo g, const double* __restrict__ y, const double* __restrict
 // written in place over the staged z (as fp32), and p^T A p is taken straight from those rounded values (stencil form:
 // the edge form with two neighbour reads per point measured slower, 2.15 against 2.08 ms).
 //
-// EDGE32 (the default, option "papply_pers" = 2): ncu showed the XU pipe -- fp32 <-> fp64 conversions, 16 per clock and
+// EDGE32 (option "papply_pers" = 2; measured 2.08 -> 1.98 ms but +0.06 PCG iterations, i.e. no net gain: not the default): ncu showed the XU pipe -- fp32 <-> fp64 conversions, 16 per clock and
 // SM -- as the busiest unit of this kernel (50 %, 8 conversions per point: 3 in the combination, 5 in the stencil).
 //   * the combination runs in fp32: p_new = fmaf(float(beta), p, z).  p_new is a ROUNDED direction anyway (fp32 transport);
 //     every later use (p^T A p here, A p / x / r in the fused update kernel) reads these stored values, so the recurrences
@@ -490,12 +490,13 @@ k_pcg_p_apply_pers(LevelGeo g, const double* __restrict__ y, const float* __rest
     SmemHdr h = smem_carve(smem_raw, nb);
     const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
     const int P = g.P, nrow = TY + 2;
-    float* stage_z[2];
-    float* stage_p[2];
-    stage_z[0] = reinterpret_cast<float*>(h.data);
-    stage_p[0] = stage_z[0] + size_t(nrow) * P;
-    stage_z[1] = stage_p[0] + size_t(nrow) * P;
-    stage_p[1] = stage_z[1] + size_t(nrow) * P;
+    // stage st: z strip at stage0 + 2 st strip_len, p strip one strip_len further (plain arithmetic on the __shared__ base:
+    // with the pointers in a runtime-indexed array the compiler kept them in local memory and issued GENERIC loads / stores
+    // for every shared-memory access of the item loop)
+    float* const stage0 = reinterpret_cast<float*>(h.data);
+    const int strip_len = nrow * P;
+    auto stage_z = [&](int st_) { return stage0 + 2 * st_ * strip_len; };
+    auto stage_p = [&](int st_) { return stage0 + (2 * st_ + 1) * strip_len; };
     uint64_t* bar = h.bar;                               // bar[0], bar[1]: one per stage
     if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); mbar_fence_init(); }
     // round-robin walk over the items of the active systems (the same order as the tile kernels: neighbouring strips of a
@@ -515,25 +516,34 @@ k_pcg_p_apply_pers(LevelGeo g, const double* __restrict__ y, const float* __rest
         const uint32_t bytes = hi > lo ? uint32_t(hi - lo) * uint32_t(P) * 4u : 0u;
         mbar_expect_tx(bar + st, 2 * bytes);
         if (bytes) {
-            bulk_g2s(stage_z[st] + size_t(lo - row0) * P, z + int64_t(kk) * g.Dp + size_t(lo) * P, bytes, bar + st);
-            bulk_g2s(stage_p[st] + size_t(lo - row0) * P, p_in + int64_t(kk) * g.Dp + size_t(lo) * P, bytes, bar + st);
+            bulk_g2s(stage_z(st) + size_t(lo - row0) * P, z + int64_t(kk) * g.Dp + size_t(lo) * P, bytes, bar + st);
+            bulk_g2s(stage_p(st) + size_t(lo - row0) * P, p_in + int64_t(kk) * g.Dp + size_t(lo) * P, bytes, bar + st);
         }
     };
+    // once per CTA (the thread's column and the grid's rows are the same for every item; the per-item version cost every
+    // thread two integer divisions and ~120 instructions per item, ncu source view): block index of every grid row in
+    // shared memory (the host takes this kernel only for R + 2 <= 768 rows), block columns left / right of column tx
+    StripCtx sc;
+    sc.g = g; sc.sa = h.sa; sc.rowq = h.rowq; sc.row0 = 0;
+    sc.tx = threadIdx.x; sc.ty = threadIdx.y; sc.TXW = blockDim.x; sc.lgTYW = __ffs(blockDim.y) - 1;
+    for (int i = tid; i <= g.R + 1; i += nt) h.rowq[i] = i / g.N;
+    {
+        const int c = max(sc.tx, 1);
+        sc.bl0 = (c - 1) / g.N; sc.br0 = c / g.N;
+    }
     __syncthreads();
     if (tid == 0 && k < K) issue(k, strip, 0);
-    uint32_t ph[2] = {0u, 0u};
+    uint32_t ph = 0u;                                    // bit st: phase parity of stage st's mbarrier
     int st = 0;
     while (k < K) {
         const int y0 = strip * TY, row0 = y0 - 1;
         int kn = k, sn = strip;
         advance(kn, sn);
-        // per-item tables: block coefficients of the system, block index of the strip's rows
+        // per-item table: block coefficients of the system
         load_coef(h.sa, y, k, nb, tid, nt);
-        StripCtx sc;
-        strip_ctx_init(sc, g, h.sa, h.rowq, row0, nrow, tid, nt);
         const double b = beta[k];
-        float* Zf = stage_z[st];
-        const float* Pf = stage_p[st];
+        float* Zf = stage_z(st);
+        const float* Pf = stage_p(st);
         const int lo_r = min(max(row0, 0), row0 + nrow), hi_r = max(min(row0 + nrow, g.R + 1), lo_r);
         {   // rows outside the grid behave as zeros (never touched by the bulk copies)
             const int ntop = (lo_r - row0) * P, nbot0 = (hi_r - row0) * P, nall = nrow * P;
@@ -544,8 +554,8 @@ k_pcg_p_apply_pers(LevelGeo g, const double* __restrict__ y, const float* __rest
             bulk_wait_read();                            // the store of the previous item has left stage st ^ 1
             issue(kn, sn, st ^ 1);
         }
-        mbar_wait(bar + st, ph[st]);
-        ph[st] ^= 1u;
+        mbar_wait(bar + st, (ph >> st) & 1u);
+        ph ^= 1u << st;
         {
             float2* Z2 = reinterpret_cast<float2*>(Zf);
             const float2* Q2 = reinterpret_cast<const float2*>(Pf);
@@ -587,18 +597,58 @@ k_pcg_p_apply_pers(LevelGeo g, const double* __restrict__ y, const float* __rest
                                  acc += e;
                              });
         } else {
-            for_points<true>(sc, y0, y0 + TY - 1, -1,
-                             [&](int r, int c, const ColW& w) {
-                                 const int i = (r - row0) * P + c;
-                                 const double u = double(Zf[i]);
-                                 const double Ap = w.wW * (u - double(Zf[i - 1])) + w.wE * (u - double(Zf[i + 1])) +
-                                                   w.wN * (u - double(Zf[i - P])) + w.wS * (u - double(Zf[i + P]));
-                                 acc = fma(u, Ap, acc);
-                             });
+            // for_points<true>(..., color -1) written out for this kernel: the same thread <-> point mapping and the same
+            // expression per point, but the thread walks down its column with the three vertical values in registers (one
+            // new row value, west and east neighbour per point: 3 shared-memory loads and 3 conversions instead of 5) and
+            // one running pointer instead of an index product per point (ncu source view: 16 % of the kernel's
+            // instructions were IMAD, 12 % F2F)
+            const LevelGeo& gg = sc.g;
+            const int rlo = max(y0, 1), rhi = min(y0 + TY - 1, gg.R - 1);
+            const int nrows_ = rhi - rlo + 1;
+            if (nrows_ > 0) {
+                const int ch = (nrows_ + (1 << sc.lgTYW) - 1) >> sc.lgTYW;
+                const int my_lo = rlo + sc.ty * ch, my_hi = min(my_lo + ch - 1, rhi);
+                for (int c = sc.tx; c < gg.C; c += sc.TXW) {
+                    if (c < 1 || my_lo > my_hi) continue;
+                    ColW w;
+                    w.a = sc.sa; w.ncb = gg.ncb; w.N = gg.N;
+                    if (c == sc.tx) { w.bl = sc.bl0; w.br = sc.br0; }
+                    else { w.bl = (c - 1) / gg.N; w.br = c / gg.N; }
+                    int r = my_lo;
+                    w.rb = sc.rowq[r - sc.row0];
+                    w.rm = r - w.rb * gg.N;
+                    w.compute();
+                    const float* q = Zf + (r - row0) * P + c;
+                    double uN = double(q[-P]), u = double(q[0]);
+                    for (;;) {
+                        const int seg_end = min(my_hi, (w.rm == 0) ? r : r + (gg.N - 1 - w.rm));
+                        const int r0 = r;
+                        for (; r <= seg_end; ++r) {
+                            const double uS = double(q[P]);
+                            const double Ap = w.wW * (u - double(q[-1])) + w.wE * (u - double(q[1])) +
+                                              w.wN * (u - uN) + w.wS * (u - uS);
+                            acc = fma(u, Ap, acc);
+                            uN = u; u = uS; q += P;
+                        }
+                        if (r > my_hi) break;
+                        w.rm += r - r0;
+                        while (w.rm >= gg.N) { w.rm -= gg.N; ++w.rb; }
+                        w.compute();
+                    }
+                }
+            }
         }
-        const double tot = block_sum(acc, h.red, tid, nt);
-        if (tid == 0) part_pAp[int64_t(k) * nstrips + strip] = tot;
-        __syncthreads();                                 // sa, rowq, red and stage st are free for the items to come
+        // block sum with ONE barrier, the one the item ends on anyway: warp partials go to the stage's half of the scratch
+        // (16 warps at most), warp 0 adds them up after the barrier -- the same tree as block_sum, bit for bit.  The next
+        // writers of this half are two items away, behind that item's barriers.
+        acc = warp_sum(acc);
+        if ((tid & 31) == 0) h.red[16 * st + (tid >> 5)] = acc;
+        __syncthreads();                                 // sa, rowq and stage st are free for the items to come
+        if (tid < 32) {
+            double tot = tid < ((nt + 31) >> 5) ? h.red[16 * st + tid] : 0.0;
+            tot = warp_sum(tot);
+            if (tid == 0) part_pAp[int64_t(k) * nstrips + strip] = tot;
+        }
         k = kn; strip = sn; st ^= 1;
     }
     if (tid == 0) bulk_wait_all();
@@ -1717,7 +1767,7 @@ int Context::solve_chunk(const double* y, int Kc, double* x, int* iters_out, dou
     for (it = 1; it <= maxit; ++it) {
         prof_window = (it <= min_check_iter);
         prof_begin(PROF_PAPPLY, st);
-        if (papply_pers && z32_out && p_f32) {
+        if (papply_pers && z32_out && p_f32 && g.R + 2 <= 768) {
             ++g_launches;
             (papply_pers >= 2 ? k_pcg_p_apply_pers<true> : k_pcg_p_apply_pers<false>)<<<pp_grid, block, pp_bytes, st>>>(g, y, reinterpret_cast<const float*>(z),
                                                                reinterpret_cast<const float*>(ws.p[cur]),
