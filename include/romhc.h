@@ -56,7 +56,7 @@ int romhc_destroy(romhc_handle h);
  * solves with a caller-supplied right-hand side always use fp64), "papply_pers" (search-direction kernel p = z + beta p, p^T A p:
  * 1, default: persistent double-buffered kernel, fp64 stencil form; 0: one CTA per strip; 2: fp32 combination + edge form on fp32
  * differences), "defer_x" (0, default; 1: the iterate is updated every second iteration with two directions at once --
- * bit-identical solutions, fewer bytes), "tile_nrg_cap" (16: most 4-row groups per tile-kernel region); process-wide A/B switches of the dense helpers:
+ * bit-identical solutions, fewer bytes); process-wide A/B switches of the dense helpers:
  * "gram_variant" (1, default: 128 x 64 DMMA tiles, two CTAs per SM; 0: 128 x 128), "tn_variant" (1, default: gemm_tn on the
  * fp64 tensor cores; 0: the plain-FMA kernel, which also serves operands whose rows are not 16-byte aligned) */
 int romhc_set_option(romhc_handle h, const char* name, double value);

@@ -16,7 +16,6 @@ namespace romhc {
 extern int g_gram_variant;
 extern int g_tn_variant;
 extern int g_sweep_variant;
-extern int g_tile_nrg_cap;
 
 static thread_local char g_err[1024] = "";
 std::atomic<long long> g_launches{0};
@@ -195,11 +194,6 @@ int romhc_set_option(romhc_handle h, const char* name, double value) {
     else if (!strcmp(name, "z32")) c->use_z32 = std::max(0, std::min(3, (int)value));
     else if (!strcmp(name, "tile_persistent")) c->tile_persistent = value != 0.0;
     else if (!strcmp(name, "tile_prefetch")) c->tile_prefetch = value != 0.0;
-    else if (!strcmp(name, "tile_nrg_cap")) {
-        romhc::g_tile_nrg_cap = std::max(4, std::min(32, (int)value));
-        for (auto& kv : c->tile_rinfo_cache) cudaFree(kv.second);
-        c->tile_rinfo_cache.clear();
-    }
     else if (!strcmp(name, "tile_ty")) c->tile_ty_cap = std::max(4, std::min(64, ((int)value) & ~3));
     else if (!strcmp(name, "threads")) c->strip_threads = ((int)value >= 512) ? 512 : 256;
     else if (!strcmp(name, "strip_kb")) c->strip_budget = (size_t)std::max(16.0, std::min(227.0, value)) * 1024;

@@ -1778,10 +1778,9 @@ bool Context::tile_level_ok(int l) const {
 
 // strip height (even) and region rows (a multiple of 4, the tile height): the tallest region whose CTA fits the
 // thread budget, capped by tile_ty_cap and by the grid height
-int g_tile_nrg_cap = 16;      // most row groups (of 4 rows) per region; option "tile_nrg_cap" (probe: whole 64-row grids as one region)
 static void tile_pick_ty(const LevelGeo& g, int extra_rows, int maxt, int cap, int* TY_out, int* NR_out) {
     const int CG = g.P / 4;
-    const int nrg = std::max(1, std::min(maxt / CG, g_tile_nrg_cap));
+    const int nrg = std::max(1, std::min(maxt / CG, 16));
     int TY = 4 * nrg - extra_rows;
     TY = std::min(TY, cap);
     TY = std::max(TY & ~1, 2);

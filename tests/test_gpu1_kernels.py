@@ -463,8 +463,8 @@ def test_solve_deferred_x_update_is_bit_identical(torch_mod, geo, N, K):
 
 def test_solve_papply_variants_agree(torch_mod):
     """option papply_pers: 0 one CTA per strip, 1 persistent kernel with the fp64 stencil form of p^T A p (default),
-    2 persistent kernel with the fp32 combination and the edge form on fp32 differences: solutions agree to 1e-11,
-    iteration counts within one, and all of them with the oracle to 1e-9"""
+    2 persistent kernel with the fp32 combination and the edge form on fp32 differences: solutions agree to 1e-11
+    (0 and 1: bit for bit), iteration counts within two, and all of them with the oracle to 1e-9"""
     from oracle import FEMOracle
     torch = torch_mod
     geo, N, K = (4, 4), 64, 80
@@ -480,7 +480,11 @@ def test_solve_papply_variants_agree(torch_mod):
     for mode in (0, 2):
         d = torch.linalg.vector_norm(res[mode][0] - res[1][0], dim=1) / torch.linalg.vector_norm(res[1][0], dim=1)
         assert float(d.max()) < 1e-11, (mode, float(d.max()))
-        assert int((res[mode][1] - res[1][1]).abs().max()) <= 1, (mode, int((res[mode][1] - res[1][1]).abs().max()))
+        # (the fp32 combination of variant 2 rounds the search direction differently: +0.06 iterations on average,
+        # single systems move by up to two)
+        assert int((res[mode][1] - res[1][1]).abs().max()) <= (2 if mode == 2 else 0), (mode, int((res[mode][1] - res[1][1]).abs().max()))
+        if mode == 0:
+            assert torch.equal(res[0][0], res[1][0])            # same arithmetic in the same order: bit-identical
     Uo = FEMOracle(geo, N).generate_solutions(yh[:2])
     for mode in (0, 1, 2):
         assert relerr(eng.unpad(res[mode][0][:2]).cpu().numpy(), Uo) < 1e-9, mode
