@@ -363,9 +363,12 @@ def main():
             gb = streams * 8.0 * eng.D * K / 1e9
             per_kind.append({"kernel": nm, "launches": int(pn[i]), "avg_ms": avg_ms, "share": 0.0,
                              "algorithmic_GB": gb, "GBps": gb / (avg_ms * 1e-3)})
-    tot_ms = sum(k["avg_ms"] for k in per_kind) or 1.0
+    # one PCG iteration = every kind weighted by its launches per iteration (the level >= 1 kinds run once per level)
+    n_it = max(1, int(pn[0]) if pn[0] > 0 else int(pn[2]))
+    tot_ms = sum(k["avg_ms"] * k["launches"] for k in per_kind) / n_it or 1.0
+    tot_gb = sum(k["algorithmic_GB"] * k["launches"] for k in per_kind) / n_it
     for k in per_kind:
-        k["share"] = k["avg_ms"] / tot_ms
+        k["share"] = k["avg_ms"] * k["launches"] / n_it / tot_ms
     dom = max(per_kind, key=lambda k: k["avg_ms"]) if per_kind else None
     roofline = None
     if dom:
@@ -382,7 +385,8 @@ def main():
         roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["GBps"], "peak": hbm_peak, "unit": "GB/s",
                     "frac": dom["GBps"] / hbm_peak, "traffic": traffic, "traffic_unit": "GB per launch (ncu dram__bytes_read+write)",
                     "algorithmic_GB_per_launch": dom["algorithmic_GB"], "peak_source": peak_src,
-                    "whole_iteration_GBps": sum(k["algorithmic_GB"] for k in per_kind) / (tot_ms * 1e-3)}
+                    "whole_iteration_GBps": tot_gb / (tot_ms * 1e-3), "whole_iteration_ms": tot_ms,
+                    "whole_iteration_algorithmic_GB": tot_gb, "whole_iteration_frac": tot_gb / (tot_ms * 1e-3) / hbm_peak}
 
     secondary = {}
     if not args.no_secondary:

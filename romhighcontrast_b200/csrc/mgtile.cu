@@ -884,7 +884,7 @@ __device__ __forceinline__ void tile_apply_row(double (&r)[4][4], const double (
     }
 }
 
-template <int CGT, bool P32>
+template <int CGT, bool P32, int XMODE>
 __global__ void __launch_bounds__(TILE_MAXT, 1)
 k_mgp_update_down(TileArgs a, const double* __restrict__ p_in, double* __restrict__ x_io, const double* __restrict__ r_in,
                   double* __restrict__ r_out, const double* __restrict__ alpha, double* __restrict__ z_out, double* __restrict__ rc_out,
@@ -923,9 +923,9 @@ k_mgp_update_down(TileArgs a, const double* __restrict__ p_in, double* __restric
             }
         }
         if (parts & 2) tile_tma_rows(s.Rs, r_in + int64_t(wk.k) * a.g.Dp, P, R, row0, NR, row0, s.bar);
-        if ((parts & 4) && a.xmode != 1) {
+        if ((parts & 4) && XMODE != 1) {
             tile_prefetch_rows(x_io, a.g, wk.k, wk.strip * a.TY, a.TY);
-            if (a.xmode == 2) {
+            if (XMODE == 2) {
                 const int lo = max(wk.strip * a.TY, 0), hi = min(wk.strip * a.TY + a.TY, R + 1);
                 if (hi > lo) bulk_prefetch_l2(a.p_prev + int64_t(wk.k) * a.g.Dp + size_t(lo) * P, uint32_t(hi - lo) * uint32_t(P) * 4u);
             }
@@ -954,7 +954,7 @@ k_mgp_update_down(TileArgs a, const double* __restrict__ p_in, double* __restric
         const int own_lo = y0 - rho0, own_hi = min(y0 + a.TY, R + 1) - rho0;   // owned tile rows: own_lo <= i < own_hi
         const int64_t goff = int64_t(k) * a.g.Dp + int64_t(rho0) * P + 4 * tx;
         double z[4][4], r[4][4];                                             // z holds p until the residual is updated
-        const int xmode = P32 ? a.xmode : 0;
+        constexpr int xmode = P32 ? XMODE : 0;       // compile time: the plain update (0) is the kernel as it was
         if (xmode != 1) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)                                       // x rows: in flight during the staging wait
@@ -1618,11 +1618,15 @@ int Context::tile_setup() {
         int& m = i < 3 ? tile_maxt_down : tile_maxt_up;
         m = std::min(m, fa.maxThreadsPerBlock);
     }
-    const void* ffns[] = {(const void*)k_mgp_update_down<64, false>, (const void*)k_mgp_update_down<32, false>,
-                          (const void*)k_mgp_update_down<16, false>, (const void*)k_mgp_update_down<0, false>,
-                          (const void*)k_mgp_update_down<64, true>,  (const void*)k_mgp_update_down<32, true>,
-                          (const void*)k_mgp_update_down<16, true>,  (const void*)k_mgp_update_down<0, true>};
-    for (int i = 0; i < 8; ++i) {
+    const void* ffns[] = {(const void*)k_mgp_update_down<64, false, 0>, (const void*)k_mgp_update_down<32, false, 0>,
+                          (const void*)k_mgp_update_down<16, false, 0>, (const void*)k_mgp_update_down<0, false, 0>,
+                          (const void*)k_mgp_update_down<64, true, 0>,  (const void*)k_mgp_update_down<32, true, 0>,
+                          (const void*)k_mgp_update_down<16, true, 0>,  (const void*)k_mgp_update_down<0, true, 0>,
+                          (const void*)k_mgp_update_down<64, true, 1>,  (const void*)k_mgp_update_down<32, true, 1>,
+                          (const void*)k_mgp_update_down<16, true, 1>,  (const void*)k_mgp_update_down<0, true, 1>,
+                          (const void*)k_mgp_update_down<64, true, 2>,  (const void*)k_mgp_update_down<32, true, 2>,
+                          (const void*)k_mgp_update_down<16, true, 2>,  (const void*)k_mgp_update_down<0, true, 2>};
+    for (int i = 0; i < 16; ++i) {
         CK(cudaFuncSetAttribute(ffns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         cudaFuncAttributes fa;
         CK(cudaFuncGetAttributes(&fa, ffns[i]));
@@ -1892,8 +1896,11 @@ int Context::tile_update_down(int l, int Kc, const double* p, double* x, const d
     const size_t sm = bytes();
     if (sm > 227 * 1024 || a.NR < 4 * nu + 6) return ROMHC_ERR_ARG;
     a.ns = (a.g.R + a.TY - 1) / a.TY;
-    auto fn = p_f32 ? (CG == 64 ? k_mgp_update_down<64, true> : (CG == 32 ? k_mgp_update_down<32, true> : (CG == 16 ? k_mgp_update_down<16, true> : k_mgp_update_down<0, true>)))
-                    : (CG == 64 ? k_mgp_update_down<64, false> : (CG == 32 ? k_mgp_update_down<32, false> : (CG == 16 ? k_mgp_update_down<16, false> : k_mgp_update_down<0, false>)));
+#define ROMHC_UD(P32_, XM_) (CG == 64 ? k_mgp_update_down<64, P32_, XM_> : (CG == 32 ? k_mgp_update_down<32, P32_, XM_> : \
+                             (CG == 16 ? k_mgp_update_down<16, P32_, XM_> : k_mgp_update_down<0, P32_, XM_>)))
+    const int xm = p_f32 ? x_mode : 0;       // deferred update of the iterate: own instantiations, the plain kernel is untouched
+    auto fn = !p_f32 ? ROMHC_UD(false, 0) : (xm == 1 ? ROMHC_UD(true, 1) : (xm == 2 ? ROMHC_UD(true, 2) : ROMHC_UD(true, 0)));
+#undef ROMHC_UD
     a.rinfo = tile_rinfo(l, a.TY, a.halo_top, a.NR);
     if (!a.rinfo) { set_error("tile kernels: row-info table allocation failed"); return ROMHC_ERR_CUDA; }
     const int grid = tile_persistent_grid((const void*)fn, CG * (a.NR / 4), sm, int64_t(Kc) * a.ns);
@@ -1904,7 +1911,7 @@ int Context::tile_update_down(int l, int Kc, const double* p, double* x, const d
     a.in_f32 = (use_z32 >= 2 && z32_want && l != bridge_level && tile_up_persistent_ok(l)) ? 1 : 0;
     za_f32 = a.in_f32 != 0;
     a.p_f32 = p_f32 ? 1 : 0;
-    a.xmode = p_f32 ? x_mode : 0;
+    a.xmode = xm;
     a.p_prev = x_p_prev;
     a.alpha_prev = x_alpha_prev;
     fn<<<grid, dim3(CG, a.NR / 4), sm, st>>>(a, p, x, ws.r[0], ws.r_alt, alpha, ws.za[0],
