@@ -1376,7 +1376,11 @@ __device__ __forceinline__ void tail_tile_load_global(double (&v)[4][4], const d
     }
 }
 
-__global__ void __launch_bounds__(256, 2)
+// MAXT = 128: the usual case (a 32 x 32 tail level is 64 threads) may use up to 168 registers (three CTAs of 128 threads
+// would still fit; shared memory allows ~6 CTAs of 64 threads) -- under the 128-register cap of the 256-thread variant the
+// per-level TileArgs and tile state spilled to local memory inside every phase
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT == 128 ? 3 : 2)
 k_mgt_tail(TailTileArgs p, const double* __restrict__ r_in, double* __restrict__ z_out, const double* __restrict__ cfac,
            const int* __restrict__ active, double* __restrict__ part_rz) {
     const int64_t k = blockIdx.x;
@@ -1642,7 +1646,8 @@ int Context::tile_setup() {
         m = std::min(m, fa.maxThreadsPerBlock);
     }
     CK(cudaDeviceGetAttribute(&tile_nsm, cudaDevAttrMultiProcessorCount, device));
-    CK(cudaFuncSetAttribute(k_mgt_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(k_mgt_tail<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(k_mgt_tail<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     // vertex-class tables of every level
     for (int* p : tile_rowv) cudaFree(p);
     for (int* p : tile_colv) cudaFree(p);
@@ -1764,7 +1769,8 @@ int Context::tile_tail(const double* y, int Kc, double* part_rz, cudaStream_t st
     const size_t sm = size_t(off) * 8;
     if (threads > 256 || sm > 227 * 1024) return ROMHC_ERR_ARG;
     ++g_launches;
-    k_mgt_tail<<<Kc, threads, sm, st>>>(p, ws.r[tail_level], ws.za[tail_level], ws.cfac, ws.active, part_rz);
+    if (threads <= 128) k_mgt_tail<128><<<Kc, threads, sm, st>>>(p, ws.r[tail_level], ws.za[tail_level], ws.cfac, ws.active, part_rz);
+    else                k_mgt_tail<256><<<Kc, threads, sm, st>>>(p, ws.r[tail_level], ws.za[tail_level], ws.cfac, ws.active, part_rz);
     return ROMHC_OK;
 }
 
