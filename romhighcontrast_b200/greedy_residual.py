@@ -86,7 +86,7 @@ class ReducedBasisGreedyResidual(BaseReducedBasis):
             V[:, 1:] = -(Cc[:, :, None] * yk[:, None, :]).reshape(yk.shape[0], n * nb)   # index 1 + j * nb + q
             W = eng.gemm_nn(V, G)
             est[k0:k0 + self.chunk] = torch.sqrt(torch.clamp((W * V).sum(dim=1), min=0.0))
-            un[k0:k0 + self.chunk] = torch.sqrt(torch.clamp(((Cc @ A1hat) * Cc).sum(dim=1), min=0.0))
+            un[k0:k0 + self.chunk] = torch.sqrt(torch.clamp((eng.gemm_nn(Cc.contiguous(), A1hat.contiguous()) * Cc).sum(dim=1), min=0.0))
             if return_coefs:
                 Cs.append(Cc)
         return (est, un, torch.cat(Cs)) if return_coefs else (est, un)
@@ -120,7 +120,8 @@ class ReducedBasisGreedyResidual(BaseReducedBasis):
             phi = u.clone()
             if Q is not None:
                 for _ in range(2):                                              # Gram-Schmidt, twice
-                    phi = phi - (phi @ Q.T) @ Q
+                    c = eng.gemm_nt(Q.contiguous(), phi.contiguous(), splitk=True)          # (j, 1) = Q phi^T (split-K DMMA product)
+                    phi = phi - eng.gemm_nn(c.T.contiguous(), Q.contiguous())                # (1, Dp)
             nrm = float(torch.linalg.vector_norm(phi))
             if not nrm > 1e-10 * float(torch.linalg.vector_norm(u)):
                 break                                                           # already in the span: nothing to add
