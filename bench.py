@@ -321,6 +321,7 @@ def main():
         sm = SolutionsManagerFEM(GEO, NPB, method="lsqsparse")
         sm.generate_solutions(y_host[:256])
         sm.generate_solutions(y_host)                               # first full call allocates the pinned bounce buffers
+        barrier()                                                   # all ranks copy at the same time, as in the e2e leg above
         t0 = time.perf_counter()
         U_api = sm.generate_solutions(y_host)
         t_api = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
