@@ -65,8 +65,8 @@ def main():
     sm, data, a, ahc = HC.experiment(name="golden", reduced_basis_builders=builders, high_contrast_blocks=HIGH_CONTRAST_BLOCKS,
                                      recalculate=True, recalculate_basis=True, **CONFIG)
     np.testing.assert_array_equal(a, a0)
-    np.testing.assert_array_equal(sm.evaluate_solutions(points, data["solutions"][:3]),
-                                  sm.evaluate_solutions(points, data["solutions"][:3]))
+    # (that `points` are the driver's own measurement points is checked by tests/test_experiment_driver_cpu.py: the restated
+    # driver draws them the same way and reproduces every state-estimation error of this record bit for bit)
     out = dict(a=a, a_high_contrast=ahc, points=points, solutions_H1norm=data["solutions_H1norm"],
                solutions=data["solutions"], names=np.array(names), data_keys=np.array(sorted(data.keys())),
                fields=np.array(HC.TypeOfProblems._fields))
@@ -91,7 +91,6 @@ def main():
     except Exception as e:                                      # noqa: BLE001
         out["cached_call_exception"] = np.array(f"{type(e).__name__}: {e}")
     print("cached call:", out["cached_call_exception"])
-    # a cached call that has to rebuild one builder (dim < vn_max_dim) takes the build branch for it
     os.makedirs(args.out, exist_ok=True)
     np.savez_compressed(os.path.join(args.out, "g9_experiment_4x4_N6.npz"), **out)
     print("wrote g9_experiment_4x4_N6.npz:", {k: np.shape(v) for k, v in list(out.items())[:12]})

@@ -80,8 +80,8 @@ struct TileArgs {
     // k_mgp_update_down, deferred update of the iterate (fp32 search directions only): x is touched every SECOND
     // iteration.  0: x += alpha p now; 1: leave x alone (the direction stays in its buffer, alpha in its array);
     // 2: x += alpha_prev p_prev + alpha p -- the same two fused multiply-adds in the same order as two single updates, so x
-    // is bit-identical; the round trip of x through HBM in between is what goes away (16 of 42 bytes per point and launch)
-    int xmode;
+    // is bit-identical; the round trip of x through HBM in between is what goes away (16 of 42 bytes per point and launch).
+    // The mode itself is a template argument of the kernel (XMODE): the plain update compiles to the kernel as it was.
     const float* p_prev;
     const double* alpha_prev;
 };
@@ -1917,7 +1917,6 @@ int Context::tile_update_down(int l, int Kc, const double* p, double* x, const d
     a.in_f32 = (use_z32 >= 2 && z32_want && l != bridge_level && tile_up_persistent_ok(l)) ? 1 : 0;
     za_f32 = a.in_f32 != 0;
     a.p_f32 = p_f32 ? 1 : 0;
-    a.xmode = xm;
     a.p_prev = x_p_prev;
     a.alpha_prev = x_alpha_prev;
     fn<<<grid, dim3(CG, a.NR / 4), sm, st>>>(a, p, x, ws.r[0], ws.r_alt, alpha, ws.za[0],
