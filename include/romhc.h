@@ -67,6 +67,10 @@ int romhc_get_info(romhc_handle h, int64_t* info16);
  * min_check_iter PCG iterations of every solve (all systems active there).  Index: 0 k_pcg_p_apply, 1 k_pcg_update,
  * 2 k_mg_down level 0, 3 k_mg_down levels >= 1, 4 k_mg_tail, 5 k_mg_up level 0, 6 k_mg_up levels >= 1. */
 int romhc_get_profile(romhc_handle h, double* ms8, int64_t* n8);
+/* with option "ws_guard" = g > 0: every sub-buffer of the solver workspace (residuals, iterates of every level, search
+ * directions, tables, scalars) is followed by g doubles of the byte 0xA5; n_bad = bytes of those zones that changed since
+ * the workspace was laid out.  Test instrument (the pool's compute-sanitizer is closed): 0 after any sequence of solves. */
+int romhc_check_guards(romhc_handle h, int64_t* n_bad);
 /* number of CUDA kernels launched by this library in this process (bench.py "gpu_launches") */
 int64_t romhc_launch_count(void);
 

@@ -34,6 +34,7 @@ SIGNATURES = {
     "romhc_set_option": (_i, [_vp, C.c_char_p, _dbl]),
     "romhc_get_info": (_i, [_vp, C.POINTER(_i64)]),
     "romhc_get_profile": (_i, [_vp, C.POINTER(_dbl), C.POINTER(_i64)]),
+    "romhc_check_guards": (_i, [_vp, C.POINTER(_i64)]),
     "romhc_launch_count": (_i64, []),
     "romhc_malloc": (_i, [C.POINTER(_vp), _sz]),
     "romhc_free": (_i, [_vp]),

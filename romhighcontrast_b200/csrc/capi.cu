@@ -187,6 +187,20 @@ int romhc_set_option(romhc_handle h, const char* name, double value) {
     else if (!strcmp(name, "gram_variant")) romhc::g_gram_variant = (int)value;
     else if (!strcmp(name, "tn_variant")) romhc::g_tn_variant = (int)value;
     else if (!strcmp(name, "fused")) c->use_fused = value != 0.0;
+    else if (!strcmp(name, "ws_guard_poke")) {                   // negative control of the detector: damage `value` bytes of a zone
+        if (c->ws_base && !c->ws_gaps.empty()) {
+            cudaSetDevice(c->device);
+            const auto& gp = c->ws_gaps[c->ws_gaps.size() / 2];
+            cudaMemset((double*)c->ws_base + gp.first, 0, (size_t)std::max(0.0, std::min(value, double(gp.second * 8))));
+        }
+    }
+    else if (!strcmp(name, "ws_guard")) {
+        cudaSetDevice(c->device);
+        cudaDeviceSynchronize();
+        c->ws_guard = std::max(0, std::min(1 << 20, (int)value));
+        if (c->ws_base) cudaFree(c->ws_base);                    // the next solve lays the workspace out again
+        c->ws_base = nullptr; c->ws_K = 0; c->ws_gaps.clear();
+    }
     else if (!strcmp(name, "defer_x")) c->defer_x = value != 0.0;
     else if (!strcmp(name, "papply_pers")) c->papply_pers = std::max(0, std::min(2, (int)value));
     else if (!strcmp(name, "sweep")) { c->use_sweep = value != 0.0; if (value != 0.0) romhc::g_sweep_variant = (int)value >= 2 ? 2 : 1; }
@@ -223,6 +237,12 @@ int romhc_get_profile(romhc_handle h, double* ms8, int64_t* n8) {
     if (!h || !ms8 || !n8) { set_error("null argument"); return ROMHC_ERR_ARG; }
     for (int i = 0; i < 8; ++i) { ms8[i] = i < PROF_NKIND ? H(h)->prof_ms[i] : 0.0; n8[i] = i < PROF_NKIND ? H(h)->prof_n[i] : 0; }
     return ROMHC_OK;
+}
+
+int romhc_check_guards(romhc_handle h, int64_t* n_bad) {
+    if (!h || !n_bad) { set_error("null argument"); return ROMHC_ERR_ARG; }
+    cudaSetDevice(H(h)->device);
+    return H(h)->check_guards(n_bad);
 }
 
 int romhc_malloc(void** p, size_t bytes) { CK(cudaMalloc(p, bytes ? bytes : 8)); return ROMHC_OK; }

@@ -150,6 +150,12 @@ struct Context {
     void* ws_base = nullptr;
     int64_t ws_K = 0;
     size_t ws_bytes = 0;
+    // option "ws_guard" (doubles, 0 = off): every sub-buffer of the solver workspace is followed by a zone of that many
+    // doubles filled with the byte 0xA5; romhc_check_guards counts the bytes that changed (an overwrite detector for the
+    // pool's closed compute-sanitizer: any kernel writing past the end of r / z / p / ... of the batch lands there)
+    int ws_guard = 0;
+    std::vector<std::pair<size_t, size_t>> ws_gaps;      // (offset, length) in doubles
+    int check_guards(int64_t* n_bad);
     SolveWorkspace ws;
     int* ws_flags = nullptr;
     int* h_flags = nullptr;     // mapped pinned host memory

@@ -1504,7 +1504,12 @@ int Context::ensure_solve_ws(int64_t Kc) {
     const int nlev_strip = std::min(tail_level, L + 1);       // levels 0..nlev_strip-1 use strip kernels
     auto al = [](size_t n) { return (n + 31) & ~size_t(31); };   // 256-byte granularity in doubles
     size_t off = 0;
-    auto take = [&](size_t n) { size_t o = off; off += al(n); return o; };
+    ws_gaps.clear();
+    auto take = [&](size_t n) {
+        size_t o = off; off += al(n);
+        if (ws_guard > 0) { ws_gaps.push_back({o + n, off - (o + n) + size_t(ws_guard)}); off += al(size_t(ws_guard)); }
+        return o;
+    };
     std::vector<size_t> o_r(L + 2, 0), o_za(L + 2, 0), o_zb(L + 2, 0);
     const int top = std::min(tail_level, L);                   // deepest level with global-memory vectors
     for (int l = 0; l <= top; ++l) {
@@ -1523,6 +1528,7 @@ int Context::ensure_solve_ws(int64_t Kc) {
     CK(cudaMalloc(&ws_base, off * 8));
     CK(cudaMemset(ws_base, 0, off * 8));
     double* b = (double*)ws_base;
+    for (const auto& gp : ws_gaps) CK(cudaMemset(b + gp.first, 0xA5, gp.second * 8));
     ws.r.assign(L + 2, nullptr); ws.za.assign(L + 2, nullptr); ws.zb.assign(L + 2, nullptr);
     for (int l = 0; l <= top; ++l) { ws.r[l] = b + o_r[l]; ws.za[l] = b + o_za[l]; ws.zb[l] = b + o_zb[l]; }
     ws.p[0] = b + o_p0; ws.p[1] = b + o_p1;
@@ -1541,6 +1547,20 @@ int Context::ensure_solve_ws(int64_t Kc) {
     }
     ws_K = Kc;
     ws_bytes = off * 8;
+    return ROMHC_OK;
+}
+
+// guard zones of the workspace (option "ws_guard"): number of bytes that no longer hold the fill pattern
+int Context::check_guards(int64_t* n_bad) {
+    *n_bad = 0;
+    if (!ws_base || ws_gaps.empty()) return ROMHC_OK;
+    CK(cudaDeviceSynchronize());
+    std::vector<unsigned char> h;
+    for (const auto& gp : ws_gaps) {
+        h.resize(gp.second * 8);
+        CK(cudaMemcpy(h.data(), (const double*)ws_base + gp.first, h.size(), cudaMemcpyDeviceToHost));
+        for (unsigned char c : h) *n_bad += (c != 0xA5);
+    }
     return ROMHC_OK;
 }
 

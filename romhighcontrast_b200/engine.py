@@ -215,6 +215,12 @@ class Engine:
                                  "status": int(stats[2]), "workspace_bytes": int(stats[3])}
         return x, iters, relres
 
+    def check_guards(self):
+        """Bytes of the workspace guard zones (option "ws_guard") that were overwritten since the workspace was laid out."""
+        n_bad = C.c_int64(0)
+        _lib.check(self.lib.romhc_check_guards(self.handle, C.byref(n_bad)))
+        return int(n_bad.value)
+
     def precond(self, y, r_pad):
         z = torch.zeros_like(r_pad)
         _lib.check(self.lib.romhc_precond(self.handle, _ptr(y), _ptr(r_pad), _ptr(z), r_pad.shape[0], self.stream()))

@@ -434,6 +434,124 @@ def test_solve_fp32_transport_modes_agree(torch_mod, z32):
     assert relerr(eng.unpad(x[:3]).cpu().numpy(), Uo) < 1e-9
 
 
+@pytest.mark.parametrize("opts", [{}, {"defer_x": 1}, {"papply_pers": 0}, {"papply_pers": 2}, {"z32": 0}, {"tile_persistent": 0},
+                                  {"tile": 0}, {"fused": 0}, {"tile_ty": 6}, {"strip_kb": 48}])
+@pytest.mark.parametrize("geo,N,K", [((4, 4), 64, 37), ((3, 3), 43, 19), ((2, 2), 32, 33), ((8, 8), 64, 5), ((2, 3), 27, 21),
+                                     ((4, 4), 16, 50), ((2, 2), 8, 64)])
+def test_no_kernel_writes_outside_its_buffers(torch_mod, geo, N, K, opts):
+    """Overwrite detector in place of compute-sanitizer (closed on this GPU pool): with option ws_guard every sub-buffer
+    of the solver workspace is followed by a zone of 0xA5 bytes, and the caller's output sits between two NaN-filled zones
+    of one allocation.  After solves with the PCG / multigrid kernel families of every option, the V-cycle test hook and a
+    solve with caller-supplied right-hand sides, all zones are untouched -- and the solutions are the unguarded ones."""
+    torch = torch_mod
+    eng = make_engine(geo, N)
+    y = eng.params(rand_y(geo, K, cmax=1e6, seed=21))
+    x_ref, it_ref, _ = eng.solve(y)
+    for name, value in opts.items():
+        eng.set_option(name, value)
+    eng.set_option("ws_guard", 512)
+    pad = 4096
+    big = torch.full((K * eng.Dp + 2 * pad,), float("nan"), dtype=torch.float64, device=eng.device)
+    x = big[pad:pad + K * eng.Dp].view(K, eng.Dp)
+    for _ in range(2):
+        eng.solve(y, out=x)
+    assert eng.check_guards() == 0
+    assert bool(torch.isnan(big[:pad]).all()) and bool(torch.isnan(big[pad + K * eng.Dp:]).all())
+    assert not bool(torch.isnan(x).any())
+    d = torch.linalg.vector_norm(x - x_ref, dim=1) / torch.linalg.vector_norm(x_ref, dim=1)
+    assert float(d.max()) < 1e-10
+    r = eng.pad(np.random.default_rng(5).standard_normal((K, eng.D)))
+    eng.precond(y, r)
+    assert eng.check_guards() == 0
+    eng.solve(None, rhs=r)                                                     # a == 1, caller's right-hand sides (all fp64)
+    assert eng.check_guards() == 0
+    if not opts and K == 37:
+        # the detector detects: the zones exist (the workspace grew) and three damaged bytes are counted as three
+        guarded = eng.last_solve_stats["workspace_bytes"]
+        eng.set_option("ws_guard_poke", 3)
+        assert eng.check_guards() == 3
+        eng.set_option("ws_guard", 0)
+        eng.solve(y, out=x)
+        assert eng.last_solve_stats["workspace_bytes"] < guarded and eng.check_guards() == 0
+
+
+class _GuardedOutputs:
+    """Stand-in for Engine.empty: every output the library's kernels write sits between two zones of a sentinel (NaN for
+    floating point, a bit pattern for integers) inside one allocation; check() verifies that no zone was touched."""
+    PAD = 512
+
+    def __init__(self, eng, torch):
+        self.eng, self.torch, self.blocks = eng, torch, []
+
+    def empty(self, *shape, dtype=None):
+        torch = self.torch
+        dtype = torch.float64 if dtype is None else dtype
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list, torch.Size)):
+            shape = tuple(shape[0])
+        n = int(np.prod(shape)) if len(shape) else 1
+        sentinel = float("nan") if dtype.is_floating_point else 0x5A5A5A5A
+        big = torch.full((n + 2 * self.PAD,), sentinel, dtype=dtype, device=self.eng.device)
+        self.blocks.append((big, n, sentinel))
+        return big[self.PAD:self.PAD + n].view(shape)
+
+    def check(self):
+        torch = self.torch
+        for big, n, sentinel in self.blocks:
+            for zone in (big[:self.PAD], big[self.PAD + n:]):
+                ok = torch.isnan(zone).all() if big.dtype.is_floating_point else (zone == sentinel).all()
+                assert bool(ok), (tuple(big.shape), n, str(big.dtype))
+        return len(self.blocks)
+
+
+@pytest.mark.parametrize("geo,N,K", [((4, 4), 16, 70), ((3, 3), 43, 37), ((2, 3), 27, 21), ((4, 4), 64, 33)])
+def test_no_kernel_writes_outside_its_outputs(torch_mod, geo, N, K):
+    """The second half of the stand-in for compute-sanitizer: every kernel family outside the solver workspace (layout, stencil,
+    norms, DMMA GEMMs incl. SYRK / split-K / TN, TSQR, projections, reduced solves of all four code paths, error sweeps,
+    point evaluation, estimators, polynomial features, argmax, and the solver's own outputs) writes its results into
+    sentinel-bordered allocations; afterwards every border is intact (ragged K, n not multiples of the tile sizes, P != C)."""
+    torch = torch_mod
+    eng = make_engine(geo, N)
+    g = _GuardedOutputs(eng, torch)
+    eng.empty = g.empty
+    rng = np.random.default_rng(K)
+    yh = rand_y(geo, K, cmax=1e4, seed=31)
+    y = eng.params(yh)
+    U = eng.pad(rng.standard_normal((K, eng.D)))                                  # pack
+    eng.unpad(U)                                                                  # unpack
+    eng.energy_norm(y, U); eng.h10_norm(U); eng.l2_norm(U)
+    for n in (5, 20, 24, 33, 70):
+        if n > eng.D:
+            continue
+        Phi = eng.pad(np.linalg.qr(rng.standard_normal((eng.D, n)))[0].T.copy())
+        Ahat, bhat = eng.project_operators(Phi)
+        eng.set_option("proj_variant", 1)
+        eng.project_operators(Phi)
+        eng.set_option("proj_variant", 0)
+        Cc = eng.reduced_solve(y, Ahat, bhat)
+        eng.reduced_solve(y, Ahat, eng.gemm_nt(U, Phi))                           # per-system right-hand sides
+        eng.gemm_nn(Cc, Phi)
+        eng.gemm_nt(Phi, U, splitk=True)
+        eng.gemm_tn(Cc, U)
+        for variant in (0, 2, 1):
+            eng.set_option("sweep", variant)
+            eng.error_norm(U, Cc, Phi)
+        if n <= 32:
+            eng.tsqr_r(Phi)
+        eng.row_dots(U, Phi[:1]); eng.row_norms(Phi)
+        eng.estimator(Cc.T.contiguous(), y[:n].contiguous() if n <= K else y[:1].repeat(n, 1).contiguous(), True)
+    eng.gemm_nt(U, U, symmetric=True)                                             # SYRK
+    eng.column_mean(U)
+    pts = rng.uniform(low=[-geo[1] / 2, -geo[0] / 2], high=[geo[1] / 2, geo[0] / 2], size=(17, 2))
+    eng.evaluate(pts, U)
+    eng.poly_features(U[:3].contiguous(), [[0, -1], [1, 2], [0, 0]])
+    eng.argmax_dev(eng.l2_norm(U))
+    x, it, rel = eng.solve(y)                                                     # x, iterations, residuals: guarded too
+    eng.solve(None, rhs=U)
+    torch.cuda.synchronize()
+    assert g.check() > 60
+    assert float(rel.max()) <= 1e-12 * 1.0000001
+
+
 @pytest.mark.parametrize("geo,N,K", [((4, 4), 64, 150), ((4, 4), 32, 97), ((3, 3), 43, 40), ((8, 8), 64, 21)])
 def test_solve_deferred_x_update_is_bit_identical(torch_mod, geo, N, K):
     """option defer_x (default 1): the iterate is touched every second PCG iteration, x += alpha_prev p_prev + alpha p, and
